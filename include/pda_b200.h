@@ -1,0 +1,180 @@
+/* pda_b200.h -- C-ABI of the B200-native residual/Jacobian engine for pressio-demoapps' hot path.
+ *
+ * The reference (Pressio/pressio-demoapps, header-only C++17) has no FFI of its own; this header IS the seam a
+ * maintainer binds (INTEGRATION.md shows the C++ shim and the pybind11/ctypes stub).  Every entry point cites the
+ * reference interface it replaces (paths relative to the reference root).
+ *
+ * Conventions
+ *  - opaque handles, plain pointers + sizes, no C++/torch types;
+ *  - every function returns a pda_status (0 = ok); pda_last_error() gives the message of the last failure on the
+ *    calling thread.  The reference throws std::runtime_error / calls exit(); nothing here throws or exits;
+ *  - all floating point is IEEE double, all indices int32_t, exactly like the reference
+ *    (include/pressiodemoapps/mesh.hpp:76-81, impl/euler_3d_prob_class.hpp:76-80);
+ *  - state / velocity layout: AoS  U[cell*ndpc + dof]  (SURVEY App. A);
+ *  - "_host" flavours take host pointers (staged through pinned buffers, H2D/D2H inside the call);
+ *    "_dev" flavours take device pointers and a cudaStream_t (passed as void*), and do not synchronise;
+ *  - there is NO CPU fallback: evaluation entry points fail with PDA_ERR_NO_DEVICE when no CUDA device is usable.
+ */
+#ifndef PDA_B200_H_
+#define PDA_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct pda_mesh_s*    pda_mesh;
+typedef struct pda_problem_s* pda_problem;
+typedef int pda_status;
+
+enum {
+  PDA_OK = 0,
+  PDA_ERR_INVALID = 1,      /* invalid argument / enum / parameter name (reference: std::runtime_error)        */
+  PDA_ERR_IO = 2,           /* missing or malformed mesh file (reference: exit(EXIT_FAILURE))                   */
+  PDA_ERR_NO_DEVICE = 3,    /* no usable CUDA device: the product path never falls back to the CPU              */
+  PDA_ERR_CUDA = 4,         /* a CUDA runtime call failed                                                       */
+  PDA_ERR_UNSUPPORTED = 5,  /* combination the engine (or the reference) does not implement                     */
+  PDA_ERR_TOO_LARGE = 6     /* nnz or dof count does not fit the reference's int32 index type                   */
+};
+
+/* problem families = the reference's problem enum TYPES */
+enum {
+  PDA_FAMILY_EULER1D = 1,              /* euler1d.hpp:64-69                  */
+  PDA_FAMILY_EULER2D = 2,              /* euler2d.hpp:66-76                  */
+  PDA_FAMILY_EULER3D = 3,              /* euler3d.hpp:65-68                  */
+  PDA_FAMILY_SWE2D = 4,                /* swe2d.hpp:65-68                    */
+  PDA_FAMILY_DIFFUSION_REACTION2D = 5, /* diffusion_reaction2d.hpp           */
+  PDA_FAMILY_ADVECTION_DIFFUSION2D = 6 /* advection_diffusion2d.hpp (Burgers)*/
+};
+/* problem ids inside a family keep the reference's enumerator order */
+enum { PDA_EULER1D_PERIODIC_SMOOTH = 0, PDA_EULER1D_SOD = 1, PDA_EULER1D_LAX = 2, PDA_EULER1D_SHU_OSHER = 3 };
+enum {
+  PDA_EULER2D_PERIODIC_SMOOTH = 0, PDA_EULER2D_KELVIN_HELMHOLTZ = 1, PDA_EULER2D_SEDOV_FULL = 2,
+  PDA_EULER2D_SEDOV_SYMMETRY = 3, PDA_EULER2D_RIEMANN = 4, PDA_EULER2D_NORMAL_SHOCK = 5,
+  PDA_EULER2D_DOUBLE_MACH_REFLECTION = 6, PDA_EULER2D_CROSS_SHOCK = 7, PDA_EULER2D_TESTING_ONLY_NEUMANN = 8
+};
+enum { PDA_EULER3D_PERIODIC_SMOOTH = 0, PDA_EULER3D_SEDOV_SYMMETRY = 1 };
+enum { PDA_SWE2D_SLIP_WALL = 0, PDA_SWE2D_CUSTOM_BCS = 1 };
+enum { PDA_DIFFREAC2D_PROBLEM_A = 0, PDA_DIFFREAC2D_GRAY_SCOTT = 1 };
+enum { PDA_ADVDIFF2D_BURGERS_PERIODIC = 0, PDA_ADVDIFF2D_BURGERS_OUTFLOW = 1 };
+/* InviscidFluxReconstruction (schemes_info.hpp:57-66) */
+enum { PDA_FIRST_ORDER = 0, PDA_WENO3 = 1, PDA_WENO5 = 2 };
+/* ghost sides, in the reference's graph-column order (GhostRelativeLocation, ghost_relative_locations.hpp) */
+enum { PDA_SIDE_LEFT = 0, PDA_SIDE_FRONT = 1, PDA_SIDE_RIGHT = 2, PDA_SIDE_BACK = 3, PDA_SIDE_BOTTOM = 4, PDA_SIDE_TOP = 5 };
+/* device-expressible custom boundary conditions (custom_bc_holder.hpp / custom_bcs_functions.hpp) */
+enum { PDA_BC_DIRICHLET = 0, PDA_BC_HOMOG_NEUMANN = 1, PDA_BC_REFLECTIVE = 2 };
+/* operand layout for apply_jacobian (adapter_cpp.hpp:231-259: vector, col-major, row-major) */
+enum { PDA_LAYOUT_COL_MAJOR = 0, PDA_LAYOUT_ROW_MAJOR = 1 };
+
+const char* pda_last_error(void);
+const char* pda_version(void);
+/* number of CUDA devices the library can use (0 on a CPU-only box; never an error) */
+int pda_device_count(void);
+
+/* ------------------------------------------------------------------ mesh ---------------------------------------- */
+/* load_cellcentered_uniform_mesh_eigen(dir)  (mesh.hpp:87-91, impl/mesh_ccu.hpp:359-448): reads info.dat,
+ * coordinates.dat, connectivity.dat written by meshing_scripts/create_{full,sample}_mesh.py */
+pda_status pda_mesh_load(const char* dir, pda_mesh* out);
+/* native replacement of meshing_scripts/create_full_mesh.py (natural row ordering): n[3] cells,
+ * bounds = {xmin,xmax,ymin,ymax,zmin,zmax}, periodic[3] flags, stencil in {3,5,7}.  dim is 1/2/3 (unused axes n=1).
+ * 3D stencil 7 is supported (extension).  Nothing O(cells) is materialised until asked for. */
+pda_status pda_mesh_make_lattice(int dim, const int32_t n[3], const double bounds[6], const int32_t periodic[3],
+                                 int stencil, pda_mesh* out);
+/* native replacement of meshing_scripts/create_sample_mesh.py: sample cells = gids (any order, sorted internally)
+ * of `full`; stencil mesh = sample cells + their stencil neighbours, renumbered by ascending full-mesh gid. */
+pda_status pda_mesh_make_sample(pda_mesh full, const int32_t* gids, int64_t ngids, pda_mesh* out);
+/* mesh from caller arrays (graph row-major [nSample][(stencil-1)*dim+1]) */
+pda_status pda_mesh_from_arrays(int dim, int stencil, int32_t nSample, int32_t nStencil, const double dxyz[3],
+                                const double* x, const double* y, const double* z, const int32_t* graph,
+                                pda_mesh* out);
+/* write info.dat / connectivity.dat / coordinates.dat (+ stencil_mesh_gids.dat for sample meshes) byte-compatible
+ * with the reference's scripts (create_full_mesh.py:151-218, create_sample_mesh.py:160-212) */
+pda_status pda_mesh_write(pda_mesh m, const char* dir);
+pda_status pda_mesh_free(pda_mesh m);
+
+/* getters = CellCenteredUniformMesh accessors (impl/mesh_ccu.hpp:115-159; python: src_py/main_binder.cc:230-243) */
+int     pda_mesh_dimensionality(pda_mesh m);
+int     pda_mesh_stencil_size(pda_mesh m);
+int32_t pda_mesh_stencil_mesh_size(pda_mesh m);
+int32_t pda_mesh_sample_mesh_size(pda_mesh m);
+int     pda_mesh_graph_cols(pda_mesh m);
+int     pda_mesh_is_fully_periodic(pda_mesh m);
+int     pda_mesh_is_lattice(pda_mesh m);
+int32_t pda_mesh_num_cells_inner(pda_mesh m);
+int32_t pda_mesh_num_cells_near_bd(pda_mesh m);
+pda_status pda_mesh_deltas(pda_mesh m, double dxyz[3], double dxyz_inv[3]);             /* dx() .. dzInv()       */
+pda_status pda_mesh_coordinates(pda_mesh m, double* x, double* y, double* z);           /* viewX/Y/Z (nStencil)  */
+pda_status pda_mesh_graph(pda_mesh m, int32_t* graph);                                  /* graph()               */
+pda_status pda_mesh_rows_inner(pda_mesh m, int32_t* rows);                   /* graphRowsOfCellsAwayFromBd()     */
+pda_status pda_mesh_rows_near_bd(pda_mesh m, int32_t* rows);                 /* graphRowsOfCellsNearBd()         */
+/* sample mesh only: full-mesh gid of every stencil-mesh cell (stencil_mesh_gids.dat) */
+pda_status pda_mesh_stencil_gids(pda_mesh m, int32_t* gids);
+
+/* ------------------------------------------------------------------ problem ------------------------------------- */
+/* create_problem_eigen(mesh, <enum>, recon[, icFlag][, {name:value}])   (euler1d.hpp:82-99, euler2d.hpp:88-186,
+ * euler3d.hpp:80-122, swe2d.hpp:134-185, diffusion_reaction2d.hpp:259-285 with names Du,Dv,F,k).
+ * The mesh must outlive the problem (reference: std::reference_wrapper, euler_2d_prob_class.hpp:1277).
+ * Unlike the reference, an incompatible mesh stencil / scheme pair is rejected (schemes_info.hpp:94-102). */
+pda_status pda_problem_create(pda_mesh mesh, int family, int problem_id, int recon, int ic_flag, int nparams,
+                              const char* const* names, const double* values, int device, pda_problem* out);
+/* custom BCs (Swe2d::CustomBCs, Euler2d Riemann/NormalShock custom-BC overloads): one device-expressible rule per side.
+ * values: ndpc doubles (Dirichlet ghost state); ignored otherwise.  (custom_bcs_functions.hpp:60-164) */
+pda_status pda_problem_set_bc(pda_problem p, int side, int kind, const double* values);
+pda_status pda_problem_free(pda_problem p);
+
+int     pda_problem_num_dof_per_cell(pda_problem p);       /* numDofPerCell()        adapter_cpp.hpp:93-95   */
+int32_t pda_problem_total_dof_sample_mesh(pda_problem p);  /* totalDofSampleMesh()   adapter_cpp.hpp:97-99   */
+int32_t pda_problem_total_dof_stencil_mesh(pda_problem p); /* totalDofStencilMesh()  adapter_cpp.hpp:101-103 */
+/* gamma() / gravity() / coriolis() / queryParameter(name) */
+pda_status pda_problem_query_parameter(pda_problem p, const char* name, double* value);
+/* initialCondition()  (host buffer, totalDofStencilMesh doubles) */
+pda_status pda_problem_initial_condition(pda_problem p, double* U);
+
+/* createJacobian(): fixed CSR pattern, bit-identical to Eigen's setFromTriplets+makeCompressed
+ * (euler_2d_prob_class.hpp:223-237).  nnz first, then the arrays (rowptr: nrows+1, colidx: nnz). */
+pda_status pda_problem_jacobian_nnz(pda_problem p, int64_t* nnz);
+pda_status pda_problem_jacobian_pattern(pda_problem p, int32_t* rowptr, int32_t* colidx);
+
+/* rightHandSide / operator()(U,t,V)                      adapter_cpp.hpp:162-199 */
+pda_status pda_problem_velocity_host(pda_problem p, const double* U, double t, double* V);
+/* rightHandSideAndJacobian / operator()(U,t,V,J,true)    adapter_cpp.hpp:170-213 ; V may be NULL (jacobian()) */
+pda_status pda_problem_velocity_and_jacobian_host(pda_problem p, const double* U, double t, double* V,
+                                                  double* jac_values);
+/* applyJacobian(U,B,t,R): R = J(U,t) * B, B is [totalDofStencilMesh x ncols]   adapter_cpp.hpp:231-259 */
+pda_status pda_problem_apply_jacobian_host(pda_problem p, const double* U, const double* B, int ncols, int layout,
+                                           double t, double* R);
+
+/* device-pointer flavours (inputs already resident in HBM; asynchronous on `stream`) */
+pda_status pda_problem_velocity_dev(pda_problem p, const double* dU, double t, double* dV, void* stream);
+pda_status pda_problem_velocity_and_jacobian_dev(pda_problem p, const double* dU, double t, double* dV,
+                                                 double* dJvalues, void* stream);
+pda_status pda_problem_apply_jacobian_dev(pda_problem p, const double* dU, const double* dB, int ncols, int layout,
+                                          double t, double* dR, void* stream);
+
+/* test hooks = viewGhostLeft/Front/Right/Back (euler_2d_prob_class.hpp:205-210): ghost rows after the last
+ * evaluation, [numCellsNearBd][ndpc*(stencil-1)/2] */
+pda_status pda_problem_ghosts(pda_problem p, int side, double* out);
+
+/* number of kernel launches issued by this problem since creation (bench.py's gpu_launches) */
+int64_t pda_problem_launch_count(pda_problem p);
+/* device time of the dominant kernel in the last *_dev/_host evaluation is not measured here: callers bracket
+ * with their own CUDA events on `stream`. */
+
+/* ---------------------------------------------- slab-decomposed lattices (multi-GPU) ---------------------------- */
+/* One process per GPU.  A rank owns planes [k0,k1) of the slowest axis of a full lattice; its local
+ * state carries `halo` = (stencil-1)/2 extra planes on each side which the caller fills (NCCL send/recv or peer
+ * copies) before the boundary planes are evaluated.  Local state layout: [(k1-k0)+2*halo planes][plane cells][ndpc]. */
+pda_status pda_problem_create_slab(pda_mesh lattice, int family, int problem_id, int recon, int rank, int nranks,
+                                   int device, pda_problem* out);
+pda_status pda_slab_extent(pda_problem p, int32_t* k0, int32_t* k1, int32_t* halo, int64_t* plane_dofs);
+/* initial condition of the owned planes (no halos), host buffer of (k1-k0)*plane_dofs doubles */
+pda_status pda_slab_initial_condition(pda_problem p, double* U_owned);
+/* velocity of the owned planes that do NOT need halo data (interior), then of the 2*halo boundary planes */
+pda_status pda_slab_velocity_interior_dev(pda_problem p, const double* dU_local, double t, double* dV_owned, void* stream);
+pda_status pda_slab_velocity_boundary_dev(pda_problem p, const double* dU_local, double t, double* dV_owned, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PDA_B200_H_ */

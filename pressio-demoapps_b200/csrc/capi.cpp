@@ -1,0 +1,278 @@
+// capi.cpp -- extern "C" boundary declared in include/pda_b200.h.  Catches every C++ exception and turns it into
+// a status code + thread-local message (the reference throws std::runtime_error or calls exit(); a drop-in
+// library must do neither across an FFI).
+#include <cuda_runtime.h>
+
+#include <cstring>
+#include <new>
+#include <string>
+
+#include "../../include/pda_b200.h"
+#include "common.hpp"
+#include "engine.hpp"
+#include "mesh.hpp"
+
+struct pda_mesh_s { pda::Mesh m; };
+struct pda_problem_s { pda::Problem* p; };
+
+namespace {
+thread_local std::string g_lastError;
+
+template <class F>
+pda_status guarded(F&& f) {
+  try {
+    f();
+    return PDA_OK;
+  } catch (const pda::Error& e) {
+    g_lastError = e.what();
+    return e.code;
+  } catch (const std::bad_alloc&) {
+    g_lastError = "out of host memory";
+    return PDA_ERR_TOO_LARGE;
+  } catch (const std::exception& e) {
+    g_lastError = e.what();
+    return PDA_ERR_INVALID;
+  } catch (...) {
+    g_lastError = "unknown error";
+    return PDA_ERR_INVALID;
+  }
+}
+
+pda::Mesh& M(pda_mesh m) {
+  if (!m) throw pda::Error(pda::kInvalid, "null mesh handle");
+  return m->m;
+}
+pda::Problem& P(pda_problem p) {
+  if (!p || !p->p) throw pda::Error(pda::kInvalid, "null problem handle");
+  return *p->p;
+}
+}  // namespace
+
+extern "C" {
+
+const char* pda_last_error(void) { return g_lastError.c_str(); }
+const char* pda_version(void) { return "pda_b200 0.1 (sm_100a)"; }
+
+int pda_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+  return n;
+}
+
+// ------------------------------------------------------------------ mesh
+pda_status pda_mesh_load(const char* dir, pda_mesh* out) {
+  return guarded([&] {
+    if (!dir || !out) throw pda::Error(pda::kInvalid, "mesh_load: null argument");
+    *out = new pda_mesh_s{pda::Mesh::load(dir)};
+  });
+}
+
+pda_status pda_mesh_make_lattice(int dim, const int32_t n[3], const double bounds[6], const int32_t periodic[3],
+                                 int stencil, pda_mesh* out) {
+  return guarded([&] {
+    if (!n || !bounds || !periodic || !out) throw pda::Error(pda::kInvalid, "mesh_make_lattice: null argument");
+    *out = new pda_mesh_s{pda::Mesh::makeLattice(dim, n, bounds, periodic, stencil)};
+  });
+}
+
+pda_status pda_mesh_make_sample(pda_mesh full, const int32_t* gids, int64_t ngids, pda_mesh* out) {
+  return guarded([&] {
+    if (!gids || !out) throw pda::Error(pda::kInvalid, "mesh_make_sample: null argument");
+    *out = new pda_mesh_s{pda::Mesh::makeSample(M(full), gids, ngids)};
+  });
+}
+
+pda_status pda_mesh_from_arrays(int dim, int stencil, int32_t nSample, int32_t nStencil, const double dxyz[3],
+                                const double* x, const double* y, const double* z, const int32_t* graph,
+                                pda_mesh* out) {
+  return guarded([&] {
+    if (!dxyz || !x || !graph || !out) throw pda::Error(pda::kInvalid, "mesh_from_arrays: null argument");
+    *out = new pda_mesh_s{pda::Mesh::fromArrays(dim, stencil, nSample, nStencil, dxyz, x, y, z, graph)};
+  });
+}
+
+pda_status pda_mesh_write(pda_mesh m, const char* dir) {
+  return guarded([&] {
+    if (!dir) throw pda::Error(pda::kInvalid, "mesh_write: null directory");
+    M(m).write(dir);
+  });
+}
+
+pda_status pda_mesh_free(pda_mesh m) {
+  delete m;
+  return PDA_OK;
+}
+
+int pda_mesh_dimensionality(pda_mesh m) { return m ? m->m.dim : -1; }
+int pda_mesh_stencil_size(pda_mesh m) { return m ? m->m.stencil : -1; }
+int32_t pda_mesh_stencil_mesh_size(pda_mesh m) { return m ? m->m.nStencil : -1; }
+int32_t pda_mesh_sample_mesh_size(pda_mesh m) { return m ? m->m.nSample : -1; }
+int pda_mesh_graph_cols(pda_mesh m) { return m ? m->m.ncols() : -1; }
+int pda_mesh_is_fully_periodic(pda_mesh m) { return m ? (m->m.fullyPeriodic ? 1 : 0) : -1; }
+int pda_mesh_is_lattice(pda_mesh m) { return m ? (m->m.lattice ? 1 : 0) : -1; }
+int32_t pda_mesh_num_cells_near_bd(pda_mesh m) { return m ? (int32_t)m->m.countNearBd() : -1; }
+int32_t pda_mesh_num_cells_inner(pda_mesh m) { return m ? (int32_t)(m->m.nSample - m->m.countNearBd()) : -1; }
+
+pda_status pda_mesh_deltas(pda_mesh m, double dxyz[3], double dxyz_inv[3]) {
+  return guarded([&] {
+    pda::Mesh& mm = M(m);
+    for (int a = 0; a < 3; ++a) {
+      if (dxyz) dxyz[a] = mm.d[a];
+      if (dxyz_inv) dxyz_inv[a] = mm.dInv[a];
+    }
+  });
+}
+
+pda_status pda_mesh_coordinates(pda_mesh m, double* x, double* y, double* z) {
+  return guarded([&] {
+    pda::Mesh& mm = M(m);
+    mm.ensureCoords();
+    const size_t nb = sizeof(double) * (size_t)mm.nStencil;
+    if (x) std::memcpy(x, mm.x.data(), nb);
+    if (y) std::memcpy(y, mm.y.data(), nb);
+    if (z) std::memcpy(z, mm.z.data(), nb);
+  });
+}
+
+pda_status pda_mesh_graph(pda_mesh m, int32_t* graph) {
+  return guarded([&] {
+    pda::Mesh& mm = M(m);
+    if (!graph) throw pda::Error(pda::kInvalid, "mesh_graph: null output");
+    mm.ensureGraph();
+    std::memcpy(graph, mm.graph.data(), sizeof(int32_t) * mm.graph.size());
+  });
+}
+
+pda_status pda_mesh_rows_inner(pda_mesh m, int32_t* rows) {
+  return guarded([&] {
+    pda::Mesh& mm = M(m);
+    mm.ensureRows();
+    if (rows && !mm.rowsInner.empty()) std::memcpy(rows, mm.rowsInner.data(), sizeof(int32_t) * mm.rowsInner.size());
+  });
+}
+
+pda_status pda_mesh_rows_near_bd(pda_mesh m, int32_t* rows) {
+  return guarded([&] {
+    pda::Mesh& mm = M(m);
+    mm.ensureRows();
+    if (rows && !mm.rowsNearBd.empty()) std::memcpy(rows, mm.rowsNearBd.data(), sizeof(int32_t) * mm.rowsNearBd.size());
+  });
+}
+
+pda_status pda_mesh_stencil_gids(pda_mesh m, int32_t* gids) {
+  return guarded([&] {
+    pda::Mesh& mm = M(m);
+    if (mm.stencilGids.empty()) throw pda::Error(pda::kInvalid, "mesh_stencil_gids: not a sample mesh built by this library");
+    std::memcpy(gids, mm.stencilGids.data(), sizeof(int32_t) * mm.stencilGids.size());
+  });
+}
+
+// ------------------------------------------------------------------ problem
+pda_status pda_problem_create(pda_mesh mesh, int family, int problem_id, int recon, int ic_flag, int nparams,
+                              const char* const* names, const double* values, int device, pda_problem* out) {
+  return guarded([&] {
+    if (!out) throw pda::Error(pda::kInvalid, "problem_create: null output");
+    if (nparams > 0 && (!names || !values)) throw pda::Error(pda::kInvalid, "problem_create: null parameter arrays");
+    *out = new pda_problem_s{new pda::Problem(&M(mesh), family, problem_id, recon, ic_flag, nparams, names, values, device)};
+  });
+}
+
+pda_status pda_problem_set_bc(pda_problem p, int side, int kind, const double* values) {
+  return guarded([&] { P(p).setBc(side, kind, values); });
+}
+
+pda_status pda_problem_free(pda_problem p) {
+  if (p) { delete p->p; delete p; }
+  return PDA_OK;
+}
+
+int pda_problem_num_dof_per_cell(pda_problem p) { return (p && p->p) ? p->p->ndpc() : -1; }
+int32_t pda_problem_total_dof_sample_mesh(pda_problem p) { return (p && p->p) ? p->p->nDofSample() : -1; }
+int32_t pda_problem_total_dof_stencil_mesh(pda_problem p) { return (p && p->p) ? p->p->nDofStencil() : -1; }
+
+pda_status pda_problem_query_parameter(pda_problem p, const char* name, double* value) {
+  return guarded([&] {
+    if (!name || !value) throw pda::Error(pda::kInvalid, "query_parameter: null argument");
+    *value = P(p).queryParameter(name);
+  });
+}
+
+pda_status pda_problem_initial_condition(pda_problem p, double* U) {
+  return guarded([&] {
+    if (!U) throw pda::Error(pda::kInvalid, "initial_condition: null output");
+    P(p).initialCondition(U);
+  });
+}
+
+pda_status pda_problem_jacobian_nnz(pda_problem p, int64_t* nnz) {
+  return guarded([&] {
+    if (!nnz) throw pda::Error(pda::kInvalid, "jacobian_nnz: null output");
+    *nnz = P(p).jacobianNnz();
+  });
+}
+
+pda_status pda_problem_jacobian_pattern(pda_problem p, int32_t* rowptr, int32_t* colidx) {
+  return guarded([&] { P(p).jacobianPattern(rowptr, colidx); });
+}
+
+pda_status pda_problem_velocity_host(pda_problem p, const double* U, double t, double* V) {
+  return guarded([&] { P(p).velocityHost(U, t, V); });
+}
+
+pda_status pda_problem_velocity_and_jacobian_host(pda_problem p, const double* U, double t, double* V, double* jv) {
+  return guarded([&] { P(p).velocityAndJacobianHost(U, t, V, jv); });
+}
+
+pda_status pda_problem_apply_jacobian_host(pda_problem p, const double* U, const double* B, int ncols, int layout,
+                                           double t, double* R) {
+  return guarded([&] { P(p).applyJacobianHost(U, B, ncols, layout, t, R); });
+}
+
+pda_status pda_problem_velocity_dev(pda_problem p, const double* dU, double t, double* dV, void* stream) {
+  return guarded([&] { P(p).velocityDev(dU, t, dV, stream); });
+}
+
+pda_status pda_problem_velocity_and_jacobian_dev(pda_problem p, const double* dU, double t, double* dV, double* dJ,
+                                                 void* stream) {
+  return guarded([&] { P(p).velocityAndJacobianDev(dU, t, dV, dJ, stream); });
+}
+
+pda_status pda_problem_apply_jacobian_dev(pda_problem p, const double* dU, const double* dB, int ncols, int layout,
+                                          double t, double* dR, void* stream) {
+  return guarded([&] { P(p).applyJacobianDev(dU, dB, ncols, layout, t, dR, stream); });
+}
+
+pda_status pda_problem_ghosts(pda_problem p, int side, double* out) {
+  return guarded([&] { P(p).ghosts(side, out); });
+}
+
+int64_t pda_problem_launch_count(pda_problem p) { return (p && p->p) ? p->p->launchCount() : -1; }
+
+// ------------------------------------------------------------------ slabs
+pda_status pda_problem_create_slab(pda_mesh lattice, int family, int problem_id, int recon, int rank, int nranks,
+                                   int device, pda_problem* out) {
+  return guarded([&] {
+    if (!out) throw pda::Error(pda::kInvalid, "problem_create_slab: null output");
+    auto* prob = new pda::Problem(&M(lattice), family, problem_id, recon, 1, 0, nullptr, nullptr, device);
+    try { prob->makeSlab(rank, nranks); } catch (...) { delete prob; throw; }
+    *out = new pda_problem_s{prob};
+  });
+}
+
+pda_status pda_slab_extent(pda_problem p, int32_t* k0, int32_t* k1, int32_t* halo, int64_t* plane_dofs) {
+  return guarded([&] { P(p).slabExtent(k0, k1, halo, plane_dofs); });
+}
+
+pda_status pda_slab_initial_condition(pda_problem p, double* U_owned) {
+  return guarded([&] { P(p).slabInitialCondition(U_owned); });
+}
+
+pda_status pda_slab_velocity_interior_dev(pda_problem p, const double* dU, double t, double* dV, void* stream) {
+  return guarded([&] { P(p).slabVelocityDev(dU, t, dV, stream, false); });
+}
+
+pda_status pda_slab_velocity_boundary_dev(pda_problem p, const double* dU, double t, double* dV, void* stream) {
+  return guarded([&] { P(p).slabVelocityDev(dU, t, dV, stream, true); });
+}
+
+}  // extern "C"

@@ -1,0 +1,1162 @@
+// engine.cu -- Problem: host logic (parameters, initial conditions, CSR pattern, ghost recipes) and the CUDA
+// launches of the velocity / Jacobian evaluation.  No CPU fallback: without a device every evaluation throws.
+#include "engine.hpp"
+
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <map>
+
+#include "common.hpp"
+#include "kernels_generic.cuh"
+#include "kernels_lattice.cuh"
+
+namespace pda {
+
+namespace {
+
+#define PDA_CUDA(call)                                                                                   \
+  do {                                                                                                   \
+    cudaError_t e_ = (call);                                                                             \
+    if (e_ != cudaSuccess)                                                                               \
+      throw Error(kCuda, std::string(#call) + " failed: " + cudaGetErrorString(e_));                     \
+  } while (0)
+
+template <class T>
+struct DevBuf {
+  T* p = nullptr;
+  size_t n = 0;
+  DevBuf() = default;
+  DevBuf(const DevBuf&) = delete;
+  DevBuf& operator=(const DevBuf&) = delete;
+  ~DevBuf() { if (p) cudaFree(p); }
+  void alloc(size_t count) {
+    if (count <= n && p) return;
+    if (p) cudaFree(p);
+    p = nullptr; n = 0;
+    if (count == 0) return;
+    PDA_CUDA(cudaMalloc(&p, count * sizeof(T)));
+    n = count;
+  }
+  void upload(const std::vector<T>& v) {
+    alloc(v.size());
+    if (!v.empty()) PDA_CUDA(cudaMemcpy(p, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice));
+  }
+};
+
+template <class T>
+struct PinnedBuf {
+  T* p = nullptr;
+  size_t n = 0;
+  ~PinnedBuf() { if (p) cudaFreeHost(p); }
+  void alloc(size_t count) {
+    if (count <= n && p) return;
+    if (p) cudaFreeHost(p);
+    p = nullptr; n = 0;
+    if (count == 0) return;
+    PDA_CUDA(cudaMallocHost(&p, count * sizeof(T)));
+    n = count;
+  }
+};
+
+// family / problem ids: include/pda_b200.h
+enum { F_EULER1D = 1, F_EULER2D = 2, F_EULER3D = 3, F_SWE2D = 4, F_DIFFREAC2D = 5, F_ADVDIFF2D = 6 };
+enum { E2_PERIODIC = 0, E2_KH = 1, E2_SEDOV_FULL = 2, E2_SEDOV_SYM = 3, E2_RIEMANN = 4, E2_NORMAL_SHOCK = 5,
+       E2_DMR = 6, E2_CROSS_SHOCK = 7, E2_NEUMANN = 8 };
+enum { BC_DIRICHLET = 0, BC_NEUMANN = 1, BC_REFLECTIVE = 2 };
+
+// Euler2d parameter indices (impl/euler_2d_parametrization_helpers.hpp:59-72)
+enum { icNormalShockMach = 0, icCrossDensity = 1, icCrossInletX = 2, icCrossBottomY = 3, icRiem1TRP = 4,
+       icRiem2TRP = 5, icRiem2TRU = 6, icRiem2TRV = 7, icRiem2TRD = 8, icRiem2BLP = 9 };
+
+int euler2dIcIndex(int prob, int icFlag, const std::string& s) {
+  if (prob == E2_NORMAL_SHOCK && icFlag == 1 && s == "mach") return icNormalShockMach;
+  if (prob == E2_CROSS_SHOCK && icFlag == 1) {
+    if (s == "crossShockDensity") return icCrossDensity;
+    if (s == "crossShockInletXVel") return icCrossInletX;
+    if (s == "crossShockBottomYVel") return icCrossBottomY;
+  }
+  if (prob == E2_RIEMANN && icFlag == 1 && s == "riemannTopRightPressure") return icRiem1TRP;
+  if (prob == E2_RIEMANN && icFlag == 2) {
+    if (s == "riemannTopRightPressure") return icRiem2TRP;
+    if (s == "riemannTopRightXVel") return icRiem2TRU;
+    if (s == "riemannTopRightYVel") return icRiem2TRV;
+    if (s == "riemannTopRightDensity") return icRiem2TRD;
+    if (s == "riemannBotLeftPressure") return icRiem2BLP;
+  }
+  return -1;
+}
+// Swe2d (impl/swe_2d_parametrization_helpers.hpp:59-72)
+int sweIcIndex(int icFlag, const std::string& s) {
+  if (icFlag == 1) {
+    if (s == "pulseMagnitude") return 0;
+    if (s == "pulseX") return 1;
+    if (s == "pulseY") return 2;
+  } else if (icFlag == 2) {
+    if (s == "pulseMagnitude1") return 3;
+    if (s == "pulseX1") return 4;
+    if (s == "pulseY1") return 5;
+    if (s == "pulseMagnitude2") return 6;
+    if (s == "pulseX2") return 7;
+    if (s == "pulseY2") return 8;
+  }
+  return -1;
+}
+
+// euler_compute_energy.hpp: E = p/(gamma-1) + 0.5 rho |v|^2
+template <int NV>
+double energyFromPrim(double gm1Inv, double rho, const double* vel, double p) {
+  double k = 0;
+  for (int m = 0; m < NV; ++m) k += vel[m] * vel[m];
+  return p * gm1Inv + 0.5 * rho * k;
+}
+
+// impl/euler_rankine_hugoniot.hpp:55-148 (pre-shock gas at rest)
+void postShockFromPreshockAtRest(double post[4], const double pre[4], double angle, double mach, double gamma) {
+  const double rho0 = pre[0], p0 = pre[3], v0 = 0.0;
+  const double m2 = mach * mach;
+  const double rho1 = rho0 * (gamma + 1.0) * m2 / (2.0 + (gamma - 1.0) * m2);
+  const double p1 = p0 * (1.0 + 2.0 * gamma / (gamma + 1.0) * (m2 - 1.0));
+  const double a0 = std::sqrt(gamma * p0 / rho0);
+  const double a1 = std::sqrt(gamma * p1 / rho1);
+  const double num = (1.0 + 0.5 * (gamma - 1.0) * m2);
+  const double den = gamma * m2 - 0.5 * (gamma - 1.0);
+  const double mrel = std::sqrt(num / den);
+  const double v1 = mrel * a1 - mach * a0 + v0;
+  post[0] = rho1;
+  post[1] = -v1 * std::cos(angle);
+  post[2] = -v1 * std::sin(angle);
+  post[3] = p1;
+}
+
+}  // namespace
+
+// =============================================================================================== device state
+struct DeviceRowSet {
+  DevBuf<int32_t> graph, rowIds;
+  DevBuf<int32_t> jBase, jLen;
+  DevBuf<uint8_t> jSlot;
+  int32_t n = 0;
+  std::vector<int32_t> hostRowIds;
+  dev::RowSet view(int ncols) const { return dev::RowSet{graph.p, rowIds.p, n, ncols}; }
+  dev::JacLayout jac(int nslotCols) const { return dev::JacLayout{jBase.p, jLen.p, jSlot.p, nslotCols}; }
+};
+
+struct DeviceState {
+  cudaStream_t stream = nullptr;
+  DeviceRowSet inner, nearBd;
+  bool innerViaLattice = false;
+  // ghosts
+  DevBuf<double> ghost[6];
+  DevBuf<dev::GhostRecipe> recipes;
+  DevBuf<double2> nbXY;
+  DevBuf<double> factors;
+  dev::GhostTables tables{};
+  int nsides = 0, hS = 0;
+  bool haveGhosts = false;
+  bool jacTablesReady = false;
+  bool innerRowsReady = false;
+  // scratch owned by the problem (host-pointer entry points, applyJacobian)
+  DevBuf<double> dU, dV, dJ, dB, dR;
+  DevBuf<int32_t> dRowptr, dColidx;
+  PinnedBuf<double> hU, hV;
+  ~DeviceState() { if (stream) cudaStreamDestroy(stream); }
+  dev::GhostView ghostView(int ndpc) const {
+    dev::GhostView gv;
+    for (int s = 0; s < 6; ++s) gv.g[s] = ghost[s].p;
+    gv.stride = ndpc * hS;
+    return gv;
+  }
+};
+
+// =============================================================================================== construction
+Problem::Problem(Mesh* mesh, int family, int problemId, int recon, int icFlag, int nparams,
+                 const char* const* names, const double* values, int device)
+    : mesh_(mesh), family_(family), probId_(problemId), recon_(recon), icFlag_(icFlag), device_(device) {
+  if (!mesh) throw Error(kInvalid, "create_problem: null mesh");
+  if (recon < 0 || recon > 2) throw Error(kInvalid, "create_problem: invalid reconstruction enum");
+  S_ = 3 + 2 * recon;
+  switch (family) {
+    case F_EULER1D: dim_ = 1; ndpc_ = 3; if (problemId < 0 || problemId > 3) throw Error(kInvalid, "Euler1d: invalid problem enum"); break;
+    case F_EULER2D: dim_ = 2; ndpc_ = 4; if (problemId < 0 || problemId > 8) throw Error(kInvalid, "Euler2d: invalid problem enum"); break;
+    case F_EULER3D: dim_ = 3; ndpc_ = 5; if (problemId < 0 || problemId > 1) throw Error(kInvalid, "Euler3d: invalid problem enum"); break;
+    case F_SWE2D: dim_ = 2; ndpc_ = 3; if (problemId < 0 || problemId > 1) throw Error(kInvalid, "Swe2d: invalid problem enum"); break;
+    case F_DIFFREAC2D:
+      dim_ = 2; ndpc_ = 2;
+      if (problemId != 1) throw Error(kUnsupported, "DiffusionReaction2d: only GrayScott runs on the device (ProblemA takes a host source functor)");
+      S_ = 3;
+      break;
+    default: throw Error(kUnsupported, "create_problem: problem family not available in this engine");
+  }
+  if (mesh->dim != dim_) throw Error(kInvalid, "create_problem: mesh dimensionality does not match the problem");
+  // the reference does not check this (schemes_info.hpp:94-102 is unused) and reads garbage columns; we refuse
+  if (mesh->stencil < S_) throw Error(kInvalid, "create_problem: mesh stencil size too small for the reconstruction scheme");
+  if (family == F_DIFFREAC2D && mesh->stencil != 3)
+    throw Error(kInvalid, "DiffusionReaction2d currently, only supports 3-pt stencil");   // diffusion_reaction_2d_prob_class.hpp:307-309
+  if ((int64_t)mesh->nStencil * ndpc_ > INT32_MAX) throw Error(kTooLarge, "create_problem: dof count exceeds int32");
+
+  // ---- parameters
+  if (family == F_EULER2D) {
+    physParams_ = {1.4};
+    icParams_ = {9, 0.1, 10., 1., 0.4, 1.5, 0.0, 0.0, 1.5, 0.029};
+    const bool valid = (problemId == E2_RIEMANN) ? (icFlag == 1 || icFlag == 2) : (problemId == E2_NEUMANN ? true : icFlag == 1);
+    if (!valid) throw Error(kInvalid, "Euler2d: invalid icFlag for the given problem enum");
+    if (nparams > 0 && problemId != E2_RIEMANN && problemId != E2_NORMAL_SHOCK && problemId != E2_CROSS_SHOCK)
+      throw Error(kInvalid, "Euler2d: custom parametrization only valid for Euler2d::{Riemann, NormalShock}");
+    for (int i = 0; i < nparams; ++i) {
+      const std::string s = names[i];
+      if (s == "gamma") { physParams_[0] = values[i]; continue; }
+      const int idx = euler2dIcIndex(problemId, icFlag, s);
+      if (idx < 0) throw Error(kInvalid, "Euler2d: invalid parameter name '" + s + "'");
+      icParams_[idx] = values[i];
+    }
+    gamma_ = physParams_[0];
+    if (problemId == E2_RIEMANN && icFlag == 2 && icParams_[icRiem2TRP] <= icParams_[icRiem2BLP])
+      throw Error(kInvalid, "INVALID: riemannTopRightPressure <= riemannBotLeftPressure");
+  } else if (family == F_SWE2D) {
+    physParams_ = {9.8, -3.0};
+    icParams_ = {1.0 / 8, 1, 1, 1.0 / 10, -2, -2, 1.0 / 8, 2, 2};
+    if (icFlag < 1 || icFlag > 2) throw Error(kInvalid, "2D swe: invalid icFlag");
+    for (int i = 0; i < nparams; ++i) {
+      const std::string s = names[i];
+      if (s == "gravity") { physParams_[0] = values[i]; continue; }
+      if (s == "coriolis") { physParams_[1] = values[i]; continue; }
+      const int idx = sweIcIndex(icFlag, s);
+      if (idx < 0) {
+        // names valid for the OTHER icFlag are accepted by the reference's name check and then written out of
+        // range; here they are rejected like any unknown name
+        throw Error(kInvalid, "2D swe: one or more params in user-provided map is invalid ('" + s + "')");
+      }
+      icParams_[idx] = values[i];
+    }
+    customBcs_ = (problemId == 1);
+  } else if (family == F_DIFFREAC2D) {
+    for (int i = 0; i < nparams; ++i) {
+      const std::string s = names[i];
+      if (s == "Du") gs_[0] = values[i];
+      else if (s == "Dv") gs_[1] = values[i];
+      else if (s == "F") gs_[2] = values[i];
+      else if (s == "k") gs_[3] = values[i];
+      else throw Error(kInvalid, "GrayScott: invalid parameter name '" + s + "'");
+    }
+  } else if (nparams > 0) {
+    throw Error(kInvalid, "create_problem: this problem takes no user parameters");
+  }
+}
+
+Problem::~Problem() = default;
+
+double Problem::queryParameter(const std::string& name) const {
+  if (family_ == F_EULER1D || family_ == F_EULER3D) {
+    if (name == "gamma") return gamma_;
+  } else if (family_ == F_EULER2D) {
+    if (name == "gamma") return physParams_[0];
+    const int idx = euler2dIcIndex(probId_, icFlag_, name);
+    if (idx >= 0) return icParams_[idx];
+  } else if (family_ == F_SWE2D) {
+    if (name == "gravity") return physParams_[0];
+    if (name == "coriolis") return physParams_[1];
+    const int idx = sweIcIndex(icFlag_, name);
+    if (idx >= 0) return icParams_[idx];
+  } else if (family_ == F_DIFFREAC2D) {
+    if (name == "Du") return gs_[0];
+    if (name == "Dv") return gs_[1];
+    if (name == "F") return gs_[2];
+    if (name == "k") return gs_[3];
+  }
+  throw Error(kInvalid, "queryParameter: unknown parameter '" + name + "'");
+}
+
+void Problem::setBc(int side, int kind, const double* values) {
+  const bool ok = (family_ == F_SWE2D && probId_ == 1) ||
+                  (family_ == F_EULER2D && (probId_ == E2_RIEMANN || probId_ == E2_NORMAL_SHOCK));
+  if (!ok) throw Error(kInvalid, "custom BCs only valid for Swe2d::CustomBCs and Euler2d::{Riemann, NormalShock}");
+  if (side < 0 || side > 3) throw Error(kInvalid, "set_bc: invalid side");
+  if (kind < 0 || kind > 2) throw Error(kInvalid, "set_bc: invalid kind");
+  bc_[side].kind = kind;
+  if (kind == BC_DIRICHLET) {
+    if (!values) throw Error(kInvalid, "set_bc: Dirichlet needs ndpc values");
+    for (int d = 0; d < ndpc_; ++d) bc_[side].values[d] = values[d];
+  }
+  customBcs_ = true;
+  if (dev_) { dev_->haveGhosts = false; dev_->jacTablesReady = false; }
+}
+
+// =============================================================================================== initial condition
+void Problem::initialCondition(double* U) const {
+  Mesh& m = *mesh_;
+  const int32_t n = m.nStencil;
+  // coordinates as the reference sees them; for a big lattice they are produced per axis, never per cell
+  std::vector<double> cx, cy, cz;
+  const bool lat = m.lattice && !m.haveCoords;
+  if (lat) {
+    cx.resize(m.n[0]); cy.resize(m.n[1]); cz.resize(m.n[2]);
+    for (int32_t i = 0; i < m.n[0]; ++i) cx[i] = m.latticeCoord(0, i);
+    for (int32_t j = 0; j < m.n[1]; ++j) cy[j] = m.latticeCoord(1, j);
+    for (int32_t k = 0; k < m.n[2]; ++k) cz[k] = m.latticeCoord(2, k);
+  }
+  const int32_t nx = m.n[0], ny = m.n[1];
+  auto X = [&](int32_t i) { return lat ? cx[i % nx] : m.x[i]; };
+  auto Y = [&](int32_t i) { return lat ? cy[(i / nx) % ny] : m.y[i]; };
+  auto Z = [&](int32_t i) { return lat ? cz[i / (nx * ny)] : m.z[i]; };
+  const double gm1Inv = 1.0 / (gamma_ - 1.0);
+
+  if (family_ == F_EULER1D) {   // impl/euler_1d_initial_condition.hpp:55-183
+#pragma omp parallel for schedule(static)
+    for (int32_t i = 0; i < n; ++i) {
+      double prim[3] = {0, 0, 0};
+      const double x = X(i);
+      switch (probId_) {
+        case 0: prim[0] = 1.0 + 0.2 * std::sin(M_PI * x); prim[1] = 1.0; prim[2] = 1.0; break;
+        case 1:
+          if (x <= 0.0) { prim[0] = 1.0; prim[1] = 0.0; prim[2] = 1.0; }
+          if (x > 0.0) { prim[0] = 0.125; prim[1] = 0.0; prim[2] = 0.1; }
+          break;
+        case 2:
+          if (x <= 0.0) { prim[0] = 0.445; prim[1] = 0.698; prim[2] = 3.528; }
+          else if (x > 0.0) { prim[0] = 0.5; prim[1] = 0.0; prim[2] = 0.571; }
+          break;
+        case 3:
+          if (x <= -4.0) { prim[0] = 27.0 / 7.0; prim[1] = 2.629369; prim[2] = 31.0 / 3.0; }
+          else { prim[0] = 1.0 + (1.0 / 5.0) * std::sin(5.0 * x); prim[1] = 0.0; prim[2] = 1.0; }
+          break;
+      }
+      U[3 * i] = prim[0];
+      U[3 * i + 1] = prim[0] * prim[1];
+      U[3 * i + 2] = energyFromPrim<1>(gm1Inv, prim[0], &prim[1], prim[2]);
+    }
+    return;
+  }
+
+  if (family_ == F_EULER2D) {   // impl/euler_2d_initial_condition.hpp
+    const double gamma = gamma_;
+    const double gm1 = gamma - 1.0;
+    auto put = [&](int32_t i, const double prim[4]) {
+      U[4 * i] = prim[0];
+      U[4 * i + 1] = prim[0] * prim[1];
+      U[4 * i + 2] = prim[0] * prim[2];
+      U[4 * i + 3] = energyFromPrim<2>(gm1Inv, prim[0], &prim[1], prim[3]);
+    };
+    switch (probId_) {
+      case E2_PERIODIC:
+#pragma omp parallel for schedule(static)
+        for (int32_t i = 0; i < n; ++i) {
+          const double prim[4] = {1.0 + (1.0 / 5.0) * std::sin(M_PI * (X(i) + Y(i))), 1.0, 1.0, 1.0};
+          put(i, prim);
+        }
+        return;
+      case E2_KH:
+#pragma omp parallel for schedule(static)
+        for (int32_t i = 0; i < n; ++i) {
+          const double freq = 4., mag = 0.025;
+          const double pert = mag * std::cos(2. * 3.14159265 / 10. * freq * X(i));
+          double* s = U + 4 * (int64_t)i;
+          if (Y(i) > -2 + pert && Y(i) < 2 + pert) { s[0] = 2.; s[1] = s[0] * 0.5; }
+          else { s[0] = 1.; s[1] = -s[0] * 0.5; }
+          s[2] = 0.;
+          s[3] = 2.5 / gm1 + 0.5 / s[0] * (s[1] * s[1] + s[2] * s[2]);
+        }
+        return;
+      case E2_SEDOV_FULL:
+      case E2_SEDOV_SYM: {
+        const bool sym = probId_ == E2_SEDOV_SYM;
+        const double sRad = (sym ? 3. : 2.0) * std::min(m.d[0], m.d[1]);
+#pragma omp parallel for schedule(static)
+        for (int32_t i = 0; i < n; ++i) {
+          const double r = std::sqrt(X(i) * X(i) + Y(i) * Y(i));
+          double prim[4] = {1.0, 0.0, 0.0, 0.0};
+          if (r <= sRad) prim[3] = sym ? gm1 * 0.851072 / (M_PI * sRad * sRad) : gm1 / (M_PI * sRad * sRad);
+          else prim[3] = sym ? 2.5e-5 : 5.e-5;
+          put(i, prim);
+        }
+        return;
+      }
+      case E2_RIEMANN: {
+        if (icFlag_ == 1) {
+          const double trp = icParams_[icRiem1TRP];
+          const double x0 = 0.5, y0 = 0.5;
+          // the reference keeps `prim` across iterations (stale value if a centre sits on x == x0 with y < y0,
+          // SURVEY C-13); the loop is therefore serial here too
+          double prim[4] = {0, 0, 0, 0};
+          for (int32_t i = 0; i < n; ++i) {
+            const double x = X(i), y = Y(i);
+            if (x >= x0 && y >= y0) { prim[0] = 0.5313; prim[1] = 0; prim[2] = 0; prim[3] = trp; }
+            else if (x < x0 && y >= y0) { prim[0] = 1; prim[1] = 0.7276; prim[2] = 0; prim[3] = 1; }
+            else if (x < x0 && y < y0) { prim[0] = 0.8; prim[1] = 0; prim[2] = 0; prim[3] = 1; }
+            else if (x > x0 && y < y0) { prim[0] = 1; prim[1] = 0; prim[2] = 0.7276; prim[3] = 1; }
+            put(i, prim);
+          }
+        } else {
+          const double p1 = icParams_[icRiem2TRP], u1 = icParams_[icRiem2TRU], v1 = icParams_[icRiem2TRV];
+          const double rho1 = icParams_[icRiem2TRD], p3 = icParams_[icRiem2BLP];
+          const double x0 = 0.8, y0 = 0.8;
+          const double eps = (gamma - 1.0) / (gamma + 1.0);
+          const double fac13 = p1 / p3;
+          const double fac43 = (1.0 / (2.0 * (1.0 + 2.0 * eps))) *
+                               (eps * (fac13 + 1.0) + std::sqrt(std::pow(eps * (fac13 + 1.0), 2) + 4.0 * (1.0 + 2.0 * eps) * fac13));
+          const double p2 = fac43 * p3, p4 = p2;
+          const double v2 = v1, u4 = u1;
+          const double rho2 = rho1 * (p2 / p1 + eps) / (1 + eps * p2 / rho1);
+          const double rho4 = rho2;
+          const double psi21 = (p2 - p1) * (rho2 - rho1) / (rho2 * rho1);
+          const double u2 = std::sqrt(psi21) + u1;
+          const double psi41 = (p4 - p1) * (rho4 - rho1) / (rho4 * rho1);
+          const double v4 = std::sqrt(psi41) + v1;
+          const double u3 = u2, v3 = v4;
+          const double rho3 = rho2 * (p3 - p2) / ((p3 - p2) - psi41 * rho2);
+          double prim[4] = {0, 0, 0, 0};
+          for (int32_t i = 0; i < n; ++i) {
+            const double x = X(i), y = Y(i);
+            if (x >= x0 && y >= y0) { prim[0] = rho1; prim[1] = u1; prim[2] = v1; prim[3] = p1; }
+            else if (x < x0 && y >= y0) { prim[0] = rho2; prim[1] = u2; prim[2] = v2; prim[3] = p2; }
+            else if (x < x0 && y < y0) { prim[0] = rho3; prim[1] = u3; prim[2] = v3; prim[3] = p3; }
+            else if (x > x0 && y < y0) { prim[0] = rho4; prim[1] = u4; prim[2] = v4; prim[3] = p4; }
+            put(i, prim);
+          }
+        }
+        return;
+      }
+      case E2_NORMAL_SHOCK:
+      case E2_DMR: {
+        const bool dmr = probId_ == E2_DMR;
+        const double mach = dmr ? 10.0 : icParams_[icNormalShockMach];
+        const double angle = dmr ? M_PI / 6.0 : 0.0;
+        const double slope = std::tan(angle);
+        const double pre[4] = {gamma, 0.0, 0.0, 1.0};
+        double post[4];
+        postShockFromPreshockAtRest(post, pre, dmr ? -angle : angle, mach, gamma);
+#pragma omp parallel for schedule(static)
+        for (int32_t i = 0; i < n; ++i) {
+          const double xShock = dmr ? (1.0 / 6.0 + slope * Y(i)) : 1.0 / 6.0;
+          put(i, (X(i) < xShock) ? post : pre);
+        }
+        return;
+      }
+      case E2_CROSS_SHOCK: {
+        const double prim[4] = {icParams_[icCrossDensity], icParams_[icCrossInletX], 0., 1.};
+#pragma omp parallel for schedule(static)
+        for (int32_t i = 0; i < n; ++i) put(i, prim);
+        return;
+      }
+      case E2_NEUMANN:   // euler_2d_prob_class.hpp:438-440: returns an uninitialised vector; zeros here
+        std::memset(U, 0, sizeof(double) * (size_t)n * 4);
+        return;
+    }
+  }
+
+  if (family_ == F_EULER3D) {   // impl/euler_3d_initial_condition.hpp:57-143
+    if (probId_ == 0) {
+#pragma omp parallel for schedule(static)
+      for (int32_t i = 0; i < n; ++i) {
+        const double rho = 1.0 + 0.2 * std::sin(M_PI * (X(i) + Y(i) + Z(i)));
+        const double vel[3] = {1.0, 1.0, 1.0};
+        double* s = U + 5 * (int64_t)i;
+        s[0] = rho; s[1] = rho; s[2] = rho; s[3] = rho;
+        s[4] = energyFromPrim<3>(gm1Inv, rho, vel, 1.0);
+      }
+    } else {
+      const double sRad = 3. * std::min(m.d[0], std::min(m.d[1], m.d[2]));
+      const double gm1 = gamma_ - 1.;
+#pragma omp parallel for schedule(static)
+      for (int32_t i = 0; i < n; ++i) {
+        const double r = std::sqrt(X(i) * X(i) + Y(i) * Y(i) + Z(i) * Z(i));
+        const double p = (r <= sRad) ? (3. * gm1 * 0.851072) / (4. * M_PI * sRad * sRad * sRad) : 2.5e-5;
+        const double vel[3] = {0, 0, 0};
+        double* s = U + 5 * (int64_t)i;
+        s[0] = 1.0; s[1] = 0.0; s[2] = 0.0; s[3] = 0.0;
+        s[4] = energyFromPrim<3>(gm1Inv, 1.0, vel, p);
+      }
+    }
+    return;
+  }
+
+  if (family_ == F_SWE2D) {   // impl/swe_2d_initial_condition.hpp:55-107
+    const double* ic = icParams_.data();
+#pragma omp parallel for schedule(static)
+    for (int32_t i = 0; i < n; ++i) {
+      double hgt;
+      if (icFlag_ == 1) {
+        const double dx1 = X(i) - ic[1], dy1 = Y(i) - ic[2];
+        const double r = std::sqrt(dx1 * dx1 + dy1 * dy1);
+        hgt = 1.0 + ic[0] * std::exp(-(r * r));
+      } else {
+        const double dx1 = X(i) - ic[4], dy1 = Y(i) - ic[5];
+        const double r1 = std::sqrt(dx1 * dx1 + dy1 * dy1);
+        const double dx2 = X(i) - ic[7], dy2 = Y(i) - ic[8];
+        const double r2 = std::sqrt(dx2 * dx2 + dy2 * dy2);
+        hgt = 1.0 + ic[3] * std::exp(-(r1 * r1)) + ic[6] * std::exp(-(r2 * r2));
+      }
+      U[3 * (int64_t)i] = hgt; U[3 * (int64_t)i + 1] = 0.0; U[3 * (int64_t)i + 2] = 0.0;
+    }
+    return;
+  }
+
+  if (family_ == F_DIFFREAC2D) {   // diffusion_reaction_2d_prob_class.hpp:141-178 (Gray-Scott)
+#pragma omp parallel for schedule(static)
+    for (int32_t i = 0; i < n; ++i) {
+      const bool in = std::abs(X(i)) < 0.1 && std::abs(Y(i)) < 0.1;
+      U[2 * (int64_t)i] = in ? 0.5 : 1.0;
+      U[2 * (int64_t)i + 1] = in ? 0.25 : 0.0;
+    }
+    return;
+  }
+  throw Error(kUnsupported, "initialCondition: family not supported");
+}
+
+// =============================================================================================== CSR pattern
+// Same triplet rule as EigenApp::initializeJacobian (euler_2d_prob_class.hpp:223-237,315-387; swe, euler1d/3d
+// alike; diffusion_reaction_2d_prob_class.hpp:180-224): inner rows = self + the (S-1)*dim scheme neighbours,
+// near-boundary rows = self + existing first-layer neighbours; setFromTriplets sorts columns and merges duplicates.
+void Problem::buildPattern() {
+  if (havePattern_) return;
+  Mesh& m = *mesh_;
+  m.ensureGraph();
+  m.ensureRows();
+  const int nc = m.ncols();
+  const int nnbInner = (S_ - 1) * dim_;
+  const int nnbFirst = 2 * dim_;
+  const bool allFirst = (family_ == F_DIFFREAC2D);
+  const int32_t ns = m.nSample;
+  slotCols_ = nnbInner + 1;
+  std::vector<uint8_t> isNb(ns, 0);
+  for (int32_t r : m.rowsNearBd) isNb[r] = 1;
+
+  cellBase_.assign(ns, 0);
+  cellLen_.assign(ns, 0);
+  slots_.assign((size_t)ns * slotCols_, 0xFF);
+  std::vector<int32_t> nblk(ns);
+  bool merged = false;
+  // pass 1: blocks per cell
+#pragma omp parallel for schedule(static) reduction(|| : merged)
+  for (int32_t r = 0; r < ns; ++r) {
+    const int32_t* row = &m.graph[(size_t)r * nc];
+    const bool first = allFirst || isNb[r];
+    const int ncand = first ? nnbFirst : nnbInner;
+    int32_t ids[20];
+    int cnt = 0;
+    ids[cnt++] = row[0];
+    for (int c = 1; c <= ncand; ++c) if (row[c] >= 0) ids[cnt++] = row[c];
+    std::sort(ids, ids + cnt);
+    const int u = (int)(std::unique(ids, ids + cnt) - ids);
+    if (u != cnt) merged = true;
+    nblk[r] = u;
+  }
+  mergedNeighbors_ = merged;
+  int64_t nnz = 0;
+  for (int32_t r = 0; r < ns; ++r) nnz += (int64_t)nblk[r] * ndpc_ * ndpc_;
+  if (nnz > INT32_MAX)
+    throw Error(kTooLarge, "jacobian: nnz = " + std::to_string(nnz) + " does not fit the reference's int32 index type");
+  rowptr_.assign((size_t)ns * ndpc_ + 1, 0);
+  {
+    int64_t acc = 0;
+    for (int32_t r = 0; r < ns; ++r) {
+      cellBase_[r] = (int32_t)acc;
+      cellLen_[r] = nblk[r] * ndpc_;
+      for (int k = 0; k < ndpc_; ++k) { rowptr_[(size_t)r * ndpc_ + k] = (int32_t)acc; acc += cellLen_[r]; }
+    }
+    rowptr_[(size_t)ns * ndpc_] = (int32_t)acc;
+  }
+  colidx_.assign((size_t)nnz, 0);
+#pragma omp parallel for schedule(static)
+  for (int32_t r = 0; r < ns; ++r) {
+    const int32_t* row = &m.graph[(size_t)r * nc];
+    const bool first = allFirst || isNb[r];
+    const int ncand = first ? nnbFirst : nnbInner;
+    int32_t ids[20];
+    int cnt = 0;
+    ids[cnt++] = row[0];
+    for (int c = 1; c <= ncand; ++c) if (row[c] >= 0) ids[cnt++] = row[c];
+    std::sort(ids, ids + cnt);
+    cnt = (int)(std::unique(ids, ids + cnt) - ids);
+    for (int k = 0; k < ndpc_; ++k) {
+      int32_t* out = &colidx_[(size_t)cellBase_[r] + (size_t)k * cellLen_[r]];
+      for (int b = 0; b < cnt; ++b)
+        for (int j = 0; j < ndpc_; ++j) out[b * ndpc_ + j] = ids[b] * ndpc_ + j;
+    }
+    uint8_t* sl = &slots_[(size_t)r * slotCols_];
+    for (int c = 0; c <= ncand; ++c) {
+      if (row[c] < 0) continue;
+      sl[c] = (uint8_t)(std::lower_bound(ids, ids + cnt, row[c]) - ids);
+    }
+  }
+  havePattern_ = true;
+}
+
+int64_t Problem::jacobianNnz() {
+  buildPattern();
+  return (int64_t)colidx_.size();
+}
+
+void Problem::jacobianPattern(int32_t* rowptr, int32_t* colidx) {
+  buildPattern();
+  if (rowptr) std::memcpy(rowptr, rowptr_.data(), rowptr_.size() * sizeof(int32_t));
+  if (colidx) std::memcpy(colidx, colidx_.data(), colidx_.size() * sizeof(int32_t));
+}
+
+// =============================================================================================== device set-up
+void Problem::ensureDevice() {
+  if (dev_) return;
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+    cudaGetLastError();
+    throw Error(kNoDevice, "no usable CUDA device: the B200 engine has no CPU fallback");
+  }
+  if (device_ < 0 || device_ >= ndev) throw Error(kInvalid, "create_problem: invalid CUDA device index");
+  PDA_CUDA(cudaSetDevice(device_));
+  auto ds = std::make_unique<DeviceState>();
+  PDA_CUDA(cudaStreamCreateWithFlags(&ds->stream, cudaStreamNonBlocking));
+
+  Mesh& m = *mesh_;
+  const int nc = m.ncols();
+  // ---- near-boundary rows (compact graph)
+  std::vector<int32_t> nb;
+  m.nearBdRows(nb);
+  ds->nearBd.n = (int32_t)nb.size();
+  if (!nb.empty()) {
+    std::vector<int32_t> g((size_t)nb.size() * nc);
+    for (size_t r = 0; r < nb.size(); ++r) {
+      if (m.haveGraph) std::memcpy(&g[r * nc], &m.graph[(size_t)nb[r] * nc], sizeof(int32_t) * nc);
+      else m.latticeRow(nb[r], &g[r * nc]);
+    }
+    ds->nearBd.graph.upload(g);
+    ds->nearBd.rowIds.upload(nb);
+  }
+  ds->nearBd.hostRowIds = nb;
+  // ---- inner rows: structured kernels on lattices, compact graph otherwise
+  ds->innerViaLattice = m.lattice && latticeKernelAvailable(family_, dim_, S_);
+  ds->hS = (S_ - 1) / 2;
+  ds->nsides = (dim_ == 1) ? 3 : 2 * dim_;
+  dev_ = std::move(ds);
+  if (!dev_->innerViaLattice) ensureInnerRows();
+}
+
+// compact graph of the inner rows (graph-driven kernels): always for non-lattice meshes, on demand for lattices
+// (Jacobian assembly of a lattice still goes through the graph kernels)
+void Problem::ensureInnerRows() {
+  DeviceState& ds = *dev_;
+  if (ds.innerRowsReady) return;
+  Mesh& m = *mesh_;
+  const int nc = m.ncols();
+  m.ensureGraph();
+  m.ensureRows();
+  std::vector<int32_t> rows;
+  if (family_ == F_DIFFREAC2D) { rows.resize(m.nSample); for (int32_t r = 0; r < m.nSample; ++r) rows[r] = r; }
+  else rows = m.rowsInner;
+  ds.inner.n = (int32_t)rows.size();
+  if (!rows.empty()) {
+    std::vector<int32_t> g((size_t)rows.size() * nc);
+    for (size_t r = 0; r < rows.size(); ++r) std::memcpy(&g[r * nc], &m.graph[(size_t)rows[r] * nc], sizeof(int32_t) * nc);
+    ds.inner.graph.upload(g);
+    ds.inner.rowIds.upload(rows);
+  }
+  ds.inner.hostRowIds = rows;
+  ds.innerRowsReady = true;
+}
+
+// ghost recipes: which cell (and which sign / constant) every needed ghost layer copies -- per-problem rules of the
+// reference's ghost fillers, evaluated ONCE on the host because they only depend on the static graph.
+void Problem::buildGhostRecipes() {
+  DeviceState& ds = *dev_;
+  if (ds.haveGhosts) return;
+  Mesh& m = *mesh_;
+  const int nc = m.ncols();
+  const int h = ds.hS;
+  const int nsides = ds.nsides;
+  const std::vector<int32_t>& nb = ds.nearBd.hostRowIds;
+  const int32_t nNb = (int32_t)nb.size();
+  dev::GhostTables& T = ds.tables;
+  std::memset(&T, 0, sizeof T);
+  int nModes = 0;
+  auto addMode = [&](std::initializer_list<double> mul, std::initializer_list<double> add) {
+    if (nModes >= dev::kMaxGhostModes) throw Error(kUnsupported, "ghost modes exhausted");
+    int d = 0; for (double v : mul) T.mul[nModes][d++] = v;
+    d = 0; for (double v : add) T.add[nModes][d++] = v;
+    return nModes++;
+  };
+  const int mCopy = addMode({1, 1, 1, 1, 1}, {0, 0, 0, 0, 0});
+  const int mNeg1 = addMode({1, -1, 1, 1, 1}, {0, 0, 0, 0, 0});
+  const int mNeg2 = addMode({1, 1, -1, 1, 1}, {0, 0, 0, 0, 0});
+  const int mNeg3 = addMode({1, 1, 1, -1, 1}, {0, 0, 0, 0, 0});
+  int mDirich[6] = {-1, -1, -1, -1, -1, -1};
+
+  // which filler applies (0 = none)
+  enum { NONE, NAIVE, PROPER, CUSTOM } style = NONE;
+  // per-side mode for mirror fills
+  int sideMode[6] = {mCopy, mCopy, mCopy, mCopy, mCopy, mCopy};
+  bool dmr = false, cross = false;
+  int mPost = -1, mPre = -1, mCrossL = -1, mCrossB0a = -1, mCrossB0b = -1, mCrossB1a = -1, mCrossB1b = -1;
+
+  if (customBcs_) {
+    style = CUSTOM;
+    for (int s = 0; s < 4; ++s) {
+      if (bc_[s].kind < 0) throw Error(kInvalid, "custom BCs: pda_problem_set_bc must be called for all four sides before evaluating");
+      if (bc_[s].kind == BC_DIRICHLET) {
+        const double* v = bc_[s].values;
+        mDirich[s] = addMode({0, 0, 0, 0, 0}, {v[0], v[1], v[2], v[3], v[4]});
+      }
+    }
+  } else if (family_ == F_EULER1D) {
+    style = (probId_ == 0) ? NONE : NAIVE;                       // euler_1d_prob_class.hpp:315-335
+  } else if (family_ == F_EULER2D) {
+    switch (probId_) {
+      case E2_SEDOV_FULL: case E2_RIEMANN: case E2_NEUMANN: style = PROPER; break;   // Ghost2dNeumannFiller
+      case E2_SEDOV_SYM: style = NAIVE; sideMode[0] = mNeg1; sideMode[3] = mNeg2; break;
+      case E2_NORMAL_SHOCK: style = NAIVE; sideMode[1] = mNeg2; sideMode[3] = mNeg2; break;
+      case E2_DMR: {
+        style = NAIVE; dmr = true;
+        // euler_2d_ghost_filler_double_mach_reflection.hpp:265-291
+        const double gamma = gamma_, gm1Inv = 1.0 / (gamma - 1.0);
+        const double pre[4] = {gamma, 0.0, 0.0, 1.0};
+        double post[4];
+        postShockFromPreshockAtRest(post, pre, -(M_PI / 6.), 10.0, gamma);
+        const double preS[4] = {pre[0], pre[0] * pre[1], pre[0] * pre[2], energyFromPrim<2>(gm1Inv, pre[0], &pre[1], pre[3])};
+        const double postS[4] = {post[0], post[0] * post[1], post[0] * post[2], energyFromPrim<2>(gm1Inv, post[0], &post[1], post[3])};
+        mPost = addMode({0, 0, 0, 0, 0}, {postS[0], postS[1], postS[2], postS[3], 0});
+        mPre = addMode({0, 0, 0, 0, 0}, {preS[0], preS[1], preS[2], preS[3], 0});
+        T.dmrWedge = 1.0 / 6.0;
+        T.dmrSpeed = 10.0 / std::cos(M_PI / 6.);
+        T.dmrSlope = std::tan(M_PI / 6.);
+        T.dy = m.d[1];
+        T.dmrModePost = mPost; T.dmrModePre = mPre;
+        break;
+      }
+      case E2_CROSS_SHOCK: {
+        style = NAIVE; cross = true;
+        const double rho = icParams_[icCrossDensity], uin = icParams_[icCrossInletX], vb = icParams_[icCrossBottomY];
+        const double vel[2] = {uin, 0.0};
+        const double E = energyFromPrim<2>(1.0 / (gamma_ - 1.0), rho, vel, 1.0);
+        mCrossL = addMode({0, 0, 0, 0, 0}, {rho, rho * uin, rho * 0.0, E, 0});
+        mCrossB0a = addMode({1, 0, 0, 1, 0}, {0, rho * uin, 0., 0, 0});
+        mCrossB0b = addMode({1, 0, 0, 1, 0}, {0, rho * uin, rho * vb, 0, 0});
+        mCrossB1a = addMode({0, 0, 0, 1, 0}, {rho, rho * uin, 0., 0, 0});
+        mCrossB1b = addMode({0, 0, 0, 1, 0}, {rho, rho * uin, rho * vb, 0, 0});
+        break;
+      }
+      default: style = NONE;   // PeriodicSmooth, KelvinHelmholtz: no ghosts (euler_2d_prob_class.hpp:562-564)
+    }
+  } else if (family_ == F_EULER3D) {
+    if (probId_ == 1) { style = NAIVE; sideMode[0] = mNeg1; sideMode[3] = mNeg2; sideMode[4] = mNeg3; }
+  } else if (family_ == F_SWE2D) {
+    style = PROPER; sideMode[0] = mNeg1; sideMode[2] = mNeg1; sideMode[1] = mNeg2; sideMode[3] = mNeg2;
+  }
+
+  if (nNb > 0 && style == NONE && !m.fullyPeriodic && family_ != F_DIFFREAC2D)
+    throw Error(kInvalid, "this problem requires a fully periodic mesh (no ghost filler in the reference)");
+
+  std::vector<dev::GhostRecipe> rec((size_t)nNb * nsides * h, dev::GhostRecipe{-1, 0, 0});
+  std::vector<double2> xy(nNb);
+  std::vector<double> fac((size_t)nNb * dim_ * ndpc_, 1.0);
+  std::vector<int32_t> rowBuf(nc);
+  static const int oppSide[6] = {2, 3, 0, 1, 5, 4};
+  for (int32_t r = 0; r < nNb; ++r) {
+    const int32_t* row;
+    if (m.haveGraph) row = &m.graph[(size_t)nb[r] * nc];
+    else { m.latticeRow(nb[r], rowBuf.data()); row = rowBuf.data(); }
+    const int32_t self = row[0];
+    double cxv, cyv;
+    if (m.haveCoords) { cxv = m.x[self]; cyv = m.y[self]; }
+    else { cxv = m.latticeCoord(0, self % m.n[0]); cyv = m.latticeCoord(1, (self / m.n[0]) % m.n[1]); }
+    xy[r] = make_double2(cxv, cyv);
+    auto nbr = [&](int side, int L) { return row[graphCol(dim_, side, L)]; };
+    auto hasBd = [&](int side) {   // hasBd{Left,..}{1,2,3}d of the MESH stencil (mesh_ccu.hpp:162-296)
+      for (int L = 0; L < m.halo(); ++L) if (nbr(side, L) == -1) return true;
+      return false;
+    };
+    for (int si = 0; si < nsides; ++si) {
+      if (dim_ == 1 && si == 1) continue;
+      const int side = si;
+      const int opp = oppSide[side];
+      for (int L = 0; L < h; ++L) {
+        if (nbr(side, L) != -1) continue;
+        dev::GhostRecipe& g = rec[((size_t)r * nsides + si) * h + L];
+        int32_t src = self;
+        if (style == NAIVE) {
+          src = (L == 0) ? self : nbr(opp, L - 1);
+        } else if (style == PROPER) {
+          if (L == 0) src = self;
+          else if (L == 1) src = (nbr(side, 0) == -1) ? nbr(opp, 0) : nbr(side, 0);
+          else {
+            const int32_t s1 = nbr(side, 1), s0 = nbr(side, 0);
+            if (s1 != -1 && s0 != -1) src = s1;
+            else if (s1 == -1 && s0 != -1) src = self;
+            else if (s1 == -1 && s0 == -1) src = nbr(opp, 1);
+            else src = self;
+          }
+        } else if (style == CUSTOM) {
+          // device-expressible rules: Dirichlet = constant state, homogeneous Neumann = the cell's own state,
+          // reflective = layer-aware mirror with the normal momentum negated
+          if (bc_[side].kind == BC_REFLECTIVE) {
+            if (L == 0) src = self;
+            else if (L == 1) src = (nbr(side, 0) == -1) ? nbr(opp, 0) : nbr(side, 0);
+            else {
+              const int32_t s1 = nbr(side, 1), s0 = nbr(side, 0);
+              src = (s1 != -1 && s0 != -1) ? s1 : ((s1 == -1 && s0 != -1) ? self : nbr(opp, 1));
+            }
+          }
+        }
+        if (src < 0) src = self;   // degenerate (mesh narrower than the stencil): the reference reads out of bounds
+        g.src = src;
+        g.kind = 0;
+        g.mode = (int16_t)sideMode[side];
+        if (style == CUSTOM) {
+          const int k = bc_[side].kind;
+          g.mode = (int16_t)((k == BC_DIRICHLET) ? mDirich[side]
+                             : (k == BC_REFLECTIVE) ? ((side == 0 || side == 2) ? mNeg1 : mNeg2) : mCopy);
+        }
+        if (dmr) {
+          if (side == 1) { g.kind = 1; g.mode = (int16_t)mPre; }
+          if (side == 3) g.mode = (int16_t)((cxv < 1.0 / 6.0) ? mCopy : mNeg2);
+        }
+        if (cross) {
+          if (side == 0) g.mode = (int16_t)mCrossL;
+          if (side == 3) g.mode = (int16_t)((L == 0) ? (cxv < 0.5 ? mCrossB0a : mCrossB0b) : (cxv < 0.5 ? mCrossB1a : mCrossB1b));
+        }
+      }
+    }
+    // ---- first-order Jacobian factors per axis (fillJacFactorsForCellBd: euler_2d_prob_class.hpp:1115-1224,
+    //      swe_2d_prob_class.hpp:839-855, euler_3d_prob_class.hpp:1017-1044, euler_1d_prob_class.hpp:608-616)
+    for (int ax = 0; ax < dim_; ++ax) {
+      double* f = &fac[((size_t)r * dim_ + ax) * ndpc_];
+      for (int d = 0; d < ndpc_; ++d) f[d] = 1.0;
+      const int sm = minusSide(ax), sp = plusSide(ax);
+      if (style == CUSTOM) {
+        // fillJacFactorsCustomBCs (custom_bcs_functions.hpp:60-103): minus side first, plus side overwrites
+        for (int s : {sm, sp}) {
+          if (!hasBd(s)) continue;
+          const int k = bc_[s].kind;
+          for (int d = 0; d < ndpc_; ++d) f[d] = (k == BC_DIRICHLET) ? 0.0 : 1.0;
+          if (k == BC_REFLECTIVE) f[1 + ax] = -1.0;
+        }
+      } else if (family_ == F_SWE2D) {
+        f[1 + ax] = -1.0;
+      } else if (family_ == F_EULER2D) {
+        if (probId_ == E2_SEDOV_SYM) { if (hasBd(sm)) f[1 + ax] = -1.0; }
+        else if (probId_ == E2_NORMAL_SHOCK) { if (ax == 1) f[2] = -1.0; }
+        else if (probId_ == E2_DMR) {
+          if (ax == 1) {
+            if (hasBd(3) && cxv < 1.0 / 6.0) { /* neumann */ }
+            else if (hasBd(3) && cxv >= 1.0 / 6.0) f[2] = -1.0;
+            else for (int d = 0; d < ndpc_; ++d) f[d] = 0.0;
+          }
+        } else if (probId_ == E2_CROSS_SHOCK) {
+          if (ax == 0) { if (hasBd(0)) for (int d = 0; d < ndpc_; ++d) f[d] = 0.0; }
+          else { if (hasBd(3)) { f[1] = 0.0; f[2] = 0.0; } }
+        }
+      } else if (family_ == F_EULER3D) {
+        if (probId_ == 1 && hasBd(sm)) f[1 + ax] = -1.0;
+      }
+    }
+  }
+  for (int s = 0; s < 6; ++s) {
+    ds.ghost[s].alloc((size_t)std::max<int32_t>(nNb, 1) * h * ndpc_);
+    PDA_CUDA(cudaMemset(ds.ghost[s].p, 0, ds.ghost[s].n * sizeof(double)));
+  }
+  ds.recipes.upload(rec);
+  ds.nbXY.upload(xy);
+  ds.factors.upload(fac);
+  ds.haveGhosts = true;
+}
+
+// =============================================================================================== evaluation
+namespace {
+
+template <class F>
+void dispatchScheme(int S, F&& f) {
+  switch (S) {
+    case 3: f(std::integral_constant<int, 3>{}); break;
+    case 5: f(std::integral_constant<int, 5>{}); break;
+    case 7: f(std::integral_constant<int, 7>{}); break;
+    default: throw Error(kInvalid, "invalid scheme stencil");
+  }
+}
+
+inline int gridFor(int64_t n, int block) { return (int)((n + block - 1) / block); }
+
+}  // namespace
+
+void Problem::evaluateDev(const double* dU, double t, double* dV, double* dJ, void* streamV) {
+  ensureDevice();
+  PDA_CUDA(cudaSetDevice(device_));
+  DeviceState& ds = *dev_;
+  cudaStream_t st = streamV ? (cudaStream_t)streamV : ds.stream;
+  Mesh& m = *mesh_;
+  const int nc = m.ncols();
+  dev::Deltas dl{{m.dInv[0], m.dInv[1], m.dInv[2]}};
+
+  if (dJ) {
+    buildPattern();
+    if (!ds.jacTablesReady) {
+      auto fill = [&](DeviceRowSet& rs) {
+        std::vector<int32_t> base(rs.n), len(rs.n);
+        std::vector<uint8_t> sl((size_t)rs.n * slotCols_);
+        for (int32_t r = 0; r < rs.n; ++r) {
+          const int32_t row = rs.hostRowIds[r];
+          base[r] = cellBase_[row]; len[r] = cellLen_[row];
+          std::memcpy(&sl[(size_t)r * slotCols_], &slots_[(size_t)row * slotCols_], slotCols_);
+        }
+        rs.jBase.upload(base); rs.jLen.upload(len); rs.jSlot.upload(sl);
+      };
+      ensureInnerRows();
+      fill(ds.inner);
+      fill(ds.nearBd);
+      ds.jacTablesReady = true;
+    }
+    PDA_CUDA(cudaMemsetAsync(dJ, 0, colidx_.size() * sizeof(double), st));
+  }
+
+  // ---- Gray-Scott: one fused kernel over all rows
+  if (family_ == F_DIFFREAC2D) {
+    dev::GrayScottParams gp{gs_[0], gs_[1], gs_[2], gs_[3], m.dInv[0] * m.dInv[0], m.dInv[1] * m.dInv[1]};
+    if (!m.fullyPeriodic) throw Error(kInvalid, "GrayScott requires a periodic mesh");
+    dev::k_gray_scott_rows<<<gridFor(ds.inner.n, 128), 128, 0, st>>>(gp, ds.inner.view(nc), dU, dV, dJ, ds.inner.jac(slotCols_));
+    ++launches_;
+    PDA_CUDA(cudaGetLastError());
+    return;
+  }
+
+  const int32_t nNb = ds.nearBd.n;
+  dev::GhostView gv{};
+  if (nNb > 0) {
+    buildGhostRecipes();
+    gv = ds.ghostView(ndpc_);
+    const int64_t tot = (int64_t)nNb * ds.nsides * ds.hS;
+    auto launchGhost = [&](auto ndpcTag) {
+      constexpr int N = decltype(ndpcTag)::value;
+      dev::k_ghost_fill<N><<<gridFor(tot, 128), 128, 0, st>>>(ds.recipes.p, ds.nbXY.p, nNb, ds.nsides, ds.hS, ds.tables, dU, gv, t);
+    };
+    switch (ndpc_) {
+      case 3: launchGhost(std::integral_constant<int, 3>{}); break;
+      case 4: launchGhost(std::integral_constant<int, 4>{}); break;
+      case 5: launchGhost(std::integral_constant<int, 5>{}); break;
+    }
+    ++launches_;
+  }
+
+  auto run = [&](auto phys) {
+    using Phys = decltype(phys);
+    dispatchScheme(S_, [&](auto sTag) {
+      constexpr int S = decltype(sTag)::value;
+      if (nNb > 0) {
+        if (dV) {
+          dev::k_velocity_rows<Phys, S, true><<<gridFor(nNb, 128), 128, 0, st>>>(phys, ds.nearBd.view(nc), dl, dU, dV, gv);
+          ++launches_;
+        }
+        if (dJ) {
+          dev::k_jacobian_nearbd_rows<Phys><<<gridFor(nNb, 128), 128, 0, st>>>(phys, ds.nearBd.view(nc), dl, dU, dJ,
+                                                                               ds.nearBd.jac(slotCols_), gv, ds.factors.p);
+          ++launches_;
+        }
+      }
+      if (ds.innerViaLattice && !dJ) {
+        launchLatticeVelocity<Phys, S>(phys, m, dl, dU, dV, st, 0, m.n[dim_ - 1], 0);
+        ++launches_;
+      } else if (ds.inner.n > 0) {
+        if (dJ) {
+          dev::k_jacobian_inner_rows<Phys, S><<<gridFor(ds.inner.n, 128), 128, 0, st>>>(phys, ds.inner.view(nc), dl, dU, dV, dJ,
+                                                                                        ds.inner.jac(slotCols_));
+        } else {
+          dev::k_velocity_rows<Phys, S, false><<<gridFor(ds.inner.n, 128), 128, 0, st>>>(phys, ds.inner.view(nc), dl, dU, dV, gv);
+        }
+        ++launches_;
+      }
+    });
+  };
+  switch (family_) {
+    case F_EULER1D: run(dev::Euler<1>{gamma_}); break;
+    case F_EULER2D: run(dev::Euler<2>{gamma_}); break;
+    case F_EULER3D: run(dev::Euler<3>{gamma_}); break;
+    case F_SWE2D: run(dev::Swe2d{physParams_[0], physParams_[1]}); break;
+    default: throw Error(kUnsupported, "family not supported on device");
+  }
+  PDA_CUDA(cudaGetLastError());
+}
+
+void Problem::velocityDev(const double* dU, double t, double* dV, void* stream) {
+  if (!dU || !dV) throw Error(kInvalid, "velocity: null pointer");
+  evaluateDev(dU, t, dV, nullptr, stream);
+}
+
+void Problem::velocityAndJacobianDev(const double* dU, double t, double* dV, double* dJ, void* stream) {
+  if (!dU || !dJ) throw Error(kInvalid, "jacobian: null pointer");
+  ensureDevice();
+  if (!dV) {   // jacobian(U,t,J): the reference evaluates into its internal m_rhs (adapter_cpp.hpp:215-221)
+    dev_->dV.alloc((size_t)nDofSample());
+    dV = dev_->dV.p;
+  }
+  evaluateDev(dU, t, dV, dJ, stream);
+}
+
+void Problem::velocityHost(const double* U, double t, double* V) {
+  if (!U || !V) throw Error(kInvalid, "velocity: null pointer");
+  ensureDevice();
+  PDA_CUDA(cudaSetDevice(device_));
+  DeviceState& ds = *dev_;
+  const size_t nU = (size_t)nDofStencil(), nV = (size_t)nDofSample();
+  ds.dU.alloc(nU); ds.dV.alloc(nV); ds.hU.alloc(nU); ds.hV.alloc(nV);
+  std::memcpy(ds.hU.p, U, nU * sizeof(double));
+  PDA_CUDA(cudaMemcpyAsync(ds.dU.p, ds.hU.p, nU * sizeof(double), cudaMemcpyHostToDevice, ds.stream));
+  evaluateDev(ds.dU.p, t, ds.dV.p, nullptr, ds.stream);
+  PDA_CUDA(cudaMemcpyAsync(ds.hV.p, ds.dV.p, nV * sizeof(double), cudaMemcpyDeviceToHost, ds.stream));
+  PDA_CUDA(cudaStreamSynchronize(ds.stream));
+  std::memcpy(V, ds.hV.p, nV * sizeof(double));
+}
+
+void Problem::velocityAndJacobianHost(const double* U, double t, double* V, double* Jvalues) {
+  if (!U || !Jvalues) throw Error(kInvalid, "jacobian: null pointer");
+  ensureDevice();
+  PDA_CUDA(cudaSetDevice(device_));
+  buildPattern();
+  DeviceState& ds = *dev_;
+  const size_t nU = (size_t)nDofStencil(), nV = (size_t)nDofSample(), nnz = colidx_.size();
+  ds.dU.alloc(nU); ds.dV.alloc(nV); ds.dJ.alloc(nnz);
+  PDA_CUDA(cudaMemcpyAsync(ds.dU.p, U, nU * sizeof(double), cudaMemcpyHostToDevice, ds.stream));
+  evaluateDev(ds.dU.p, t, ds.dV.p, ds.dJ.p, ds.stream);
+  if (V) PDA_CUDA(cudaMemcpyAsync(V, ds.dV.p, nV * sizeof(double), cudaMemcpyDeviceToHost, ds.stream));
+  PDA_CUDA(cudaMemcpyAsync(Jvalues, ds.dJ.p, nnz * sizeof(double), cudaMemcpyDeviceToHost, ds.stream));
+  PDA_CUDA(cudaStreamSynchronize(ds.stream));
+}
+
+void Problem::applyJacobianDev(const double* dU, const double* dB, int ncols, int layout, double t, double* dR,
+                               void* streamV) {
+  if (!dU || !dB || !dR) throw Error(kInvalid, "applyJacobian: null pointer");
+  if (ncols < 1) throw Error(kInvalid, "applyJacobian: ncols must be >= 1");
+  ensureDevice();
+  PDA_CUDA(cudaSetDevice(device_));
+  buildPattern();
+  DeviceState& ds = *dev_;
+  cudaStream_t st = streamV ? (cudaStream_t)streamV : ds.stream;
+  ds.dV.alloc((size_t)nDofSample());
+  ds.dJ.alloc(colidx_.size());
+  if (!ds.dRowptr.p) { ds.dRowptr.upload(rowptr_); ds.dColidx.upload(colidx_); }
+  evaluateDev(dU, t, ds.dV.p, ds.dJ.p, st);
+  const int32_t nrows = nDofSample();
+  const int64_t nJc = nDofStencil();
+  // row-major: B[r*ncols + c]; col-major: B[c*rows + r]
+  const int64_t ldbRow = (layout == 1) ? ncols : 1, ldbCol = (layout == 1) ? 1 : nJc;
+  const int64_t ldrRow = (layout == 1) ? ncols : 1, ldrCol = (layout == 1) ? 1 : nrows;
+  dev::k_spmm_csr<<<gridFor((int64_t)nrows * 32, 256), 256, 0, st>>>(nrows, ds.dRowptr.p, ds.dColidx.p, ds.dJ.p, dB, ncols,
+                                                                   ldbRow, ldbCol, dR, ldrRow, ldrCol);
+  ++launches_;
+  PDA_CUDA(cudaGetLastError());
+}
+
+void Problem::applyJacobianHost(const double* U, const double* B, int ncols, int layout, double t, double* R) {
+  if (!U || !B || !R) throw Error(kInvalid, "applyJacobian: null pointer");
+  if (ncols < 1) throw Error(kInvalid, "applyJacobian: ncols must be >= 1");
+  ensureDevice();
+  PDA_CUDA(cudaSetDevice(device_));
+  DeviceState& ds = *dev_;
+  const size_t nU = (size_t)nDofStencil(), nR = (size_t)nDofSample();
+  ds.dU.alloc(nU); ds.dB.alloc(nU * ncols); ds.dR.alloc(nR * ncols);
+  PDA_CUDA(cudaMemcpyAsync(ds.dU.p, U, nU * sizeof(double), cudaMemcpyHostToDevice, ds.stream));
+  PDA_CUDA(cudaMemcpyAsync(ds.dB.p, B, nU * ncols * sizeof(double), cudaMemcpyHostToDevice, ds.stream));
+  applyJacobianDev(ds.dU.p, ds.dB.p, ncols, layout, t, ds.dR.p, ds.stream);
+  PDA_CUDA(cudaMemcpyAsync(R, ds.dR.p, nR * ncols * sizeof(double), cudaMemcpyDeviceToHost, ds.stream));
+  PDA_CUDA(cudaStreamSynchronize(ds.stream));
+}
+
+void Problem::ghosts(int side, double* out) {
+  if (!dev_ || !dev_->haveGhosts) throw Error(kInvalid, "ghosts: no evaluation with ghost cells has run yet");
+  if (side < 0 || side >= 6) throw Error(kInvalid, "ghosts: invalid side");
+  PDA_CUDA(cudaSetDevice(device_));
+  DeviceState& ds = *dev_;
+  PDA_CUDA(cudaStreamSynchronize(ds.stream));
+  const size_t n = (size_t)ds.nearBd.n * ds.hS * ndpc_;
+  if (n) PDA_CUDA(cudaMemcpy(out, ds.ghost[side].p, n * sizeof(double), cudaMemcpyDeviceToHost));
+}
+
+// =============================================================================================== slab (multi-GPU)
+void Problem::makeSlab(int rank, int nranks) {
+  Mesh& m = *mesh_;
+  if (!m.lattice || !m.fullyPeriodic) throw Error(kUnsupported, "slab decomposition needs a fully periodic full lattice");
+  if (nranks < 1 || rank < 0 || rank >= nranks) throw Error(kInvalid, "slab: invalid rank / nranks");
+  const int32_t nk = m.n[dim_ - 1];
+  if (nk % nranks != 0) throw Error(kInvalid, "slab: the slowest axis must be divisible by the number of ranks");
+  const int32_t per = nk / nranks;
+  if (per < (S_ - 1) / 2) throw Error(kInvalid, "slab: fewer planes per rank than the stencil halo");
+  if (!latticeKernelAvailable(family_, dim_, S_)) throw Error(kUnsupported, "slab: no structured kernel for this problem");
+  slab_ = true;
+  slabK0_ = rank * per;
+  slabK1_ = slabK0_ + per;
+}
+
+void Problem::slabExtent(int32_t* k0, int32_t* k1, int32_t* halo, int64_t* planeDofs) const {
+  if (!slab_) throw Error(kInvalid, "not a slab problem");
+  const Mesh& m = *mesh_;
+  int64_t plane = 1;
+  for (int a = 0; a < dim_ - 1; ++a) plane *= m.n[a];
+  if (k0) *k0 = slabK0_;
+  if (k1) *k1 = slabK1_;
+  if (halo) *halo = (S_ - 1) / 2;
+  if (planeDofs) *planeDofs = plane * ndpc_;
+}
+
+void Problem::slabInitialCondition(double* Uowned) const {
+  if (!slab_) throw Error(kInvalid, "not a slab problem");
+  if (!(family_ == F_EULER3D && probId_ == 0) && !(family_ == F_EULER2D && probId_ == E2_PERIODIC))
+    throw Error(kUnsupported, "slab initial condition: only the periodic smooth Euler problems");
+  const Mesh& m = *mesh_;
+  const double gm1Inv = 1.0 / (gamma_ - 1.0);
+  std::vector<double> cx(m.n[0]), cy(m.n[1]), cz(m.n[2]);
+  for (int32_t i = 0; i < m.n[0]; ++i) cx[i] = m.latticeCoord(0, i);
+  for (int32_t j = 0; j < m.n[1]; ++j) cy[j] = m.latticeCoord(1, j);
+  for (int32_t k = 0; k < m.n[2]; ++k) cz[k] = m.latticeCoord(2, k);
+  if (dim_ == 3) {
+#pragma omp parallel for schedule(static)
+    for (int32_t k = slabK0_; k < slabK1_; ++k)
+      for (int32_t j = 0; j < m.n[1]; ++j)
+        for (int32_t i = 0; i < m.n[0]; ++i) {
+          const double rho = 1.0 + 0.2 * std::sin(M_PI * (cx[i] + cy[j] + cz[k]));
+          const double vel[3] = {1.0, 1.0, 1.0};
+          double* s = Uowned + 5 * (((int64_t)(k - slabK0_) * m.n[1] + j) * m.n[0] + i);
+          s[0] = rho; s[1] = rho; s[2] = rho; s[3] = rho;
+          s[4] = energyFromPrim<3>(gm1Inv, rho, vel, 1.0);
+        }
+  } else {
+#pragma omp parallel for schedule(static)
+    for (int32_t j = slabK0_; j < slabK1_; ++j)
+      for (int32_t i = 0; i < m.n[0]; ++i) {
+        const double rho = 1.0 + (1.0 / 5.0) * std::sin(M_PI * (cx[i] + cy[j]));
+        const double vel[2] = {1.0, 1.0};
+        double* s = Uowned + 4 * ((int64_t)(j - slabK0_) * m.n[0] + i);
+        s[0] = rho; s[1] = rho; s[2] = rho;
+        s[3] = energyFromPrim<2>(gm1Inv, rho, vel, 1.0);
+      }
+  }
+}
+
+void Problem::slabVelocityDev(const double* dUlocal, double /*t*/, double* dVowned, void* streamV, bool boundary) {
+  if (!slab_) throw Error(kInvalid, "not a slab problem");
+  ensureDevice();
+  PDA_CUDA(cudaSetDevice(device_));
+  DeviceState& ds = *dev_;
+  cudaStream_t st = streamV ? (cudaStream_t)streamV : ds.stream;
+  Mesh& m = *mesh_;
+  dev::Deltas dl{{m.dInv[0], m.dInv[1], m.dInv[2]}};
+  const int h = (S_ - 1) / 2;
+  const int32_t nOwned = slabK1_ - slabK0_;
+  auto run = [&](auto phys) {
+    using Phys = decltype(phys);
+    dispatchScheme(S_, [&](auto sTag) {
+      constexpr int S = decltype(sTag)::value;
+      // local plane index p in [0, nOwned): interior planes [h, nOwned-h) need no halo data
+      if (!boundary) {
+        if (nOwned - 2 * h > 0) { launchLatticeVelocitySlab<Phys, S>(phys, m, dl, dUlocal, dVowned, st, nOwned, h, nOwned - h); ++launches_; }
+      } else {
+        const int32_t hi0 = std::max<int32_t>(h, nOwned - h);
+        launchLatticeVelocitySlab<Phys, S>(phys, m, dl, dUlocal, dVowned, st, nOwned, 0, std::min<int32_t>(h, nOwned)); ++launches_;
+        if (hi0 < nOwned) { launchLatticeVelocitySlab<Phys, S>(phys, m, dl, dUlocal, dVowned, st, nOwned, hi0, nOwned); ++launches_; }
+      }
+    });
+  };
+  switch (family_) {
+    case F_EULER2D: run(dev::Euler<2>{gamma_}); break;
+    case F_EULER3D: run(dev::Euler<3>{gamma_}); break;
+    default: throw Error(kUnsupported, "slab: family not supported");
+  }
+  PDA_CUDA(cudaGetLastError());
+}
+
+}  // namespace pda

@@ -1,0 +1,387 @@
+// kernels_generic.cuh -- graph-driven kernels: one thread per cell, neighbours gathered through the connectivity
+// graph (sample meshes, near-boundary rows of any mesh, and every problem on small meshes).
+//
+// Reference loop nests replaced: ghost fill (euler_2d_prob_class.hpp:465-565 + fillers), inner-cell
+// velocity (:991-1044), near-boundary velocity (:1046-1113), inner velocity+Jacobian (:633-720 + scatter
+// mixin_directional_flux_balance_jacobian.hpp:142-284), near-boundary first-order Jacobian (:723-989, :287-371),
+// Gray-Scott (diffusion_reaction_2d_prob_class.hpp:459-529), SWE Coriolis (swe_2d_prob_class.hpp:984-1012).
+#pragma once
+#include <cstdint>
+
+#include "physics.cuh"
+
+namespace pda {
+namespace dev {
+
+// graph column of layer L on side s; device twin of pda::graphCol
+template <int DIM> PDA_DEVFN int gcol(int side, int layer) {
+  if (DIM == 1) return 1 + 2 * layer + (side == 2 ? 1 : 0);
+  return 1 + (DIM == 2 ? 4 : 6) * layer + side;
+}
+template <int AX> PDA_DEVFN constexpr int sideMinus() { return AX == 0 ? 0 : (AX == 1 ? 3 : 4); }
+template <int AX> PDA_DEVFN constexpr int sidePlus() { return AX == 0 ? 2 : (AX == 1 ? 1 : 5); }
+
+struct RowSet {
+  const int32_t* graph;   // compact [n][ncols]
+  const int32_t* rowIds;  // sample-mesh row of compact row r
+  int32_t n;
+  int32_t ncols;
+};
+
+struct GhostView {
+  double* g[6];     // per side: [numNearBd][stride]
+  int32_t stride;   // ndpc * (schemeStencil-1)/2
+};
+
+// ------------------------------------------------------------------------------------------------ ghost fill
+// One recipe per (near-bd row, side, layer): ghost[d] = mul[mode][d] * U[src*ndpc+d] + add[mode][d].
+// kind 1 (double Mach reflection, top wall): mode is chosen at run time from the shock position at time t
+// (euler_2d_ghost_filler_double_mach_reflection.hpp:112-125,176-189,...).
+struct GhostRecipe {
+  int32_t src;     // source cell (stencil-mesh id); -1 = ghost not needed (neighbour exists)
+  int16_t mode;    // index into the mul/add tables
+  int16_t kind;    // 0 affine, 1 DMR top wall
+};
+constexpr int kMaxGhostModes = 12;
+struct GhostTables {
+  double mul[kMaxGhostModes][5];
+  double add[kMaxGhostModes][5];
+  // DMR: dist = x - wedge - speed*t - slope*(y + (layer+1)*dy) < 0 -> modePost else modePre
+  double dmrWedge, dmrSpeed, dmrSlope, dy;
+  int32_t dmrModePost, dmrModePre;
+};
+
+template <int NDPC>
+__global__ void k_ghost_fill(const GhostRecipe* __restrict__ rec, const double2* __restrict__ nbXY, int32_t nNb,
+                             int nsides, int h, GhostTables tab, const double* __restrict__ U, GhostView gv,
+                             double t) {
+  const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t total = (int64_t)nNb * nsides * h;
+  if (tid >= total) return;
+  const int layer = (int)(tid % h);
+  const int side = (int)((tid / h) % nsides);
+  const int32_t r = (int32_t)(tid / ((int64_t)h * nsides));
+  const GhostRecipe gr = rec[tid];
+  if (gr.src < 0) return;
+  int mode = gr.mode;
+  if (gr.kind == 1) {
+    const double2 xy = nbXY[r];
+    const double yIn = __dadd_rn(xy.y, __dmul_rn((double)(layer + 1), tab.dy));
+    double dist = __dsub_rn(xy.x, tab.dmrWedge);
+    dist = __dsub_rn(dist, __dmul_rn(tab.dmrSpeed, t));
+    dist = __dsub_rn(dist, __dmul_rn(tab.dmrSlope, yIn));
+    mode = (dist < 0.0) ? tab.dmrModePost : tab.dmrModePre;
+  }
+  double* out = gv.g[side] + (int64_t)r * gv.stride + layer * NDPC;
+  const double* in = U + (int64_t)gr.src * NDPC;
+#pragma unroll
+  for (int d = 0; d < NDPC; ++d) out[d] = tab.mul[mode][d] * in[d] + tab.add[mode][d];
+}
+
+// ------------------------------------------------------------------------------------------------ helpers
+// value of dof d in the stencil cell `c` (or the ghost of `layer` on `side` when c == -1)
+template <int NDPC, bool NEARBD>
+PDA_DEVFN double stencilVal(const double* __restrict__ U, int32_t c, const GhostView& gv, int32_t nbRow, int side,
+                            int layer, int d) {
+  if (NEARBD && c < 0) return gv.g[side][(int64_t)nbRow * gv.stride + layer * NDPC + d];
+  return U[(int64_t)c * NDPC + d];
+}
+
+// gather the S stencil cell ids of one axis: pos 0..h-1 = minus layers (far..near), h = self, h+1.. = plus layers
+template <int DIM, int S, int AX>
+PDA_DEVFN void stencilCells(const int32_t* __restrict__ row, int32_t* cells) {
+  constexpr int h = (S - 1) / 2;
+  cells[h] = row[0];
+#pragma unroll
+  for (int L = 0; L < h; ++L) {
+    cells[h - 1 - L] = row[gcol<DIM>(sideMinus<AX>(), L)];
+    cells[h + 1 + L] = row[gcol<DIM>(sidePlus<AX>(), L)];
+  }
+}
+
+// accumulate hInv*(F_L - F_R) of axis AX into v[]
+template <class Phys, int S, int AX, bool NEARBD>
+PDA_DEVFN void axisVelocity(const Phys& phys, const int32_t* __restrict__ row, const double* __restrict__ U,
+                            const GhostView& gv, int32_t nbRow, double hInv, double* v) {
+  constexpr int N = Phys::ndpc;
+  constexpr int h = (S - 1) / 2;
+  int32_t cells[S];
+  stencilCells<Phys::dim, S, AX>(row, cells);
+  double uLn[N], uLp[N], uRn[N], uRp[N];
+#pragma unroll
+  for (int d = 0; d < N; ++d) {
+    double q[S];
+#pragma unroll
+    for (int p = 0; p < S; ++p) {
+      const int layer = (p < h) ? (h - 1 - p) : (p - h - 1);
+      const int side = (p < h) ? sideMinus<AX>() : sidePlus<AX>();
+      q[p] = stencilVal<N, NEARBD>(U, cells[p], gv, nbRow, side, layer, d);
+    }
+    Recon<S>::face(q, uLn[d], uLp[d]);
+    Recon<S>::face(q + 1, uRn[d], uRp[d]);
+  }
+  double FL[N], FR[N];
+  phys.template flux<AX>(uLn, uLp, FL);
+  phys.template flux<AX>(uRn, uRp, FR);
+#pragma unroll
+  for (int d = 0; d < N; ++d) v[d] += hInv * (FL[d] - FR[d]);
+}
+
+template <class Phys> PDA_DEVFN void addForcing(const Phys&, const double*, double*) {}
+template <> PDA_DEVFN void addForcing<Swe2d>(const Swe2d& phys, const double* u, double* v) {
+  v[1] -= phys.coriolis * u[2] / u[0];
+  v[2] += phys.coriolis * u[1] / u[0];
+}
+
+struct Deltas { double hInv[3]; };
+
+// ------------------------------------------------------------------------------------------------ velocity
+template <class Phys, int S, bool NEARBD>
+__global__ void __launch_bounds__(128)
+k_velocity_rows(Phys phys, RowSet rs, Deltas dl, const double* __restrict__ U, double* __restrict__ V, GhostView gv) {
+  constexpr int N = Phys::ndpc;
+  const int32_t r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= rs.n) return;
+  const int32_t* row = rs.graph + (int64_t)r * rs.ncols;
+  double v[N];
+#pragma unroll
+  for (int d = 0; d < N; ++d) v[d] = 0.0;
+  axisVelocity<Phys, S, 0, NEARBD>(phys, row, U, gv, r, dl.hInv[0], v);
+  if constexpr (Phys::dim >= 2) axisVelocity<Phys, S, 1, NEARBD>(phys, row, U, gv, r, dl.hInv[1], v);
+  if constexpr (Phys::dim >= 3) axisVelocity<Phys, S, 2, NEARBD>(phys, row, U, gv, r, dl.hInv[2], v);
+  addForcing<Phys>(phys, U + (int64_t)row[0] * N, v);
+  double* out = V + (int64_t)rs.rowIds[r] * N;
+#pragma unroll
+  for (int d = 0; d < N; ++d) out[d] = v[d];
+}
+
+// ------------------------------------------------------------------------------------------------ Jacobian
+// Where the blocks of a cell live in the CSR value array: all ndpc rows of a cell share one column pattern, so
+// entry (k, block slot s, j) sits at  base + k*len + s*ndpc + j.
+struct JacLayout {
+  const int32_t* base;   // [n] rowptr of the cell's first row
+  const int32_t* len;    // [n] entries per row
+  const uint8_t* slot;   // [n][nslotCols] block position of graph column c in the (sorted) row; 0xFF = absent
+  int32_t nslotCols;
+};
+
+template <int N>
+PDA_DEVFN void addBlockColumn(double* __restrict__ Jv, int64_t base, int32_t len, int slot, int j, const double* col) {
+#pragma unroll
+  for (int k = 0; k < N; ++k) Jv[base + (int64_t)k * len + slot * N + j] += col[k];
+}
+
+// inner rows, scheme S: velocity and Jacobian (values accumulated into zero-initialised Jv)
+template <class Phys, int S, int AX>
+PDA_DEVFN void axisJacobianInner(const Phys& phys, const int32_t* __restrict__ row, const double* __restrict__ U,
+                                 double hInv, double* v, double* __restrict__ Jv, int64_t base, int32_t len,
+                                 const uint8_t* __restrict__ slots) {
+  constexpr int N = Phys::ndpc;
+  constexpr int h = (S - 1) / 2;
+  constexpr int DIM = Phys::dim;
+  int32_t cells[S];
+  stencilCells<DIM, S, AX>(row, cells);
+  // graph column of each stencil position (for the slot lookup)
+  int cols[S];
+  cols[h] = 0;
+#pragma unroll
+  for (int L = 0; L < h; ++L) {
+    cols[h - 1 - L] = gcol<DIM>(sideMinus<AX>(), L);
+    cols[h + 1 + L] = gcol<DIM>(sidePlus<AX>(), L);
+  }
+#pragma unroll
+  for (int face = 0; face < 2; ++face) {   // 0: left face (stencil pos 0..S-2), 1: right face (pos 1..S-1)
+    const double sgn = (face == 0) ? hInv : -hInv;
+    double un[N], up[N];
+#pragma unroll
+    for (int d = 0; d < N; ++d) {
+      double q[S - 1];
+#pragma unroll
+      for (int p = 0; p < S - 1; ++p) q[p] = U[(int64_t)cells[p + face] * N + d];
+      Recon<S>::face(q, un[d], up[d]);
+    }
+    double F[N], JN[N * N], JP[N * N];
+    phys.template flux<AX>(un, up, F);
+    phys.template fluxJac<AX>(un, up, JN, JP);
+#pragma unroll
+    for (int d = 0; d < N; ++d) v[d] += sgn * F[d];
+    // chain rule: d(flux)/d(u_m) = JN * diag(d uNeg/d u_m) + JP * diag(d uPos/d u_m)
+#pragma unroll
+    for (int j = 0; j < N; ++j) {
+      double q[S - 1], gN[S - 1], gP[S - 1], t0, t1;
+#pragma unroll
+      for (int p = 0; p < S - 1; ++p) q[p] = U[(int64_t)cells[p + face] * N + j];
+      Recon<S>::faceGrad(q, t0, t1, gN, gP);
+#pragma unroll
+      for (int m = 0; m < S - 1; ++m) {
+        double col[N];
+#pragma unroll
+        for (int k = 0; k < N; ++k) col[k] = sgn * (JN[k * N + j] * gN[m] + JP[k * N + j] * gP[m]);
+        addBlockColumn<N>(Jv, base, len, slots[cols[m + face]], j, col);
+      }
+    }
+  }
+}
+
+template <class Phys> PDA_DEVFN void addForcingJac(const Phys&, const double*, double*, int64_t, int32_t, int) {}
+template <> PDA_DEVFN void addForcingJac<Swe2d>(const Swe2d& phys, const double* u, double* Jv, int64_t base,
+                                                int32_t len, int slot) {
+  const double f = phys.coriolis;
+  Jv[base + 1 * (int64_t)len + slot * 3 + 0] += f * u[2] / (u[0] * u[0]);
+  Jv[base + 1 * (int64_t)len + slot * 3 + 2] += -f / u[0];
+  Jv[base + 2 * (int64_t)len + slot * 3 + 1] += f / u[0];
+  Jv[base + 2 * (int64_t)len + slot * 3 + 0] += -f * u[1] / (u[0] * u[0]);
+}
+
+template <class Phys, int S>
+__global__ void __launch_bounds__(128)
+k_jacobian_inner_rows(Phys phys, RowSet rs, Deltas dl, const double* __restrict__ U, double* __restrict__ V,
+                      double* __restrict__ Jv, JacLayout jl) {
+  constexpr int N = Phys::ndpc;
+  const int32_t r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= rs.n) return;
+  const int32_t* row = rs.graph + (int64_t)r * rs.ncols;
+  const int64_t base = jl.base[r];
+  const int32_t len = jl.len[r];
+  const uint8_t* slots = jl.slot + (int64_t)r * jl.nslotCols;
+  double v[N];
+#pragma unroll
+  for (int d = 0; d < N; ++d) v[d] = 0.0;
+  axisJacobianInner<Phys, S, 0>(phys, row, U, dl.hInv[0], v, Jv, base, len, slots);
+  if constexpr (Phys::dim >= 2) axisJacobianInner<Phys, S, 1>(phys, row, U, dl.hInv[1], v, Jv, base, len, slots);
+  if constexpr (Phys::dim >= 3) axisJacobianInner<Phys, S, 2>(phys, row, U, dl.hInv[2], v, Jv, base, len, slots);
+  const double* uSelf = U + (int64_t)row[0] * N;
+  addForcing<Phys>(phys, uSelf, v);
+  addForcingJac<Phys>(phys, uSelf, Jv, base, len, slots[0]);
+  if (V) {
+    double* out = V + (int64_t)rs.rowIds[r] * N;
+#pragma unroll
+    for (int d = 0; d < N; ++d) out[d] = v[d];
+  }
+}
+
+// near-boundary rows: FIRST-ORDER Jacobian whatever the velocity scheme is ("DifferentScheme" path), missing
+// first-layer neighbours folded into the self block with per-dof factors
+// (mixin_directional_flux_balance_jacobian.hpp:287-371).  The velocity of these rows is k_velocity_rows<.,S,true>.
+template <class Phys, int AX>
+PDA_DEVFN void axisJacobianNearBd(const Phys& phys, const int32_t* __restrict__ row, const double* __restrict__ U,
+                                  const GhostView& gv, int32_t nbRow, double hInv, const double* __restrict__ fac,
+                                  double* __restrict__ Jv, int64_t base, int32_t len,
+                                  const uint8_t* __restrict__ slots) {
+  constexpr int N = Phys::ndpc;
+  constexpr int DIM = Phys::dim;
+  const int cl = gcol<DIM>(sideMinus<AX>(), 0), cr = gcol<DIM>(sidePlus<AX>(), 0);
+  const int32_t l0 = row[cl], r0 = row[cr];
+  double qL[N], qC[N], qR[N];
+#pragma unroll
+  for (int d = 0; d < N; ++d) {
+    qL[d] = stencilVal<N, true>(U, l0, gv, nbRow, sideMinus<AX>(), 0, d);
+    qC[d] = U[(int64_t)row[0] * N + d];
+    qR[d] = stencilVal<N, true>(U, r0, gv, nbRow, sidePlus<AX>(), 0, d);
+  }
+  double JN[N * N], JP[N * N];
+  const int sSelf = slots[0];
+  // left face: flux(qL, qC)
+  phys.template fluxJac<AX>(qL, qC, JN, JP);
+#pragma unroll
+  for (int j = 0; j < N; ++j) {
+    double col[N];
+#pragma unroll
+    for (int k = 0; k < N; ++k) col[k] = hInv * JP[k * N + j];
+    addBlockColumn<N>(Jv, base, len, sSelf, j, col);
+#pragma unroll
+    for (int k = 0; k < N; ++k) col[k] = hInv * JN[k * N + j] * (l0 >= 0 ? 1.0 : fac[j]);
+    addBlockColumn<N>(Jv, base, len, (l0 >= 0) ? slots[cl] : sSelf, j, col);
+  }
+  // right face: flux(qC, qR)
+  phys.template fluxJac<AX>(qC, qR, JN, JP);
+#pragma unroll
+  for (int j = 0; j < N; ++j) {
+    double col[N];
+#pragma unroll
+    for (int k = 0; k < N; ++k) col[k] = -hInv * JN[k * N + j];
+    addBlockColumn<N>(Jv, base, len, sSelf, j, col);
+#pragma unroll
+    for (int k = 0; k < N; ++k) col[k] = -hInv * JP[k * N + j] * (r0 >= 0 ? 1.0 : fac[j]);
+    addBlockColumn<N>(Jv, base, len, (r0 >= 0) ? slots[cr] : sSelf, j, col);
+  }
+}
+
+template <class Phys>
+__global__ void __launch_bounds__(128)
+k_jacobian_nearbd_rows(Phys phys, RowSet rs, Deltas dl, const double* __restrict__ U, double* __restrict__ Jv,
+                       JacLayout jl, GhostView gv, const double* __restrict__ factors /*[n][dim][ndpc]*/) {
+  constexpr int N = Phys::ndpc;
+  constexpr int DIM = Phys::dim;
+  const int32_t r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= rs.n) return;
+  const int32_t* row = rs.graph + (int64_t)r * rs.ncols;
+  const int64_t base = jl.base[r];
+  const int32_t len = jl.len[r];
+  const uint8_t* slots = jl.slot + (int64_t)r * jl.nslotCols;
+  const double* fac = factors + (int64_t)r * DIM * N;
+  axisJacobianNearBd<Phys, 0>(phys, row, U, gv, r, dl.hInv[0], fac, Jv, base, len, slots);
+  if constexpr (DIM >= 2) axisJacobianNearBd<Phys, 1>(phys, row, U, gv, r, dl.hInv[1], fac + N, Jv, base, len, slots);
+  if constexpr (DIM >= 3) axisJacobianNearBd<Phys, 2>(phys, row, U, gv, r, dl.hInv[2], fac + 2 * N, Jv, base, len, slots);
+  addForcingJac<Phys>(phys, U + (int64_t)row[0] * N, Jv, base, len, slots[0]);
+}
+
+// ------------------------------------------------------------------------------------------------ Gray-Scott
+// diffusion_reaction_2d_prob_class.hpp:459-529: V is ASSIGNED; J: 2x2 self block + diagonal neighbour blocks
+// (off-diagonal entries of the neighbour blocks are stored zeros).
+struct GrayScottParams { double Du, Dv, F, k, dxInvSq, dyInvSq; };
+
+__global__ void k_gray_scott_rows(GrayScottParams gp, RowSet rs, const double* __restrict__ U,
+                                  double* __restrict__ V, double* __restrict__ Jv, JacLayout jl) {
+  const int32_t r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= rs.n) return;
+  const int32_t* row = rs.graph + (int64_t)r * rs.ncols;
+  const int64_t c = row[0], l = row[1], f = row[2], rt = row[3], b = row[4];
+  const double u = U[2 * c], w = U[2 * c + 1];
+  const double uDx = gp.Du * gp.dxInvSq, uDy = gp.Du * gp.dyInvSq;
+  const double vDx = gp.Dv * gp.dxInvSq, vDy = gp.Dv * gp.dyInvSq;
+  const double uvv = u * w * w;
+  if (V) {
+    const int64_t o = (int64_t)rs.rowIds[r] * 2;
+    V[o] = gp.F * (1.0 - u) - uvv + uDx * (U[2 * rt] - 2.0 * u + U[2 * l]) + uDy * (U[2 * b] - 2.0 * u + U[2 * f]);
+    V[o + 1] = -(gp.F + gp.k) * w + uvv + vDx * (U[2 * rt + 1] - 2.0 * w + U[2 * l + 1]) +
+               vDy * (U[2 * b + 1] - 2.0 * w + U[2 * f + 1]);
+  }
+  if (Jv) {
+    const int64_t base = jl.base[r];
+    const int32_t len = jl.len[r];
+    const uint8_t* slots = jl.slot + (int64_t)r * jl.nslotCols;
+    double* r0 = Jv + base;
+    double* r1 = Jv + base + len;
+    const int s = slots[0];
+    r0[2 * s] += -2.0 * uDx - 2.0 * uDy - w * w - gp.F;
+    r0[2 * s + 1] -= 2.0 * u * w;
+    r1[2 * s] += w * w;
+    r1[2 * s + 1] += -2.0 * vDx - 2.0 * vDy + 2.0 * u * w - (gp.F + gp.k);
+    const int sl = slots[1], sf = slots[2], sr = slots[3], sb = slots[4];
+    r0[2 * sl] += uDx; r0[2 * sf] += uDy; r0[2 * sr] += uDx; r0[2 * sb] += uDy;
+    r1[2 * sl + 1] += vDx; r1[2 * sf + 1] += vDy; r1[2 * sr + 1] += vDx; r1[2 * sb + 1] += vDy;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ J * B
+// applyJacobian (adapter_cpp.hpp:231-259): R = J * B with the fixed CSR pattern; one warp per row, lanes over
+// the row's entries, B row-major [ncol_J][nB] or col-major (ldb = rows).
+__global__ void k_spmm_csr(int32_t nrows, const int32_t* __restrict__ rowptr, const int32_t* __restrict__ colidx,
+                           const double* __restrict__ vals, const double* __restrict__ B, int nB, int64_t ldbRow,
+                           int64_t ldbCol, double* __restrict__ R, int64_t ldrRow, int64_t ldrCol) {
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (warp >= nrows) return;
+  const int32_t b = rowptr[warp], e = rowptr[warp + 1];
+  for (int c = 0; c < nB; ++c) {
+    double acc = 0.0;
+    for (int32_t p = b + lane; p < e; p += 32) acc += vals[p] * B[(int64_t)colidx[p] * ldbRow + c * ldbCol];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if (lane == 0) R[(int64_t)warp * ldrRow + c * ldrCol] = acc;
+  }
+}
+
+}  // namespace dev
+}  // namespace pda

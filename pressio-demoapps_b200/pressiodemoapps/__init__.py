@@ -1,0 +1,573 @@
+"""pressiodemoapps (B200 engine) -- Python mirror of the reference's `pressiodemoapps` module.
+
+Same names, argument meaning and error behaviour as the reference's pybind11 module
+(`/root/reference/src_py/main_binder.cc`, `pressiodemoapps/__init__.py`), but every evaluation runs as CUDA kernels
+behind the C-ABI in `include/pda_b200.h` (loaded with ctypes from `../lib/libpda_b200.so`).  There is no CPU
+fallback: `rightHandSide` & friends raise if the library or a CUDA device is missing.
+
+Extras beyond the reference's Python surface (which only exposes `applyJacobian`):
+`createJacobian()/jacobian()/rightHandSideAndJacobian()` (the C++ API, adapter_cpp.hpp:105-229), native mesh tools
+(`create_full_mesh`, `create_sample_mesh`, `mesh.write`) and device-pointer entry points for callers that keep the
+state in HBM (`rightHandSideDevice`).
+"""
+import ctypes as _C
+import os as _os
+
+import numpy as _np
+
+from enum import IntEnum as _IntEnum
+
+__all__ = [
+    "CellCenteredUniformMesh", "load_cellcentered_uniform_mesh", "create_full_mesh", "create_sample_mesh",
+    "InviscidFluxReconstruction", "InviscidFluxScheme", "ViscousFluxReconstruction", "ViscousFluxScheme",
+    "Euler1d", "Euler2d", "Euler3d", "Swe2d", "DiffusionReaction2d", "AdvectionDiffusion2d",
+    "create_problem", "create_gray_scott_2d_problem", "create_slip_wall_swe_2d_problem", "create_cross_shock_problem",
+    "advanceRK2", "advanceRK4", "advanceSSP3", "PdaError", "device_count", "BC",
+]
+
+_HERE = _os.path.dirname(_os.path.abspath(__file__))
+_LIBPATH = _os.path.join(_os.path.dirname(_HERE), "lib", "libpda_b200.so")
+
+
+class PdaError(RuntimeError):
+    """Raised where the reference throws std::runtime_error (or calls exit())."""
+
+    def __init__(self, code, msg):
+        super().__init__(msg)
+        self.code = code
+
+
+def _load():
+    if not _os.path.exists(_LIBPATH):
+        raise ImportError(
+            "libpda_b200.so not built (%s); run `python -c 'import __graft_entry__ as g; g.build()'` "
+            "at the repo root -- there is no Python/CPU fallback" % _LIBPATH)
+    return _C.CDLL(_LIBPATH)
+
+
+_lib = _load()
+_vp, _i32, _i64, _dbl, _cp = _C.c_void_p, _C.c_int32, _C.c_int64, _C.c_double, _C.c_char_p
+_pi32 = _C.POINTER(_C.c_int32)
+
+
+def _sig(name, restype, *argtypes):
+    f = getattr(_lib, name)
+    f.restype = restype
+    f.argtypes = list(argtypes)
+    return f
+
+
+_sig("pda_last_error", _cp)
+_sig("pda_version", _cp)
+_sig("pda_device_count", _C.c_int)
+_sig("pda_mesh_load", _C.c_int, _cp, _C.POINTER(_vp))
+_sig("pda_mesh_make_lattice", _C.c_int, _C.c_int, _vp, _vp, _vp, _C.c_int, _C.POINTER(_vp))
+_sig("pda_mesh_make_sample", _C.c_int, _vp, _vp, _i64, _C.POINTER(_vp))
+_sig("pda_mesh_from_arrays", _C.c_int, _C.c_int, _C.c_int, _i32, _i32, _vp, _vp, _vp, _vp, _vp, _C.POINTER(_vp))
+_sig("pda_mesh_write", _C.c_int, _vp, _cp)
+_sig("pda_mesh_free", _C.c_int, _vp)
+for _n in ("dimensionality", "stencil_size", "graph_cols", "is_fully_periodic", "is_lattice"):
+    _sig("pda_mesh_" + _n, _C.c_int, _vp)
+for _n in ("stencil_mesh_size", "sample_mesh_size", "num_cells_inner", "num_cells_near_bd"):
+    _sig("pda_mesh_" + _n, _i32, _vp)
+_sig("pda_mesh_deltas", _C.c_int, _vp, _vp, _vp)
+_sig("pda_mesh_coordinates", _C.c_int, _vp, _vp, _vp, _vp)
+_sig("pda_mesh_graph", _C.c_int, _vp, _vp)
+_sig("pda_mesh_rows_inner", _C.c_int, _vp, _vp)
+_sig("pda_mesh_rows_near_bd", _C.c_int, _vp, _vp)
+_sig("pda_mesh_stencil_gids", _C.c_int, _vp, _vp)
+_sig("pda_problem_create", _C.c_int, _vp, _C.c_int, _C.c_int, _C.c_int, _C.c_int, _C.c_int, _vp, _vp, _C.c_int,
+     _C.POINTER(_vp))
+_sig("pda_problem_set_bc", _C.c_int, _vp, _C.c_int, _C.c_int, _vp)
+_sig("pda_problem_free", _C.c_int, _vp)
+_sig("pda_problem_num_dof_per_cell", _C.c_int, _vp)
+_sig("pda_problem_total_dof_sample_mesh", _i32, _vp)
+_sig("pda_problem_total_dof_stencil_mesh", _i32, _vp)
+_sig("pda_problem_query_parameter", _C.c_int, _vp, _cp, _C.POINTER(_dbl))
+_sig("pda_problem_initial_condition", _C.c_int, _vp, _vp)
+_sig("pda_problem_jacobian_nnz", _C.c_int, _vp, _C.POINTER(_i64))
+_sig("pda_problem_jacobian_pattern", _C.c_int, _vp, _vp, _vp)
+_sig("pda_problem_velocity_host", _C.c_int, _vp, _vp, _dbl, _vp)
+_sig("pda_problem_velocity_and_jacobian_host", _C.c_int, _vp, _vp, _dbl, _vp, _vp)
+_sig("pda_problem_apply_jacobian_host", _C.c_int, _vp, _vp, _vp, _C.c_int, _C.c_int, _dbl, _vp)
+_sig("pda_problem_velocity_dev", _C.c_int, _vp, _vp, _dbl, _vp, _vp)
+_sig("pda_problem_velocity_and_jacobian_dev", _C.c_int, _vp, _vp, _dbl, _vp, _vp, _vp)
+_sig("pda_problem_apply_jacobian_dev", _C.c_int, _vp, _vp, _vp, _C.c_int, _C.c_int, _dbl, _vp, _vp)
+_sig("pda_problem_ghosts", _C.c_int, _vp, _C.c_int, _vp)
+_sig("pda_problem_launch_count", _i64, _vp)
+_sig("pda_problem_create_slab", _C.c_int, _vp, _C.c_int, _C.c_int, _C.c_int, _C.c_int, _C.c_int, _C.c_int,
+     _C.POINTER(_vp))
+_sig("pda_slab_extent", _C.c_int, _vp, _C.POINTER(_i32), _C.POINTER(_i32), _C.POINTER(_i32), _C.POINTER(_i64))
+_sig("pda_slab_initial_condition", _C.c_int, _vp, _vp)
+_sig("pda_slab_velocity_interior_dev", _C.c_int, _vp, _vp, _dbl, _vp, _vp)
+_sig("pda_slab_velocity_boundary_dev", _C.c_int, _vp, _vp, _dbl, _vp, _vp)
+
+
+def _check(status):
+    if status != 0:
+        raise PdaError(status, _lib.pda_last_error().decode())
+
+
+def device_count():
+    return int(_lib.pda_device_count())
+
+
+def _f64(a, n=None, name="array"):
+    """float64, 1-D (or C/F 2-D) contiguous numpy view -- like Eigen::Ref the reference binds (adapter_py.hpp)."""
+    if not isinstance(a, _np.ndarray) or a.dtype != _np.float64:
+        raise TypeError("%s must be a float64 numpy array" % name)
+    if n is not None and a.size != n:
+        raise ValueError("%s has %d entries, expected %d" % (name, a.size, n))
+    return a
+
+
+# ------------------------------------------------------------------------------------------------ enums
+class InviscidFluxReconstruction(_IntEnum):
+    FirstOrder = 0
+    Weno3 = 1
+    Weno5 = 2
+
+
+class InviscidFluxScheme(_IntEnum):
+    Rusanov = 0
+
+
+class ViscousFluxReconstruction(_IntEnum):
+    FirstOrder = 0
+
+
+class ViscousFluxScheme(_IntEnum):
+    Central = 0
+
+
+class Euler1d(_IntEnum):
+    PeriodicSmooth = 0
+    Sod = 1
+    Lax = 2
+    ShuOsher = 3
+
+
+class Euler2d(_IntEnum):
+    PeriodicSmooth = 0
+    KelvinHelmholtz = 1
+    SedovFull = 2
+    SedovSymmetry = 3
+    Riemann = 4
+    NormalShock = 5
+    DoubleMachReflection = 6
+    CrossShock = 7
+    testingonlyneumann = 8
+
+
+class Euler3d(_IntEnum):
+    PeriodicSmooth = 0
+    SedovSymmetry = 1
+
+
+class Swe2d(_IntEnum):
+    SlipWall = 0
+    CustomBCs = 1
+
+
+class DiffusionReaction2d(_IntEnum):
+    ProblemA = 0
+    GrayScott = 1
+
+
+class AdvectionDiffusion2d(_IntEnum):
+    BurgersPeriodic = 0
+    BurgersOutflow = 1
+
+
+class BC(_IntEnum):
+    """Device-expressible custom boundary rules (custom_bcs_functions.hpp)."""
+    Dirichlet = 0
+    HomogNeumann = 1
+    Reflective = 2
+
+
+_FAMILY = {Euler1d: 1, Euler2d: 2, Euler3d: 3, Swe2d: 4, DiffusionReaction2d: 5, AdvectionDiffusion2d: 6}
+
+
+# ------------------------------------------------------------------------------------------------ mesh
+class CellCenteredUniformMesh:
+    """impl/mesh_ccu.hpp:67-473; python methods of src_py/main_binder.cc:230-243 (+ the C++-only row lists)."""
+
+    def __init__(self, meshDir=None, _handle=None):
+        if _handle is None:
+            h = _vp()
+            _check(_lib.pda_mesh_load(str(meshDir).encode(), _C.byref(h)))
+            _handle = h
+        self._h = _handle
+        self._keep = []
+
+    def __del__(self):
+        h = getattr(self, "_h", None)
+        if h:
+            _lib.pda_mesh_free(h)
+            self._h = None
+
+    def dimensionality(self): return _lib.pda_mesh_dimensionality(self._h)
+    def stencilMeshSize(self): return _lib.pda_mesh_stencil_mesh_size(self._h)
+    def sampleMeshSize(self): return _lib.pda_mesh_sample_mesh_size(self._h)
+    def stencilSize(self): return _lib.pda_mesh_stencil_size(self._h)
+    def isFullyPeriodic(self): return bool(_lib.pda_mesh_is_fully_periodic(self._h))
+    def isLattice(self): return bool(_lib.pda_mesh_is_lattice(self._h))
+    def numCellsInner(self): return _lib.pda_mesh_num_cells_inner(self._h)
+    def numCellsNearBd(self): return _lib.pda_mesh_num_cells_near_bd(self._h)
+
+    def _deltas(self):
+        d = _np.zeros(3)
+        di = _np.zeros(3)
+        _check(_lib.pda_mesh_deltas(self._h, d.ctypes.data, di.ctypes.data))
+        return d, di
+
+    def dx(self): return float(self._deltas()[0][0])
+    def dy(self): return float(self._deltas()[0][1])
+    def dz(self): return float(self._deltas()[0][2])
+    def dxInv(self): return float(self._deltas()[1][0])
+    def dyInv(self): return float(self._deltas()[1][1])
+    def dzInv(self): return float(self._deltas()[1][2])
+
+    def _coords(self):
+        n = self.stencilMeshSize()
+        x, y, z = _np.zeros(n), _np.zeros(n), _np.zeros(n)
+        _check(_lib.pda_mesh_coordinates(self._h, x.ctypes.data, y.ctypes.data, z.ctypes.data))
+        return x, y, z
+
+    def viewX(self): return self._coords()[0]
+    def viewY(self): return self._coords()[1]
+    def viewZ(self): return self._coords()[2]
+
+    def graph(self):
+        g = _np.zeros((self.sampleMeshSize(), _lib.pda_mesh_graph_cols(self._h)), dtype=_np.int32)
+        _check(_lib.pda_mesh_graph(self._h, g.ctypes.data))
+        return g
+
+    def graphRowsOfCellsAwayFromBd(self):
+        r = _np.zeros(self.numCellsInner(), dtype=_np.int32)
+        _check(_lib.pda_mesh_rows_inner(self._h, r.ctypes.data))
+        return r
+
+    def graphRowsOfCellsNearBd(self):
+        r = _np.zeros(self.numCellsNearBd(), dtype=_np.int32)
+        _check(_lib.pda_mesh_rows_near_bd(self._h, r.ctypes.data))
+        return r
+
+    def stencilMeshGids(self):
+        r = _np.zeros(self.stencilMeshSize(), dtype=_np.int32)
+        _check(_lib.pda_mesh_stencil_gids(self._h, r.ctypes.data))
+        return r
+
+    def write(self, outDir):
+        """info.dat / connectivity.dat / coordinates.dat in the reference's text format."""
+        _os.makedirs(outDir, exist_ok=True)
+        _check(_lib.pda_mesh_write(self._h, str(outDir).encode()))
+
+
+def load_cellcentered_uniform_mesh(meshDir):
+    """mesh.hpp:87-91 / src_py/main_binder.cc:246-250."""
+    return CellCenteredUniformMesh(meshDir)
+
+
+def create_full_mesh(numCells, bounds, stencilSize=3, periodic=()):
+    """Native `meshing_scripts/create_full_mesh.py -n .. --bounds .. -s .. --periodic ..` (in memory)."""
+    numCells = list(numCells)
+    dim = len(numCells)
+    if dim == 2 and numCells[1] == 1:
+        dim = 1
+    n = (_C.c_int32 * 3)(*(numCells + [1, 1, 1])[:3])
+    b = list(bounds) + [0.0] * 6
+    bd = (_C.c_double * 6)(*b[:6])
+    per = (_C.c_int32 * 3)(*[1 if a in periodic else 0 for a in ("x", "y", "z")])
+    h = _vp()
+    _check(_lib.pda_mesh_make_lattice(dim, n, bd, per, int(stencilSize), _C.byref(h)))
+    return CellCenteredUniformMesh(_handle=h)
+
+
+def create_sample_mesh(fullMesh, sampleMeshGids):
+    """Native `meshing_scripts/create_sample_mesh.py` (in memory)."""
+    g = _np.ascontiguousarray(_np.asarray(sampleMeshGids, dtype=_np.int32))
+    h = _vp()
+    _check(_lib.pda_mesh_make_sample(fullMesh._h, g.ctypes.data, g.size, _C.byref(h)))
+    return CellCenteredUniformMesh(_handle=h)
+
+
+# ------------------------------------------------------------------------------------------------ problems
+class Problem:
+    """adapter_py.hpp:57-199 (python names) + adapter_cpp.hpp:59-264 (C++ names)."""
+
+    def __init__(self, mesh, family, problemId, recon, icFlag=1, params=None, device=0, _slab=None):
+        self._mesh = mesh   # the mesh must outlive the problem (euler_2d_prob_class.hpp:1277)
+        h = _vp()
+        if _slab is not None:
+            rank, nranks = _slab
+            _check(_lib.pda_problem_create_slab(mesh._h, family, int(problemId), int(recon), rank, nranks, device,
+                                                _C.byref(h)))
+        else:
+            params = params or {}
+            names = (_cp * max(len(params), 1))(*[k.encode() for k in params])
+            vals = (_dbl * max(len(params), 1))(*[float(v) for v in params.values()])
+            _check(_lib.pda_problem_create(mesh._h, family, int(problemId), int(recon), int(icFlag), len(params),
+                                           names, vals, device, _C.byref(h)))
+        self._h = h
+        self._pattern = None
+
+    def __del__(self):
+        h = getattr(self, "_h", None)
+        if h:
+            _lib.pda_problem_free(h)
+            self._h = None
+
+    # ---- sizes / parameters
+    def numDofPerCell(self): return _lib.pda_problem_num_dof_per_cell(self._h)
+    def totalDofSampleMesh(self): return _lib.pda_problem_total_dof_sample_mesh(self._h)
+    def totalDofStencilMesh(self): return _lib.pda_problem_total_dof_stencil_mesh(self._h)
+
+    def queryParameter(self, name):
+        v = _dbl()
+        _check(_lib.pda_problem_query_parameter(self._h, name.encode(), _C.byref(v)))
+        return v.value
+
+    def gamma(self): return self.queryParameter("gamma")
+    def gravity(self): return self.queryParameter("gravity")
+    def coriolis(self): return self.queryParameter("coriolis")
+
+    def setBC(self, side, kind, values=None):
+        v = None if values is None else _np.ascontiguousarray(values, dtype=_np.float64)
+        _check(_lib.pda_problem_set_bc(self._h, int(side), int(kind), None if v is None else v.ctypes.data))
+
+    # ---- creators
+    def initialCondition(self):
+        U = _np.zeros(self.totalDofStencilMesh())
+        _check(_lib.pda_problem_initial_condition(self._h, U.ctypes.data))
+        return U
+
+    def createState(self): return _np.zeros(self.totalDofStencilMesh())
+    def createRightHandSide(self): return _np.zeros(self.totalDofSampleMesh())
+    createRhs = createRightHandSide
+    createVelocity = createRightHandSide
+
+    def jacobianPattern(self):
+        if self._pattern is None:
+            nnz = _i64()
+            _check(_lib.pda_problem_jacobian_nnz(self._h, _C.byref(nnz)))
+            rowptr = _np.zeros(self.totalDofSampleMesh() + 1, dtype=_np.int32)
+            colidx = _np.zeros(nnz.value, dtype=_np.int32)
+            _check(_lib.pda_problem_jacobian_pattern(self._h, rowptr.ctypes.data, colidx.ctypes.data))
+            self._pattern = (rowptr, colidx)
+        return self._pattern
+
+    def createJacobian(self):
+        """scipy.sparse.csr_matrix with the fixed pattern (explicit zeros kept), like Eigen's RowMajor SparseMatrix."""
+        import scipy.sparse as sp
+        rowptr, colidx = self.jacobianPattern()
+        return sp.csr_matrix((_np.zeros(colidx.size), colidx.copy(), rowptr.copy()),
+                             shape=(self.totalDofSampleMesh(), self.totalDofStencilMesh()))
+
+    def createApplyJacobianResult(self, operand):
+        operand = _np.asarray(operand)
+        if operand.ndim == 1:
+            return _np.zeros(self.totalDofSampleMesh())
+        order = "F" if operand.flags["F_CONTIGUOUS"] and not operand.flags["C_CONTIGUOUS"] else "C"
+        return _np.zeros((self.totalDofSampleMesh(), operand.shape[1]), order=order)
+
+    createResultOfJacobianActionOn = createApplyJacobianResult
+
+    # ---- evaluation (host buffers)
+    def rightHandSide(self, state, time, V):
+        _f64(state, self.totalDofStencilMesh(), "state")
+        _f64(V, self.totalDofSampleMesh(), "rhs")
+        _check(_lib.pda_problem_velocity_host(self._h, state.ctypes.data, float(time), V.ctypes.data))
+
+    rhs = rightHandSide
+    velocity = rightHandSide
+
+    def __call__(self, state, time, V, J=None, computeJacobian=False):
+        if J is not None and computeJacobian:
+            self.rightHandSideAndJacobian(state, time, V, J)
+        else:
+            self.rightHandSide(state, time, V)
+
+    def rightHandSideAndJacobian(self, state, time, V, J):
+        _f64(state, self.totalDofStencilMesh(), "state")
+        vals = J.data if hasattr(J, "data") and not isinstance(J, _np.ndarray) else J
+        _f64(vals, self.jacobianPattern()[1].size, "jacobian values")
+        vp = None if V is None else _f64(V, self.totalDofSampleMesh(), "rhs").ctypes.data
+        _check(_lib.pda_problem_velocity_and_jacobian_host(self._h, state.ctypes.data, float(time), vp,
+                                                           vals.ctypes.data))
+
+    def jacobian(self, state, time, J):
+        self.rightHandSideAndJacobian(state, time, None, J)
+
+    def applyJacobian(self, state, operand, time, result):
+        _f64(state, self.totalDofStencilMesh(), "state")
+        _f64(operand, None, "operand")
+        _f64(result, None, "result")
+        ncols = 1 if operand.ndim == 1 else operand.shape[1]
+        if operand.shape[0] != self.totalDofStencilMesh():
+            raise ValueError("operand has %d rows, expected %d" % (operand.shape[0], self.totalDofStencilMesh()))
+        if operand.ndim == 1 or (operand.flags["F_CONTIGUOUS"] and not operand.flags["C_CONTIGUOUS"]):
+            layout = 0
+            if operand.ndim == 2 and not result.flags["F_CONTIGUOUS"]:
+                raise ValueError("col-major operand needs a col-major result")
+        else:
+            if not operand.flags["C_CONTIGUOUS"] or not result.flags["C_CONTIGUOUS"]:
+                raise ValueError("operand/result must be contiguous")
+            layout = 1
+        _check(_lib.pda_problem_apply_jacobian_host(self._h, state.ctypes.data, operand.ctypes.data, ncols, layout,
+                                                    float(time), result.ctypes.data))
+
+    # ---- evaluation (device pointers: ints from tensor.data_ptr(); stream = cudaStream_t as int)
+    def rightHandSideDevice(self, dU, time, dV, stream=0):
+        _check(_lib.pda_problem_velocity_dev(self._h, dU, float(time), dV, stream))
+
+    def rightHandSideAndJacobianDevice(self, dU, time, dV, dJvalues, stream=0):
+        _check(_lib.pda_problem_velocity_and_jacobian_dev(self._h, dU, float(time), dV, dJvalues, stream))
+
+    def applyJacobianDevice(self, dU, dB, ncols, layout, time, dR, stream=0):
+        _check(_lib.pda_problem_apply_jacobian_dev(self._h, dU, dB, int(ncols), int(layout), float(time), dR, stream))
+
+    # ---- test hooks / instrumentation
+    def viewGhost(self, side):
+        """viewGhostLeft/Front/Right/Back (euler_2d_prob_class.hpp:205-210): rows after the last evaluation."""
+        nb = self._mesh.numCellsNearBd()
+        out = _np.zeros((nb, max(1, self._ghost_stride())))
+        _check(_lib.pda_problem_ghosts(self._h, int(side), out.ctypes.data))
+        return out
+
+    def _ghost_stride(self):
+        return self.numDofPerCell() * ((self._stencil - 1) // 2)
+
+    def launchCount(self):
+        return int(_lib.pda_problem_launch_count(self._h))
+
+    # ---- slab decomposition (one process per GPU)
+    def slabExtent(self):
+        k0, k1, h, pd = _i32(), _i32(), _i32(), _i64()
+        _check(_lib.pda_slab_extent(self._h, _C.byref(k0), _C.byref(k1), _C.byref(h), _C.byref(pd)))
+        return k0.value, k1.value, h.value, pd.value
+
+    def slabInitialCondition(self):
+        k0, k1, _, pd = self.slabExtent()
+        U = _np.zeros((k1 - k0) * pd)
+        _check(_lib.pda_slab_initial_condition(self._h, U.ctypes.data))
+        return U
+
+    def slabVelocityInteriorDevice(self, dU, time, dV, stream=0):
+        _check(_lib.pda_slab_velocity_interior_dev(self._h, dU, float(time), dV, stream))
+
+    def slabVelocityBoundaryDevice(self, dU, time, dV, stream=0):
+        _check(_lib.pda_slab_velocity_boundary_dev(self._h, dU, float(time), dV, stream))
+
+
+def _make(mesh, family, probEnum, recon, icFlag=1, params=None, device=0):
+    p = Problem(mesh, family, probEnum, recon, icFlag, params, device)
+    p._stencil = 3 + 2 * int(recon)
+    return p
+
+
+def create_problem(mesh, probEnum, *args, device=0):
+    """Overload set of `create_problem` (src_py/main_binder.cc:255-546, C++ create_problem_eigen):
+       (mesh, Euler1d|Euler3d, recon) ; (mesh, Euler2d|Swe2d, recon[, icFlag][, {name: value}]) ;
+       (mesh, DiffusionReaction2d.GrayScott[, ViscousFluxReconstruction])."""
+    fam = _FAMILY.get(type(probEnum))
+    if fam is None:
+        raise TypeError("create_problem: unknown problem enum %r" % (probEnum,))
+    if fam == 5:
+        if probEnum != DiffusionReaction2d.GrayScott:
+            raise PdaError(5, "DiffusionReaction2d.ProblemA needs a host source functor: not available on the device")
+        return _make(mesh, fam, probEnum, 0, 1, None, device)
+    if not args:
+        raise TypeError("create_problem: missing reconstruction enum")
+    recon = args[0]
+    icFlag, params = 1, None
+    for a in args[1:]:
+        if a is None or isinstance(a, (ViscousFluxReconstruction,)):
+            continue
+        if isinstance(a, dict):
+            params = a
+        else:
+            icFlag = int(a)
+    return _make(mesh, fam, probEnum, recon, icFlag, params, device)
+
+
+def create_problem_slab(mesh, probEnum, recon, rank, nranks, device=0):
+    """One z-slab (3D) / y-slab (2D) of a periodic full lattice per rank."""
+    fam = _FAMILY[type(probEnum)]
+    p = Problem(mesh, fam, probEnum, recon, device=device, _slab=(rank, nranks))
+    p._stencil = 3 + 2 * int(recon)
+    return p
+
+
+def create_gray_scott_2d_problem(mesh, viscRecon, Du, Dv, F, k, device=0):
+    """diffusion_reaction2d.hpp:259-285."""
+    return _make(mesh, 5, DiffusionReaction2d.GrayScott, 0, 1, {"Du": Du, "Dv": Dv, "F": F, "k": k}, device)
+
+
+def create_slip_wall_swe_2d_problem(mesh, recon, gravity, coriolis, pulseMagnitude, device=0):
+    """swe2d.hpp:283-309 (legacy overload)."""
+    return _make(mesh, 4, Swe2d.SlipWall, recon, 1,
+                 {"gravity": gravity, "coriolis": coriolis, "pulseMagnitude": pulseMagnitude}, device)
+
+
+def create_cross_shock_problem(mesh, recon, density, inletXVel, bottomYVel, device=0):
+    """euler2d.hpp:252-283."""
+    return _make(mesh, 2, Euler2d.CrossShock, recon, 1,
+                 {"crossShockDensity": density, "crossShockInletXVel": inletXVel,
+                  "crossShockBottomYVel": bottomYVel}, device)
+
+
+# ------------------------------------------------------------------------------------------------ time loops
+# pressiodemoapps/__init__.py:90-185 of the reference (host-side RK loops around rightHandSide)
+def advanceRK2(appObj, state, dt, Nsteps, startTime=0.0, observer=None, showProgress=False):
+    v = appObj.createRightHandSide()
+    time = startTime
+    for step in range(1, Nsteps + 1):
+        appObj.rightHandSide(state, time, v)
+        if observer is not None:
+            observer(step - 1, state, v)
+        k1 = dt * v
+        tmp = state + k1
+        appObj.rightHandSide(tmp, time + dt, v)
+        k2 = dt * v
+        state[:] = state + k2 * 0.5 + k1 * 0.5
+        time += dt
+
+
+def advanceRK4(appObj, state, dt, Nsteps, startTime=0.0, observer=None, showProgress=False):
+    v = appObj.createRightHandSide()
+    time = startTime
+    for step in range(1, Nsteps + 1):
+        appObj.rightHandSide(state, time, v)
+        if observer is not None:
+            observer(step - 1, state, v)
+        k1 = dt * v
+        tmp = state + 0.5 * k1
+        appObj.rightHandSide(tmp, time + 0.5 * dt, v)
+        k2 = dt * v
+        tmp = state + 0.5 * k2
+        appObj.rightHandSide(tmp, time + 0.5 * dt, v)
+        k3 = dt * v
+        tmp = state + k3
+        appObj.rightHandSide(tmp, time + dt, v)
+        k4 = dt * v
+        state[:] = state + (k1 + 2. * k2 + 2. * k3 + k4) * (1. / 6.)
+        time += dt
+
+
+def advanceSSP3(appObj, state, dt, Nsteps, startTime=0.0, observer=None, showProgress=False):
+    v = appObj.createRightHandSide()
+    t1 = state.copy()
+    t2 = state.copy()
+    time = startTime
+    for step in range(1, Nsteps + 1):
+        appObj.rightHandSide(state, time, v)
+        if observer is not None:
+            observer(step - 1, state, v)
+        t1[:] = state + dt * v
+        appObj.rightHandSide(t1, time + dt, v)
+        t2[:] = (3. / 4.) * state + (1. / 4.) * t1 + (1. / 4.) * dt * v
+        appObj.rightHandSide(t2, time + dt * 0.5, v)
+        state[:] = (1. / 3.) * (state + 2. * t2 + 2. * dt * v)
+        time += dt

@@ -1,0 +1,265 @@
+"""ctypes front-end of the checkers under oracle/_ref (TEST INFRASTRUCTURE ONLY).
+
+`RefProblem`   -> oracle/_ref/libpda_ref.so : the UNMODIFIED reference compiled from /root/reference (oracle/ref_driver.cc)
+`OracleProblem`-> oracle/_ref/libpda_oracle.so : the plain-C restatement oracle/pda_oracle.c
+Both expose the same methods so a parity test can be written once and pointed at either checker.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+REFDIR = os.path.join(ROOT, "oracle", "_ref")
+
+FAM = {"euler1d": 1, "euler2d": 2, "euler3d": 3, "swe2d": 4, "diffreac2d": 5, "advdiff2d": 6}
+
+
+def ref_lib_path(omp=False):
+    return os.path.join(REFDIR, "libpda_ref_omp.so" if omp else "libpda_ref.so")
+
+
+def have_ref(omp=False):
+    return os.path.exists(ref_lib_path(omp))
+
+
+_libs = {}
+
+
+def _ref(omp=False):
+    key = ("ref", omp)
+    if key not in _libs:
+        L = C.CDLL(ref_lib_path(omp))
+        vp, ci, cd = C.c_void_p, C.c_int, C.c_double
+        L.pdaref_last_error.restype = C.c_char_p
+        L.pdaref_num_threads.restype = ci
+        L.pdaref_create.restype = vp
+        L.pdaref_create.argtypes = [C.c_char_p, ci, ci, ci, ci, ci, vp, vp]
+        L.pdaref_destroy.argtypes = [vp]
+        L.pdaref_query.restype = C.c_longlong
+        L.pdaref_query.argtypes = [vp, ci]
+        L.pdaref_mesh_arrays.argtypes = [vp] * 8
+        L.pdaref_ic.argtypes = [vp, vp]
+        L.pdaref_velocity.restype = ci
+        L.pdaref_velocity.argtypes = [vp, vp, cd, vp]
+        L.pdaref_velocity_and_jacobian.restype = ci
+        L.pdaref_velocity_and_jacobian.argtypes = [vp, vp, cd, vp, vp]
+        L.pdaref_pattern.argtypes = [vp, vp, vp]
+        L.pdaref_apply_jacobian.restype = ci
+        L.pdaref_apply_jacobian.argtypes = [vp, vp, vp, cd, vp]
+        L.pdaref_ghosts.restype = ci
+        L.pdaref_ghosts.argtypes = [vp, ci, vp]
+        L.pdaref_time_velocity.restype = cd
+        L.pdaref_time_velocity.argtypes = [vp, vp, cd, ci, ci]
+        L.pdaref_time_jacobian.restype = cd
+        L.pdaref_time_jacobian.argtypes = [vp, vp, cd, ci, ci]
+        _libs[key] = L
+    return _libs[key]
+
+
+class RefProblem:
+    """The reference's own problem object (mesh read from the text files in `meshDir`)."""
+
+    def __init__(self, meshDir, family, probEnum, recon, icFlag=1, params=None, omp=False):
+        self.L = _ref(omp)
+        params = params or {}
+        names = (C.c_char_p * max(1, len(params)))(*[k.encode() for k in params])
+        vals = (C.c_double * max(1, len(params)))(*[float(v) for v in params.values()])
+        fam = FAM[family] if isinstance(family, str) else int(family)
+        self.h = self.L.pdaref_create(str(meshDir).encode(), fam, int(probEnum), int(recon), int(icFlag),
+                                      len(params), names, vals)
+        if not self.h:
+            raise RuntimeError("reference: " + self.L.pdaref_last_error().decode())
+        q = lambda i: int(self.L.pdaref_query(self.h, i))
+        (self.dim, self.stencil, self.nSample, self.nStencil, self.ncols, self.nInner, self.nNearBd,
+         self.periodic, self.ndpc, self.nDofStencil, self.nDofSample, self.nnz) = [q(i) for i in range(12)]
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            self.L.pdaref_destroy(self.h)
+            self.h = None
+
+    def num_threads(self):
+        return int(self.L.pdaref_num_threads())
+
+    def mesh_arrays(self):
+        g = np.zeros((self.nSample, self.ncols), dtype=np.int32)
+        x, y, z = (np.zeros(self.nStencil) for _ in range(3))
+        ri = np.zeros(self.nInner, dtype=np.int32)
+        rb = np.zeros(self.nNearBd, dtype=np.int32)
+        d = np.zeros(6)
+        self.L.pdaref_mesh_arrays(self.h, g.ctypes.data, x.ctypes.data, y.ctypes.data, z.ctypes.data,
+                                  ri.ctypes.data if ri.size else None, rb.ctypes.data if rb.size else None,
+                                  d.ctypes.data)
+        return dict(graph=g, x=x, y=y, z=z, rowsInner=ri, rowsNearBd=rb, d=d[:3], dInv=d[3:])
+
+    def initialCondition(self):
+        U = np.zeros(self.nDofStencil)
+        self.L.pdaref_ic(self.h, U.ctypes.data)
+        return U
+
+    def velocity(self, U, t=0.0):
+        V = np.zeros(self.nDofSample)
+        if self.L.pdaref_velocity(self.h, U.ctypes.data, float(t), V.ctypes.data):
+            raise RuntimeError("reference: " + self.L.pdaref_last_error().decode())
+        return V
+
+    def velocityAndJacobian(self, U, t=0.0):
+        V = np.zeros(self.nDofSample)
+        vals = np.zeros(self.nnz)
+        if self.L.pdaref_velocity_and_jacobian(self.h, U.ctypes.data, float(t), V.ctypes.data, vals.ctypes.data):
+            raise RuntimeError("reference: " + self.L.pdaref_last_error().decode())
+        return V, vals
+
+    def pattern(self):
+        rowptr = np.zeros(self.nDofSample + 1, dtype=np.int32)
+        colidx = np.zeros(self.nnz, dtype=np.int32)
+        self.L.pdaref_pattern(self.h, rowptr.ctypes.data, colidx.ctypes.data)
+        return rowptr, colidx
+
+    def applyJacobian(self, U, B, t=0.0):
+        R = np.zeros(self.nDofSample)
+        if self.L.pdaref_apply_jacobian(self.h, U.ctypes.data, B.ctypes.data, float(t), R.ctypes.data):
+            raise RuntimeError("reference: " + self.L.pdaref_last_error().decode())
+        return R
+
+    def ghosts(self, side):
+        n = self.L.pdaref_ghosts(self.h, side, None)
+        if n < 0:
+            return None
+        out = np.zeros(max(n, 1))
+        self.L.pdaref_ghosts(self.h, side, out.ctypes.data)
+        return out[:n].reshape(self.nNearBd, -1) if self.nNearBd else out[:0]
+
+    def time_velocity(self, U, t=0.0, warmup=1, reps=5):
+        return float(self.L.pdaref_time_velocity(self.h, U.ctypes.data, float(t), warmup, reps))
+
+    def time_jacobian(self, U, t=0.0, warmup=1, reps=3):
+        return float(self.L.pdaref_time_jacobian(self.h, U.ctypes.data, float(t), warmup, reps))
+
+
+# ------------------------------------------------------------------------------------------------ C restatement
+def oracle_lib_path(omp=False):
+    return os.path.join(REFDIR, "libpda_oracle_omp.so" if omp else "libpda_oracle.so")
+
+
+def have_oracle(omp=False):
+    return os.path.exists(oracle_lib_path(omp))
+
+
+def _oracle(omp=False):
+    key = ("oracle", omp)
+    if key not in _libs:
+        L = C.CDLL(oracle_lib_path(omp))
+        vp, ci, cd = C.c_void_p, C.c_int, C.c_double
+        L.or_last_error.restype = C.c_char_p
+        L.or_num_threads.restype = ci
+        L.or_create.restype = vp
+        L.or_create.argtypes = [C.c_char_p, ci, ci, ci, ci, ci, vp, vp]
+        L.or_create_from_arrays.restype = vp
+        L.or_create_from_arrays.argtypes = [ci, ci, C.c_int32, C.c_int32, vp, vp, vp, vp, vp, ci, ci, ci, ci, ci, vp, vp]
+        L.or_destroy.argtypes = [vp]
+        L.or_query.restype = C.c_longlong
+        L.or_query.argtypes = [vp, ci]
+        L.or_mesh_arrays.argtypes = [vp] * 8
+        L.or_ic.argtypes = [vp, vp]
+        L.or_velocity.restype = ci
+        L.or_velocity.argtypes = [vp, vp, cd, vp]
+        L.or_velocity_and_jacobian.restype = ci
+        L.or_velocity_and_jacobian.argtypes = [vp, vp, cd, vp, vp]
+        L.or_pattern.argtypes = [vp, vp, vp]
+        L.or_ghosts.restype = ci
+        L.or_ghosts.argtypes = [vp, ci, vp]
+        L.or_time_velocity.restype = cd
+        L.or_time_velocity.argtypes = [vp, vp, cd, ci, ci]
+        L.or_weno5.argtypes = [vp, vp] + [cd] * 6
+        L.or_weno3.argtypes = [vp, vp] + [cd] * 4
+        L.or_weno5_grad.argtypes = [vp] * 4 + [cd] * 6
+        L.or_weno3_grad.argtypes = [vp] * 4 + [cd] * 4
+        L.or_euler_flux.argtypes = [ci, vp, vp, vp, vp, cd]
+        L.or_euler_flux_jac.argtypes = [ci, vp, vp, vp, vp, vp, cd]
+        L.or_swe_flux.argtypes = [vp, vp, vp, vp, cd]
+        L.or_swe_flux_jac.argtypes = [vp, vp, vp, vp, vp, cd]
+        _libs[key] = L
+    return _libs[key]
+
+
+class OracleProblem:
+    """Plain-C restatement (oracle/pda_oracle.c); same interface as RefProblem."""
+
+    def __init__(self, meshDir, family, probEnum, recon, icFlag=1, params=None, omp=False, arrays=None):
+        self.L = _oracle(omp)
+        params = params or {}
+        names = (C.c_char_p * max(1, len(params)))(*[k.encode() for k in params])
+        vals = (C.c_double * max(1, len(params)))(*[float(v) for v in params.values()])
+        fam = FAM[family] if isinstance(family, str) else int(family)
+        if arrays is not None:
+            a = arrays
+            d = np.ascontiguousarray(a["d"], dtype=np.float64)
+            g = np.ascontiguousarray(a["graph"], dtype=np.int32)
+            x, y, z = (np.ascontiguousarray(a[k], dtype=np.float64) for k in ("x", "y", "z"))
+            self.h = self.L.or_create_from_arrays(a["dim"], a["stencil"], g.shape[0], x.size, d.ctypes.data,
+                                                  x.ctypes.data, y.ctypes.data, z.ctypes.data, g.ctypes.data, fam,
+                                                  int(probEnum), int(recon), int(icFlag), len(params), names, vals)
+        else:
+            self.h = self.L.or_create(str(meshDir).encode(), fam, int(probEnum), int(recon), int(icFlag),
+                                      len(params), names, vals)
+        if not self.h:
+            raise RuntimeError("oracle: " + self.L.or_last_error().decode())
+        q = lambda i: int(self.L.or_query(self.h, i))
+        (self.dim, self.stencil, self.nSample, self.nStencil, self.ncols, self.nInner, self.nNearBd,
+         self.periodic, self.ndpc, self.nDofStencil, self.nDofSample, self.nnz) = [q(i) for i in range(12)]
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            self.L.or_destroy(self.h)
+            self.h = None
+
+    def num_threads(self):
+        return int(self.L.or_num_threads())
+
+    def mesh_arrays(self):
+        g = np.zeros((self.nSample, self.ncols), dtype=np.int32)
+        x, y, z = (np.zeros(self.nStencil) for _ in range(3))
+        ri = np.zeros(max(self.nInner, 1), dtype=np.int32)
+        rb = np.zeros(max(self.nNearBd, 1), dtype=np.int32)
+        d = np.zeros(6)
+        self.L.or_mesh_arrays(self.h, g.ctypes.data, x.ctypes.data, y.ctypes.data, z.ctypes.data, ri.ctypes.data,
+                              rb.ctypes.data, d.ctypes.data)
+        return dict(graph=g, x=x, y=y, z=z, rowsInner=ri[:self.nInner], rowsNearBd=rb[:self.nNearBd], d=d[:3],
+                    dInv=d[3:])
+
+    def initialCondition(self):
+        U = np.zeros(self.nDofStencil)
+        self.L.or_ic(self.h, U.ctypes.data)
+        return U
+
+    def velocity(self, U, t=0.0):
+        V = np.zeros(self.nDofSample)
+        self.L.or_velocity(self.h, U.ctypes.data, float(t), V.ctypes.data)
+        return V
+
+    def velocityAndJacobian(self, U, t=0.0):
+        V = np.zeros(self.nDofSample)
+        vals = np.zeros(self.nnz)
+        self.L.or_velocity_and_jacobian(self.h, U.ctypes.data, float(t), V.ctypes.data, vals.ctypes.data)
+        return V, vals
+
+    def pattern(self):
+        rowptr = np.zeros(self.nDofSample + 1, dtype=np.int32)
+        colidx = np.zeros(self.nnz, dtype=np.int32)
+        self.L.or_pattern(self.h, rowptr.ctypes.data, colidx.ctypes.data)
+        return rowptr, colidx
+
+    def ghosts(self, side):
+        n = self.L.or_ghosts(self.h, side, None)
+        out = np.zeros(max(n, 1))
+        self.L.or_ghosts(self.h, side, out.ctypes.data)
+        return out[:n].reshape(self.nNearBd, -1) if self.nNearBd else out[:0]
+
+    def time_velocity(self, U, t=0.0, warmup=1, reps=5):
+        return float(self.L.or_time_velocity(self.h, U.ctypes.data, float(t), warmup, reps))
+
+
+def oracle_leaf():
+    return _oracle(False)
