@@ -1,0 +1,385 @@
+#!/usr/bin/env python
+"""bench.py -- BASELINE.json's metric on BASELINE.json's config: velocity (RHS) cell-evals/s of the 3D Euler
+PeriodicSmooth WENO5 512^3 problem (cfg 5), slab-decomposed over N B200s, plus Jacobian nnz/s (cfg 2) as a sub-object.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--n 512]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P \
+        bench.py --gpus N --steps K --warmup W
+
+A step = one evaluation of V = f(U, t) over the whole 512^3 mesh (strong scaling: the mesh is fixed, each rank owns
+512/N z-planes and exchanges 3 halo planes per side with its ring neighbours every step).
+  value  : cells/s with U and V resident in HBM (device-pointer C-ABI entry points), CUDA events, max over ranks
+  e2e    : cells/s through the host-pointer C-ABI call (pda_problem_velocity_host) with pinned host buffers,
+           H2D of U and D2H of V inside the timed region
+  roofline: dominant kernel (structured WENO5 velocity kernel); HBM bytes = 80 B/cell (read U once, write V once);
+            the binding roofline of this kernel is the FP64 pipe, reported beside it from a measured DFMA peak
+  cpu_baseline / --impl reference: the CPU implementation on the box's host cores (OpenMP).  3D WENO5 does not exist
+           in the reference so that leg is the oracle port (kind "port"); the unmodified reference's own 3D
+           WENO3 throughput (oracle/_ref/libpda_ref_omp.so) is reported next to it for calibration.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.join(ROOT, "pressio-demoapps_b200"))
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+METRIC = "rhs_cell_evals_per_s"
+UNIT = "cells/s"
+FLOPS_PER_CELL = 2673.0    # 3*(5*152+116)+45, each face once
+BYTES_PER_CELL = 80.0      # 2*ndpc*8
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            d = json.load(f)
+        return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index = index
+        self.proc = None
+        self.path = None
+
+    def start(self):
+        try:
+            fd, self.path = tempfile.mkstemp(suffix=".csv")
+            os.close(fd)
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        with open(self.path) as f:
+            for line in f:
+                c = [x.strip() for x in line.split(",")]
+                if len(c) < 9:
+                    continue
+                try:
+                    sm.append(float(c[1]))
+                    mx.append(float(c[2]))
+                except ValueError:
+                    continue
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), c[5:9]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+        os.unlink(self.path)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------ CPU legs
+def cpu_leg(n_cpu, target_s=12.0):
+    """3D Euler WENO5 periodic n_cpu^3 velocity on the host cores: the oracle port with OpenMP (kind 'port')."""
+    import pressiodemoapps as pda
+    from refdrv import OracleProblem
+    mesh = pda.create_full_mesh([n_cpu] * 3, [-1, 1, -1, 1, -1, 1], 7, ("x", "y", "z"))
+    x, y, z = mesh._coords()
+    arrays = dict(dim=3, stencil=7, d=mesh._deltas()[0], graph=mesh.graph(), x=x, y=y, z=z)
+    o = OracleProblem(None, "euler3d", 0, 2, arrays=arrays, omp=True)
+    U = o.initialCondition()
+    t1 = o.time_velocity(U, 0.0, 1, 1)
+    reps = int(max(2, min(200, target_s / max(t1, 1e-6))))
+    sec = o.time_velocity(U, 0.0, 0, reps)
+    return dict(value=n_cpu ** 3 / sec, unit=UNIT, cores=o.num_threads(), kind="port",
+                sample="%d^3 periodic 3D Euler WENO5 (oracle/pda_oracle.c, OpenMP), %d evals, %.3f s/eval"
+                       % (n_cpu, reps, sec)), sec, reps
+
+
+def ref_weno3_leg(n_cpu, target_s=6.0):
+    """the UNMODIFIED reference (OpenMP build) on 3D Euler WENO3 -- the closest config it implements"""
+    from refdrv import RefProblem, have_ref
+    import pressiodemoapps as pda
+    if not have_ref(omp=True):
+        return None
+    d = tempfile.mkdtemp(prefix="bench_mesh_")
+    mesh = pda.create_full_mesh([n_cpu] * 3, [-1, 1, -1, 1, -1, 1], 5, ("x", "y", "z"))
+    mesh.write(d)
+    r = RefProblem(d, "euler3d", 0, 1, omp=True)
+    U = r.initialCondition()
+    t1 = r.time_velocity(U, 0.0, 1, 1)
+    reps = int(max(2, min(100, target_s / max(t1, 1e-6))))
+    sec = r.time_velocity(U, 0.0, 0, reps)
+    import shutil
+    shutil.rmtree(d, ignore_errors=True)
+    return dict(value=n_cpu ** 3 / sec, unit=UNIT, cores=r.num_threads(), kind="reference",
+                sample="%d^3 periodic 3D Euler WENO3 (unmodified reference, OpenMP), %d evals" % (n_cpu, reps))
+
+
+def run_reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    n_cpu = 128
+    steps, warmup = args.steps, args.warmup
+    base, sec1, _ = cpu_leg(n_cpu, target_s=3.0)
+    # each step = one bounded sample: `per` evaluations of the n_cpu^3 mesh
+    per = int(max(1, min(50, 4.0 / sec1)))
+    import pressiodemoapps as pda
+    from refdrv import OracleProblem
+    mesh = pda.create_full_mesh([n_cpu] * 3, [-1, 1, -1, 1, -1, 1], 7, ("x", "y", "z"))
+    x, y, z = mesh._coords()
+    o = OracleProblem(None, "euler3d", 0, 2, arrays=dict(dim=3, stencil=7, d=mesh._deltas()[0], graph=mesh.graph(),
+                                                         x=x, y=y, z=z), omp=True)
+    U = o.initialCondition()
+    for _ in range(warmup):
+        o.time_velocity(U, 0.0, 0, 1)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        o.time_velocity(U, 0.0, 0, per)
+    dt = time.perf_counter() - t0
+    val = n_cpu ** 3 * per * steps / dt
+    cb = dict(value=val, unit=UNIT, cores=o.num_threads(), kind="port",
+              sample="each step = %d evals of a %d^3 periodic 3D Euler WENO5 mesh (oracle port, OpenMP; the reference "
+                     "has no 3D WENO5)" % (per, n_cpu))
+    line = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
+            "warmup": warmup, "ms_per_step": 1e3 * dt / steps, "higher_is_better": True, "scaling": "strong",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": "3D Euler PeriodicSmooth WENO5 %d^3 velocity (cfg 5)" % args.n,
+                       "sampled_on": "%d^3" % n_cpu},
+            "cpu_baseline": cb,
+            "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "reference_weno3": ref_weno3_leg(n_cpu, 4.0)}
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------ B200 arm
+def jacobian_leg(torch, pda, dev, n2=2048, steps=3, warmup=1):
+    """cfg 2: 2D Euler Riemann WENO5 n2^2 full mesh, velocity + Jacobian on one GPU -> stored nnz per second"""
+    R = pda.InviscidFluxReconstruction
+    mesh = pda.create_full_mesh([n2, n2], [0, 1, 0, 1], 7)
+    p = pda.create_problem(mesh, pda.Euler2d.Riemann, R.Weno5, device=dev)
+    rowptr, colidx = p.jacobianPattern()
+    nnz = int(colidx.size)
+    U = torch.from_numpy(p.initialCondition()).cuda()
+    V = torch.empty(p.totalDofSampleMesh(), dtype=torch.float64, device="cuda")
+    Jv = torch.empty(nnz, dtype=torch.float64, device="cuda")
+    st = torch.cuda.current_stream().cuda_stream
+    for _ in range(warmup):
+        p.rightHandSideAndJacobianDevice(U.data_ptr(), 0.0, V.data_ptr(), Jv.data_ptr(), st)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    l0 = p.launchCount()
+    e0.record()
+    for _ in range(steps):
+        p.rightHandSideAndJacobianDevice(U.data_ptr(), 0.0, V.data_ptr(), Jv.data_ptr(), st)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / steps
+    peak, _ = load_peaks()
+    bytes_per_eval = nnz * 8.0 + 2 * 8.0 * p.totalDofSampleMesh()
+    return {"metric": "jacobian_nnz_per_s", "value": nnz / (ms * 1e-3), "unit": "nnz/s", "ms_per_eval": ms, "nnz": nnz,
+            "workload": "2D Euler Riemann WENO5 %dx%d velocity+Jacobian (cfg 2)" % (n2, n2),
+            "gpu_launches": p.launchCount() - l0,
+            "roofline": {"bound": "hbm", "achieved": bytes_per_eval / (ms * 1e-3) * 1e-9, "peak": peak, "unit": "GB/s",
+                         "frac": bytes_per_eval / (ms * 1e-3) * 1e-9 / peak}}
+
+
+def run_b200_arm(args):
+    import torch
+    import pressiodemoapps as pda
+    from pressiodemoapps.halo import post_halo_exchange, wait_all
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus:
+        if world == 1 and args.gpus > 1:
+            raise SystemExit("bench.py --gpus %d must be launched with torchrun (one rank per GPU)" % args.gpus)
+    if pda.device_count() < 1:
+        raise SystemExit("bench.py: no CUDA device (the engine has no CPU fallback)")
+    torch.cuda.set_device(local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    n = args.n
+    K, W = args.steps, args.warmup
+    R = pda.InviscidFluxReconstruction
+    mesh = pda.create_full_mesh([n, n, n], [-1, 1, -1, 1, -1, 1], 7, ("x", "y", "z"))
+    ncells = n ** 3
+    st = torch.cuda.current_stream().cuda_stream
+    hbm_peak, peak_src = load_peaks()
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x):
+        if dist is None:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    fp64_peak = pda.measure_fp64_peak(local_rank)
+
+    if world == 1:
+        p = pda.create_problem(mesh, pda.Euler3d.PeriodicSmooth, R.Weno5, device=local_rank)
+        hU = torch.empty(p.totalDofStencilMesh(), dtype=torch.float64, pin_memory=True)
+        hV = torch.empty(p.totalDofSampleMesh(), dtype=torch.float64, pin_memory=True)
+        hU.numpy()[:] = p.initialCondition()
+        dU = hU.cuda()
+        dV = torch.empty_like(dU)
+
+        def step():
+            p.rightHandSideDevice(dU.data_ptr(), 0.0, dV.data_ptr(), st)
+
+        def e2e_step():
+            p.rightHandSide(hU.numpy(), 0.0, hV.numpy())
+        kernel_cells = ncells
+    else:
+        p = pda.create_problem_slab(mesh, pda.Euler3d.PeriodicSmooth, R.Weno5, rank, world, device=local_rank)
+        k0, k1, h, pd = p.slabExtent()
+        nown = (k1 - k0) * pd
+        hU = torch.empty(nown, dtype=torch.float64, pin_memory=True)
+        hV = torch.empty(nown, dtype=torch.float64, pin_memory=True)
+        hU.numpy()[:] = p.slabInitialCondition()
+        dUl = torch.empty(nown + 2 * h * pd, dtype=torch.float64, device="cuda")
+        dUl[h * pd: h * pd + nown].copy_(hU)
+        dV = torch.empty(nown, dtype=torch.float64, device="cuda")
+
+        def step():
+            works = post_halo_exchange(dUl, h, pd, rank, world)          # NCCL send/recv over NVLink, own stream
+            p.slabVelocityInteriorDevice(dUl.data_ptr(), 0.0, dV.data_ptr(), st)   # overlaps the exchange
+            wait_all(works)
+            p.slabVelocityBoundaryDevice(dUl.data_ptr(), 0.0, dV.data_ptr(), st)
+
+        def e2e_step():
+            dUl[h * pd: h * pd + nown].copy_(hU, non_blocking=True)
+            step()
+            hV.copy_(dV, non_blocking=True)
+            torch.cuda.current_stream().synchronize()
+        kernel_cells = (k1 - k0 - 2 * h) * (pd // 5)
+
+    # ---- device-resident timing
+    for _ in range(W):
+        step()
+    barrier()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    l0 = p.launchCount()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(K):
+        step()
+    e1.record()
+    barrier()
+    ms_total = max_over_ranks(e0.elapsed_time(e1))
+    launches = p.launchCount() - l0
+    clocks = sampler.stop() if rank == 0 else None
+    ms_step = ms_total / K
+    value = ncells / (ms_step * 1e-3)
+
+    # ---- dominant kernel alone (CUDA events on the launching stream): the structured velocity kernel
+    kev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
+    for a, b in kev:
+        a.record()
+        if world == 1:
+            step()
+        else:
+            p.slabVelocityInteriorDevice(dUl.data_ptr(), 0.0, dV.data_ptr(), st)
+        b.record()
+    torch.cuda.synchronize()
+    k_ms = float(np.mean([a.elapsed_time(b) for a, b in kev]))
+    ach_gbs = kernel_cells * BYTES_PER_CELL / (k_ms * 1e-3) * 1e-9
+    ach_tf = kernel_cells * FLOPS_PER_CELL / (k_ms * 1e-3) * 1e-12
+
+    # ---- end to end through the host-pointer C-ABI call (pinned host buffers, copies inside the timed region)
+    for _ in range(min(W, 2)):
+        e2e_step()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(K):
+        e2e_step()
+    barrier()
+    e2e_s = max_over_ranks(time.perf_counter() - t0) / K
+    e2e = {"value": ncells / e2e_s, "unit": UNIT, "h2d_bytes_per_step": int(hU.numel() * 8 * world),
+           "d2h_bytes_per_step": int(hV.numel() * 8 * world), "ms_per_step": e2e_s * 1e3,
+           "api": "pda_problem_velocity_host" if world == 1 else "slab: H2D + halo exchange + pda_slab_velocity_*_dev + D2H"}
+
+    if rank == 0:
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
+                "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+                "dtype": "f64", "data": "synthetic",
+                "config": {"workload": "3D Euler PeriodicSmooth WENO5 %d^3 velocity (cfg 5)" % n, "mesh": [n, n, n],
+                           "partition": "z-slabs x%d, halo 3 planes/side via NCCL send/recv" % world if world > 1 else "single GPU",
+                           "l2": "inputs larger than L2 (state %.2f GB per GPU)" % (ncells * 40e-9 / world)},
+                "gpu_launches": int(launches), "clocks": clocks, "e2e": e2e,
+                "roofline": {"bound": "hbm", "achieved": ach_gbs, "peak": hbm_peak, "unit": "GB/s",
+                             "frac": ach_gbs / hbm_peak, "traffic": None, "peak_source": peak_src,
+                             "kernel": "k_velocity_lattice", "kernel_ms": k_ms, "binding": "fp64",
+                             "fp64": {"achieved": ach_tf, "peak": fp64_peak, "unit": "TFLOP/s",
+                                      "frac": ach_tf / fp64_peak if fp64_peak else None,
+                                      "peak_source": "measured DFMA loop (pda_measure_fp64_peak), same process",
+                                      "flops_per_cell": FLOPS_PER_CELL}}}
+        if world == 1 and not args.no_cpu:
+            cb, _, _ = cpu_leg(128, target_s=12.0)
+            line["cpu_baseline"] = cb
+            try:
+                line["cpu_reference_weno3"] = ref_weno3_leg(128, 5.0)
+            except Exception as e:   # the compiled reference is optional on the GPU box
+                line["cpu_reference_weno3"] = {"unavailable": str(e)}
+        if world == 1 and not args.no_jacobian:
+            del dU, dV
+            torch.cuda.empty_cache()
+            try:
+                line["jacobian"] = jacobian_leg(torch, pda, local_rank, n2=args.n2)
+            except Exception as e:
+                line["jacobian"] = {"error": str(e)}
+        print(json.dumps(line), flush=True)
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--n", type=int, default=512, help="cells per axis of the 3D mesh (BASELINE: 512)")
+    ap.add_argument("--n2", type=int, default=2048, help="cells per axis of the 2D Jacobian mesh (BASELINE: 2048)")
+    ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-jacobian", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
+    if args.impl == "reference":
+        run_reference_arm(args)
+    else:
+        run_b200_arm(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -72,6 +72,10 @@ const char* pda_version(void);
 /* number of CUDA devices the library can use (0 on a CPU-only box; never an error) */
 int pda_device_count(void);
 
+/* measurement helper (not on the evaluation path): peak FP64 FMA throughput of `device` in TFLOP/s from a pure DFMA
+ * loop -- the FP64 roofline denominator bench.py reports beside the HBM one (MEASURED_PEAKS.json has no FP64 entry) */
+pda_status pda_measure_fp64_peak(int device, double* tflops, double* sm_mhz_hint);
+
 /* ------------------------------------------------------------------ mesh ---------------------------------------- */
 /* load_cellcentered_uniform_mesh_eigen(dir)  (mesh.hpp:87-91, impl/mesh_ccu.hpp:359-448): reads info.dat,
  * coordinates.dat, connectivity.dat written by meshing_scripts/create_{full,sample}_mesh.py */

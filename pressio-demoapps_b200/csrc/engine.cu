@@ -161,8 +161,25 @@ struct DeviceState {
   // scratch owned by the problem (host-pointer entry points, applyJacobian)
   DevBuf<double> dU, dV, dJ, dB, dR;
   DevBuf<int32_t> dRowptr, dColidx;
-  PinnedBuf<double> hU, hV;
-  ~DeviceState() { if (stream) cudaStreamDestroy(stream); }
+  // host-pointer pipeline (velocityHost on large lattices)
+  static constexpr int kMaxChunks = 32;
+  cudaStream_t sH2D = nullptr, sD2H = nullptr;
+  cudaEvent_t evIn[kMaxChunks] = {}, evOut[kMaxChunks] = {};
+  void ensurePipeline() {
+    if (sH2D) return;
+    PDA_CUDA(cudaStreamCreateWithFlags(&sH2D, cudaStreamNonBlocking));
+    PDA_CUDA(cudaStreamCreateWithFlags(&sD2H, cudaStreamNonBlocking));
+    for (int i = 0; i < kMaxChunks; ++i) {
+      PDA_CUDA(cudaEventCreateWithFlags(&evIn[i], cudaEventDisableTiming));
+      PDA_CUDA(cudaEventCreateWithFlags(&evOut[i], cudaEventDisableTiming));
+    }
+  }
+  ~DeviceState() {
+    if (stream) cudaStreamDestroy(stream);
+    if (sH2D) cudaStreamDestroy(sH2D);
+    if (sD2H) cudaStreamDestroy(sD2H);
+    for (int i = 0; i < kMaxChunks; ++i) { if (evIn[i]) cudaEventDestroy(evIn[i]); if (evOut[i]) cudaEventDestroy(evOut[i]); }
+  }
   dev::GhostView ghostView(int ndpc) const {
     dev::GhostView gv;
     for (int s = 0; s < 6; ++s) gv.g[s] = ghost[s].p;
@@ -973,6 +990,30 @@ void Problem::evaluateDev(const double* dU, double t, double* dV, double* dJ, vo
   PDA_CUDA(cudaGetLastError());
 }
 
+// structured velocity of the slowest-axis planes [p0,p1) of a fully periodic lattice (host pipeline, slab interior)
+void Problem::evaluatePlanes(const double* dU, double /*t*/, double* dV, void* streamV, int32_t p0, int32_t p1) {
+  DeviceState& ds = *dev_;
+  cudaStream_t st = streamV ? (cudaStream_t)streamV : ds.stream;
+  Mesh& m = *mesh_;
+  dev::Deltas dl{{m.dInv[0], m.dInv[1], m.dInv[2]}};
+  auto run = [&](auto phys) {
+    using Phys = decltype(phys);
+    dispatchScheme(S_, [&](auto sTag) {
+      constexpr int S = decltype(sTag)::value;
+      launchLatticeVelocity<Phys, S>(phys, m, dl, dU, dV, st, p0, p1, 0);
+      ++launches_;
+    });
+  };
+  switch (family_) {
+    case F_EULER1D: run(dev::Euler<1>{gamma_}); break;
+    case F_EULER2D: run(dev::Euler<2>{gamma_}); break;
+    case F_EULER3D: run(dev::Euler<3>{gamma_}); break;
+    case F_SWE2D: run(dev::Swe2d{physParams_[0], physParams_[1]}); break;
+    default: throw Error(kUnsupported, "family not supported on device");
+  }
+  PDA_CUDA(cudaGetLastError());
+}
+
 void Problem::velocityDev(const double* dU, double t, double* dV, void* stream) {
   if (!dU || !dV) throw Error(kInvalid, "velocity: null pointer");
   evaluateDev(dU, t, dV, nullptr, stream);
@@ -993,14 +1034,55 @@ void Problem::velocityHost(const double* U, double t, double* V) {
   ensureDevice();
   PDA_CUDA(cudaSetDevice(device_));
   DeviceState& ds = *dev_;
+  Mesh& m = *mesh_;
   const size_t nU = (size_t)nDofStencil(), nV = (size_t)nDofSample();
-  ds.dU.alloc(nU); ds.dV.alloc(nV); ds.hU.alloc(nU); ds.hV.alloc(nV);
-  std::memcpy(ds.hU.p, U, nU * sizeof(double));
-  PDA_CUDA(cudaMemcpyAsync(ds.dU.p, ds.hU.p, nU * sizeof(double), cudaMemcpyHostToDevice, ds.stream));
-  evaluateDev(ds.dU.p, t, ds.dV.p, nullptr, ds.stream);
-  PDA_CUDA(cudaMemcpyAsync(ds.hV.p, ds.dV.p, nV * sizeof(double), cudaMemcpyDeviceToHost, ds.stream));
+  ds.dU.alloc(nU); ds.dV.alloc(nV);
+  // Host buffers are handed to cudaMemcpyAsync as they are: pinned buffers (cudaHostAlloc / cudaHostRegister /
+  // torch pin_memory) stream at PCIe speed and overlap, pageable ones are staged by the driver.
+  const int64_t nPlanes = m.n[dim_ - 1];
+  const bool pipelined = ds.innerViaLattice && ds.nearBd.n == 0 && m.fullyPeriodic && dim_ >= 2 &&
+                         (int64_t)m.nSample >= (int64_t)(1 << 22) && nPlanes >= 16;
+  if (!pipelined) {
+    PDA_CUDA(cudaMemcpyAsync(ds.dU.p, U, nU * sizeof(double), cudaMemcpyHostToDevice, ds.stream));
+    evaluateDev(ds.dU.p, t, ds.dV.p, nullptr, ds.stream);
+    PDA_CUDA(cudaMemcpyAsync(V, ds.dV.p, nV * sizeof(double), cudaMemcpyDeviceToHost, ds.stream));
+    PDA_CUDA(cudaStreamSynchronize(ds.stream));
+    return;
+  }
+  // ---- large periodic lattice: chunks of planes flow H2D -> kernel -> D2H on three streams, so the call costs
+  //      max(H2D, D2H) instead of H2D + kernel + D2H.  Chunk c needs the planes of chunk c+1 (upper stencil halo)
+  //      and c-1; the wrap-around planes of chunk 0 come from the last chunk, which is therefore uploaded first.
+  ds.ensurePipeline();
+  const int h = (S_ - 1) / 2;
+  const int nChunks = (int)std::min<int64_t>(DeviceState::kMaxChunks, nPlanes / std::max(4, 2 * h));
+  const size_t planeDofs = nU / (size_t)nPlanes;
+  auto c0 = [&](int c) { return (int32_t)((int64_t)nPlanes * c / nChunks); };
+  auto h2d = [&](int c) {
+    const size_t off = (size_t)c0(c) * planeDofs, cnt = (size_t)(c0(c + 1) - c0(c)) * planeDofs;
+    PDA_CUDA(cudaMemcpyAsync(ds.dU.p + off, U + off, cnt * sizeof(double), cudaMemcpyHostToDevice, ds.sH2D));
+    PDA_CUDA(cudaEventRecord(ds.evIn[c], ds.sH2D));
+  };
+  auto compute = [&](int c) {
+    for (int w : {c - 1, c, c + 1}) PDA_CUDA(cudaStreamWaitEvent(ds.stream, ds.evIn[(w + nChunks) % nChunks], 0));
+    evaluatePlanes(ds.dU.p, t, ds.dV.p, ds.stream, c0(c), c0(c + 1));
+    PDA_CUDA(cudaEventRecord(ds.evOut[c], ds.stream));
+    PDA_CUDA(cudaStreamWaitEvent(ds.sD2H, ds.evOut[c], 0));
+    const size_t off = (size_t)c0(c) * planeDofs, cnt = (size_t)(c0(c + 1) - c0(c)) * planeDofs;
+    PDA_CUDA(cudaMemcpyAsync(V + off, ds.dV.p + off, cnt * sizeof(double), cudaMemcpyDeviceToHost, ds.sD2H));
+  };
+  // the previous call's kernels/copies on ds.stream must be done before dU is overwritten
+  PDA_CUDA(cudaEventRecord(ds.evOut[0], ds.stream));
+  PDA_CUDA(cudaStreamWaitEvent(ds.sH2D, ds.evOut[0], 0));
+  h2d(nChunks - 1);
+  h2d(0);
+  for (int c = 1; c < nChunks - 1; ++c) {
+    h2d(c);
+    compute(c - 1);
+  }
+  compute(nChunks - 2);
+  compute(nChunks - 1);
+  PDA_CUDA(cudaStreamSynchronize(ds.sD2H));
   PDA_CUDA(cudaStreamSynchronize(ds.stream));
-  std::memcpy(V, ds.hV.p, nV * sizeof(double));
 }
 
 void Problem::velocityAndJacobianHost(const double* U, double t, double* V, double* Jvalues) {

@@ -58,6 +58,7 @@ class Problem {
   void ensureInnerRows();
   void buildGhostRecipes();
   void evaluateDev(const double* dU, double t, double* dV, double* dJ, void* stream);
+  void evaluatePlanes(const double* dU, double t, double* dV, void* stream, int32_t p0, int32_t p1);
 
   Mesh* mesh_;
   int family_, probId_, recon_, icFlag_;

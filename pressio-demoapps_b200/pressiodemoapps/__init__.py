@@ -18,7 +18,7 @@ import numpy as _np
 from enum import IntEnum as _IntEnum
 
 __all__ = [
-    "CellCenteredUniformMesh", "load_cellcentered_uniform_mesh", "create_full_mesh", "create_sample_mesh",
+    "CellCenteredUniformMesh", "load_cellcentered_uniform_mesh", "create_full_mesh", "create_sample_mesh", "mesh_from_arrays",
     "InviscidFluxReconstruction", "InviscidFluxScheme", "ViscousFluxReconstruction", "ViscousFluxScheme",
     "Euler1d", "Euler2d", "Euler3d", "Swe2d", "DiffusionReaction2d", "AdvectionDiffusion2d",
     "create_problem", "create_gray_scott_2d_problem", "create_slip_wall_swe_2d_problem", "create_cross_shock_problem",
@@ -60,6 +60,7 @@ def _sig(name, restype, *argtypes):
 _sig("pda_last_error", _cp)
 _sig("pda_version", _cp)
 _sig("pda_device_count", _C.c_int)
+_sig("pda_measure_fp64_peak", _C.c_int, _C.c_int, _C.POINTER(_dbl), _vp)
 _sig("pda_mesh_load", _C.c_int, _cp, _C.POINTER(_vp))
 _sig("pda_mesh_make_lattice", _C.c_int, _C.c_int, _vp, _vp, _vp, _C.c_int, _C.POINTER(_vp))
 _sig("pda_mesh_make_sample", _C.c_int, _vp, _vp, _i64, _C.POINTER(_vp))
@@ -110,6 +111,13 @@ def _check(status):
 
 def device_count():
     return int(_lib.pda_device_count())
+
+
+def measure_fp64_peak(device=0):
+    """peak FP64 FMA throughput (TFLOP/s) of `device` from a pure DFMA loop: the FP64 roofline denominator"""
+    v = _dbl()
+    _check(_lib.pda_measure_fp64_peak(int(device), _C.byref(v), None))
+    return v.value
 
 
 def _f64(a, n=None, name="array"):
@@ -282,6 +290,18 @@ def create_full_mesh(numCells, bounds, stencilSize=3, periodic=()):
     per = (_C.c_int32 * 3)(*[1 if a in periodic else 0 for a in ("x", "y", "z")])
     h = _vp()
     _check(_lib.pda_mesh_make_lattice(dim, n, bd, per, int(stencilSize), _C.byref(h)))
+    return CellCenteredUniformMesh(_handle=h)
+
+
+def mesh_from_arrays(dim, stencilSize, dxyz, x, y, z, graph, detect_lattice=False):
+    """Mesh from caller arrays (graph row-major [nSample][(stencil-1)*dim+1]); always evaluated by the graph-driven
+    kernels (no lattice detection)."""
+    g = _np.ascontiguousarray(graph, dtype=_np.int32)
+    x, y, z = (_np.ascontiguousarray(a, dtype=_np.float64) for a in (x, y, z))
+    d = _np.ascontiguousarray(dxyz, dtype=_np.float64)
+    h = _vp()
+    _check(_lib.pda_mesh_from_arrays(int(dim), int(stencilSize), g.shape[0], x.size, d.ctypes.data, x.ctypes.data,
+                                     y.ctypes.data, z.ctypes.data, g.ctypes.data, _C.byref(h)))
     return CellCenteredUniformMesh(_handle=h)
 
 

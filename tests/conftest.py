@@ -1,0 +1,88 @@
+"""pytest configuration: the `gpu` marker, import paths, and the shared helpers of the parity tests.
+
+`-m "not gpu"`: oracle vs the committed golden vectors, host logic (mesh, CSR pattern, initial conditions) through
+the C-ABI, symbol export of the shared library, gloo halo-exchange logic.  No compute call needs a GPU there.
+`-m gpu`: the parity tests proper -- the CUDA path, called through the C-ABI, against the golden vectors, the
+oracle and (when oracle/_ref/libpda_ref.so travelled with the snapshot) the compiled reference itself.
+"""
+import glob
+import json
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "pressio-demoapps_b200"))
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+GOLDEN = os.path.join(ROOT, "tests", "golden")
+
+# parity tolerance stated by BASELINE.json's north_star: 1e-12 relative, 1e-10 absolute near zero
+RTOL, ATOL = 1e-12, 1e-10
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box)")
+
+
+def _ensure_built():
+    lib = os.path.join(ROOT, "pressio-demoapps_b200", "lib", "libpda_b200.so")
+    ora = os.path.join(ROOT, "oracle", "_ref", "libpda_oracle.so")
+    if not (os.path.exists(lib) and os.path.exists(ora)):
+        import __graft_entry__ as g
+        g.build()
+
+
+_ensure_built()
+
+
+def golden_names():
+    return sorted(os.path.basename(p)[:-4] for p in glob.glob(os.path.join(GOLDEN, "*.npz")))
+
+
+class Golden:
+    def __init__(self, name):
+        z = np.load(os.path.join(GOLDEN, name + ".npz"))
+        self.meta = json.loads(str(z["meta"]))
+        self.z = z
+        self.name = name
+
+    def __getitem__(self, k):
+        return self.z[k]
+
+    def __contains__(self, k):
+        return k in self.z.files
+
+
+@pytest.fixture(scope="session")
+def load_golden():
+    cache = {}
+
+    def get(name):
+        if name not in cache:
+            cache[name] = Golden(name)
+        return cache[name]
+    return get
+
+
+def scaled_err(a, b, rtol=RTOL, atol=ATOL):
+    """max |a-b| / (atol + rtol |b|) over finite entries; <= 1 <=> numpy.allclose(a, b, rtol, atol).  NaNs must sit
+    at identical positions (the reference itself produces NaN for DMR+WENO5 at the shock foot)."""
+    a = np.asarray(a)
+    b = np.asarray(b)
+    assert a.shape == b.shape
+    na, nb = np.isnan(a), np.isnan(b)
+    assert np.array_equal(na, nb), "NaN positions differ"
+    ok = ~nb
+    if not ok.any():
+        return 0.0
+    return float(np.max(np.abs(a[ok] - b[ok]) / (atol + rtol * np.abs(b[ok]))))
+
+
+def oracle_arrays(g):
+    """mesh arrays of a golden case in the form OracleProblem(arrays=...) takes"""
+    m = g.meta
+    return dict(dim=m["dim"], stencil=m["stencil"], d=g["d"], graph=g["graph"], x=g["x"], y=g["y"], z=g["z"])

@@ -1,0 +1,155 @@
+"""Host-side logic of the engine, reached through the C-ABI (include/pda_b200.h), against the golden fixtures made
+by the reference: native mesh synthesis (vs the reference's Python mesh scripts, byte-identical files), sample-mesh
+extraction, row classification, initial conditions, the fixed CSR pattern (bit-exact vs Eigen's), error behaviour.
+No compute call needs a GPU here."""
+import ctypes as C
+import hashlib
+import os
+import re
+
+import numpy as np
+import pytest
+
+import pressiodemoapps as pda
+from conftest import ROOT, golden_names
+
+R = pda.InviscidFluxReconstruction
+ENUM = {"euler1d": pda.Euler1d, "euler2d": pda.Euler2d, "euler3d": pda.Euler3d, "swe2d": pda.Swe2d,
+        "diffreac2d": pda.DiffusionReaction2d}
+
+
+def make_mesh(g):
+    m = g.meta
+    mesh = pda.create_full_mesh(m["n"], m["bounds"], m["stencil"], m["periodic"])
+    if m["sample"]:
+        return pda.create_sample_mesh(mesh, g["sampleGids"]), mesh
+    return mesh, mesh
+
+
+def make_problem(g, mesh):
+    m = g.meta
+    e = ENUM[m["family"]](m["prob"])
+    if m["family"] == "diffreac2d":
+        if m["params"]:
+            p = m["params"]
+            return pda.create_gray_scott_2d_problem(mesh, pda.ViscousFluxReconstruction.FirstOrder, p["Du"], p["Dv"],
+                                                    p["F"], p["k"])
+        return pda.create_problem(mesh, e)
+    return pda.create_problem(mesh, e, R(m["recon"]), m["ic"], m["params"] or None)
+
+
+def sha(path):
+    with open(path, "rb") as f:
+        return hashlib.sha256(f.read()).hexdigest()
+
+
+@pytest.mark.parametrize("name", golden_names())
+def test_mesh_matches_reference(name, load_golden, tmp_path):
+    g = load_golden(name)
+    m = g.meta
+    mesh, _full = make_mesh(g)
+    assert mesh.dimensionality() == m["dim"] and mesh.stencilSize() == m["stencil"]
+    assert np.array_equal(mesh.graph(), g["graph"])
+    assert np.array_equal(mesh.viewX(), g["x"])
+    if m["dim"] > 1:
+        assert np.array_equal(mesh.viewY(), g["y"])
+    if m["dim"] > 2:
+        assert np.array_equal(mesh.viewZ(), g["z"])
+    d, dinv = mesh._deltas()
+    assert np.array_equal(d[:m["dim"]], g["d"][:m["dim"]]) and np.array_equal(dinv[:m["dim"]], g["dInv"][:m["dim"]])
+    assert np.array_equal(mesh.graphRowsOfCellsAwayFromBd(), g["rowsInner"])
+    assert np.array_equal(mesh.graphRowsOfCellsNearBd(), g["rowsNearBd"])
+    assert mesh.isFullyPeriodic() == (len(g["rowsNearBd"]) == 0 and not m["sample"] and len(m["periodic"]) == m["dim"]) \
+        or m["sample"]
+    if m["sample"]:
+        assert np.array_equal(mesh.stencilMeshGids(), g["stencilGids"])
+    # the files written by the native writer are byte-identical to the reference scripts' output
+    mesh.write(str(tmp_path))
+    for f, h in m["sha"].items():
+        assert sha(os.path.join(str(tmp_path), f)) == h, f
+    # and load back to the same mesh
+    again = pda.load_cellcentered_uniform_mesh(str(tmp_path))
+    assert np.array_equal(again.graph(), g["graph"]) and np.array_equal(again.viewX(), g["x"])
+
+
+@pytest.mark.parametrize("name", golden_names())
+def test_ic_and_pattern_match_reference(name, load_golden):
+    g = load_golden(name)
+    mesh, _full = make_mesh(g)
+    p = make_problem(g, mesh)
+    assert p.numDofPerCell() == g.meta["ndpc"]
+    assert p.totalDofStencilMesh() == g["U"].size and p.totalDofSampleMesh() == g["V"].size
+    assert np.array_equal(p.initialCondition(), g["IC"])
+    rowptr, colidx = p.jacobianPattern()
+    assert rowptr.dtype == np.int32 and colidx.dtype == np.int32
+    assert np.array_equal(rowptr, g["rowptr"]) and np.array_equal(colidx, g["colidx"])
+
+
+def test_3d_stencil7_lattice_extension():
+    """3D stencil-7 meshes do not exist in the reference; the lattice follows the documented column
+    layout: cols 13-18 = third layer [left front right back bottom top]."""
+    mesh = pda.create_full_mesh([9, 8, 7], [-1, 1, -1, 1, -1, 1], 7, ("x", "y", "z"))
+    g = mesh.graph()
+    assert g.shape == (9 * 8 * 7, 19)
+    nx, ny, nz = 9, 8, 7
+    gid = lambda i, j, k: (k % nz) * nx * ny + (j % ny) * nx + (i % nx)
+    for (i, j, k) in ((0, 0, 0), (4, 3, 2), (8, 7, 6)):
+        row = g[gid(i, j, k)]
+        for L in range(3):
+            exp = [gid(i - L - 1, j, k), gid(i, j + L + 1, k), gid(i + L + 1, j, k), gid(i, j - L - 1, k),
+                   gid(i, j, k - L - 1), gid(i, j, k + L + 1)]
+            assert list(row[1 + 6 * L: 7 + 6 * L]) == exp
+    assert mesh.isFullyPeriodic() and mesh.numCellsNearBd() == 0
+    m2 = pda.create_full_mesh([9, 8, 7], [-1, 1, -1, 1, -1, 1], 7)
+    # near-boundary = within 3 cells of any face
+    assert m2.numCellsInner() == 3 * 2 * 1
+
+
+def test_errors_mirror_reference():
+    mesh = pda.create_full_mesh([10, 10], [0, 1, 0, 1], 5)
+    with pytest.raises(pda.PdaError):   # scheme wider than the mesh stencil (reference reads garbage; we refuse)
+        pda.create_problem(mesh, pda.Euler2d.Riemann, R.Weno5)
+    with pytest.raises(pda.PdaError):   # euler2d.hpp:157-162 invalid icFlag
+        pda.create_problem(mesh, pda.Euler2d.Riemann, R.Weno3, 3)
+    with pytest.raises(pda.PdaError):   # invalid parameter name
+        pda.create_problem(mesh, pda.Euler2d.Riemann, R.Weno3, 1, {"nope": 1.0})
+    with pytest.raises(pda.PdaError):   # wrong dimensionality
+        pda.create_problem(mesh, pda.Euler3d.PeriodicSmooth, R.Weno3)
+    with pytest.raises(pda.PdaError):   # missing mesh dir: the reference exit()s, we return PDA_ERR_IO
+        pda.load_cellcentered_uniform_mesh("/nonexistent/mesh/dir")
+    p = pda.create_problem(mesh, pda.Euler2d.Riemann, R.Weno3, 2, {"riemannTopRightPressure": 2.0})
+    assert p.queryParameter("riemannTopRightPressure") == 2.0 and p.gamma() == 1.4
+    swe = pda.create_problem(pda.create_full_mesh([10, 10], [-5, 5, -5, 5], 3), pda.Swe2d.SlipWall, R.FirstOrder)
+    assert swe.gravity() == 9.8 and swe.coriolis() == -3.0
+
+
+def test_int32_nnz_limit_reported():
+    """a Jacobian whose nnz exceeds int32 cannot exist behind the reference API -> PDA_ERR_TOO_LARGE,
+    while the velocity-only problem on the same lattice is fine (nothing O(cells) is materialised)."""
+    mesh = pda.create_full_mesh([512, 512, 512], [-1, 1, -1, 1, -1, 1], 7, ("x", "y", "z"))
+    assert mesh.sampleMeshSize() == 512 ** 3 and mesh.isFullyPeriodic() and mesh.isLattice()
+    p = pda.create_problem(mesh, pda.Euler3d.PeriodicSmooth, R.Weno5)
+    assert p.totalDofStencilMesh() == 5 * 512 ** 3
+
+
+@pytest.mark.skipif(pda.device_count() > 0, reason="needs a box WITHOUT a GPU")
+def test_no_cpu_fallback():
+    mesh = pda.create_full_mesh([10, 10], [0, 1, 0, 1], 3)
+    p = pda.create_problem(mesh, pda.Euler2d.Riemann, R.FirstOrder)
+    U = p.initialCondition()
+    V = p.createRightHandSide()
+    with pytest.raises(pda.PdaError) as e:
+        p.rightHandSide(U, 0.0, V)
+    assert e.value.code == 3   # PDA_ERR_NO_DEVICE
+
+
+def test_cabi_exports_every_declared_symbol():
+    hdr = open(os.path.join(ROOT, "include", "pda_b200.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    names = sorted(set(re.findall(r"\b(pda_[a-z0-9_]+)\s*\(", hdr)))
+    assert len(names) > 40
+    lib = C.CDLL(os.path.join(ROOT, "pressio-demoapps_b200", "lib", "libpda_b200.so"))
+    missing = [n for n in names if not hasattr(lib, n)]
+    assert not missing, missing
+    lib.pda_version.restype = C.c_char_p
+    assert b"sm_100a" in lib.pda_version()
