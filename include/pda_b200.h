@@ -12,7 +12,8 @@
  *    (include/pressiodemoapps/mesh.hpp:76-81, impl/euler_3d_prob_class.hpp:76-80);
  *  - state / velocity layout: AoS  U[cell*ndpc + dof]  (SURVEY App. A);
  *  - "_host" flavours take host pointers (staged through pinned buffers, H2D/D2H inside the call);
- *    "_dev" flavours take device pointers and a cudaStream_t (passed as void*), and do not synchronise;
+ *    "_dev" flavours take device pointers and a cudaStream_t (passed as void*; NULL = the legacy default stream),
+ *    enqueue their kernels on that stream and do not synchronise;
  *  - there is NO CPU fallback: evaluation entry points fail with PDA_ERR_NO_DEVICE when no CUDA device is usable.
  */
 #ifndef PDA_B200_H_

@@ -897,7 +897,7 @@ void Problem::evaluateDev(const double* dU, double t, double* dV, double* dJ, vo
   ensureDevice();
   PDA_CUDA(cudaSetDevice(device_));
   DeviceState& ds = *dev_;
-  cudaStream_t st = streamV ? (cudaStream_t)streamV : ds.stream;
+  cudaStream_t st = (cudaStream_t)streamV;   // NULL = the legacy default stream (CUDA convention)
   Mesh& m = *mesh_;
   const int nc = m.ncols();
   dev::Deltas dl{{m.dInv[0], m.dInv[1], m.dInv[2]}};
@@ -993,7 +993,7 @@ void Problem::evaluateDev(const double* dU, double t, double* dV, double* dJ, vo
 // structured velocity of the slowest-axis planes [p0,p1) of a fully periodic lattice (host pipeline, slab interior)
 void Problem::evaluatePlanes(const double* dU, double /*t*/, double* dV, void* streamV, int32_t p0, int32_t p1) {
   DeviceState& ds = *dev_;
-  cudaStream_t st = streamV ? (cudaStream_t)streamV : ds.stream;
+  cudaStream_t st = (cudaStream_t)streamV;   // NULL = the legacy default stream (CUDA convention)
   Mesh& m = *mesh_;
   dev::Deltas dl{{m.dInv[0], m.dInv[1], m.dInv[2]}};
   auto run = [&](auto phys) {
@@ -1108,7 +1108,7 @@ void Problem::applyJacobianDev(const double* dU, const double* dB, int ncols, in
   PDA_CUDA(cudaSetDevice(device_));
   buildPattern();
   DeviceState& ds = *dev_;
-  cudaStream_t st = streamV ? (cudaStream_t)streamV : ds.stream;
+  cudaStream_t st = (cudaStream_t)streamV;   // NULL = the legacy default stream (CUDA convention)
   ds.dV.alloc((size_t)nDofSample());
   ds.dJ.alloc(colidx_.size());
   if (!ds.dRowptr.p) { ds.dRowptr.upload(rowptr_); ds.dColidx.upload(colidx_); }
@@ -1144,7 +1144,7 @@ void Problem::ghosts(int side, double* out) {
   if (side < 0 || side >= 6) throw Error(kInvalid, "ghosts: invalid side");
   PDA_CUDA(cudaSetDevice(device_));
   DeviceState& ds = *dev_;
-  PDA_CUDA(cudaStreamSynchronize(ds.stream));
+  PDA_CUDA(cudaDeviceSynchronize());
   const size_t n = (size_t)ds.nearBd.n * ds.hS * ndpc_;
   if (n) PDA_CUDA(cudaMemcpy(out, ds.ghost[side].p, n * sizeof(double), cudaMemcpyDeviceToHost));
 }
@@ -1214,7 +1214,7 @@ void Problem::slabVelocityDev(const double* dUlocal, double /*t*/, double* dVown
   ensureDevice();
   PDA_CUDA(cudaSetDevice(device_));
   DeviceState& ds = *dev_;
-  cudaStream_t st = streamV ? (cudaStream_t)streamV : ds.stream;
+  cudaStream_t st = (cudaStream_t)streamV;   // NULL = the legacy default stream (CUDA convention)
   Mesh& m = *mesh_;
   dev::Deltas dl{{m.dInv[0], m.dInv[1], m.dInv[2]}};
   const int h = (S_ - 1) / 2;

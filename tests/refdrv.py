@@ -263,3 +263,37 @@ class OracleProblem:
 
 def oracle_leaf():
     return _oracle(False)
+
+
+# ------------------------------------------------------------------------------------------------ 80-bit restatement
+def have_oracle_ld():
+    return os.path.exists(os.path.join(REFDIR, "libpda_oracle_ld.so"))
+
+
+def exact_velocity_and_jacobian(meshDir, family, probEnum, recon, icFlag, params, U, t):
+    """The C restatement compiled in 80-bit long double (oracle/Makefile: libpda_oracle_ld.so): V and J accurate to
+    ~1e-19, returned rounded to double.  Used ONLY to bound the reference's own rounding noise in the WENO Jacobians
+    (tools/jacobian_noise.py, DESIGN.md 'Jacobian tolerance')."""
+    LD = np.longdouble
+    L = C.CDLL(os.path.join(REFDIR, "libpda_oracle_ld.so"))
+    L.or_create.restype = C.c_void_p
+    L.or_create.argtypes = [C.c_char_p] + [C.c_int] * 5 + [C.c_void_p] * 2
+    L.or_query.restype = C.c_longlong
+    L.or_query.argtypes = [C.c_void_p, C.c_int]
+    L.or_destroy.argtypes = [C.c_void_p]
+    params = params or {}
+    names = (C.c_char_p * max(1, len(params)))(*[k.encode() for k in params])
+    vals = np.array([float(v) for v in params.values()] or [0.0], dtype=LD)
+    fam = FAM[family] if isinstance(family, str) else int(family)
+    h = L.or_create(str(meshDir).encode(), fam, int(probEnum), int(recon), int(icFlag), len(params), names,
+                    vals.ctypes.data)
+    if not h:
+        raise RuntimeError("oracle_ld: create failed")
+    nnz, nv = L.or_query(h, 11), L.or_query(h, 10)
+    Ul = np.ascontiguousarray(U, dtype=LD)
+    V = np.zeros(nv, dtype=LD)
+    J = np.zeros(nnz, dtype=LD)
+    L.or_velocity_and_jacobian.argtypes = [C.c_void_p, C.c_void_p, C.c_longdouble, C.c_void_p, C.c_void_p]
+    L.or_velocity_and_jacobian(h, Ul.ctypes.data, C.c_longdouble(t), V.ctypes.data, J.ctypes.data)
+    L.or_destroy(h)
+    return V.astype(np.float64), J.astype(np.float64)

@@ -8,8 +8,8 @@ import numpy as np
 import pytest
 
 import pressiodemoapps as pda
-from conftest import golden_names, oracle_arrays, scaled_err
-from refdrv import OracleProblem
+from conftest import assert_jacobian_parity, golden_names, oracle_arrays, scaled_err
+from refdrv import OracleProblem, exact_velocity_and_jacobian
 from test_host_cpu import make_mesh, make_problem
 
 pytestmark = pytest.mark.gpu
@@ -29,7 +29,7 @@ def perturbed(p, seed=20261017, amp=1e-3):
 
 
 @pytest.mark.parametrize("name", golden_names())
-def test_cuda_matches_reference_golden(name, load_golden):
+def test_cuda_matches_reference_golden(name, load_golden, tmp_path):
     g = load_golden(name)
     m = g.meta
     mesh, _ = make_mesh(g)
@@ -43,7 +43,11 @@ def test_cuda_matches_reference_golden(name, load_golden):
     V2 = p.createRightHandSide()
     p.rightHandSideAndJacobian(U, t, V2, J)
     assert scaled_err(V2, g["V2"]) <= 1.0
-    assert scaled_err(J.data, g["Jv"]) <= 1.0
+
+    def exact():
+        mesh.write(str(tmp_path))
+        return exact_velocity_and_jacobian(str(tmp_path), m["family"], m["prob"], m["recon"], m["ic"], m["params"], U, t)[1]
+    assert_jacobian_parity(J.data, g["Jv"], exact)
     # jacobian(U,t,J) alone (adapter_cpp.hpp:215-221) gives the same values; evaluation is repeatable
     J2 = p.createJacobian()
     p.jacobian(U, t, J2)
@@ -58,7 +62,7 @@ def test_cuda_matches_reference_golden(name, load_golden):
 
 @pytest.mark.parametrize("n,per", [((16, 16, 16), ("x", "y", "z")), ((20, 9, 7), ("x", "y", "z")),
                                    ((7, 7, 7), ("x", "y", "z"))])
-def test_3d_weno5_extension_matches_oracle(n, per):
+def test_3d_weno5_extension_matches_oracle(n, per, tmp_path):
     """3D WENO5 has no reference implementation: the CUDA kernels are checked against the oracle's
     restatement of the natural extension (the oracle is pinned to the reference for 3D WENO3/first order and 2D WENO5)."""
     mesh = pda.create_full_mesh(list(n), [-1, 1, -1, 1, -1, 1], 7, per)
@@ -75,7 +79,13 @@ def test_3d_weno5_extension_matches_oracle(n, per):
         V2 = p.createRightHandSide()
         p.rightHandSideAndJacobian(U, 0.0, V2, J)
         Vo, Jo = o.velocityAndJacobian(U, 0.0)
-        assert scaled_err(V2, Vo) <= 1.0 and scaled_err(J.data, Jo) <= 1.0
+        assert scaled_err(V2, Vo) <= 1.0
+        assert_jacobian_parity(J.data, Jo, lambda: _exact(mesh, tmp_path, "euler3d", 0, 2, U, 0.0))
+
+
+def _exact(mesh, tmp_path, fam, prob, recon, U, t):
+    mesh.write(str(tmp_path))
+    return exact_velocity_and_jacobian(str(tmp_path), fam, int(prob), int(recon), 1, None, U, t)[1]
 
 
 @pytest.mark.parametrize("fam,prob,recon,n,bounds,per,sten", [
@@ -87,7 +97,7 @@ def test_3d_weno5_extension_matches_oracle(n, per):
     ("euler1d", pda.Euler1d.Sod, R.Weno5, [1000, 1], [-0.5, 0.5], (), 7),
     ("diffreac2d", pda.DiffusionReaction2d.GrayScott, 0, [128, 96], [-1.25, 1.25, -1.25, 1.25], ("x", "y"), 3),
 ])
-def test_medium_sizes_match_oracle(fam, prob, recon, n, bounds, per, sten):
+def test_medium_sizes_match_oracle(fam, prob, recon, n, bounds, per, sten, tmp_path):
     """sizes between the reference's test meshes and the BASELINE configs, against the (pinned) oracle run live"""
     mesh = pda.create_full_mesh(n, bounds, sten, per)
     p = pda.create_problem(mesh, prob) if fam == "diffreac2d" else pda.create_problem(mesh, prob, recon)
@@ -102,7 +112,8 @@ def test_medium_sizes_match_oracle(fam, prob, recon, n, bounds, per, sten):
         V2 = p.createRightHandSide()
         p.rightHandSideAndJacobian(U, 0.0, V2, J)
         Vo, Jo = o.velocityAndJacobian(U, 0.0)
-        assert scaled_err(V2, Vo) <= 1.0 and scaled_err(J.data, Jo) <= 1.0
+        assert scaled_err(V2, Vo) <= 1.0
+        assert_jacobian_parity(J.data, Jo, lambda: _exact(mesh, tmp_path, fam, prob, recon, U, 0.0))
 
 
 @pytest.mark.parametrize("prob,recon,n,bounds,sten,frac", [
