@@ -12,6 +12,7 @@
 #include "common.hpp"
 #include "kernels_generic.cuh"
 #include "kernels_lattice.cuh"
+#include "kernels_tiled.cuh"
 
 namespace pda {
 

@@ -130,6 +130,11 @@ inline bool latticeKernelAvailable(int family, int dim, int /*S*/) {
   (void)dim;
 }
 
+// 3D: tiled, face-sharing kernel (kernels_tiled.cuh)
+template <class Phys, int S>
+void launchLattice3dTiled(const Phys& phys, const dev::LatticeDesc& L, const dev::Deltas& dl, const double* dU,
+                          double* dV, cudaStream_t st);
+
 template <class Phys, int S>
 void launchLatticeVelocity(const Phys& phys, const Mesh& m, const dev::Deltas& dl, const double* dU, double* dV,
                            cudaStream_t st, int32_t planeBegin, int32_t planeEnd, int /*flags*/) {
@@ -140,6 +145,12 @@ void launchLatticeVelocity(const Phys& phys, const Mesh& m, const dev::Deltas& d
   for (int a = 0; a < Phys::dim - 1; ++a) planeCells *= m.n[a];
   const int64_t nwork = planeCells * (planeEnd - planeBegin);
   if (nwork <= 0) return;
+  if constexpr (Phys::dim == 3) {
+    if (m.n[0] >= 2 * m.halo() && m.n[1] >= 2 * m.halo() && m.n[2] >= 2 * m.halo()) {
+      launchLattice3dTiled<Phys, S>(phys, L, dl, dU, dV, st);
+      return;
+    }
+  }
   const int block = 128;
   dev::k_velocity_lattice_v1<Phys, S><<<(unsigned)((nwork + block - 1) / block), block, 0, st>>>(phys, L, dl, dU, dV);
 }
@@ -156,6 +167,12 @@ void launchLatticeVelocitySlab(const Phys& phys, const Mesh& m, const dev::Delta
   for (int a = 0; a < Phys::dim - 1; ++a) planeCells *= m.n[a];
   const int64_t nwork = planeCells * (pEnd - pBegin);
   if (nwork <= 0) return;
+  if constexpr (Phys::dim == 3) {
+    if (m.n[0] >= 2 * m.halo() && m.n[1] >= 2 * m.halo()) {
+      launchLattice3dTiled<Phys, S>(phys, L, dl, dUlocal, dVowned, st);
+      return;
+    }
+  }
   const int block = 128;
   dev::k_velocity_lattice_v1<Phys, S><<<(unsigned)((nwork + block - 1) / block), block, 0, st>>>(phys, L, dl, dUlocal, dVowned);
 }

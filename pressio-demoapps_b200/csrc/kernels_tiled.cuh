@@ -1,0 +1,365 @@
+// kernels_tiled.cuh -- the headline kernel: structured 3D Euler velocity with every face flux computed ONCE.
+//
+// Replaces the reference's inner-cell velocity loop (euler_3d_prob_class.hpp:861-927), which computes both faces of
+// every axis per cell (each face flux twice).  The kernel is bound by the FP64 pipe (WENO5: ~33 flop/B,
+// B200 balance ~5 flop/B), so the design minimises FP64 instructions per cell and keeps that pipe fed:
+//
+//   * a CTA owns a 32 x TY tile of (x,y) columns and MARCHES along z over LZ planes: the z-face flux of step k is
+//     the bottom flux of step k+1 (registers) -> z faces computed once;
+//   * the current plane, with its x/y stencil halo, is staged in shared memory (SoA, cp.async issued one z-face
+//     computation ahead of its use): coalesced HBM reads, conflict-free stencil reads;
+//   * x faces: each lane computes the left face of its cell, the right face arrives by warp shuffle from lane+1;
+//     y faces: each thread computes the back face, the front face is read from shared memory after a barrier;
+//     the TY + 32 tile-edge faces that no thread owns are computed by two rotating warps (2/(3*TY) extra passes);
+//   * the z stencil of a column lives in a thread-private shared-memory ring (2h planes), the next plane is
+//     prefetched into registers one step ahead: no barrier on the z path;
+//   * ONE copy of the face code (reconstruction + Rusanov) serves all four face tasks through a task loop, so the
+//     hot loop stays resident in the instruction cache;
+//   * leaf arithmetic restated for the FP64 pipe: difference-form WENO5 with one reciprocal per (face, dof) for BOTH
+//     sides, branch-free Newton reciprocal / square root from the MUFU seeds (no IEEE slow paths, no calls);
+//   * V is written once per cell (no zero + "+=" passes, mixin_directional_flux_balance.hpp:68-84).
+//
+// Works for scheme stencils 3/5/7, periodic or not per axis (cells whose mesh stencil leaves a non-periodic domain
+// belong to the near-boundary kernel and are not stored), and for slab-local storage (multi-GPU).
+#pragma once
+#include <cstdint>
+
+#include "kernels_lattice.cuh"
+
+namespace pda {
+namespace dev {
+
+PDA_DEVFN void cpAsync8(void* smemDst, const void* gmemSrc) {
+  const unsigned s = (unsigned)__cvta_generic_to_shared(smemDst);
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"(s), "l"(gmemSrc) : "memory");
+}
+PDA_DEVFN void cpAsyncCommit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
+PDA_DEVFN void cpAsyncWaitAll() { asm volatile("cp.async.wait_group 0;\n" ::: "memory"); }
+
+PDA_DEVFN int32_t fixIdx(int32_t idx, int32_t n, int32_t periodic) {
+  if (periodic) return idx < 0 ? idx + n : (idx >= n ? idx - n : idx);
+  return idx < 0 ? 0 : (idx >= n ? n - 1 : idx);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Branch-free FP64 reciprocal and square root: MUFU seed (>= 20 good bits) + Newton steps; relative error ~2 ulp.
+// Arguments are positive normal numbers here (densities, Roe averages, sums of squared smoothness indicators >=
+// eps^2), so the IEEE slow paths (denormals, inf, signed zero) that make `/` and sqrt() a subroutine call with a
+// divergent branch are not needed.  The reference's tolerance (1e-12) is four orders above this error.
+// ---------------------------------------------------------------------------------------------------------------
+PDA_DEVFN double rcpFast(double x) {
+  double r;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+  double e = fma(-x, r, 1.0);
+  r = fma(r, e, r);
+  e = fma(-x, r, 1.0);
+  r = fma(r, e, r);
+  return r;
+}
+PDA_DEVFN double sqrtFast(double x) {
+  double y;
+  asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+  // two Newton steps on y ~ x^-1/2:  y <- y + y*(1 - x*y*y)/2
+  double t = x * y;
+  double e = fma(-t, y, 1.0);
+  y = fma(0.5 * y, e, y);
+  t = x * y;
+  e = fma(-t, y, 1.0);
+  y = fma(0.5 * y, e, y);
+  // s = x*y with one residual correction
+  double s = x * y;
+  const double r = fma(-s, s, x);
+  s = fma(r, 0.5 * y, s);
+  return (x == 0.0) ? 0.0 : s;   // x == 0: the seed is inf and the chain NaN; x < 0 stays NaN like sqrt()
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// WENO5 (Jiang-Shu) at one face from the six cells around it, both sides (impl/weno5.hpp:56-178):
+// q = (a,b,c,d,e,f) = cells i-3..i+2, face between c and d; uNeg from (a..e), uPos from (b..f).
+//   * smoothness indicators from first/second differences; E_k = 4*(eps + B_k), the common factor 16 cancels in the
+//     weights: w_k = c_k/E_k^2 / sum;  multiplied through by E_0^2 E_1^2 E_2^2 -> no division per weight;
+//   * candidate polynomials in difference form around c / d (fewer operations, less cancellation);
+//   * uNeg = Nn/Dn, uPos = Np/Dp with ONE reciprocal: r = 1/(Dn*Dp).
+// ~75 FP64 instructions per (face, dof) instead of ~135.
+// ---------------------------------------------------------------------------------------------------------------
+PDA_DEVFN void weno5FaceFast(const double* q, double& uNeg, double& uPos) {
+  constexpr double k133 = 13.0 / 3.0, eps4 = 4.0e-6, s6 = 1.0 / 6.0;
+  const double c = q[2], d = q[3];
+  const double d0 = q[1] - q[0], d1 = c - q[1], d2 = d - c, d3 = q[4] - d, d4 = q[5] - q[4];
+  const double tb = d1 - d0, tc = d2 - d1, td = d3 - d2, te = d4 - d3;
+  const double tb2 = tb * tb, tc2 = tc * tc, td2 = td * td, te2 = te * te;
+  // neg side: s0 = a-4b+3c = 3 d1 - d0 ; s1 = b-d = -(d1+d2) ; s2 = 3c-4d+e = d3 - 3 d2
+  const double sn0 = fma(3.0, d1, -d0), sn1 = d1 + d2, sn2 = fma(-3.0, d2, d3);
+  // pos side: s0 = b-4c+3d = 3 d2 - d1 ; s1 = c-e = -(d2+d3) ; s2 = 3d-4e+f = d4 - 3 d3
+  const double sp0 = fma(3.0, d2, -d1), sp1 = d2 + d3, sp2 = fma(-3.0, d3, d4);
+  const double En0 = fma(sn0, sn0, fma(k133, tb2, eps4));
+  const double En1 = fma(sn1, sn1, fma(k133, tc2, eps4));
+  const double En2 = fma(sn2, sn2, fma(k133, td2, eps4));
+  const double Ep0 = fma(sp0, sp0, fma(k133, tc2, eps4));
+  const double Ep1 = fma(sp1, sp1, fma(k133, td2, eps4));
+  const double Ep2 = fma(sp2, sp2, fma(k133, te2, eps4));
+  const double Gn0 = En0 * En0, Gn1 = En1 * En1, Gn2 = En2 * En2;
+  const double Gp0 = Ep0 * Ep0, Gp1 = Ep1 * Ep1, Gp2 = Ep2 * Ep2;
+  // candidates: p(a,b,c) = c + (5 d1 - 2 d0)/6 ; p(b,c,d) = c + (2 d2 + d1)/6 ; p(c,d,e) = d - (2 d2 + d3)/6 ;
+  //             p(d,e,f) = d + (2 d4 - 5 d3)/6
+  const double pabc = fma(s6, fma(5.0, d1, -2.0 * d0), c);
+  const double pbcd = fma(s6, fma(2.0, d2, d1), c);
+  const double pcde = fma(-s6, fma(2.0, d2, d3), d);
+  const double pdef = fma(s6, fma(2.0, d4, -5.0 * d3), d);
+  // neg: linear weights (1,6,3)/10 ; pos: (3,6,1)/10
+  const double n0 = Gn1 * Gn2, n1 = 6.0 * (Gn0 * Gn2), n2 = 3.0 * (Gn0 * Gn1);
+  const double m0 = 3.0 * (Gp1 * Gp2), m1 = 6.0 * (Gp0 * Gp2), m2 = Gp0 * Gp1;
+  const double Dn = n0 + (n1 + n2), Dp = m0 + (m1 + m2);
+  const double Nn = fma(n0, pabc, fma(n1, pbcd, n2 * pcde));
+  const double Np = fma(m0, pbcd, fma(m1, pcde, m2 * pdef));
+  const double r = rcpFast(Dn * Dp);
+  uNeg = Nn * (Dp * r);
+  uPos = Np * (Dn * r);
+}
+
+template <int S> PDA_DEVFN void reconFaceFast(const double* q, double& uNeg, double& uPos) {
+  if constexpr (S == 7) weno5FaceFast(q, uNeg, uPos);
+  else Recon<S>::face(q, uNeg, uPos);
+}
+
+// 3D Euler Rusanov flux along axis `ax` (runtime), impl/euler_rusanov_flux_values_function.hpp:151-208:
+// F = 1/2 (F(qL) + F(qR) + smax (qL - qR)), smax = |v_roe| + a_roe.   ~115 FP64 instructions, no calls.
+PDA_DEVFN void eulerFlux3dFast(double gamma, int ax, const double* qL, const double* qR, double* F) {
+  const double gm1 = gamma - 1.0;
+  const double rL = qL[0], rR = qR[0];
+  const double iL = rcpFast(rL), iR = rcpFast(rR);
+  const double uL = qL[1] * iL, vL = qL[2] * iL, wL = qL[3] * iL;
+  const double uR = qR[1] * iR, vR = qR[2] * iR, wR = qR[3] * iR;
+  const double kL = fma(wL, wL, fma(vL, vL, uL * uL));
+  const double kR = fma(wR, wR, fma(vR, vR, uR * uR));
+  const double pL = gm1 * fma(-0.5 * rL, kL, qL[4]);
+  const double pR = gm1 * fma(-0.5 * rR, kR, qR[4]);
+  const double HL = (qL[4] + pL) * iL;
+  const double HR = (qR[4] + pR) * iR;
+  const double unL = (ax == 0) ? uL : ((ax == 1) ? vL : wL);
+  const double unR = (ax == 0) ? uR : ((ax == 1) ? vR : wR);
+  const double mL = rL * unL, mR = rR * unR;
+  // Roe averages
+  const double RT = sqrtFast(rR * iL);
+  const double iRT = rcpFast(1.0 + RT);
+  const double u = fma(RT, uR, uL) * iRT, v = fma(RT, vR, vL) * iRT, w = fma(RT, wR, wL) * iRT;
+  const double H = fma(RT, HR, HL) * iRT;
+  const double k = fma(w, w, fma(v, v, u * u));
+  const double a = sqrtFast(gm1 * fma(-0.5, k, H));
+  const double smax = sqrtFast(k) + a;
+  const double pS = pL + pR;
+  F[0] = 0.5 * fma(smax, rL - rR, mL + mR);
+  F[1] = 0.5 * (fma(smax, qL[1] - qR[1], fma(mL, uL, mR * uR)) + ((ax == 0) ? pS : 0.0));
+  F[2] = 0.5 * (fma(smax, qL[2] - qR[2], fma(mL, vL, mR * vR)) + ((ax == 1) ? pS : 0.0));
+  F[3] = 0.5 * (fma(smax, qL[3] - qR[3], fma(mL, wL, mR * wR)) + ((ax == 2) ? pS : 0.0));
+  F[4] = 0.5 * fma(smax, qL[4] - qR[4], fma(mL, HL, mR * HR));
+}
+
+template <int S, int TY>
+struct Tile3dSmem {
+  static constexpr int h = (S - 1) / 2;
+  static constexpr int TX = 32;
+  static constexpr int PX = TX + 2 * h, PY = TY + 2 * h;
+  static constexpr int R = 2 * h;   // z ring: planes k-h+1 .. k+h
+  template <int N> static constexpr size_t bytes() {
+    return sizeof(double) * (size_t)(N * PY * PX + R * N * TY * TX + N * (TY + 1) * TX + N * TY);
+  }
+};
+
+template <int S, int TY>
+__global__ void __launch_bounds__(32 * TY, (TY <= 8 ? 2 : 1))
+k_euler3d_velocity_tiled(double gamma, LatticeDesc L, Deltas dl, const double* __restrict__ U, double* __restrict__ V,
+                         int LZ) {
+  constexpr int N = 5;
+  using T = Tile3dSmem<S, TY>;
+  constexpr int h = T::h, TX = T::TX, PX = T::PX, PY = T::PY, R = T::R;
+  constexpr int NT = TX * TY;
+  constexpr int oP = 0;                        // [N][PY][PX]      current plane with x/y halo
+  constexpr int oZ = oP + N * PY * PX;         // [R][N][TY][TX]   thread-private z columns
+  constexpr int oFy = oZ + R * N * TY * TX;    // [N][TY+1][TX]    y-face fluxes
+  constexpr int oXe = oFy + N * (TY + 1) * TX; // [N][TY]          tile-edge x-face fluxes
+
+  extern __shared__ double smem[];
+
+  const int tx = threadIdx.x, ty = threadIdx.y;
+  const int tid = ty * TX + tx;
+  const int x0 = blockIdx.x * TX, y0 = blockIdx.y * TY;
+  const int k0 = L.planeBegin + blockIdx.z * LZ;
+  const int k1 = min(k0 + LZ, L.planeEnd);
+  const int nx = L.n[0], ny = L.n[1], nz = L.n[2];
+  const int perZ = L.per[2];
+
+  // storage plane of lattice plane p (slab: halo planes precede plane 0, no wrap)
+  auto planeOf = [&](int p) -> int64_t { return L.slab ? (int64_t)(p + L.haloPlanes) : (int64_t)fixIdx(p, nz, perZ); };
+  const int64_t rowStride = (int64_t)nx * N, planeStride = (int64_t)nx * ny * N;
+
+  // own column (clamped into the domain for threads of a ragged tile)
+  const int ci = min(x0 + tx, nx - 1), cj = min(y0 + ty, ny - 1);
+  const double* colBase = U + ((int64_t)cj * nx + ci) * N;
+  const int zMine = oZ + ty * TX + tx;   // + slot*N*TY*TX + d*TY*TX
+  auto zSlotOff = [&](int p) -> int {
+    int s = p % R; if (s < 0) s += R;
+    return zMine + s * (N * TY * TX);
+  };
+
+  // cooperative async load of plane p (with x/y halo)
+  auto loadPlane = [&](int p) {
+    const double* src = U + planeOf(p) * planeStride;
+    for (int e = tid; e < PY * PX * N; e += NT) {
+      const int r = e / (PX * N);
+      const int rem = e - r * (PX * N);
+      const int cc = rem / N;
+      const int d = rem - cc * N;
+      const int gy = fixIdx(y0 - h + r, ny, L.per[1]);
+      const int gx = fixIdx(x0 - h + cc, nx, L.per[0]);
+      cpAsync8(&smem[oP + (d * PY + r) * PX + cc], src + (int64_t)gy * rowStride + (int64_t)gx * N + d);
+    }
+    cpAsyncCommit();
+  };
+
+  // ---- prologue: ring <- planes (k0-1)-h+1 .. (k0-1)+h-1, registers <- plane (k0-1)+h
+  double zNew[N];
+  {
+    const int kg = k0 - 1;
+#pragma unroll
+    for (int o = -h + 1; o <= h - 1; ++o) {
+      const double* src = colBase + planeOf(kg + o) * planeStride;
+      const int off = zSlotOff(kg + o);
+#pragma unroll
+      for (int d = 0; d < N; ++d) smem[off + d * TY * TX] = src[d];
+    }
+    const double* src = colBase + planeOf(kg + h) * planeStride;
+#pragma unroll
+    for (int d = 0; d < N; ++d) zNew[d] = src[d];
+  }
+  loadPlane(k0);
+
+  double Fz[N];   // flux through the bottom face of the current cell
+#pragma unroll
+  for (int d = 0; d < N; ++d) Fz[d] = 0.0;
+
+  const bool inX = (x0 + tx < nx) && (L.per[0] || (x0 + tx >= L.meshHalo && x0 + tx < nx - L.meshHalo));
+  const bool inY = (y0 + ty < ny) && (L.per[1] || (y0 + ty >= L.meshHalo && y0 + ty < ny - L.meshHalo));
+
+  for (int k = k0 - 1; k < k1; ++k) {
+    // the plane prefetched last step enters the ring; prefetch the next one (consumed next step)
+    {
+      const int off = zSlotOff(k + h);
+#pragma unroll
+      for (int d = 0; d < N; ++d) smem[off + d * TY * TX] = zNew[d];
+      if (k + 1 < k1) {
+        const double* src = colBase + planeOf(k + 1 + h) * planeStride;
+#pragma unroll
+        for (int d = 0; d < N; ++d) zNew[d] = src[d];
+      }
+    }
+    const bool yExtra = (ty == (k & (TY - 1)));
+    const bool xExtra = (ty == ((k + TY / 2) & (TY - 1)));
+    const int ntasks = (k < k0) ? 1 : ((yExtra || xExtra) ? 4 : 3);
+    double v[N], dFx[N];
+
+    // ---- face tasks: 0 = z face k+1/2 (thread-private), 1 = y back face, 2 = x left face, 3 = tile-edge faces
+#pragma unroll 1
+    for (int task = 0; task < ntasks; ++task) {
+      if (task == 1) {   // plane k (issued one z-face computation ago) must have landed for everybody
+        cpAsyncWaitAll();
+        __syncthreads();
+      }
+      int offs[2 * h];
+      int ax;
+      if (task == 0) {
+#pragma unroll
+        for (int o = 0; o < 2 * h; ++o) offs[o] = zSlotOff(k - h + 1 + o);
+        ax = 2;
+      } else if (task == 1 || (task == 3 && yExtra)) {
+        const int row0 = (task == 1) ? ty : TY;
+#pragma unroll
+        for (int o = 0; o < 2 * h; ++o) offs[o] = oP + (row0 + o) * PX + (tx + h);
+        ax = 1;
+      } else {
+        const int row = (task == 2) ? (ty + h) : (min(tx, TY - 1) + h);
+        const int col0 = (task == 2) ? tx : TX;
+#pragma unroll
+        for (int o = 0; o < 2 * h; ++o) offs[o] = oP + row * PX + col0 + o;
+        ax = 0;
+      }
+      const int dofStride = (task == 0) ? (TY * TX) : (PY * PX);
+      double uN[N], uP[N], F[N];
+#pragma unroll
+      for (int d = 0; d < N; ++d) {
+        double q[2 * h];
+#pragma unroll
+        for (int o = 0; o < 2 * h; ++o) q[o] = smem[offs[o] + d * dofStride];
+        reconFaceFast<S>(q, uN[d], uP[d]);
+      }
+      eulerFlux3dFast(gamma, ax, uN, uP, F);
+      if (task == 0) {
+#pragma unroll
+        for (int d = 0; d < N; ++d) { v[d] = dl.hInv[2] * (Fz[d] - F[d]); Fz[d] = F[d]; }   // z term, added last
+      } else if (task == 1) {
+#pragma unroll
+        for (int d = 0; d < N; ++d) smem[oFy + (d * (TY + 1) + ty) * TX + tx] = F[d];
+      } else if (task == 2) {
+        // FxL - FxR, the right face being lane+1's left face (lane 31: FxL - 0 until the barrier: exact)
+#pragma unroll
+        for (int d = 0; d < N; ++d) {
+          const double r = __shfl_down_sync(0xffffffffu, F[d], 1);
+          dFx[d] = F[d] - ((tx == TX - 1) ? 0.0 : r);
+        }
+      } else if (yExtra) {
+#pragma unroll
+        for (int d = 0; d < N; ++d) smem[oFy + (d * (TY + 1) + TY) * TX + tx] = F[d];
+      } else if (tx < TY) {
+#pragma unroll
+        for (int d = 0; d < N; ++d) smem[oXe + d * TY + tx] = F[d];
+      }
+    }
+    if (k < k0) continue;   // ghost step: only the bottom flux of the first plane
+
+    __syncthreads();                      // fluxes exchanged; nobody reads the plane buffer any more
+    if (k + 1 < k1) loadPlane(k + 1);     // lands while the next z face is computed
+#pragma unroll
+    for (int d = 0; d < N; ++d) {
+      if (tx == TX - 1) dFx[d] -= smem[oXe + d * TY + ty];
+      const double FyB = smem[oFy + (d * (TY + 1) + ty) * TX + tx];
+      const double FyF = smem[oFy + (d * (TY + 1) + ty + 1) * TX + tx];
+      // V = hx(FxL-FxR) + hy(FyB-FyF) + hz(FzB-FzT): same x,y,z accumulation order as the reference
+      v[d] = (dl.hInv[0] * dFx[d] + dl.hInv[1] * (FyB - FyF)) + v[d];
+    }
+    const bool inZ = L.slab || perZ || (k >= L.meshHalo && k < nz - L.meshHalo);
+    if (inX && inY && inZ) {
+      double* out = V + (((int64_t)k * ny + (y0 + ty)) * nx + (x0 + tx)) * N;
+#pragma unroll
+      for (int d = 0; d < N; ++d) out[d] = v[d];
+    }
+  }
+}
+
+}  // namespace dev
+
+template <class Phys, int S>
+void launchLattice3dTiled(const Phys& phys, const dev::LatticeDesc& L, const dev::Deltas& dl, const double* dU,
+                          double* dV, cudaStream_t st) {
+  static_assert(Phys::dim == 3 && Phys::ndpc == 5, "Euler3d kernel");
+  constexpr int TY = 8;
+  using T = dev::Tile3dSmem<S, TY>;
+  constexpr size_t smem = T::template bytes<5>();
+  auto kern = dev::k_euler3d_velocity_tiled<S, TY>;
+  static bool configured = false;
+  if (!configured) {
+    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+    configured = true;
+  }
+  const int planes = L.planeEnd - L.planeBegin;
+  if (planes <= 0) return;
+  const int gx = (L.n[0] + 31) / 32, gy = (L.n[1] + TY - 1) / TY;
+  // z chunks: long enough to amortise the ghost step (1/LZ extra z faces), short enough to fill 148 SMs x 2 CTAs
+  int LZ = 64;
+  while (LZ > 8 && (int64_t)gx * gy * ((planes + LZ - 1) / LZ) < 148 * 2 * 4) LZ /= 2;
+  const int gz = (planes + LZ - 1) / LZ;
+  dim3 grid(gx, gy, gz), block(32, TY);
+  kern<<<grid, block, smem, st>>>(phys.gamma, L, dl, dU, dV, LZ);
+}
+
+}  // namespace pda
