@@ -6,13 +6,14 @@
 //
 //   * a CTA owns a 32 x TY tile of (x,y) columns and MARCHES along z over LZ planes: the z-face flux of step k is
 //     the bottom flux of step k+1 (registers) -> z faces computed once;
-//   * the current plane, with its x/y stencil halo, is staged in shared memory (SoA, cp.async issued one z-face
-//     computation ahead of its use): coalesced HBM reads, conflict-free stencil reads;
+//   * the current plane, with its x/y stencil halo, is staged in shared memory by TMA (cp.async.bulk, one copy per
+//     tile row, completion on an mbarrier, issued one z-face computation ahead of its use);
 //   * x faces: each lane computes the left face of its cell, the right face arrives by warp shuffle from lane+1;
 //     y faces: each thread computes the back face, the front face is read from shared memory after a barrier;
-//     the TY + 32 tile-edge faces that no thread owns are computed by two rotating warps (2/(3*TY) extra passes);
-//   * the z stencil of a column lives in a thread-private shared-memory ring (2h planes), the next plane is
-//     prefetched into registers one step ahead: no barrier on the z path;
+//     the TY + 32 tile-edge faces that no cell thread owns are computed by a ninth "edge" warp (two face tasks per
+//     step against three for the cell warps: off the critical path, barriers see balanced work);
+//   * the z stencil of a column lives in a thread-private shared-memory ring (2h planes + one in flight, fetched
+//     by cp.async one step ahead): no barrier and no registers on the z path;
 //   * ONE copy of the face code (reconstruction + Rusanov) serves all four face tasks through a task loop, so the
 //     hot loop stays resident in the instruction cache;
 //   * leaf arithmetic restated for the FP64 pipe: difference-form WENO5 with one reciprocal per (face, dof) for BOTH
@@ -155,34 +156,65 @@ PDA_DEVFN void eulerFlux3dFast(double gamma, int ax, const double* qL, const dou
   F[4] = 0.5 * fma(smax, qL[4] - qR[4], fma(mL, HL, mR * HR));
 }
 
+// ---- TMA (bulk async copy) + mbarrier wrappers: sm_90+ PTX, SASS UBLKCP / SYNCS
+PDA_DEVFN unsigned smemU32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+PDA_DEVFN void mbarInit(uint64_t* bar, unsigned count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(smemU32(bar)), "r"(count) : "memory");
+}
+PDA_DEVFN void mbarArriveExpectTx(uint64_t* bar, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(smemU32(bar)), "r"(bytes) : "memory");
+}
+PDA_DEVFN void mbarWait(uint64_t* bar, unsigned parity) {
+  unsigned ok;
+  do {
+    asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}\n"
+                 : "=r"(ok) : "r"(smemU32(bar)), "r"(parity) : "memory");
+  } while (!ok);
+}
+PDA_DEVFN void bulkCopyG2S(void* dst, const void* src, unsigned bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n"
+               ::"r"(smemU32(dst)), "l"(src), "r"(bytes), "r"(smemU32(bar)) : "memory");
+}
+
 template <int S, int TY>
 struct Tile3dSmem {
   static constexpr int h = (S - 1) / 2;
   static constexpr int TX = 32;
-  static constexpr int PX = TX + 2 * h, PY = TY + 2 * h;
-  static constexpr int R = 2 * h;   // z ring: planes k-h+1 .. k+h
+  static constexpr int HX = (h + 1) & ~1;          // x halo rounded up to an even cell count: 16-byte aligned rows
+  static constexpr int PX = TX + 2 * HX, PY = TY + 2 * h;
+  static constexpr int R = 2 * h + 1;              // z ring: planes k-h+1 .. k+h in use, k+h+1 in flight
   template <int N> static constexpr size_t bytes() {
-    return sizeof(double) * (size_t)(N * PY * PX + R * N * TY * TX + N * (TY + 1) * TX + N * TY);
+    return sizeof(double) * (size_t)(N * PY * PX + R * N * TY * TX + N * (TY + 1) * TX + N * TY + 2);
   }
 };
 
+// Thread block = TY "cell" warps (one tile row each) + ONE "edge" warp that (a) issues the TMA bulk copies of the
+// next plane and (b) computes the tile-edge faces nobody owns (y face row TY, x face column 32): two face tasks per
+// step against three for the cell warps, so it never sits on the critical path.
+// All shared-memory tiles are AoS ([..][cell][dof], 40-byte cells): a lane stride of 40 bytes is conflict-free for
+// 8-byte accesses, the dof index becomes an immediate offset, and a row of the plane tile is ONE contiguous range
+// of the AoS state in HBM -> one cp.async.bulk per row (two where the periodic wrap splits it).
 template <int S, int TY>
-__global__ void __launch_bounds__(32 * TY, (TY <= 8 ? 2 : 1))
+__global__ void __launch_bounds__(32 * (TY + 1), (TY <= 7 ? 2 : 1))
 k_euler3d_velocity_tiled(double gamma, LatticeDesc L, Deltas dl, const double* __restrict__ U, double* __restrict__ V,
-                         int LZ) {
+                         int LZ, int useTma) {
   constexpr int N = 5;
   using T = Tile3dSmem<S, TY>;
-  constexpr int h = T::h, TX = T::TX, PX = T::PX, PY = T::PY, R = T::R;
-  constexpr int NT = TX * TY;
-  constexpr int oP = 0;                        // [N][PY][PX]      current plane with x/y halo
-  constexpr int oZ = oP + N * PY * PX;         // [R][N][TY][TX]   thread-private z columns
-  constexpr int oFy = oZ + R * N * TY * TX;    // [N][TY+1][TX]    y-face fluxes
-  constexpr int oXe = oFy + N * (TY + 1) * TX; // [N][TY]          tile-edge x-face fluxes
+  constexpr int h = T::h, TX = T::TX, HX = T::HX, PX = T::PX, PY = T::PY, R = T::R;
+  constexpr int NT = TX * (TY + 1);
+  constexpr int oP = 0;                        // [PY][PX][N]      current plane with x/y halo
+  constexpr int oZ = oP + N * PY * PX;         // [R][TY][TX][N]   thread-private z columns
+  constexpr int oFy = oZ + R * N * TY * TX;    // [TY+1][TX][N]    y-face fluxes
+  constexpr int oXe = oFy + N * (TY + 1) * TX; // [TY][N]          tile-edge x-face fluxes
+  constexpr int oBar = oXe + N * TY;           // mbarrier (8 bytes)
+  constexpr int slotStride = N * TY * TX;
 
-  extern __shared__ double smem[];
+  extern __shared__ __align__(16) double smem[];
+  uint64_t* bar = reinterpret_cast<uint64_t*>(&smem[oBar + (oBar & 1)]);
 
   const int tx = threadIdx.x, ty = threadIdx.y;
   const int tid = ty * TX + tx;
+  const bool edgeWarp = (ty == TY);
   const int x0 = blockIdx.x * TX, y0 = blockIdx.y * TY;
   const int k0 = L.planeBegin + blockIdx.z * LZ;
   const int k1 = min(k0 + LZ, L.planeEnd);
@@ -193,103 +225,131 @@ k_euler3d_velocity_tiled(double gamma, LatticeDesc L, Deltas dl, const double* _
   auto planeOf = [&](int p) -> int64_t { return L.slab ? (int64_t)(p + L.haloPlanes) : (int64_t)fixIdx(p, nz, perZ); };
   const int64_t rowStride = (int64_t)nx * N, planeStride = (int64_t)nx * ny * N;
 
-  // own column (clamped into the domain for threads of a ragged tile)
-  const int ci = min(x0 + tx, nx - 1), cj = min(y0 + ty, ny - 1);
+  // own column (clamped into the domain for threads of a ragged tile; the edge warp has none)
+  const int ci = min(x0 + tx, nx - 1), cj = min(y0 + min(ty, TY - 1), ny - 1);
   const double* colBase = U + ((int64_t)cj * nx + ci) * N;
-  const int zMine = oZ + ty * TX + tx;   // + slot*N*TY*TX + d*TY*TX
-  auto zSlotOff = [&](int p) -> int {
-    int s = p % R; if (s < 0) s += R;
-    return zMine + s * (N * TY * TX);
-  };
-
-  // cooperative async load of plane p (with x/y halo)
-  auto loadPlane = [&](int p) {
-    const double* src = U + planeOf(p) * planeStride;
-    for (int e = tid; e < PY * PX * N; e += NT) {
-      const int r = e / (PX * N);
-      const int rem = e - r * (PX * N);
-      const int cc = rem / N;
-      const int d = rem - cc * N;
-      const int gy = fixIdx(y0 - h + r, ny, L.per[1]);
-      const int gx = fixIdx(x0 - h + cc, nx, L.per[0]);
-      cpAsync8(&smem[oP + (d * PY + r) * PX + cc], src + (int64_t)gy * rowStride + (int64_t)gx * N + d);
-    }
+  const int zMine = oZ + (min(ty, TY - 1) * TX + tx) * N;   // + slot*slotStride + d
+  // thread-private async copy of this column's cell of plane p into ring slot `slot`
+  auto fetchColumn = [&](int p, int slot) {
+    const double* src = colBase + planeOf(p) * planeStride;
+    const int off = zMine + slot * slotStride;
+#pragma unroll
+    for (int d = 0; d < N; ++d) cpAsync8(&smem[off + d], src + d);
     cpAsyncCommit();
   };
 
-  // ---- prologue: ring <- planes (k0-1)-h+1 .. (k0-1)+h-1, registers <- plane (k0-1)+h
-  double zNew[N];
-  {
-    const int kg = k0 - 1;
+  // plane p (with x/y halo) -> sP.  TMA path: lane r of the edge warp copies tile row r (cells x0-HX .. x0+TX+HX-1)
+  // with one bulk copy per contiguous segment; fallback: every thread issues 8-byte cp.async copies.
+  auto loadPlane = [&](int p) {
+    const double* src = U + planeOf(p) * planeStride;
+    if (useTma) {
+      if (!edgeWarp) return;
+      unsigned bytes = 0;
+      int segG[3], segD[3], segL[3], nseg = 0;
+      if (tx < PY) {
+        int start = x0 - HX, remaining = PX, dcol = 0;
+        while (remaining > 0 && nseg < 3) {
+          int g = start;
+          if (g < 0) {
+            if (L.per[0]) g += nx;
+            else { const int skip = min(remaining, -g); start += skip; dcol += skip; remaining -= skip; continue; }
+          } else if (g >= nx) {
+            if (L.per[0]) g -= nx; else break;
+          }
+          const int len = min(remaining, nx - g);
+          segG[nseg] = g; segD[nseg] = dcol; segL[nseg] = len; ++nseg;
+          bytes += (unsigned)len * (N * 8);
+          start += len; dcol += len; remaining -= len;
+        }
+      }
+      unsigned total = bytes;
 #pragma unroll
-    for (int o = -h + 1; o <= h - 1; ++o) {
-      const double* src = colBase + planeOf(kg + o) * planeStride;
-      const int off = zSlotOff(kg + o);
-#pragma unroll
-      for (int d = 0; d < N; ++d) smem[off + d * TY * TX] = src[d];
+      for (int o = 16; o > 0; o >>= 1) total += __shfl_xor_sync(0xffffffffu, total, o);
+      if (tx == 0) mbarArriveExpectTx(bar, total);
+      __syncwarp();
+      if (tx < PY) {
+        const int gy = fixIdx(y0 - h + tx, ny, L.per[1]);
+        for (int sI = 0; sI < nseg; ++sI)
+          bulkCopyG2S(&smem[oP + (tx * PX + segD[sI]) * N], src + (int64_t)gy * rowStride + (int64_t)segG[sI] * N,
+                      (unsigned)segL[sI] * (N * 8), bar);
+      }
+    } else {
+      for (int e = tid; e < PY * (TX + 2 * h) * N; e += NT) {
+        const int r = e / ((TX + 2 * h) * N);
+        const int rem = e - r * ((TX + 2 * h) * N);
+        const int cc = rem / N;
+        const int d = rem - cc * N;
+        const int gy = fixIdx(y0 - h + r, ny, L.per[1]);
+        const int gx = fixIdx(x0 - h + cc, nx, L.per[0]);
+        cpAsync8(&smem[oP + (r * PX + (HX - h) + cc) * N + d], src + (int64_t)gy * rowStride + (int64_t)gx * N + d);
+      }
+      cpAsyncCommit();
     }
-    const double* src = colBase + planeOf(kg + h) * planeStride;
+  };
+
+  if (tid == 0) mbarInit(bar, 1);
+  asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+  __syncthreads();
+
+  // ---- prologue: ring <- planes (k0-1)-h+1 .. (k0-1)+h ; slot of plane p = (p - (k0-h)) mod R
+  if (!edgeWarp) {
 #pragma unroll
-    for (int d = 0; d < N; ++d) zNew[d] = src[d];
+    for (int o = 0; o < 2 * h; ++o) fetchColumn(k0 - h + o, o);
   }
   loadPlane(k0);
+  int slot0 = 0;          // ring slot of plane k-h+1 at step k
+  unsigned parity = 0;    // mbarrier phase of the plane awaited next
 
   double Fz[N];   // flux through the bottom face of the current cell
 #pragma unroll
   for (int d = 0; d < N; ++d) Fz[d] = 0.0;
 
   const bool inX = (x0 + tx < nx) && (L.per[0] || (x0 + tx >= L.meshHalo && x0 + tx < nx - L.meshHalo));
-  const bool inY = (y0 + ty < ny) && (L.per[1] || (y0 + ty >= L.meshHalo && y0 + ty < ny - L.meshHalo));
+  const bool inY = !edgeWarp && (y0 + ty < ny) && (L.per[1] || (y0 + ty >= L.meshHalo && y0 + ty < ny - L.meshHalo));
 
   for (int k = k0 - 1; k < k1; ++k) {
-    // the plane prefetched last step enters the ring; prefetch the next one (consumed next step)
-    {
-      const int off = zSlotOff(k + h);
-#pragma unroll
-      for (int d = 0; d < N; ++d) smem[off + d * TY * TX] = zNew[d];
-      if (k + 1 < k1) {
-        const double* src = colBase + planeOf(k + 1 + h) * planeStride;
-#pragma unroll
-        for (int d = 0; d < N; ++d) zNew[d] = src[d];
-      }
+    const bool ghost = (k < k0);
+    if (!edgeWarp) {
+      cpAsyncWaitAll();   // this thread's column cell of plane k+h (fetched one step ago) has landed
+      // prefetch the plane the NEXT z face needs into the free slot (slot0 + 2h) mod R
+      if (k + 1 < k1) { int sl = slot0 + 2 * h; if (sl >= R) sl -= R; fetchColumn(k + 1 + h, sl); }
     }
-    const bool yExtra = (ty == (k & (TY - 1)));
-    const bool xExtra = (ty == ((k + TY / 2) & (TY - 1)));
-    const int ntasks = (k < k0) ? 1 : ((yExtra || xExtra) ? 4 : 3);
+    // face tasks: 0 = z face k+1/2 (thread-private), 1 = y back face, 2 = x left face (cell warps);
+    //             3 = y faces of row TY, 4 = x faces of column TX (edge warp)
+    const int tBegin = edgeWarp ? 3 : 0;
+    const int tEnd = edgeWarp ? (ghost ? 3 : 5) : (ghost ? 1 : 3);
     double v[N], dFx[N];
-
-    // ---- face tasks: 0 = z face k+1/2 (thread-private), 1 = y back face, 2 = x left face, 3 = tile-edge faces
 #pragma unroll 1
-    for (int task = 0; task < ntasks; ++task) {
-      if (task == 1) {   // plane k (issued one z-face computation ago) must have landed for everybody
-        cpAsyncWaitAll();
-        __syncthreads();
+    for (int task = tBegin; task < tEnd; ++task) {
+      if (task == 1 || task == 3) {   // plane k (issued one z-face computation ago) must have landed
+        if (useTma) { mbarWait(bar, parity); parity ^= 1u; }
+        else { cpAsyncWaitAll(); __syncthreads(); }
       }
       int offs[2 * h];
       int ax;
       if (task == 0) {
+        int sl = slot0;
 #pragma unroll
-        for (int o = 0; o < 2 * h; ++o) offs[o] = zSlotOff(k - h + 1 + o);
+        for (int o = 0; o < 2 * h; ++o) { offs[o] = zMine + sl * slotStride; sl = (sl + 1 == R) ? 0 : sl + 1; }
         ax = 2;
-      } else if (task == 1 || (task == 3 && yExtra)) {
+      } else if (task == 1 || task == 3) {
         const int row0 = (task == 1) ? ty : TY;
 #pragma unroll
-        for (int o = 0; o < 2 * h; ++o) offs[o] = oP + (row0 + o) * PX + (tx + h);
+        for (int o = 0; o < 2 * h; ++o) offs[o] = oP + ((row0 + o) * PX + (tx + HX)) * N;
         ax = 1;
       } else {
         const int row = (task == 2) ? (ty + h) : (min(tx, TY - 1) + h);
-        const int col0 = (task == 2) ? tx : TX;
+        const int col0 = ((task == 2) ? tx : TX) + (HX - h);
 #pragma unroll
-        for (int o = 0; o < 2 * h; ++o) offs[o] = oP + row * PX + col0 + o;
+        for (int o = 0; o < 2 * h; ++o) offs[o] = oP + (row * PX + col0 + o) * N;
         ax = 0;
       }
-      const int dofStride = (task == 0) ? (TY * TX) : (PY * PX);
       double uN[N], uP[N], F[N];
 #pragma unroll
       for (int d = 0; d < N; ++d) {
         double q[2 * h];
 #pragma unroll
-        for (int o = 0; o < 2 * h; ++o) q[o] = smem[offs[o] + d * dofStride];
+        for (int o = 0; o < 2 * h; ++o) q[o] = smem[offs[o] + d];
         reconFaceFast<S>(q, uN[d], uP[d]);
       }
       eulerFlux3dFast(gamma, ax, uN, uP, F);
@@ -298,7 +358,7 @@ k_euler3d_velocity_tiled(double gamma, LatticeDesc L, Deltas dl, const double* _
         for (int d = 0; d < N; ++d) { v[d] = dl.hInv[2] * (Fz[d] - F[d]); Fz[d] = F[d]; }   // z term, added last
       } else if (task == 1) {
 #pragma unroll
-        for (int d = 0; d < N; ++d) smem[oFy + (d * (TY + 1) + ty) * TX + tx] = F[d];
+        for (int d = 0; d < N; ++d) smem[oFy + (ty * TX + tx) * N + d] = F[d];
       } else if (task == 2) {
         // FxL - FxR, the right face being lane+1's left face (lane 31: FxL - 0 until the barrier: exact)
 #pragma unroll
@@ -306,23 +366,25 @@ k_euler3d_velocity_tiled(double gamma, LatticeDesc L, Deltas dl, const double* _
           const double r = __shfl_down_sync(0xffffffffu, F[d], 1);
           dFx[d] = F[d] - ((tx == TX - 1) ? 0.0 : r);
         }
-      } else if (yExtra) {
+      } else if (task == 3) {
 #pragma unroll
-        for (int d = 0; d < N; ++d) smem[oFy + (d * (TY + 1) + TY) * TX + tx] = F[d];
+        for (int d = 0; d < N; ++d) smem[oFy + (TY * TX + tx) * N + d] = F[d];
       } else if (tx < TY) {
 #pragma unroll
-        for (int d = 0; d < N; ++d) smem[oXe + d * TY + tx] = F[d];
+        for (int d = 0; d < N; ++d) smem[oXe + tx * N + d] = F[d];
       }
     }
-    if (k < k0) continue;   // ghost step: only the bottom flux of the first plane
+    slot0 = (slot0 + 1 == R) ? 0 : slot0 + 1;
+    if (ghost) continue;   // ghost step: only the bottom flux of the first plane
 
     __syncthreads();                      // fluxes exchanged; nobody reads the plane buffer any more
     if (k + 1 < k1) loadPlane(k + 1);     // lands while the next z face is computed
+    if (edgeWarp) continue;
 #pragma unroll
     for (int d = 0; d < N; ++d) {
-      if (tx == TX - 1) dFx[d] -= smem[oXe + d * TY + ty];
-      const double FyB = smem[oFy + (d * (TY + 1) + ty) * TX + tx];
-      const double FyF = smem[oFy + (d * (TY + 1) + ty + 1) * TX + tx];
+      if (tx == TX - 1) dFx[d] -= smem[oXe + ty * N + d];
+      const double FyB = smem[oFy + (ty * TX + tx) * N + d];
+      const double FyF = smem[oFy + ((ty + 1) * TX + tx) * N + d];
       // V = hx(FxL-FxR) + hy(FyB-FyF) + hz(FzB-FzT): same x,y,z accumulation order as the reference
       v[d] = (dl.hInv[0] * dFx[d] + dl.hInv[1] * (FyB - FyF)) + v[d];
     }
@@ -341,7 +403,7 @@ template <class Phys, int S>
 void launchLattice3dTiled(const Phys& phys, const dev::LatticeDesc& L, const dev::Deltas& dl, const double* dU,
                           double* dV, cudaStream_t st) {
   static_assert(Phys::dim == 3 && Phys::ndpc == 5, "Euler3d kernel");
-  constexpr int TY = 8;
+  constexpr int TY = 7;   // 7 cell warps + 1 edge warp = 256 threads, 2 CTAs per SM at 128 registers
   using T = dev::Tile3dSmem<S, TY>;
   constexpr size_t smem = T::template bytes<5>();
   auto kern = dev::k_euler3d_velocity_tiled<S, TY>;
@@ -358,8 +420,10 @@ void launchLattice3dTiled(const Phys& phys, const dev::LatticeDesc& L, const dev
   int LZ = 64;
   while (LZ > 8 && (int64_t)gx * gy * ((planes + LZ - 1) / LZ) < 148 * 2 * 4) LZ /= 2;
   const int gz = (planes + LZ - 1) / LZ;
-  dim3 grid(gx, gy, gz), block(32, TY);
-  kern<<<grid, block, smem, st>>>(phys.gamma, L, dl, dU, dV, LZ);
+  dim3 grid(gx, gy, gz), block(32, TY + 1);
+  // TMA rows need 16-byte aligned segments: even cell counts (40-byte cells) and an aligned base
+  const int useTma = (L.n[0] % 2 == 0) && (L.n[0] >= T::PX) && ((reinterpret_cast<uintptr_t>(dU) & 15) == 0);
+  kern<<<grid, block, smem, st>>>(phys.gamma, L, dl, dU, dV, LZ, useTma);
 }
 
 }  // namespace pda
