@@ -49,7 +49,7 @@ def load_peaks():
 
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
-    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,utilization.gpu,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
 
@@ -83,6 +83,8 @@ class ClockSampler:
                 if len(c) < 9:
                     continue
                 try:
+                    if float(c[4]) < 50.0:   # keep the samples taken under load
+                        continue
                     sm.append(float(c[1]))
                     mx.append(float(c[2]))
                 except ValueError:
@@ -281,13 +283,14 @@ def run_b200_arm(args):
             torch.cuda.current_stream().synchronize()
         kernel_cells = (k1 - k0 - 2 * h) * (pd // 5)
 
-    # ---- device-resident timing
-    for _ in range(W):
-        step()
-    barrier()
+    # ---- device-resident timing (the clock sampler runs from the warm-up on so that the short timed region is covered)
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
+        time.sleep(0.5)
+    for _ in range(W):
+        step()
+    barrier()
     l0 = p.launchCount()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
