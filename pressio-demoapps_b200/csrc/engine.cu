@@ -13,6 +13,7 @@
 #include "kernels_generic.cuh"
 #include "kernels_lattice.cuh"
 #include "kernels_tiled.cuh"
+#include "kernels_jacobian.cuh"
 
 namespace pda {
 
@@ -921,7 +922,14 @@ void Problem::evaluateDev(const double* dU, double t, double* dV, double* dJ, vo
       fill(ds.nearBd);
       ds.jacTablesReady = true;
     }
-    PDA_CUDA(cudaMemsetAsync(dJ, 0, colidx_.size() * sizeof(double), st));
+    // the staged inner-row kernel writes every value once; only rows assembled by read-modify-write need zeros
+    if (family_ == F_DIFFREAC2D || mergedNeighbors_) {
+      PDA_CUDA(cudaMemsetAsync(dJ, 0, colidx_.size() * sizeof(double), st));
+    } else if (ds.nearBd.n > 0) {
+      dev::k_zero_cell_chunks<<<gridFor((int64_t)ds.nearBd.n * 32, 256), 256, 0, st>>>(ds.nearBd.jBase.p, ds.nearBd.jLen.p,
+                                                                                     ds.nearBd.n, ndpc_, dJ);
+      ++launches_;
+    }
   }
 
   // ---- Gray-Scott: one fused kernel over all rows
@@ -971,7 +979,18 @@ void Problem::evaluateDev(const double* dU, double t, double* dV, double* dJ, vo
         launchLatticeVelocity<Phys, S>(phys, m, dl, dU, dV, st, 0, m.n[dim_ - 1], 0);
         ++launches_;
       } else if (ds.inner.n > 0) {
-        if (dJ) {
+        if (dJ && !mergedNeighbors_) {
+          // staged assembly: every value of the inner rows written once, coalesced (no memset needed for them)
+          using JS = dev::JacStage<Phys, S>;
+          auto kern = dev::k_jacobian_inner_staged<Phys, S>;
+          static bool configured = false;
+          if (!configured) {
+            PDA_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)JS::smemBytes));
+            configured = true;
+          }
+          kern<<<gridFor(ds.inner.n, JS::CELLS), JS::THREADS, JS::smemBytes, st>>>(phys, ds.inner.view(nc), dl, dU, dV, dJ,
+                                                                               ds.inner.jac(slotCols_));
+        } else if (dJ) {
           dev::k_jacobian_inner_rows<Phys, S><<<gridFor(ds.inner.n, 128), 128, 0, st>>>(phys, ds.inner.view(nc), dl, dU, dV, dJ,
                                                                                         ds.inner.jac(slotCols_));
         } else {
