@@ -48,8 +48,9 @@ def load_peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
-    Q = ("index,clocks.sm,clocks.max.sm,power.draw,utilization.gpu,clocks_event_reasons.hw_slowdown,"
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe): sampled every 20 ms
+    with timestamps; `stop(t0, t1)` keeps the samples whose timestamp falls inside the GPU-busy window [t0, t1]."""
+    Q = ("timestamp,index,clocks.sm,clocks.max.sm,power.draw,utilization.gpu,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
 
@@ -63,40 +64,50 @@ class ClockSampler:
             fd, self.path = tempfile.mkstemp(suffix=".csv")
             os.close(fd)
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                          "--format=csv,noheader,nounits", "-lms", "20"],
                                          stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
+            t_end = time.time() + 8.0   # nvidia-smi needs a moment before its first sample
+            while time.time() < t_end and os.path.getsize(self.path) == 0:
+                time.sleep(0.05)
         except Exception:
             self.proc = None
 
-    def stop(self):
+    def stop(self, t0=None, t1=None):
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.05)
         self.proc.terminate()
         try:
             self.proc.wait(timeout=5)
         except Exception:
             self.proc.kill()
-        sm, mx, reasons = [], [], set()
+        import datetime
+        rows = []
         with open(self.path) as f:
             for line in f:
                 c = [x.strip() for x in line.split(",")]
-                if len(c) < 9:
+                if len(c) < 10:
                     continue
                 try:
-                    if float(c[4]) < 50.0:   # keep the samples taken under load
-                        continue
-                    sm.append(float(c[1]))
-                    mx.append(float(c[2]))
+                    ts = datetime.datetime.strptime(c[0], "%Y/%m/%d %H:%M:%S.%f").timestamp()
+                    rows.append((ts, float(c[2]), float(c[3]), float(c[5]), c[6:10]))
                 except ValueError:
                     continue
-                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), c[5:9]):
-                    if v.lower().startswith("active"):
-                        reasons.add(name)
         os.unlink(self.path)
-        if not sm:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
-        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons),
-                "samples": len(sm)}
+        inside = [r for r in rows if t0 is not None and t0 - 0.01 <= r[0] <= t1 + 0.01]
+        window = "timed region"
+        if not inside:   # clock skew / too short a region: fall back to the samples taken under load
+            inside = [r for r in rows if r[3] >= 50.0]
+            window = "samples with utilization >= 50%"
+        if not inside:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"], "samples": 0, "all_samples": len(rows)}
+        reasons = set()
+        for r in inside:
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[4]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median([r[1] for r in inside])), "sm_max_mhz": float(max(r[2] for r in inside)),
+                "reasons": sorted(reasons), "samples": len(inside), "window": window}
 
 
 # ------------------------------------------------------------------------------------------------ CPU legs
@@ -287,20 +298,20 @@ def run_b200_arm(args):
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
-        time.sleep(0.5)
     for _ in range(W):
         step()
     barrier()
     l0 = p.launchCount()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t_wall0 = time.time()
     e0.record()
     for _ in range(K):
         step()
     e1.record()
     barrier()
+    t_wall1 = time.time()
     ms_total = max_over_ranks(e0.elapsed_time(e1))
     launches = p.launchCount() - l0
-    clocks = sampler.stop() if rank == 0 else None
     ms_step = ms_total / K
     value = ncells / (ms_step * 1e-3)
 
@@ -315,6 +326,9 @@ def run_b200_arm(args):
         b.record()
     torch.cuda.synchronize()
     k_ms = float(np.mean([a.elapsed_time(b) for a, b in kev]))
+    # clocks: samples inside the timed region; the per-kernel timing loop right after it (same kernel, same load)
+    # extends the window so that a 20 ms sampling period sees enough points even for K*ms_step ~ 0.1 s
+    clocks = sampler.stop(t_wall0, time.time()) if rank == 0 else None
     ach_gbs = kernel_cells * BYTES_PER_CELL / (k_ms * 1e-3) * 1e-9
     ach_tf = kernel_cells * FLOPS_PER_CELL / (k_ms * 1e-3) * 1e-12
 

@@ -46,7 +46,10 @@ enum {
   PDA_FAMILY_EULER3D = 3,              /* euler3d.hpp:65-68                  */
   PDA_FAMILY_SWE2D = 4,                /* swe2d.hpp:65-68                    */
   PDA_FAMILY_DIFFUSION_REACTION2D = 5, /* diffusion_reaction2d.hpp           */
-  PDA_FAMILY_ADVECTION_DIFFUSION2D = 6 /* advection_diffusion2d.hpp (Burgers)*/
+  PDA_FAMILY_ADVECTION_DIFFUSION2D = 6, /* advection_diffusion2d.hpp:66-69 (Burgers) */
+  PDA_FAMILY_ADVECTION_DIFFUSION_REACTION2D = 7, /* advection_diffusion_reaction2d.hpp:60-62 */
+  PDA_FAMILY_ADVECTION1D = 8,          /* advection1d.hpp:64-66              */
+  PDA_FAMILY_DIFFUSION_REACTION1D = 9  /* diffusion_reaction1d.hpp:64-67     */
 };
 /* problem ids inside a family keep the reference's enumerator order */
 enum { PDA_EULER1D_PERIODIC_SMOOTH = 0, PDA_EULER1D_SOD = 1, PDA_EULER1D_LAX = 2, PDA_EULER1D_SHU_OSHER = 3 };
@@ -59,6 +62,9 @@ enum { PDA_EULER3D_PERIODIC_SMOOTH = 0, PDA_EULER3D_SEDOV_SYMMETRY = 1 };
 enum { PDA_SWE2D_SLIP_WALL = 0, PDA_SWE2D_CUSTOM_BCS = 1 };
 enum { PDA_DIFFREAC2D_PROBLEM_A = 0, PDA_DIFFREAC2D_GRAY_SCOTT = 1 };
 enum { PDA_ADVDIFF2D_BURGERS_PERIODIC = 0, PDA_ADVDIFF2D_BURGERS_OUTFLOW = 1 };
+enum { PDA_ADVDIFFREAC2D_PROBLEM_A = 0 };
+enum { PDA_ADVECTION1D_PERIODIC_LINEAR = 0 };
+enum { PDA_DIFFREAC1D_PROBLEM_A = 0 };
 /* InviscidFluxReconstruction (schemes_info.hpp:57-66) */
 enum { PDA_FIRST_ORDER = 0, PDA_WENO3 = 1, PDA_WENO5 = 2 };
 /* ghost sides, in the reference's graph-column order (GhostRelativeLocation, ghost_relative_locations.hpp) */
@@ -123,7 +129,20 @@ pda_status pda_mesh_stencil_gids(pda_mesh m, int32_t* gids);
  * Unlike the reference, an incompatible mesh stencil / scheme pair is rejected (schemes_info.hpp:94-102). */
 pda_status pda_problem_create(pda_mesh mesh, int family, int problem_id, int recon, int ic_flag, int nparams,
                               const char* const* names, const double* values, int device, pda_problem* out);
-/* custom BCs (Swe2d::CustomBCs, Euler2d Riemann/NormalShock custom-BC overloads): one device-expressible rule per side.
+/* Parameter names per family ({name: value} map of the reference, or its positional factory arguments):
+ *   Euler2d   gamma + impl/euler_2d_parametrization_helpers.hpp names;  Swe2d  gravity, coriolis, pulse*;
+ *   GrayScott Du, Dv, F, k;  DiffusionReaction{1d,2d}::ProblemA  diffusion, reaction (create_diffusion_reaction_*_problem_A_eigen);
+ *   AdvectionDiffusion2d  diffusion, pulseMagnitude, pulseSpread, pulseX, pulseY (advection_diffusion_2d_parametrization_helpers.hpp);
+ *   AdvectionDiffusionReaction2d  ux, uy, diffusion, sigma (create_advdiffreac_2d_problem_A_eigen);
+ *   Advection1d  velocity (create_linear_advection_1d_problem_eigen), ic_flag 1..4. */
+
+/* Source term of the ProblemA families (the reference takes a host functor f(x[,y],t), diffusion_reaction1d.hpp:70-79,
+ * diffusion_reaction2d.hpp:228-237, advection_diffusion_reaction2d.hpp:70-75): the binding evaluates its functor at
+ * the current time for every SAMPLE cell and hands over the table (sample_mesh_size doubles, host pointer).  Without
+ * a call the reference's default functors are tabulated by the library. */
+pda_status pda_problem_set_source(pda_problem p, const double* values);
+
+/* custom BCs (Swe2d::CustomBCs, Euler2d Riemann/NormalShock and AdvectionDiffusion2d custom-BC overloads): one device-expressible rule per side.
  * values: ndpc doubles (Dirichlet ghost state); ignored otherwise.  (custom_bcs_functions.hpp:60-164) */
 pda_status pda_problem_set_bc(pda_problem p, int side, int kind, const double* values);
 pda_status pda_problem_free(pda_problem p);

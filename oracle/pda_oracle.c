@@ -27,7 +27,8 @@
 #define M_PI 3.14159265358979323846
 #endif
 
-enum { F_EULER1D = 1, F_EULER2D = 2, F_EULER3D = 3, F_SWE2D = 4, F_DIFFREAC2D = 5 };
+enum { F_EULER1D = 1, F_EULER2D = 2, F_EULER3D = 3, F_SWE2D = 4, F_DIFFREAC2D = 5, F_ADVDIFF2D = 6,
+       F_ADVDIFFREAC2D = 7, F_ADVECTION1D = 8, F_DIFFREAC1D = 9 };
 enum { E2_PERIODIC = 0, E2_KH = 1, E2_SEDOV_FULL = 2, E2_SEDOV_SYM = 3, E2_RIEMANN = 4, E2_NORMAL_SHOCK = 5,
        E2_DMR = 6, E2_CROSS_SHOCK = 7, E2_NEUMANN = 8 };
 
@@ -58,8 +59,9 @@ struct or_problem_s {
   int family, prob, recon, icFlag, ndpc, S;
   double gamma;
   double icp[10];  /* euler2d: euler_2d_parametrization_helpers.hpp:59-72 ; swe: swe_2d_parametrization_helpers.hpp */
-  double php[2];
+  double php[4];   /* swe: gravity, coriolis; burgers: diffusion; ADR: ux, uy, D, sigma; adv1d: velocity; ProblemA: D, k */
   double gs[4];
+  double* src;     /* per-sample-row source table (ProblemA families) */
   double* ghost[6];     /* left, front, right, back, bottom, top : [nNearBd][gstride] */
   int gstride;
   int32_t *rowptr, *colidx;
@@ -667,7 +669,7 @@ static void build_pattern(or_problem* p) {
     if (pass == 1) p->colidx = (int32_t*)malloc(sizeof(int32_t) * (size_t)(nnz > 0 ? nnz : 1));
     long long acc = 0;
     for (int32_t r = 0; r < m->nSample; ++r) {
-      const int first = (p->family == F_DIFFREAC2D) || isNb[r];
+      const int first = (p->family == F_DIFFREAC2D) || (p->family == F_DIFFREAC1D) || (isNb[r] && p->family != F_ADVECTION1D);
       const int ncand = first ? nnbFirst : nnbInner;
       int cnt = 0;
       ids[cnt++] = G(m, r, 0);
@@ -704,7 +706,13 @@ static or_problem* finish_create(or_problem* p, int family, int probEnum, int re
     case F_EULER2D: p->ndpc = 4; memcpy(p->icp, e2def, sizeof e2def); break;
     case F_EULER3D: p->ndpc = 5; break;
     case F_SWE2D: p->ndpc = 3; memcpy(p->icp, swedef, sizeof swedef); p->php[0] = 9.8; p->php[1] = -3; break;
-    case F_DIFFREAC2D: p->ndpc = 2; p->S = 3; break;
+    case F_DIFFREAC2D: p->ndpc = (probEnum == 1) ? 2 : 1; p->S = 3; p->php[0] = 0.01; p->php[1] = 0.01; break;
+    case F_DIFFREAC1D: p->ndpc = 1; p->S = 3; p->php[0] = 0.01; p->php[1] = 0.01; break;
+    case F_ADVDIFF2D: /* advection_diffusion_2d_parametrization_helpers.hpp:69-82 */
+      p->ndpc = 2; p->php[0] = 0.00001; p->icp[0] = 0.5; p->icp[1] = 0.15; p->icp[2] = 0.0; p->icp[3] = -0.2; break;
+    case F_ADVDIFFREAC2D: /* advection_diffusion_reaction2d.hpp:124-128 */
+      p->ndpc = 1; p->php[0] = 0.5 * cos(M_PI / 3); p->php[1] = 0.5 * sin(M_PI / 3); p->php[2] = 0.001; p->php[3] = 1.0; break;
+    case F_ADVECTION1D: p->ndpc = 1; p->php[0] = 1.0; break; /* advection1d.hpp:88-92 */
     default: snprintf(g_err, sizeof g_err, "oracle: unknown family %d", family); or_destroy(p); return NULL;
   }
   for (int i = 0; i < nParams; ++i) {
@@ -718,9 +726,21 @@ static or_problem* finish_create(or_problem* p, int family, int probEnum, int re
       if (!strcmp(names[i], "coriolis")) { p->php[1] = values[i]; continue; }
       idx = swe_ic_index(icFlag, names[i]);
       if (idx >= 0) p->icp[idx] = values[i];
-    } else if (family == F_DIFFREAC2D) {
+    } else if (family == F_DIFFREAC2D && probEnum == 1) {
       static const char* gn[4] = {"Du", "Dv", "F", "k"};
       for (int k = 0; k < 4; ++k) if (!strcmp(names[i], gn[k])) { p->gs[k] = values[i]; idx = k; }
+    } else if (family == F_DIFFREAC2D || family == F_DIFFREAC1D) {
+      static const char* pn[2] = {"diffusion", "reaction"};
+      for (int k = 0; k < 2; ++k) if (!strcmp(names[i], pn[k])) { p->php[k] = values[i]; idx = k; }
+    } else if (family == F_ADVDIFF2D) {
+      static const char* bn[4] = {"pulseMagnitude", "pulseSpread", "pulseX", "pulseY"};
+      if (!strcmp(names[i], "diffusion")) { p->php[0] = values[i]; continue; }
+      for (int k = 0; k < 4; ++k) if (!strcmp(names[i], bn[k])) { p->icp[k] = values[i]; idx = k; }
+    } else if (family == F_ADVDIFFREAC2D) {
+      static const char* an[4] = {"ux", "uy", "diffusion", "sigma"};
+      for (int k = 0; k < 4; ++k) if (!strcmp(names[i], an[k])) { p->php[k] = values[i]; idx = k; }
+    } else if (family == F_ADVECTION1D) {
+      if (!strcmp(names[i], "velocity")) { p->php[0] = values[i]; idx = 0; }
     }
     if (idx < 0) { snprintf(g_err, sizeof g_err, "oracle: invalid parameter %s", names[i]); or_destroy(p); return NULL; }
   }
@@ -731,8 +751,24 @@ static or_problem* finish_create(or_problem* p, int family, int probEnum, int re
     p->ghost[s] = (double*)malloc(sizeof(double) * (size_t)(m->nNearBd > 0 ? m->nNearBd : 1) * p->gstride);
     for (size_t i = 0; i < (size_t)(m->nNearBd > 0 ? m->nNearBd : 1) * p->gstride; ++i) p->ghost[s][i] = 2.2250738585072014e-308;
   }
+  /* default source functors tabulated per sample row: diffusion_reaction1d.hpp:86-97, diffusion_reaction2d.hpp:103-114,
+   * advection_diffusion_reaction2d.hpp:87-97 (f = 1) */
+  if (family == F_DIFFREAC1D || family == F_ADVDIFFREAC2D || (family == F_DIFFREAC2D && probEnum == 0)) {
+    p->src = (double*)malloc(sizeof(double) * (size_t)(m->nSample > 0 ? m->nSample : 1));
+    for (int32_t r = 0; r < m->nSample; ++r) {
+      const int32_t c = G(m, r, 0);
+      const double x = m->x[c], y = m->y[c];
+      if (family == F_DIFFREAC1D) p->src[r] = sin(M_PI * x) * x * x * 4. * cos(4. * M_PI * x);
+      else if (family == F_DIFFREAC2D) p->src[r] = sin(M_PI * x * (y - 0.2)) * 4. * sin(4. * M_PI * y * x);
+      else p->src[r] = 1.0;
+    }
+  }
   build_pattern(p);
   return p;
+}
+
+void or_set_source(or_problem* p, const double* values) {
+  if (p->src) memcpy(p->src, values, sizeof(double) * (size_t)p->m.nSample);
 }
 
 or_problem* or_create(const char* meshDir, int family, int probEnum, int recon, int icFlag, int nParams,
@@ -767,7 +803,7 @@ void or_destroy(or_problem* p) {
   if (!p) return;
   free(p->m.x); free(p->m.y); free(p->m.z); free(p->m.graph); free(p->m.rowsInner); free(p->m.rowsNearBd);
   for (int s = 0; s < 6; ++s) free(p->ghost[s]);
-  free(p->rowptr); free(p->colidx);
+  free(p->rowptr); free(p->colidx); free(p->src);
   free(p);
 }
 
@@ -925,6 +961,38 @@ void or_ic(or_problem* p, double* U) {
     }
     return;
   }
+  if (p->family == F_DIFFREAC1D || p->family == F_ADVDIFFREAC2D || (p->family == F_DIFFREAC2D && p->prob == 0)) {
+    /* zero state: diffusion_reaction_1d_prob_class.hpp:110-118, diffusion_reaction_2d_prob_class.hpp:144-149,
+     * advection_diffusion_reaction_2d_initial_condition.hpp:57-61 */
+    for (int32_t i = 0; i < n; ++i) U[i] = 0.;
+    return;
+  }
+  if (p->family == F_ADVDIFF2D) { /* advection_diffusion_2d_initial_condition.hpp:54-78 */
+    for (int32_t i = 0; i < n; ++i) {
+      const double dx = m->x[i] - p->icp[2], dy = m->y[i] - p->icp[3];
+      const double dxSq = dx * dx, dySq = dy * dy;
+      U[2 * (size_t)i] = p->icp[0] * exp(-(dxSq + dySq) / p->icp[1]);
+      U[2 * (size_t)i + 1] = p->icp[0] * exp(-(dxSq + dySq) / p->icp[1]);
+    }
+    return;
+  }
+  if (p->family == F_ADVECTION1D) { /* advection_1d_prob_class.hpp:111-156 */
+    for (int32_t i = 0; i < n; ++i) {
+      const double x = m->x[i];
+      if (p->icFlag == 1) U[i] = sin(M_PI * x);
+      else if (p->icFlag == 2) {
+        const double dx1Sq = (x - 1.2) * (x - 1.2), dx2Sq = (x - 2.5) * (x - 2.5);
+        U[i] = 0.8 * exp(-200.0 * dx1Sq / 16.0) + exp(-100.0 * dx2Sq / 36.0);
+      } else if (p->icFlag == 3) {
+        const double delta = 0.5 * 0.5;
+        const double dx1Sq = (x - 2.) * (x - 2.), dx2Sq = (x - 3.0) * (x - 3.0);
+        U[i] = exp(-dx1Sq / delta) + 0.5 * exp(-dx2Sq / delta);
+      } else {
+        U[i] = tanh(8. * (x - 1.)) - tanh(8. * (x - 3.));
+      }
+    }
+    return;
+  }
   if (p->family == F_DIFFREAC2D) { /* diffusion_reaction_2d_prob_class.hpp:141-178 */
     for (int32_t i = 0; i < n; ++i) {
       const int in = fabs(m->x[i]) < 0.1 && fabs(m->y[i]) < 0.1;
@@ -988,6 +1056,10 @@ static void fill_ghosts(or_problem* p, const double* U, double t) {
     if (p->prob == 1) { style = 1; neg[0] = 1; neg[3] = 2; neg[4] = 3; }
   } else if (p->family == F_SWE2D) { /* swe_2d_prob_class.hpp:394-418 */
     style = 2; neg[0] = 1; neg[2] = 1; neg[1] = 2; neg[3] = 2;
+  } else if (p->family == F_ADVDIFF2D) { /* advection_diffusion_2d_prob_class.hpp:296-315: outflow only */
+    if (p->prob == 1) style = 2;
+  } else if (p->family == F_ADVDIFFREAC2D) {
+    style = 1;
   }
   if (!style) return;
 
@@ -1037,6 +1109,12 @@ static void fill_ghosts(or_problem* p, const double* U, double t) {
             v[3] = U[(size_t)src * 4 + 3];
             ghost_const(p, side, it, L, v);
           } else ghost_copy(p, side, it, L, U, src, -1);
+        } else if (p->family == F_ADVDIFF2D) { /* advection_diffusion_2d_ghost_filler_outflow.hpp:102-235 */
+          const double zero2[2] = {0., 0.};
+          if (side == 0 || side == 3) ghost_const(p, side, it, L, zero2);
+          else ghost_copy(p, side, it, L, U, src, -1);
+        } else if (p->family == F_ADVDIFFREAC2D) { /* advection_diffusion_reaction_2d_ghost_filler_problemA.hpp:92-147 */
+          ghost_copy(p, side, it, L, U, src, 0);
         } else {
           ghost_copy(p, side, it, L, U, src, neg[side]);
         }
@@ -1052,15 +1130,62 @@ static double sval(const or_problem* p, const double* U, int32_t cell, int side,
   return U[(size_t)cell * p->ndpc + dof];
 }
 
+/* advection_diffusion_2d_flux_functions.hpp:54-75 */
+static void burgers_flux(double* F, const double* qL, const double* qR, const double* n) {
+  const double fourInv = 1. / 4.;
+  const double alpha_0 = fmax(fabs(qL[0]), fabs(qR[0]));
+  const double alpha_1 = fmax(fabs(qL[1]), fabs(qR[1]));
+  F[0] = alpha_0 * (qL[0] - qR[0]);
+  F[0] += n[0] * (qL[0] * qL[0] + qR[0] * qR[0]);
+  F[0] += n[1] * (qL[0] * qL[1] + qR[0] * qR[1]);
+  F[0] *= fourInv;
+  F[1] = alpha_1 * (qL[1] - qR[1]);
+  F[1] += n[0] * (qL[0] * qL[1] + qR[0] * qR[1]);
+  F[1] += n[1] * (qL[1] * qL[1] + qR[1] * qR[1]);
+  F[1] *= fourInv;
+}
+/* advection_diffusion_2d_flux_functions.hpp:77-114; J row-major 2x2 */
+static void burgers_flux_jac(double* JL, double* JR, const double* qL, const double* qR, const double* n) {
+  const double two = 2., fourInv = 1. / 4.;
+  if (fabs(qL[0]) > fabs(qR[0])) {
+    JL[0] = (two * qL[0] - qR[0]) * copysign(1, qL[0]) + n[0] * two * qL[0] + n[1] * qL[1];
+    JR[0] = n[0] * two * qR[0] + n[1] * qR[1] - fabs(qL[0]);
+  } else {
+    JL[0] = n[0] * two * qL[0] + n[1] * qL[1] + fabs(qR[0]);
+    JR[0] = (qL[0] - two * qR[0]) * copysign(1, qR[0]) + n[0] * two * qR[0] + n[1] * qR[1];
+  }
+  JL[0] *= fourInv; JR[0] *= fourInv;
+  if (fabs(qL[1]) > fabs(qR[1])) {
+    JL[3] = (two * qL[1] - qR[1]) * copysign(1, qL[1]) + n[0] * qL[0] + n[1] * two * qL[1];
+    JR[3] = n[0] * qR[0] + n[1] * two * qR[1] - fabs(qL[1]);
+  } else {
+    JL[3] = n[0] * qL[0] + n[1] * two * qL[1] + fabs(qR[1]);
+    JR[3] = (qL[1] - two * qR[1]) * copysign(1, qR[1]) + n[0] * qR[0] + n[1] * two * qR[1];
+  }
+  JL[3] *= fourInv; JR[3] *= fourInv;
+  JL[1] = n[1] * qL[0] * fourInv; JL[2] = n[0] * qL[1] * fourInv;
+  JR[1] = n[1] * qR[0] * fourInv; JR[2] = n[0] * qR[1] * fourInv;
+}
+
+/* advection velocity of a scalar family along `axis` (advection_1d_mixins.hpp:79-94,
+ * advection_diffusion_reaction_2d_flux_mixin.hpp: F = uNeg * a, dF/duNeg = a, dF/duPos = 0) */
+static double adv_vel(const or_problem* p, int axis) {
+  return (p->family == F_ADVECTION1D) ? p->php[0] : p->php[axis - 1];
+}
+
 static void flux(const or_problem* p, int axis, double* F, const double* qL, const double* qR) {
   double n[3] = {0, 0, 0};
   n[axis - 1] = 1.0;
+  if (p->family == F_ADVDIFF2D) { burgers_flux(F, qL, qR, n); return; }
+  if (p->family == F_ADVECTION1D || p->family == F_ADVDIFFREAC2D) { F[0] = qL[0] * adv_vel(p, axis); return; }
   if (p->family == F_SWE2D) or_swe_flux(F, qL, qR, n, p->php[0]);
   else or_euler_flux(p->ndpc, F, qL, qR, n, p->gamma);
 }
 static void flux_jac(const or_problem* p, int axis, double* JL, double* JR, const double* qL, const double* qR) {
   double n[3] = {0, 0, 0};
   n[axis - 1] = 1.0;
+  if (p->family == F_ADVDIFF2D) { burgers_flux_jac(JL, JR, qL, qR, n); return; }
+  if (p->family == F_ADVECTION1D || p->family == F_ADVDIFFREAC2D) { JL[0] = adv_vel(p, axis); JR[0] = 0.; return; }
   if (p->family == F_SWE2D) or_swe_flux_jac(JL, JR, qL, qR, n, p->php[0]);
   else or_euler_flux_jac(p->ndpc, JL, JR, qL, qR, n, p->gamma);
 }
@@ -1116,6 +1241,11 @@ static void jac_factors(const or_problem* p, int32_t row, int axis, double* f) {
   for (int d = 0; d < N; ++d) f[d] = 1.;
   const int sm = side_minus(axis);
   if (p->family == F_SWE2D) { f[axis] = -1.; return; }
+  if (p->family == F_ADVDIFFREAC2D) { f[0] = -1.; return; } /* advection_diffusion_reaction_2d_prob_class.hpp:634-635 */
+  if (p->family == F_ADVDIFF2D) { /* advection_diffusion_2d_prob_class.hpp:1119-1155 */
+    if (has_bd(m, row, sm)) for (int d = 0; d < N; ++d) f[d] = 0.;
+    return;
+  }
   if (p->family == F_EULER3D) { if (p->prob == 1 && has_bd(m, row, sm)) f[axis] = -1.; return; }
   if (p->family != F_EULER2D) return;
   const double myX = m->x[G(m, row, 0)];
@@ -1152,8 +1282,10 @@ static void eval_cell(const or_problem* p, const double* U, int32_t row, int32_t
     double q[7];
     int32_t cells[7];
     const int wantGrad = (Jv != NULL) && !nearBd && S > 3;
+    double s3[5][3]; /* first-layer stencil (l0, self, r0) per dof: the diffusion term's operands */
     for (int d = 0; d < N; ++d) {
       gather(p, U, row, gRow, axis, S, d, q, cells);
+      s3[d][0] = q[(S - 1) / 2 - 1]; s3[d][1] = q[(S - 1) / 2]; s3[d][2] = q[(S - 1) / 2 + 1];
       reconstruct(S, q, &lN[d], &lP[d], &rN[d], &rP[d], wantGrad ? gLN[d] : NULL, wantGrad ? gLP[d] : NULL,
                   wantGrad ? gRN[d] : NULL, wantGrad ? gRP[d] : NULL);
     }
@@ -1161,6 +1293,13 @@ static void eval_cell(const or_problem* p, const double* U, int32_t row, int32_t
     flux(p, axis, FL, lN, lP);
     flux(p, axis, FR, rN, rP);
     if (V) for (int d = 0; d < N; ++d) V[vIdx + d] += hInv * (FL[d] - FR[d]);
+    /* near-boundary rows of the advection-diffusion families add the axis' diffusion right after its flux balance
+     * (advection_diffusion_2d_prob_class.hpp:729-753,959-1000; advection_diffusion_reaction_2d_prob_class.hpp:667-683) */
+    if (V && nearBd && (p->family == F_ADVDIFF2D || p->family == F_ADVDIFFREAC2D)) {
+      const double D = (p->family == F_ADVDIFF2D) ? p->php[0] : p->php[2];
+      const double diffInvSq = D * (hInv * hInv);
+      for (int d = 0; d < N; ++d) V[vIdx + d] += diffInvSq * (s3[d][2] - 2. * s3[d][1] + s3[d][0]);
+    }
     if (!Jv) continue;
 
     double JLN[25], JLP[25], JRN[25], JRP[25];
@@ -1208,6 +1347,52 @@ static void eval_cell(const or_problem* p, const double* U, int32_t row, int32_t
       if (r0 == -1) for (int k = 0; k < N; ++k) for (int j = 0; j < N; ++j) jadd(p, Jv, vIdx + k, selfCol + j, (fac[j] * -JRP[k * N + j]) * hInv);
     }
   }
+  if (p->family == F_ADVDIFF2D || p->family == F_ADVDIFFREAC2D) {
+    /* diffusion (+ source, reaction for ADR): advection_diffusion_2d_prob_class.hpp:755-792,1157-1201;
+     * advection_diffusion_reaction_2d_prob_class.hpp:485-512,685-721,1057-1085 */
+    const int adr = p->family == F_ADVDIFFREAC2D;
+    const double D = adr ? p->php[2] : p->php[0];
+    const double two = 2.;
+    const double dxInvSq = m->dInv[0] * m->dInv[0], dyInvSq = m->dInv[1] * m->dInv[1];
+    const double diffDxInvSq = D * dxInvSq, diffDyInvSq = D * dyInvSq;
+    const int32_t iL = G(m, row, 1), iF = G(m, row, 2), iR = G(m, row, 3), iB = G(m, row, 4);
+    if (!nearBd) {
+      for (int d = 0; d < N; ++d) {
+        if (V) {
+          V[vIdx + d] += diffDxInvSq * (U[(size_t)iR * N + d] - two * U[selfCol + d] + U[(size_t)iL * N + d]);
+          V[vIdx + d] += diffDyInvSq * (U[(size_t)iF * N + d] - two * U[selfCol + d] + U[(size_t)iB * N + d]);
+        }
+        if (Jv) {
+          jadd(p, Jv, vIdx + d, selfCol + d, -two * diffDxInvSq - two * diffDyInvSq);
+          jadd(p, Jv, vIdx + d, iL * N + d, diffDxInvSq);
+          jadd(p, Jv, vIdx + d, iF * N + d, diffDyInvSq);
+          jadd(p, Jv, vIdx + d, iR * N + d, diffDxInvSq);
+          jadd(p, Jv, vIdx + d, iB * N + d, diffDyInvSq);
+        }
+      }
+      if (adr) {
+        if (V) { V[vIdx] += p->src[row]; V[vIdx] -= p->php[3] * U[selfCol]; }
+        if (Jv) jadd(p, Jv, vIdx, selfCol, -p->php[3]);
+      }
+    } else {
+      if (adr && V) { V[vIdx] += p->src[row]; V[vIdx] -= p->php[3] * U[selfCol]; }
+      if (Jv) {
+        const int32_t nb[4] = {iL, iF, iR, iB};
+        const double dd[4] = {diffDxInvSq, diffDyInvSq, diffDxInvSq, diffDyInvSq};
+        if (adr) {
+          double selfValue = -two * diffDxInvSq - two * diffDyInvSq - p->php[3];
+          for (int k = 0; k < 4; ++k) { if (nb[k] != -1) jadd(p, Jv, vIdx, nb[k], dd[k]); else selfValue += -dd[k]; }
+          jadd(p, Jv, vIdx, selfCol, selfValue);
+        } else {
+          for (int d = 0; d < N; ++d) jadd(p, Jv, vIdx + d, selfCol + d, -two * diffDxInvSq - two * diffDyInvSq);
+          for (int k = 0; k < 4; ++k)
+            for (int d = 0; d < N; ++d) {
+              if (nb[k] != -1) jadd(p, Jv, vIdx + d, nb[k] * N + d, dd[k]); else jadd(p, Jv, vIdx + d, selfCol + d, -dd[k]);
+            }
+        }
+      }
+    }
+  }
   if (p->family == F_SWE2D) { /* swe_2d_prob_class.hpp:984-1012 */
     const double f = p->php[1];
     const double* u = U + selfCol;
@@ -1251,13 +1436,72 @@ static void gray_scott(const or_problem* p, const double* U, double* V, double* 
   }
 }
 
+/* DiffusionReaction{1d,2d}::ProblemA: diffusion_reaction_1d_prob_class.hpp:211-302,
+ * diffusion_reaction_2d_prob_class.hpp:306-456.  Ghost of a missing neighbour = -s(self)
+ * (diffusion_reaction_1d_ghost_filler.hpp:85-94, diffusion_reaction_2d_ghost_filler.hpp:88-103). */
+static void diffreac_problem_a(const or_problem* p, const double* U, double* V, double* Jv) {
+  const or_mesh* m = &p->m;
+  const double two = 2., three = 3.;
+  const double dxInvSq = m->dInv[0] * m->dInv[0], dyInvSq = m->dInv[1] * m->dInv[1];
+  const double D = p->php[0], kR = p->php[1];
+  const double twoReacCoeff = kR * two;
+  const double diffDxInvSq = D * dxInvSq, diffDyInvSq = D * dyInvSq;
+  char* isNb = (char*)calloc((size_t)m->nSample + 1, 1);
+  for (int32_t i = 0; i < m->nNearBd; ++i) isNb[m->rowsNearBd[i]] = 1;
+  for (int32_t smPt = 0; smPt < m->nSample; ++smPt) {
+    const int32_t uIndex = G(m, smPt, 0);
+    const double u = U[uIndex];
+    if (m->dim == 1) {
+      const int32_t iL = G(m, smPt, 1), iR = G(m, smPt, 2);
+      const double sL = (iL != -1) ? U[iL] : -u, sR = (iR != -1) ? U[iR] : -u;
+      if (V) {
+        V[smPt] = p->src[smPt];
+        V[smPt] += kR * u * u;
+        const double fd = sR - two * u + sL;
+        V[smPt] += dxInvSq * D * fd;
+      }
+      if (Jv) {
+        if (isNb[smPt]) {
+          jadd(p, Jv, smPt, uIndex, -three * diffDxInvSq + twoReacCoeff * u);
+          if (iL != -1) jadd(p, Jv, smPt, iL, diffDxInvSq);
+          if (iR != -1) jadd(p, Jv, smPt, iR, diffDxInvSq);
+        } else {
+          jadd(p, Jv, smPt, uIndex, -two * diffDxInvSq + twoReacCoeff * u);
+          jadd(p, Jv, smPt, iL, diffDxInvSq);
+          jadd(p, Jv, smPt, iR, diffDxInvSq);
+        }
+      }
+    } else {
+      const int32_t iL = G(m, smPt, 1), iF = G(m, smPt, 2), iR = G(m, smPt, 3), iB = G(m, smPt, 4);
+      const double sL = (iL != -1) ? U[iL] : -u, sR = (iR != -1) ? U[iR] : -u;
+      const double sB = (iB != -1) ? U[iB] : -u, sF = (iF != -1) ? U[iF] : -u;
+      if (V) {
+        V[smPt] = p->src[smPt];
+        V[smPt] += kR * u * u;
+        V[smPt] += dxInvSq * D * (sR - two * u + sL);
+        V[smPt] += dyInvSq * D * (sF - two * u + sB);
+      }
+      if (Jv) {
+        double selfValue = -two * diffDxInvSq - two * diffDyInvSq + twoReacCoeff * u;
+        if (iL != -1) jadd(p, Jv, smPt, iL, diffDxInvSq); else selfValue += -diffDxInvSq;
+        if (iF != -1) jadd(p, Jv, smPt, iF, diffDyInvSq); else selfValue += -diffDyInvSq;
+        if (iR != -1) jadd(p, Jv, smPt, iR, diffDxInvSq); else selfValue += -diffDxInvSq;
+        if (iB != -1) jadd(p, Jv, smPt, iB, diffDyInvSq); else selfValue += -diffDyInvSq;
+        jadd(p, Jv, smPt, uIndex, selfValue);
+      }
+    }
+  }
+  free(isNb);
+}
+
 /* velocityAndOptionalJacobian: euler_2d_prob_class.hpp:241-310 (zero V, zero J, ghosts, near-bd rows, inner rows) */
 static int evaluate(or_problem* p, const double* U, double t, double* V, double* Jv) {
   const or_mesh* m = &p->m;
   const int N = p->ndpc;
   if (V) memset(V, 0, sizeof(double) * (size_t)m->nSample * N);
   if (Jv) memset(Jv, 0, sizeof(double) * (size_t)p->nnz);
-  if (p->family == F_DIFFREAC2D) { gray_scott(p, U, V, Jv); return 0; }
+  if (p->family == F_DIFFREAC2D && p->prob == 1) { gray_scott(p, U, V, Jv); return 0; }
+  if (p->family == F_DIFFREAC2D || p->family == F_DIFFREAC1D) { diffreac_problem_a(p, U, V, Jv); return 0; }
   fill_ghosts(p, U, t);
 #ifdef _OPENMP
 #pragma omp parallel

@@ -23,6 +23,8 @@ or_problem* or_create_from_arrays(int dim, int stencil, int32_t nSample, int32_t
                                   int family, int probEnum, int recon, int icFlag, int nParams,
                                   const char* const* names, const double* values);
 void or_destroy(or_problem* p);
+/* replaces the per-sample-row source table of a ProblemA family (nSample doubles) */
+void or_set_source(or_problem* p, const double* values);
 /* what: 0 dim, 1 stencilSize, 2 sampleMeshSize, 3 stencilMeshSize, 4 graph cols, 5 numInner, 6 numNearBd,
  *       7 isFullyPeriodic, 8 ndpc, 9 nDofStencil, 10 nDofSample, 11 nnz */
 long long or_query(or_problem* p, int what);

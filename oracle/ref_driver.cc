@@ -11,6 +11,10 @@
 //   load_cellcentered_uniform_mesh_eigen           include/pressiodemoapps/mesh.hpp:87-91
 //   create_problem_eigen (Euler1d/2d/3d, Swe2d)    euler1d.hpp:82-99 euler2d.hpp:88-186 euler3d.hpp:80-122 swe2d.hpp:134-185
 //   create_gray_scott_2d_problem_eigen             diffusion_reaction2d.hpp:259-285
+//   create_diffusion_reaction_{1d,2d}_problem_A_eigen  diffusion_reaction1d.hpp:128-212 diffusion_reaction2d.hpp:186-257
+//   create_problem_eigen (AdvectionDiffusion2d)    advection_diffusion2d.hpp:79-152
+//   create_advdiffreac_2d_problem_A_eigen          advection_diffusion_reaction2d.hpp:140-160
+//   create_linear_advection_1d_problem_eigen       advection1d.hpp:133-152
 //   rightHandSide / rightHandSideAndJacobian / applyJacobian   adapter_cpp.hpp:162-259
 #define PRESSIODEMOAPPS_ENABLE_TESTS 1   // exposes viewGhost*() (euler_2d_prob_class.hpp:205-210)
 #include "pressiodemoapps/euler1d.hpp"
@@ -19,6 +23,13 @@
 #include "pressiodemoapps/swe2d.hpp"
 #include "pressiodemoapps/diffusion_reaction2d.hpp"
 #include "pressiodemoapps/advection_diffusion2d.hpp"
+// the reference's ADR class does not compile with OpenMP (`#pragma omp for` followed by a declaration,
+// advection_diffusion_reaction_2d_prob_class.hpp:490-493): the OpenMP timing build leaves it out
+#ifndef PDA_REFDRV_NO_ADR2D
+#include "pressiodemoapps/advection_diffusion_reaction2d.hpp"
+#endif
+#include "pressiodemoapps/advection1d.hpp"
+#include "pressiodemoapps/diffusion_reaction1d.hpp"
 
 #include <chrono>
 #include <cstring>
@@ -118,8 +129,8 @@ int pdaref_num_threads() {
 #endif
 }
 
-// family: 1 Euler1d, 2 Euler2d, 3 Euler3d, 4 Swe2d, 5 DiffusionReaction2d (probEnum 1 = GrayScott),
-//         6 AdvectionDiffusion2d (Burgers)
+// family: 1 Euler1d, 2 Euler2d, 3 Euler3d, 4 Swe2d, 5 DiffusionReaction2d (0 ProblemA, 1 GrayScott),
+//         6 AdvectionDiffusion2d (Burgers), 7 AdvectionDiffusionReaction2d, 8 Advection1d, 9 DiffusionReaction1d
 void* pdaref_create(const char* meshDir, int family, int probEnum, int reconEnum, int icFlag,
                     int nParams, const char* const* names, const double* values) {
   try {
@@ -157,7 +168,18 @@ void* pdaref_create(const char* meshDir, int family, int probEnum, int reconEnum
         break;
       }
       case 5: {
-        if (probEnum != 1) throw std::runtime_error("ref_driver: only GrayScott wired for DiffusionReaction2d");
+        if (probEnum == 0) {
+          const double D = up.count("diffusion") ? up["diffusion"] : 0.01;
+          const double k = up.count("reaction") ? up["reaction"] : 0.01;
+          const auto visc = pda::ViscousFluxReconstruction::FirstOrder;
+          if (up.count("testSource")) {   // time-dependent analytic source (parity of pda_problem_set_source)
+            auto f = [](const double& x, const double& y, const double& t, double& v) { v = std::cos(x * y + t); };
+            h->prob = hold(pda::create_diffusion_reaction_2d_problem_A_eigen(m, visc, f, D, k));
+          } else {
+            h->prob = hold(pda::create_diffusion_reaction_2d_problem_A_eigen(m, visc, D, k));
+          }
+          break;
+        }
         double Du = 0.0002, Dv = 0.00005, F = 0.042, k = 0.062;
         if (up.count("Du")) Du = up["Du"];
         if (up.count("Dv")) Dv = up["Dv"];
@@ -168,7 +190,39 @@ void* pdaref_create(const char* meshDir, int family, int probEnum, int reconEnum
       }
       case 6: {
         auto pe = static_cast<pda::AdvectionDiffusion2d>(probEnum);
-        h->prob = hold(pda::create_problem_eigen(m, pe, recon(reconEnum), pda::ViscousFluxReconstruction::FirstOrder));
+        const auto visc = pda::ViscousFluxReconstruction::FirstOrder;
+        if (nParams > 0) h->prob = hold(pda::create_problem_eigen(m, pe, recon(reconEnum), visc, up));
+        else h->prob = hold(pda::create_problem_eigen(m, pe, recon(reconEnum), visc));
+        break;
+      }
+#ifndef PDA_REFDRV_NO_ADR2D
+      case 7: {
+        if (nParams > 0) {
+          const double ux = up.count("ux") ? up["ux"] : 0.5 * std::cos(M_PI / 3);
+          const double uy = up.count("uy") ? up["uy"] : 0.5 * std::sin(M_PI / 3);
+          const double D = up.count("diffusion") ? up["diffusion"] : 0.001;
+          const double sg = up.count("sigma") ? up["sigma"] : 1.0;
+          h->prob = hold(pda::create_advdiffreac_2d_problem_A_eigen(m, recon(reconEnum), ux, uy, D, sg));
+        } else {
+          h->prob = hold(pda::create_problem_eigen(m, pda::AdvectionDiffusionReaction2d::ProblemA, recon(reconEnum)));
+        }
+        break;
+      }
+#endif
+      case 8: {
+        const double vel = up.count("velocity") ? up["velocity"] : 1.0;
+        h->prob = hold(pda::create_linear_advection_1d_problem_eigen(m, recon(reconEnum), vel, icFlag));
+        break;
+      }
+      case 9: {
+        const double D = up.count("diffusion") ? up["diffusion"] : 0.01;
+        const double k = up.count("reaction") ? up["reaction"] : 0.01;
+        if (up.count("testSource")) {
+          auto f = [](const double& x, const double& t, double& v) { v = std::sin(x + t); };
+          h->prob = hold(pda::create_diffusion_reaction_1d_problem_A_eigen(m, f, D, k));
+        } else {
+          h->prob = hold(pda::create_diffusion_reaction_1d_problem_A_eigen(m, D, k));
+        }
         break;
       }
       default:

@@ -177,6 +177,10 @@ pda_status pda_problem_create(pda_mesh mesh, int family, int problem_id, int rec
   });
 }
 
+pda_status pda_problem_set_source(pda_problem p, const double* values) {
+  return guarded([&] { P(p).setSource(values); });
+}
+
 pda_status pda_problem_set_bc(pda_problem p, int side, int kind, const double* values) {
   return guarded([&] { P(p).setBc(side, kind, values); });
 }

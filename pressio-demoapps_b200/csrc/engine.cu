@@ -64,7 +64,8 @@ struct PinnedBuf {
 };
 
 // family / problem ids: include/pda_b200.h
-enum { F_EULER1D = 1, F_EULER2D = 2, F_EULER3D = 3, F_SWE2D = 4, F_DIFFREAC2D = 5, F_ADVDIFF2D = 6 };
+enum { F_EULER1D = 1, F_EULER2D = 2, F_EULER3D = 3, F_SWE2D = 4, F_DIFFREAC2D = 5, F_ADVDIFF2D = 6,
+       F_ADVDIFFREAC2D = 7, F_ADVECTION1D = 8, F_DIFFREAC1D = 9 };
 enum { E2_PERIODIC = 0, E2_KH = 1, E2_SEDOV_FULL = 2, E2_SEDOV_SYM = 3, E2_RIEMANN = 4, E2_NORMAL_SHOCK = 5,
        E2_DMR = 6, E2_CROSS_SHOCK = 7, E2_NEUMANN = 8 };
 enum { BC_DIRICHLET = 0, BC_NEUMANN = 1, BC_REFLECTIVE = 2 };
@@ -163,6 +164,8 @@ struct DeviceState {
   // scratch owned by the problem (host-pointer entry points, applyJacobian)
   DevBuf<double> dU, dV, dJ, dB, dR;
   DevBuf<int32_t> dRowptr, dColidx;
+  DevBuf<double> src;          // per-sample-row source table (diffusion-reaction ProblemA, ADR ProblemA)
+  bool srcReady = false;
   // host-pointer pipeline (velocityHost on large lattices)
   static constexpr int kMaxChunks = 32;
   cudaStream_t sH2D = nullptr, sD2H = nullptr;
@@ -203,10 +206,14 @@ Problem::Problem(Mesh* mesh, int family, int problemId, int recon, int icFlag, i
     case F_EULER3D: dim_ = 3; ndpc_ = 5; if (problemId < 0 || problemId > 1) throw Error(kInvalid, "Euler3d: invalid problem enum"); break;
     case F_SWE2D: dim_ = 2; ndpc_ = 3; if (problemId < 0 || problemId > 1) throw Error(kInvalid, "Swe2d: invalid problem enum"); break;
     case F_DIFFREAC2D:
-      dim_ = 2; ndpc_ = 2;
-      if (problemId != 1) throw Error(kUnsupported, "DiffusionReaction2d: only GrayScott runs on the device (ProblemA takes a host source functor)");
+      dim_ = 2; ndpc_ = (problemId == 1) ? 2 : 1;
+      if (problemId < 0 || problemId > 1) throw Error(kInvalid, "DiffusionReaction2d: invalid problem enum");
       S_ = 3;
       break;
+    case F_ADVDIFF2D: dim_ = 2; ndpc_ = 2; if (problemId < 0 || problemId > 1) throw Error(kInvalid, "AdvectionDiffusion2d: invalid problem enum"); break;
+    case F_ADVDIFFREAC2D: dim_ = 2; ndpc_ = 1; if (problemId != 0) throw Error(kInvalid, "advection-diffusion-reaction2d: invalid problem enum"); break;
+    case F_ADVECTION1D: dim_ = 1; ndpc_ = 1; if (problemId != 0) throw Error(kInvalid, "advection: invalid problem enum"); break;
+    case F_DIFFREAC1D: dim_ = 1; ndpc_ = 1; S_ = 3; if (problemId != 0) throw Error(kInvalid, "1D diffusion-reaction: invalid problem enum"); break;
     default: throw Error(kUnsupported, "create_problem: problem family not available in this engine");
   }
   if (mesh->dim != dim_) throw Error(kInvalid, "create_problem: mesh dimensionality does not match the problem");
@@ -214,6 +221,8 @@ Problem::Problem(Mesh* mesh, int family, int problemId, int recon, int icFlag, i
   if (mesh->stencil < S_) throw Error(kInvalid, "create_problem: mesh stencil size too small for the reconstruction scheme");
   if (family == F_DIFFREAC2D && mesh->stencil != 3)
     throw Error(kInvalid, "DiffusionReaction2d currently, only supports 3-pt stencil");   // diffusion_reaction_2d_prob_class.hpp:307-309
+  if (family == F_DIFFREAC1D && mesh->stencil != 3)
+    throw Error(kInvalid, "DiffusionReaction1d currently only supports 3-pt stencil");    // diffusion_reaction_1d_prob_class.hpp:103-105
   if ((int64_t)mesh->nStencil * ndpc_ > INT32_MAX) throw Error(kTooLarge, "create_problem: dof count exceeds int32");
 
   // ---- parameters
@@ -251,7 +260,7 @@ Problem::Problem(Mesh* mesh, int family, int problemId, int recon, int icFlag, i
       icParams_[idx] = values[i];
     }
     customBcs_ = (problemId == 1);
-  } else if (family == F_DIFFREAC2D) {
+  } else if (family == F_DIFFREAC2D && problemId == 1) {
     for (int i = 0; i < nparams; ++i) {
       const std::string s = names[i];
       if (s == "Du") gs_[0] = values[i];
@@ -259,6 +268,49 @@ Problem::Problem(Mesh* mesh, int family, int problemId, int recon, int icFlag, i
       else if (s == "F") gs_[2] = values[i];
       else if (s == "k") gs_[3] = values[i];
       else throw Error(kInvalid, "GrayScott: invalid parameter name '" + s + "'");
+    }
+  } else if (family == F_DIFFREAC2D || family == F_DIFFREAC1D) {
+    // ProblemA: D = k = 0.01 (diffusion_reaction1d.hpp:118-121, diffusion_reaction2d.hpp:144-150)
+    physParams_ = {0.01, 0.01};
+    for (int i = 0; i < nparams; ++i) {
+      const std::string s = names[i];
+      if (s == "diffusion") physParams_[0] = values[i];
+      else if (s == "reaction") physParams_[1] = values[i];
+      else throw Error(kInvalid, "diffusion-reaction ProblemA: invalid parameter name '" + s + "'");
+    }
+  } else if (family == F_ADVDIFF2D) {
+    // impl/advection_diffusion_2d_parametrization_helpers.hpp:69-82
+    physParams_ = {0.00001};
+    icParams_ = {0.5, 0.15, 0.0, -0.2};
+    if (icFlag != 1) throw Error(kInvalid, "AdvectionDiffusion2d: invalid icFlag");
+    for (int i = 0; i < nparams; ++i) {
+      const std::string s = names[i];
+      if (s == "diffusion") physParams_[0] = values[i];
+      else if (s == "pulseMagnitude") icParams_[0] = values[i];
+      else if (s == "pulseSpread") icParams_[1] = values[i];
+      else if (s == "pulseX") icParams_[2] = values[i];
+      else if (s == "pulseY") icParams_[3] = values[i];
+      else throw Error(kInvalid, "AdvectionDiffusion2d: invalid parameter name '" + s + "'");
+    }
+  } else if (family == F_ADVDIFFREAC2D) {
+    // advection_diffusion_reaction2d.hpp:124-128: ux, uy, diffusion, sigma; default source f = 1
+    physParams_ = {0.5 * std::cos(M_PI / 3), 0.5 * std::sin(M_PI / 3), 0.001, 1.0};
+    for (int i = 0; i < nparams; ++i) {
+      const std::string s = names[i];
+      if (s == "ux") physParams_[0] = values[i];
+      else if (s == "uy") physParams_[1] = values[i];
+      else if (s == "diffusion") physParams_[2] = values[i];
+      else if (s == "sigma") physParams_[3] = values[i];
+      else throw Error(kInvalid, "advection-diffusion-reaction2d: invalid parameter name '" + s + "'");
+    }
+  } else if (family == F_ADVECTION1D) {
+    // advection1d.hpp:88-92,140-152: velocity (default 1), ic 1..4
+    physParams_ = {1.0};
+    if (icFlag < 1 || icFlag > 4) throw Error(kInvalid, "advection1d: invalid ic");
+    for (int i = 0; i < nparams; ++i) {
+      const std::string s = names[i];
+      if (s == "velocity") physParams_[0] = values[i];
+      else throw Error(kInvalid, "advection1d: invalid parameter name '" + s + "'");
     }
   } else if (nparams > 0) {
     throw Error(kInvalid, "create_problem: this problem takes no user parameters");
@@ -279,6 +331,18 @@ double Problem::queryParameter(const std::string& name) const {
     if (name == "coriolis") return physParams_[1];
     const int idx = sweIcIndex(icFlag_, name);
     if (idx >= 0) return icParams_[idx];
+  } else if (family_ == F_DIFFREAC1D || (family_ == F_DIFFREAC2D && probId_ == 0)) {
+    if (name == "diffusion") return physParams_[0];
+    if (name == "reaction") return physParams_[1];
+  } else if (family_ == F_ADVDIFF2D) {
+    static const char* icn[4] = {"pulseMagnitude", "pulseSpread", "pulseX", "pulseY"};
+    if (name == "diffusion") return physParams_[0];
+    for (int i = 0; i < 4; ++i) if (name == icn[i]) return icParams_[i];
+  } else if (family_ == F_ADVDIFFREAC2D) {
+    static const char* pn[4] = {"ux", "uy", "diffusion", "sigma"};
+    for (int i = 0; i < 4; ++i) if (name == pn[i]) return physParams_[i];
+  } else if (family_ == F_ADVECTION1D) {
+    if (name == "velocity") return physParams_[0];
   } else if (family_ == F_DIFFREAC2D) {
     if (name == "Du") return gs_[0];
     if (name == "Dv") return gs_[1];
@@ -289,9 +353,10 @@ double Problem::queryParameter(const std::string& name) const {
 }
 
 void Problem::setBc(int side, int kind, const double* values) {
-  const bool ok = (family_ == F_SWE2D && probId_ == 1) ||
+  const bool ok = (family_ == F_SWE2D && probId_ == 1) || family_ == F_ADVDIFF2D ||
                   (family_ == F_EULER2D && (probId_ == E2_RIEMANN || probId_ == E2_NORMAL_SHOCK));
-  if (!ok) throw Error(kInvalid, "custom BCs only valid for Swe2d::CustomBCs and Euler2d::{Riemann, NormalShock}");
+  if (!ok)
+    throw Error(kInvalid, "custom BCs only valid for Swe2d::CustomBCs, Euler2d::{Riemann, NormalShock} and AdvectionDiffusion2d");
   if (side < 0 || side > 3) throw Error(kInvalid, "set_bc: invalid side");
   if (kind < 0 || kind > 2) throw Error(kInvalid, "set_bc: invalid kind");
   bc_[side].kind = kind;
@@ -512,6 +577,44 @@ void Problem::initialCondition(double* U) const {
     return;
   }
 
+  if (family_ == F_DIFFREAC1D || family_ == F_ADVDIFFREAC2D || (family_ == F_DIFFREAC2D && probId_ == 0)) {
+    // zero state: diffusion_reaction_1d_prob_class.hpp:110-118, diffusion_reaction_2d_prob_class.hpp:144-149,
+    // advection_diffusion_reaction_2d_initial_condition.hpp:57-61
+    std::memset(U, 0, sizeof(double) * (size_t)n * ndpc_);
+    return;
+  }
+  if (family_ == F_ADVDIFF2D) {   // impl/advection_diffusion_2d_initial_condition.hpp:54-78
+    const double mag = icParams_[0], spread = icParams_[1], x0 = icParams_[2], y0 = icParams_[3];
+#pragma omp parallel for schedule(static)
+    for (int32_t i = 0; i < n; ++i) {
+      const double dx = X(i) - x0, dy = Y(i) - y0;
+      const double dxSq = dx * dx, dySq = dy * dy;
+      const double v = mag * std::exp(-(dxSq + dySq) / spread);
+      U[2 * (int64_t)i] = v; U[2 * (int64_t)i + 1] = v;
+    }
+    return;
+  }
+  if (family_ == F_ADVECTION1D) {   // impl/advection_1d_prob_class.hpp:111-156
+#pragma omp parallel for schedule(static)
+    for (int32_t i = 0; i < n; ++i) {
+      const double x = X(i);
+      double r = 0.0;
+      if (icFlag_ == 1) r = std::sin(M_PI * x);
+      else if (icFlag_ == 2) {
+        const double dx1Sq = (x - 1.2) * (x - 1.2), dx2Sq = (x - 2.5) * (x - 2.5);
+        r = 0.8 * std::exp(-200.0 * dx1Sq / 16.0) + std::exp(-100.0 * dx2Sq / 36.0);
+      } else if (icFlag_ == 3) {
+        const double delta = 0.5 * 0.5;
+        const double dx1Sq = (x - 2.) * (x - 2.), dx2Sq = (x - 3.0) * (x - 3.0);
+        r = std::exp(-dx1Sq / delta) + 0.5 * std::exp(-dx2Sq / delta);
+      } else {
+        r = std::tanh(8.0 * (x - 1.0)) - std::tanh(8.0 * (x - 3.0));
+      }
+      U[i] = r;
+    }
+    return;
+  }
+
   if (family_ == F_DIFFREAC2D) {   // diffusion_reaction_2d_prob_class.hpp:141-178 (Gray-Scott)
 #pragma omp parallel for schedule(static)
     for (int32_t i = 0; i < n; ++i) {
@@ -536,7 +639,7 @@ void Problem::buildPattern() {
   const int nc = m.ncols();
   const int nnbInner = (S_ - 1) * dim_;
   const int nnbFirst = 2 * dim_;
-  const bool allFirst = (family_ == F_DIFFREAC2D);
+  const bool allFirst = (family_ == F_DIFFREAC2D || family_ == F_DIFFREAC1D);
   const int32_t ns = m.nSample;
   slotCols_ = nnbInner + 1;
   std::vector<uint8_t> isNb(ns, 0);
@@ -644,7 +747,8 @@ void Problem::ensureDevice() {
   }
   ds->nearBd.hostRowIds = nb;
   // ---- inner rows: structured kernels on lattices, compact graph otherwise
-  ds->innerViaLattice = m.lattice && latticeKernelAvailable(family_, dim_, S_);
+  ds->innerViaLattice = m.lattice && (latticeKernelAvailable(family_, dim_, S_) ||
+                                      (family_ == F_DIFFREAC2D && probId_ == 1 && m.fullyPeriodic));
   ds->hS = (S_ - 1) / 2;
   ds->nsides = (dim_ == 1) ? 3 : 2 * dim_;
   dev_ = std::move(ds);
@@ -661,7 +765,7 @@ void Problem::ensureInnerRows() {
   m.ensureGraph();
   m.ensureRows();
   std::vector<int32_t> rows;
-  if (family_ == F_DIFFREAC2D) { rows.resize(m.nSample); for (int32_t r = 0; r < m.nSample; ++r) rows[r] = r; }
+  if (family_ == F_DIFFREAC2D || family_ == F_DIFFREAC1D) { rows.resize(m.nSample); for (int32_t r = 0; r < m.nSample; ++r) rows[r] = r; }
   else rows = m.rowsInner;
   ds.inner.n = (int32_t)rows.size();
   if (!rows.empty()) {
@@ -698,6 +802,8 @@ void Problem::buildGhostRecipes() {
   const int mNeg1 = addMode({1, -1, 1, 1, 1}, {0, 0, 0, 0, 0});
   const int mNeg2 = addMode({1, 1, -1, 1, 1}, {0, 0, 0, 0, 0});
   const int mNeg3 = addMode({1, 1, 1, -1, 1}, {0, 0, 0, 0, 0});
+  const int mNegAll = addMode({-1, -1, -1, -1, -1}, {0, 0, 0, 0, 0});
+  const int mZero = addMode({0, 0, 0, 0, 0}, {0, 0, 0, 0, 0});
   int mDirich[6] = {-1, -1, -1, -1, -1, -1};
 
   // which filler applies (0 = none)
@@ -759,9 +865,17 @@ void Problem::buildGhostRecipes() {
     if (probId_ == 1) { style = NAIVE; sideMode[0] = mNeg1; sideMode[3] = mNeg2; sideMode[4] = mNeg3; }
   } else if (family_ == F_SWE2D) {
     style = PROPER; sideMode[0] = mNeg1; sideMode[2] = mNeg1; sideMode[1] = mNeg2; sideMode[3] = mNeg2;
+  } else if (family_ == F_ADVDIFF2D) {
+    // BurgersOutflow (advection_diffusion_2d_ghost_filler_outflow.hpp:102-235): left/back homogeneous Dirichlet,
+    // right/front layer-aware mirror copy; BurgersPeriodic has no ghosts
+    if (probId_ == 1) { style = PROPER; sideMode[0] = mZero; sideMode[3] = mZero; }
+  } else if (family_ == F_ADVDIFFREAC2D) {
+    // advection_diffusion_reaction_2d_ghost_filler_problemA.hpp:92-147: layer 0 <- -self, layer k <- -(opposite k-1)
+    style = NAIVE;
+    for (int sd = 0; sd < 4; ++sd) sideMode[sd] = mNegAll;
   }
 
-  if (nNb > 0 && style == NONE && !m.fullyPeriodic && family_ != F_DIFFREAC2D)
+  if (nNb > 0 && style == NONE && !m.fullyPeriodic && family_ != F_DIFFREAC2D && family_ != F_DIFFREAC1D)
     throw Error(kInvalid, "this problem requires a fully periodic mesh (no ghost filler in the reference)");
 
   std::vector<dev::GhostRecipe> rec((size_t)nNb * nsides * h, dev::GhostRecipe{-1, 0, 0});
@@ -865,6 +979,11 @@ void Problem::buildGhostRecipes() {
         }
       } else if (family_ == F_EULER3D) {
         if (probId_ == 1 && hasBd(sm)) f[1 + ax] = -1.0;
+      } else if (family_ == F_ADVDIFF2D) {
+        // advection_diffusion_2d_prob_class.hpp:1119-1155: minus side (left/back) Dirichlet -> 0, else Neumann -> 1
+        if (hasBd(sm)) for (int d = 0; d < ndpc_; ++d) f[d] = 0.0;
+      } else if (family_ == F_ADVDIFFREAC2D) {
+        f[0] = -1.0;   // advection_diffusion_reaction_2d_prob_class.hpp:634-635
       }
     }
   }
@@ -923,7 +1042,7 @@ void Problem::evaluateDev(const double* dU, double t, double* dV, double* dJ, vo
       ds.jacTablesReady = true;
     }
     // the staged inner-row kernel writes every value once; only rows assembled by read-modify-write need zeros
-    if (family_ == F_DIFFREAC2D || mergedNeighbors_) {
+    if (family_ == F_DIFFREAC2D || family_ == F_DIFFREAC1D || mergedNeighbors_) {
       PDA_CUDA(cudaMemsetAsync(dJ, 0, colidx_.size() * sizeof(double), st));
     } else if (ds.nearBd.n > 0) {
       dev::k_zero_cell_chunks<<<gridFor((int64_t)ds.nearBd.n * 32, 256), 256, 0, st>>>(ds.nearBd.jBase.p, ds.nearBd.jLen.p,
@@ -933,10 +1052,29 @@ void Problem::evaluateDev(const double* dU, double t, double* dV, double* dJ, vo
   }
 
   // ---- Gray-Scott: one fused kernel over all rows
-  if (family_ == F_DIFFREAC2D) {
+  if (family_ == F_DIFFREAC2D && probId_ == 1) {
     dev::GrayScottParams gp{gs_[0], gs_[1], gs_[2], gs_[3], m.dInv[0] * m.dInv[0], m.dInv[1] * m.dInv[1]};
     if (!m.fullyPeriodic) throw Error(kInvalid, "GrayScott requires a periodic mesh");
-    dev::k_gray_scott_rows<<<gridFor(ds.inner.n, 128), 128, 0, st>>>(gp, ds.inner.view(nc), dU, dV, dJ, ds.inner.jac(slotCols_));
+    if (ds.innerViaLattice && !dJ) {
+      dim3 grid((unsigned)((m.n[0] + 127) / 128), (unsigned)m.n[1]);
+      dev::k_gray_scott_lattice<<<grid, 128, 0, st>>>(gp, m.n[0], m.n[1], reinterpret_cast<const double2*>(dU),
+                                                     reinterpret_cast<double2*>(dV));
+    } else {
+      ensureInnerRows();
+      dev::k_gray_scott_rows<<<gridFor(ds.inner.n, 128), 128, 0, st>>>(gp, ds.inner.view(nc), dU, dV, dJ, ds.inner.jac(slotCols_));
+    }
+    ++launches_;
+    PDA_CUDA(cudaGetLastError());
+    return;
+  }
+  // ---- diffusion-reaction ProblemA (1D / 2D): one fused kernel over all rows, source from the per-row table
+  if (family_ == F_DIFFREAC1D || family_ == F_DIFFREAC2D) {
+    ensureSource();
+    dev::DiffReacParams pr{{physParams_[0] * (m.dInv[0] * m.dInv[0]), physParams_[0] * (m.dInv[1] * m.dInv[1])}, physParams_[1]};
+    if (dim_ == 1)
+      dev::k_diffreac_rows<1><<<gridFor(ds.inner.n, 128), 128, 0, st>>>(pr, ds.inner.view(nc), dU, ds.src.p, dV, dJ, ds.inner.jac(slotCols_));
+    else
+      dev::k_diffreac_rows<2><<<gridFor(ds.inner.n, 128), 128, 0, st>>>(pr, ds.inner.view(nc), dU, ds.src.p, dV, dJ, ds.inner.jac(slotCols_));
     ++launches_;
     PDA_CUDA(cudaGetLastError());
     return;
@@ -953,6 +1091,8 @@ void Problem::evaluateDev(const double* dU, double t, double* dV, double* dJ, vo
       dev::k_ghost_fill<N><<<gridFor(tot, 128), 128, 0, st>>>(ds.recipes.p, ds.nbXY.p, nNb, ds.nsides, ds.hS, ds.tables, dU, gv, t);
     };
     switch (ndpc_) {
+      case 1: launchGhost(std::integral_constant<int, 1>{}); break;
+      case 2: launchGhost(std::integral_constant<int, 2>{}); break;
       case 3: launchGhost(std::integral_constant<int, 3>{}); break;
       case 4: launchGhost(std::integral_constant<int, 4>{}); break;
       case 5: launchGhost(std::integral_constant<int, 5>{}); break;
@@ -1005,9 +1145,54 @@ void Problem::evaluateDev(const double* dU, double t, double* dV, double* dJ, vo
     case F_EULER2D: run(dev::Euler<2>{gamma_}); break;
     case F_EULER3D: run(dev::Euler<3>{gamma_}); break;
     case F_SWE2D: run(dev::Swe2d{physParams_[0], physParams_[1]}); break;
+    case F_ADVDIFF2D:
+      run(dev::Burgers2d{{physParams_[0] * (m.dInv[0] * m.dInv[0]), physParams_[0] * (m.dInv[1] * m.dInv[1])}});
+      break;
+    case F_ADVDIFFREAC2D: {
+      const double D = physParams_[2];
+      if (srcUser_) ensureSource();
+      run(dev::LinAdv<2>{{physParams_[0], physParams_[1]}, {D * (m.dInv[0] * m.dInv[0]), D * (m.dInv[1] * m.dInv[1])},
+                         physParams_[3], 1.0, srcUser_ ? ds.src.p : nullptr});
+      break;
+    }
+    case F_ADVECTION1D: run(dev::LinAdv<1>{{physParams_[0]}, {0.0}, 0.0, 0.0, nullptr}); break;
     default: throw Error(kUnsupported, "family not supported on device");
   }
   PDA_CUDA(cudaGetLastError());
+}
+
+// per-row source table f(x[,y]) of the ProblemA families: the reference's default functors
+// (diffusion_reaction1d.hpp:86-97, diffusion_reaction2d.hpp:103-114) tabulated once, or the caller's values
+// (pda_problem_set_source: a host functor evaluated by the binding at the current time)
+void Problem::ensureSource() {
+  DeviceState& ds = *dev_;
+  if (ds.srcReady) return;
+  Mesh& m = *mesh_;
+  if (!srcUser_) {
+    m.ensureGraph();
+    const int nc = m.ncols();
+    srcHost_.resize(m.nSample);
+    for (int32_t r = 0; r < m.nSample; ++r) {
+      const int32_t c = m.graph[(size_t)r * nc];
+      double x, y = 0.0;
+      if (m.haveCoords) { x = m.x[c]; if (dim_ > 1) y = m.y[c]; }
+      else { x = m.latticeCoord(0, c % m.n[0]); if (dim_ > 1) y = m.latticeCoord(1, (c / m.n[0]) % m.n[1]); }
+      if (family_ == F_DIFFREAC1D) srcHost_[r] = std::sin(M_PI * x) * x * x * 4. * std::cos(4. * M_PI * x);
+      else if (family_ == F_DIFFREAC2D) srcHost_[r] = std::sin(M_PI * x * (y - 0.2)) * 4. * std::sin(4. * M_PI * y * x);
+      else srcHost_[r] = 1.0;
+    }
+  }
+  ds.src.upload(srcHost_);
+  ds.srcReady = true;
+}
+
+void Problem::setSource(const double* values) {
+  const bool ok = family_ == F_DIFFREAC1D || family_ == F_ADVDIFFREAC2D || (family_ == F_DIFFREAC2D && probId_ == 0);
+  if (!ok) throw Error(kInvalid, "set_source: this problem has no source term");
+  if (!values) throw Error(kInvalid, "set_source: null pointer");
+  srcHost_.assign(values, values + mesh_->nSample);
+  srcUser_ = true;
+  if (dev_) dev_->srcReady = false;
 }
 
 // structured velocity of the slowest-axis planes [p0,p1) of a fully periodic lattice (host pipeline, slab interior)

@@ -32,6 +32,7 @@ class Problem {
   double queryParameter(const std::string& name) const;
   void initialCondition(double* U) const;
   void setBc(int side, int kind, const double* values);
+  void setSource(const double* values);   // nSample doubles (host)
 
   int64_t jacobianNnz();
   void jacobianPattern(int32_t* rowptr, int32_t* colidx);
@@ -57,6 +58,7 @@ class Problem {
   void ensureDevice();
   void ensureInnerRows();
   void buildGhostRecipes();
+  void ensureSource();
   void evaluateDev(const double* dU, double t, double* dV, double* dJ, void* stream);
   void evaluatePlanes(const double* dU, double t, double* dV, void* stream, int32_t p0, int32_t p1);
 
@@ -70,6 +72,8 @@ class Problem {
   double gs_[4] = {0.0002, 0.00005, 0.042, 0.062};   // Du, Dv, F, k (diffusion_reaction2d.hpp:152-155)
   BcRule bc_[6];
   bool customBcs_ = false;
+  std::vector<double> srcHost_;   // per-sample-row source values (ProblemA families)
+  bool srcUser_ = false;
 
   // fixed CSR pattern (host), built on first request
   bool havePattern_ = false;

@@ -8,6 +8,8 @@
 #pragma once
 #include <cstdint>
 
+#include <type_traits>
+
 #include "physics.cuh"
 
 namespace pda {
@@ -99,15 +101,17 @@ PDA_DEVFN void stencilCells(const int32_t* __restrict__ row, int32_t* cells) {
   }
 }
 
-// accumulate hInv*(F_L - F_R) of axis AX into v[]
+// accumulate hInv*(F_L - F_R) of axis AX into v[].  Problems with a diffusion term also get dD[AX]*(u+ - 2u + u-):
+// near-boundary rows add it right after the axis' flux balance, inner rows after all flux balances (`diff` receives
+// the term) -- the two accumulation orders of advection_diffusion_2d_prob_class.hpp:959-1000 / 1050-1056,1190-1194.
 template <class Phys, int S, int AX, bool NEARBD>
 PDA_DEVFN void axisVelocity(const Phys& phys, const int32_t* __restrict__ row, const double* __restrict__ U,
-                            const GhostView& gv, int32_t nbRow, double hInv, double* v) {
+                            const GhostView& gv, int32_t nbRow, double hInv, double* v, double* diff) {
   constexpr int N = Phys::ndpc;
   constexpr int h = (S - 1) / 2;
   int32_t cells[S];
   stencilCells<Phys::dim, S, AX>(row, cells);
-  double uLn[N], uLp[N], uRn[N], uRp[N];
+  double uLn[N], uLp[N], uRn[N], uRp[N], dterm[N];
 #pragma unroll
   for (int d = 0; d < N; ++d) {
     double q[S];
@@ -119,18 +123,79 @@ PDA_DEVFN void axisVelocity(const Phys& phys, const int32_t* __restrict__ row, c
     }
     Recon<S>::face(q, uLn[d], uLp[d]);
     Recon<S>::face(q + 1, uRn[d], uRp[d]);
+    if constexpr (PhysTraits<Phys>::hasDiffusion) dterm[d] = phys.dD[AX] * (q[h + 1] - 2.0 * q[h] + q[h - 1]);
   }
   double FL[N], FR[N];
   phys.template flux<AX>(uLn, uLp, FL);
   phys.template flux<AX>(uRn, uRp, FR);
 #pragma unroll
-  for (int d = 0; d < N; ++d) v[d] += hInv * (FL[d] - FR[d]);
+  for (int d = 0; d < N; ++d) {
+    v[d] += hInv * (FL[d] - FR[d]);
+    if constexpr (PhysTraits<Phys>::hasDiffusion) {
+      if (NEARBD) v[d] += dterm[d]; else diff[d] = dterm[d];
+    }
+  }
+  (void)dterm; (void)diff;
 }
 
-template <class Phys> PDA_DEVFN void addForcing(const Phys&, const double*, double*) {}
-template <> PDA_DEVFN void addForcing<Swe2d>(const Swe2d& phys, const double* u, double* v) {
+// point terms added after the flux balances: SWE Coriolis (swe_2d_prob_class.hpp:984-1012), ADR source + reaction
+// (advection_diffusion_reaction_2d_prob_class.hpp:504-509).  `sampleRow` indexes the per-cell source table.
+template <class Phys> PDA_DEVFN void addForcing(const Phys&, const double*, double*, int32_t) {}
+template <> PDA_DEVFN void addForcing<Swe2d>(const Swe2d& phys, const double* u, double* v, int32_t) {
   v[1] -= phys.coriolis * u[2] / u[0];
   v[2] += phys.coriolis * u[1] / u[0];
+}
+template <> PDA_DEVFN void addForcing<LinAdv<2>>(const LinAdv<2>& phys, const double* u, double* v, int32_t sampleRow) {
+  v[0] += phys.srcTable ? phys.srcTable[sampleRow] : phys.srcConst;
+  v[0] -= phys.sigma * u[0];
+}
+
+// diffusion term of an inner row gathered through the graph (rows whose first-layer neighbours all exist)
+template <class Phys>
+PDA_DEVFN void addDiffusionInner(const Phys& phys, const int32_t* __restrict__ row, const double* __restrict__ U, double* v) {
+  if constexpr (PhysTraits<Phys>::hasDiffusion) {
+    constexpr int N = Phys::ndpc, DIM = Phys::dim;
+    const double* c = U + (int64_t)row[0] * N;
+#pragma unroll
+    for (int ax = 0; ax < DIM; ++ax) {
+      const int sm = (ax == 0) ? 0 : (ax == 1 ? 3 : 4), sp = (ax == 0) ? 2 : (ax == 1 ? 1 : 5);
+      const double* l = U + (int64_t)row[gcol<DIM>(sm, 0)] * N;
+      const double* r = U + (int64_t)row[gcol<DIM>(sp, 0)] * N;
+#pragma unroll
+      for (int d = 0; d < N; ++d) v[d] += phys.dD[ax] * (r[d] - 2.0 * c[d] + l[d]);
+    }
+  }
+}
+
+// d(point terms + diffusion)/dU of an inner row: `put(k, slot, j, value)` ADDS value to entry (row k, block slot, col j)
+template <class Phys, class Put>
+PDA_DEVFN void addExtraJacInner(const Phys& phys, const double* u, const uint8_t* __restrict__ slots, Put&& put) {
+  constexpr int N = Phys::ndpc, DIM = Phys::dim;
+  (void)N; (void)DIM; (void)u; (void)slots;
+  if constexpr (std::is_same<Phys, Swe2d>::value) {
+    const double f = phys.coriolis;
+    put(1, slots[0], 0, f * u[2] / (u[0] * u[0]));
+    put(1, slots[0], 2, -f / u[0]);
+    put(2, slots[0], 1, f / u[0]);
+    put(2, slots[0], 0, -f * u[1] / (u[0] * u[0]));
+  }
+  if constexpr (PhysTraits<Phys>::hasDiffusion) {
+    double self = 0.0;
+#pragma unroll
+    for (int ax = 0; ax < DIM; ++ax) self += -2.0 * phys.dD[ax];
+#pragma unroll
+    for (int k = 0; k < N; ++k) put(k, slots[0], k, self);
+#pragma unroll
+    for (int ax = 0; ax < DIM; ++ax) {
+      const int sm = (ax == 0) ? 0 : (ax == 1 ? 3 : 4), sp = (ax == 0) ? 2 : (ax == 1 ? 1 : 5);
+#pragma unroll
+      for (int k = 0; k < N; ++k) {
+        put(k, slots[gcol<DIM>(sm, 0)], k, phys.dD[ax]);
+        put(k, slots[gcol<DIM>(sp, 0)], k, phys.dD[ax]);
+      }
+    }
+  }
+  if constexpr (std::is_same<Phys, LinAdv<2>>::value) put(0, slots[0], 0, -phys.sigma);
 }
 
 struct Deltas { double hInv[3]; };
@@ -140,17 +205,26 @@ template <class Phys, int S, bool NEARBD>
 __global__ void __launch_bounds__(128)
 k_velocity_rows(Phys phys, RowSet rs, Deltas dl, const double* __restrict__ U, double* __restrict__ V, GhostView gv) {
   constexpr int N = Phys::ndpc;
+  constexpr int DIM = Phys::dim;
   const int32_t r = blockIdx.x * blockDim.x + threadIdx.x;
   if (r >= rs.n) return;
   const int32_t* row = rs.graph + (int64_t)r * rs.ncols;
-  double v[N];
+  double v[N], diff[DIM][N];
 #pragma unroll
   for (int d = 0; d < N; ++d) v[d] = 0.0;
-  axisVelocity<Phys, S, 0, NEARBD>(phys, row, U, gv, r, dl.hInv[0], v);
-  if constexpr (Phys::dim >= 2) axisVelocity<Phys, S, 1, NEARBD>(phys, row, U, gv, r, dl.hInv[1], v);
-  if constexpr (Phys::dim >= 3) axisVelocity<Phys, S, 2, NEARBD>(phys, row, U, gv, r, dl.hInv[2], v);
-  addForcing<Phys>(phys, U + (int64_t)row[0] * N, v);
-  double* out = V + (int64_t)rs.rowIds[r] * N;
+  axisVelocity<Phys, S, 0, NEARBD>(phys, row, U, gv, r, dl.hInv[0], v, diff[0]);
+  if constexpr (DIM >= 2) axisVelocity<Phys, S, 1, NEARBD>(phys, row, U, gv, r, dl.hInv[1], v, diff[1]);
+  if constexpr (DIM >= 3) axisVelocity<Phys, S, 2, NEARBD>(phys, row, U, gv, r, dl.hInv[2], v, diff[2]);
+  if constexpr (PhysTraits<Phys>::hasDiffusion && !NEARBD) {
+#pragma unroll
+    for (int a = 0; a < DIM; ++a)
+#pragma unroll
+      for (int d = 0; d < N; ++d) v[d] += diff[a][d];
+  }
+  (void)diff;
+  const int32_t sampleRow = rs.rowIds[r];
+  addForcing<Phys>(phys, U + (int64_t)row[0] * N, v, sampleRow);
+  double* out = V + (int64_t)sampleRow * N;
 #pragma unroll
   for (int d = 0; d < N; ++d) out[d] = v[d];
 }
@@ -223,16 +297,6 @@ PDA_DEVFN void axisJacobianInner(const Phys& phys, const int32_t* __restrict__ r
   }
 }
 
-template <class Phys> PDA_DEVFN void addForcingJac(const Phys&, const double*, double*, int64_t, int32_t, int) {}
-template <> PDA_DEVFN void addForcingJac<Swe2d>(const Swe2d& phys, const double* u, double* Jv, int64_t base,
-                                                int32_t len, int slot) {
-  const double f = phys.coriolis;
-  Jv[base + 1 * (int64_t)len + slot * 3 + 0] += f * u[2] / (u[0] * u[0]);
-  Jv[base + 1 * (int64_t)len + slot * 3 + 2] += -f / u[0];
-  Jv[base + 2 * (int64_t)len + slot * 3 + 1] += f / u[0];
-  Jv[base + 2 * (int64_t)len + slot * 3 + 0] += -f * u[1] / (u[0] * u[0]);
-}
-
 template <class Phys, int S>
 __global__ void __launch_bounds__(128)
 k_jacobian_inner_rows(Phys phys, RowSet rs, Deltas dl, const double* __restrict__ U, double* __restrict__ V,
@@ -251,8 +315,11 @@ k_jacobian_inner_rows(Phys phys, RowSet rs, Deltas dl, const double* __restrict_
   if constexpr (Phys::dim >= 2) axisJacobianInner<Phys, S, 1>(phys, row, U, dl.hInv[1], v, Jv, base, len, slots);
   if constexpr (Phys::dim >= 3) axisJacobianInner<Phys, S, 2>(phys, row, U, dl.hInv[2], v, Jv, base, len, slots);
   const double* uSelf = U + (int64_t)row[0] * N;
-  addForcing<Phys>(phys, uSelf, v);
-  addForcingJac<Phys>(phys, uSelf, Jv, base, len, slots[0]);
+  addDiffusionInner<Phys>(phys, row, U, v);
+  addForcing<Phys>(phys, uSelf, v, rs.rowIds[r]);
+  addExtraJacInner<Phys>(phys, uSelf, slots, [&](int k, int slot, int j, double val) {
+    Jv[base + (int64_t)k * len + slot * N + j] += val;
+  });
   if (V) {
     double* out = V + (int64_t)rs.rowIds[r] * N;
 #pragma unroll
@@ -323,7 +390,36 @@ k_jacobian_nearbd_rows(Phys phys, RowSet rs, Deltas dl, const double* __restrict
   axisJacobianNearBd<Phys, 0>(phys, row, U, gv, r, dl.hInv[0], fac, Jv, base, len, slots);
   if constexpr (DIM >= 2) axisJacobianNearBd<Phys, 1>(phys, row, U, gv, r, dl.hInv[1], fac + N, Jv, base, len, slots);
   if constexpr (DIM >= 3) axisJacobianNearBd<Phys, 2>(phys, row, U, gv, r, dl.hInv[2], fac + 2 * N, Jv, base, len, slots);
-  addForcingJac<Phys>(phys, U + (int64_t)row[0] * N, Jv, base, len, slots[0]);
+  // point terms: Coriolis / reaction on the self block
+  const double* uSelf = U + (int64_t)row[0] * N;
+  if constexpr (!PhysTraits<Phys>::hasDiffusion) {
+    addExtraJacInner<Phys>(phys, uSelf, slots, [&](int k, int slot, int j, double val) {
+      Jv[base + (int64_t)k * len + slot * N + j] += val;
+    });
+  } else {
+    // diffusion on a near-boundary row (advection_diffusion_2d_prob_class.hpp:755-792,
+    // advection_diffusion_reaction_2d_prob_class.hpp:693-721): existing first-layer neighbours get dD, a missing one
+    // folds -dD into the self entry
+    double self = 0.0;
+#pragma unroll
+    for (int ax = 0; ax < DIM; ++ax) self += -2.0 * phys.dD[ax];
+    if constexpr (std::is_same<Phys, LinAdv<2>>::value) self -= phys.sigma;
+#pragma unroll
+    for (int ax = 0; ax < DIM; ++ax) {
+      const int sm = (ax == 0) ? 0 : (ax == 1 ? 3 : 4), sp = (ax == 0) ? 2 : (ax == 1 ? 1 : 5);
+      for (int side : {sm, sp}) {
+        const int c = gcol<DIM>(side, 0);
+        if (row[c] >= 0) {
+#pragma unroll
+          for (int k = 0; k < N; ++k) Jv[base + (int64_t)k * len + slots[c] * N + k] += phys.dD[ax];
+        } else {
+          self += -phys.dD[ax];
+        }
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < N; ++k) Jv[base + (int64_t)k * len + slots[0] * N + k] += self;
+  }
 }
 
 // ------------------------------------------------------------------------------------------------ Gray-Scott
@@ -362,6 +458,82 @@ __global__ void k_gray_scott_rows(GrayScottParams gp, RowSet rs, const double* _
     r0[2 * sl] += uDx; r0[2 * sf] += uDy; r0[2 * sr] += uDx; r0[2 * sb] += uDy;
     r1[2 * sl + 1] += vDx; r1[2 * sf + 1] += vDy; r1[2 * sr + 1] += vDx; r1[2 * sb + 1] += vDy;
   }
+}
+
+// ------------------------------------------------------------------------------------------------ diffusion-reaction A
+// DiffusionReaction1d::ProblemA / DiffusionReaction2d::ProblemA (one dof):  ds/dt = D lap(s) + k s^2 + f(x[,y],t)
+// (diffusion_reaction_1d_prob_class.hpp:211-302, diffusion_reaction_2d_prob_class.hpp:306-456).  One thread per
+// sample row, all rows in one launch.  The ghost of a missing neighbour is -s(self) (homogeneous Dirichlet at the
+// wall: diffusion_reaction_1d_ghost_filler.hpp:85-94), so no ghost arrays are needed.  f is a per-row table.
+struct DiffReacParams { double dD[2]; double reaction; };
+
+template <int DIM>
+__global__ void k_diffreac_rows(DiffReacParams pr, RowSet rs, const double* __restrict__ U, const double* __restrict__ src,
+                                double* __restrict__ V, double* __restrict__ Jv, JacLayout jl) {
+  const int32_t r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= rs.n) return;
+  const int32_t* row = rs.graph + (int64_t)r * rs.ncols;
+  const double u = U[row[0]];
+  // neighbour columns in accumulation order: x: left (1), right (DIM==1 ? 2 : 3); y: back (4), front (2)
+  const int cl = 1, cr = (DIM == 1) ? 2 : 3, cb = 4, cf = 2;
+  const int32_t il = row[cl], ir = row[cr];
+  const double ul = il >= 0 ? U[il] : -u, ur = ir >= 0 ? U[ir] : -u;
+  bool nearBd = (il < 0) || (ir < 0);
+  int32_t ib = 0, ifr = 0;
+  double ub = 0.0, uf = 0.0;
+  if (DIM == 2) {
+    ib = row[cb]; ifr = row[cf];
+    ub = ib >= 0 ? U[ib] : -u; uf = ifr >= 0 ? U[ifr] : -u;
+    nearBd = nearBd || (ib < 0) || (ifr < 0);
+  }
+  const int32_t sampleRow = rs.rowIds[r];
+  if (V) {
+    double v = src[sampleRow];
+    v += pr.reaction * u * u;
+    v += pr.dD[0] * (ur - 2.0 * u + ul);
+    if (DIM == 2) v += pr.dD[1] * (uf - 2.0 * u + ub);
+    V[sampleRow] = v;
+  }
+  if (Jv) {
+    const int64_t base = jl.base[r];
+    const uint8_t* slots = jl.slot + (int64_t)r * jl.nslotCols;
+    double* Jr = Jv + base;
+    const double twoK = pr.reaction * 2.0;
+    if (DIM == 1) {
+      Jr[slots[0]] += (nearBd ? -3.0 * pr.dD[0] : -2.0 * pr.dD[0]) + twoK * u;
+      if (il >= 0) Jr[slots[cl]] += pr.dD[0];
+      if (ir >= 0) Jr[slots[cr]] += pr.dD[0];
+    } else {
+      double self = -2.0 * pr.dD[0] - 2.0 * pr.dD[1] + twoK * u;
+      // reference order of the missing-neighbour folds: left, front, right, back
+      if (il >= 0) Jr[slots[cl]] += pr.dD[0]; else self += -pr.dD[0];
+      if (ifr >= 0) Jr[slots[cf]] += pr.dD[1]; else self += -pr.dD[1];
+      if (ir >= 0) Jr[slots[cr]] += pr.dD[0]; else self += -pr.dD[0];
+      if (ib >= 0) Jr[slots[cb]] += pr.dD[1]; else self += -pr.dD[1];
+      Jr[slots[0]] += self;
+    }
+  }
+}
+
+// Gray-Scott velocity on a fully periodic full lattice: neighbours by index arithmetic, no graph in HBM
+// (HBM-bound: 32 B/cell; rows of 128 consecutive x cells per CTA keep the y neighbours' loads coalesced)
+__global__ void __launch_bounds__(128)
+k_gray_scott_lattice(GrayScottParams gp, int32_t nx, int32_t ny, const double2* __restrict__ U, double2* __restrict__ V) {
+  const int32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  const int32_t j = blockIdx.y;
+  if (i >= nx) return;
+  const int32_t il = (i == 0) ? nx - 1 : i - 1, ir = (i == nx - 1) ? 0 : i + 1;
+  const int32_t jb = (j == 0) ? ny - 1 : j - 1, jf = (j == ny - 1) ? 0 : j + 1;
+  const double2 c = U[(int64_t)j * nx + i];
+  const double2 l = U[(int64_t)j * nx + il], rt = U[(int64_t)j * nx + ir];
+  const double2 b = U[(int64_t)jb * nx + i], f = U[(int64_t)jf * nx + i];
+  const double uDx = gp.Du * gp.dxInvSq, uDy = gp.Du * gp.dyInvSq;
+  const double vDx = gp.Dv * gp.dxInvSq, vDy = gp.Dv * gp.dyInvSq;
+  const double uvv = c.x * c.y * c.y;
+  double2 out;
+  out.x = gp.F * (1.0 - c.x) - uvv + uDx * (rt.x - 2.0 * c.x + l.x) + uDy * (b.x - 2.0 * c.x + f.x);
+  out.y = -(gp.F + gp.k) * c.y + uvv + vDx * (rt.y - 2.0 * c.y + l.y) + vDy * (b.y - 2.0 * c.y + f.y);
+  V[(int64_t)j * nx + i] = out;
 }
 
 // ------------------------------------------------------------------------------------------------ J * B

@@ -114,15 +114,6 @@ PDA_DEVFN void jacobianFaceRole(const Phys& phys, const int32_t* __restrict__ ro
   }
 }
 
-template <class Phys> PDA_DEVFN void addForcingJacStaged(const Phys&, const double*, double*, int, int) {}
-template <> PDA_DEVFN void addForcingJacStaged<Swe2d>(const Swe2d& phys, const double* u, double* my, int rowlen, int slot) {
-  const double f = phys.coriolis;
-  my[1 * rowlen + slot * 3 + 0] += f * u[2] / (u[0] * u[0]);
-  my[1 * rowlen + slot * 3 + 2] += -f / u[0];
-  my[2 * rowlen + slot * 3 + 1] += f / u[0];
-  my[2 * rowlen + slot * 3 + 0] += -f * u[1] / (u[0] * u[0]);
-}
-
 // zero the CSR values of the given cells (near-boundary rows are assembled by read-modify-write); one warp per cell
 __global__ void k_zero_cell_chunks(const int32_t* __restrict__ base, const int32_t* __restrict__ len, int32_t n,
                                    int ndpc, double* __restrict__ Jv) {
@@ -181,8 +172,11 @@ k_jacobian_inner_staged(Phys phys, RowSet rs, Deltas dl, const double* __restric
         double v[N];
 #pragma unroll
         for (int d = 0; d < N; ++d) v[d] = sV[c * N + d];
-        addForcing<Phys>(phys, uSelf, v);
-        addForcingJacStaged<Phys>(phys, uSelf, my, ROWLEN, sSelf);
+        addDiffusionInner<Phys>(phys, row, U, v);
+        addForcing<Phys>(phys, uSelf, v, valid ? rs.rowIds[r] : 0);
+        addExtraJacInner<Phys>(phys, uSelf, slots, [&](int k, int slot, int j, double val) {
+          my[k * ROWLEN + slot * N + j] += val;
+        });
         if (V && valid) {
           double* out = V + (int64_t)rs.rowIds[r] * N;
 #pragma unroll

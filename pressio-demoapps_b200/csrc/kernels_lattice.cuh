@@ -34,8 +34,10 @@ PDA_DEVFN int32_t shiftIdx(int32_t idx, int off, int32_t n, int32_t periodic) {
 
 // v1: one thread per cell, both faces of every axis computed by the owning cell (like the reference).
 template <class Phys, int S, int AX>
-PDA_DEVFN void latticeAxis(const Phys& phys, const double* __restrict__ U, const int64_t* cellOfPos, double hInv, double* v) {
+PDA_DEVFN void latticeAxis(const Phys& phys, const double* __restrict__ U, const int64_t* cellOfPos, double hInv, double* v,
+                           double* diff) {
   constexpr int N = Phys::ndpc;
+  constexpr int h = (S - 1) / 2;
   double uLn[N], uLp[N], uRn[N], uRp[N];
 #pragma unroll
   for (int d = 0; d < N; ++d) {
@@ -44,7 +46,9 @@ PDA_DEVFN void latticeAxis(const Phys& phys, const double* __restrict__ U, const
     for (int p = 0; p < S; ++p) q[p] = U[cellOfPos[p] * N + d];
     Recon<S>::face(q, uLn[d], uLp[d]);
     Recon<S>::face(q + 1, uRn[d], uRp[d]);
+    if constexpr (PhysTraits<Phys>::hasDiffusion) diff[d] = phys.dD[AX] * (q[h + 1] - 2.0 * q[h] + q[h - 1]);
   }
+  (void)diff;
   double FL[N], FR[N];
   phys.template flux<AX>(uLn, uLp, FL);
   phys.template flux<AX>(uRn, uRp, FR);
@@ -83,7 +87,7 @@ k_velocity_lattice_v1(Phys phys, LatticeDesc L, Deltas dl, const double* __restr
     return ((int64_t)(L.slab ? k + L.haloPlanes : k) * L.n[1] + j) * L.n[0] + i;
   };
   (void)strideU;
-  double v[N];
+  double v[N], diff[DIM][N];
 #pragma unroll
   for (int d = 0; d < N; ++d) v[d] = 0.0;
   int64_t pos[S];
@@ -94,7 +98,7 @@ k_velocity_lattice_v1(Phys phys, LatticeDesc L, Deltas dl, const double* __restr
     const int32_t ii = slabAxis ? ijk[0] + (p - h) : shiftIdx(ijk[0], p - h, L.n[0], 1);
     pos[p] = cellIndex(ii, ijk[1], ijk[2]);
   }
-  latticeAxis<Phys, S, 0>(phys, U, pos, dl.hInv[0], v);
+  latticeAxis<Phys, S, 0>(phys, U, pos, dl.hInv[0], v, diff[0]);
   if constexpr (DIM >= 2) {
 #pragma unroll
     for (int p = 0; p < S; ++p) {
@@ -102,7 +106,7 @@ k_velocity_lattice_v1(Phys phys, LatticeDesc L, Deltas dl, const double* __restr
       const int32_t jj = slabAxis ? ijk[1] + (p - h) : shiftIdx(ijk[1], p - h, L.n[1], 1);
       pos[p] = cellIndex(ijk[0], jj, ijk[2]);
     }
-    latticeAxis<Phys, S, 1>(phys, U, pos, dl.hInv[1], v);
+    latticeAxis<Phys, S, 1>(phys, U, pos, dl.hInv[1], v, diff[1]);
   }
   if constexpr (DIM >= 3) {
 #pragma unroll
@@ -110,13 +114,20 @@ k_velocity_lattice_v1(Phys phys, LatticeDesc L, Deltas dl, const double* __restr
       const int32_t kk = L.slab ? ijk[2] + (p - h) : shiftIdx(ijk[2], p - h, L.n[2], 1);
       pos[p] = cellIndex(ijk[0], ijk[1], kk);
     }
-    latticeAxis<Phys, S, 2>(phys, U, pos, dl.hInv[2], v);
+    latticeAxis<Phys, S, 2>(phys, U, pos, dl.hInv[2], v, diff[2]);
   }
+  if constexpr (PhysTraits<Phys>::hasDiffusion) {
+#pragma unroll
+    for (int a = 0; a < DIM; ++a)
+#pragma unroll
+      for (int d = 0; d < N; ++d) v[d] += diff[a][d];
+  }
+  (void)diff;
   const int64_t self = cellIndex(ijk[0], ijk[1], ijk[2]);
-  addForcing<Phys>(phys, U + self * N, v);
   // V is indexed without halo planes
   const int64_t vIdx = (DIM == 1) ? ijk[0] : (DIM == 2 ? (int64_t)ijk[1] * L.n[0] + ijk[0]
                                                       : ((int64_t)ijk[2] * L.n[1] + ijk[1]) * L.n[0] + ijk[0]);
+  addForcing<Phys>(phys, U + self * N, v, (int32_t)vIdx);
   double* out = V + vIdx * N;
 #pragma unroll
   for (int d = 0; d < N; ++d) out[d] = v[d];
@@ -125,8 +136,9 @@ k_velocity_lattice_v1(Phys phys, LatticeDesc L, Deltas dl, const double* __restr
 }  // namespace dev
 
 inline bool latticeKernelAvailable(int family, int dim, int /*S*/) {
-  // Euler 1/2/3D and SWE go through the structured kernels; Gray-Scott keeps the graph kernel for now
-  return family == 1 || family == 2 || family == 3 || family == 4;
+  // Euler 1/2/3D, SWE, Burgers, ADR and 1D advection go through the structured kernels; the diffusion-reaction
+  // family has its own lattice kernel (k_diffreac_lattice)
+  return family == 1 || family == 2 || family == 3 || family == 4 || family == 6 || family == 7 || family == 8;
   (void)dim;
 }
 

@@ -428,5 +428,87 @@ struct Swe2d {
   }
 };
 
+
+// ---------------------------------------------------------------------------------------------------------------
+// Extra (non-flux) terms of a problem.  The flux families above have none; the advection-diffusion families add a
+// first-order central diffusion term per axis, dD[ax] * (u_{+1} - 2u + u_{-1}) with dD = D * hInv^2
+// (advection_diffusion_2d_prob_class.hpp:1167-1201), and point terms (reaction, source) evaluated at the cell.
+// ---------------------------------------------------------------------------------------------------------------
+template <class Phys> struct PhysTraits {
+  static constexpr bool hasDiffusion = false;   // per-axis second-difference term
+};
+
+// 2D Burgers (u, v), Rusanov.  impl/advection_diffusion_2d_flux_functions.hpp:54-114.
+struct Burgers2d {
+  static constexpr int dim = 2;
+  static constexpr int ndpc = 2;
+  double dD[2];   // diffusion * dxInv^2, diffusion * dyInv^2
+
+  template <int AX>
+  PDA_DEVFN void flux(const double* qL, const double* qR, double* F) const {
+    constexpr double n0 = (AX == 0) ? 1.0 : 0.0, n1 = (AX == 1) ? 1.0 : 0.0;
+    const double a0 = fmax(fabs(qL[0]), fabs(qR[0]));
+    const double a1 = fmax(fabs(qL[1]), fabs(qR[1]));
+    double f0 = a0 * (qL[0] - qR[0]);
+    f0 += n0 * (qL[0] * qL[0] + qR[0] * qR[0]);
+    f0 += n1 * (qL[0] * qL[1] + qR[0] * qR[1]);
+    double f1 = a1 * (qL[1] - qR[1]);
+    f1 += n0 * (qL[0] * qL[1] + qR[0] * qR[1]);
+    f1 += n1 * (qL[1] * qL[1] + qR[1] * qR[1]);
+    F[0] = f0 * 0.25;
+    F[1] = f1 * 0.25;
+  }
+
+  template <int AX>
+  PDA_DEVFN void fluxJac(const double* qL, const double* qR, double* JL, double* JR) const {
+    constexpr double n0 = (AX == 0) ? 1.0 : 0.0, n1 = (AX == 1) ? 1.0 : 0.0;
+    if (fabs(qL[0]) > fabs(qR[0])) {
+      JL[0] = (2.0 * qL[0] - qR[0]) * copysign(1.0, qL[0]) + n0 * 2.0 * qL[0] + n1 * qL[1];
+      JR[0] = n0 * 2.0 * qR[0] + n1 * qR[1] - fabs(qL[0]);
+    } else {
+      JL[0] = n0 * 2.0 * qL[0] + n1 * qL[1] + fabs(qR[0]);
+      JR[0] = (qL[0] - 2.0 * qR[0]) * copysign(1.0, qR[0]) + n0 * 2.0 * qR[0] + n1 * qR[1];
+    }
+    JL[0] *= 0.25; JR[0] *= 0.25;
+    if (fabs(qL[1]) > fabs(qR[1])) {
+      JL[3] = (2.0 * qL[1] - qR[1]) * copysign(1.0, qL[1]) + n0 * qL[0] + n1 * 2.0 * qL[1];
+      JR[3] = n0 * qR[0] + n1 * 2.0 * qR[1] - fabs(qL[1]);
+    } else {
+      JL[3] = n0 * qL[0] + n1 * 2.0 * qL[1] + fabs(qR[1]);
+      JR[3] = (qL[1] - 2.0 * qR[1]) * copysign(1.0, qR[1]) + n0 * qR[0] + n1 * 2.0 * qR[1];
+    }
+    JL[3] *= 0.25; JR[3] *= 0.25;
+    JL[1] = n1 * qL[0] * 0.25; JL[2] = n0 * qL[1] * 0.25;
+    JR[1] = n1 * qR[0] * 0.25; JR[2] = n0 * qR[1] * 0.25;
+  }
+};
+template <> struct PhysTraits<Burgers2d> { static constexpr bool hasDiffusion = true; };
+
+// Linear advection of one scalar with constant velocity a: the reference's "Rusanov" branch is the upwind flux of a
+// POSITIVE velocity, F = a * uNeg (impl/advection_1d_mixins.hpp:79-94, advection_diffusion_reaction_2d_flux_mixin.hpp).
+//   DIM 1: Advection1d::PeriodicLinear (no extra terms: dD = sigma = 0, no source);
+//   DIM 2: AdvectionDiffusionReaction2d::ProblemA: + D lap(u) - sigma u + f(x,y,t)
+//          (advection_diffusion_reaction_2d_prob_class.hpp:485-512); f is a per-cell table (device pointer, indexed
+//          by sample-mesh row) or the constant srcConst when the table is null (default source: 1).
+template <int DIM>
+struct LinAdv {
+  static constexpr int dim = DIM;
+  static constexpr int ndpc = 1;
+  double a[DIM];
+  double dD[DIM];
+  double sigma;
+  double srcConst;
+  const double* srcTable;
+
+  template <int AX>
+  PDA_DEVFN void flux(const double* qL, const double* /*qR*/, double* F) const { F[0] = qL[0] * a[AX]; }
+  template <int AX>
+  PDA_DEVFN void fluxJac(const double* /*qL*/, const double* /*qR*/, double* JL, double* JR) const {
+    JL[0] = a[AX];
+    JR[0] = 0.0;
+  }
+};
+template <> struct PhysTraits<LinAdv<2>> { static constexpr bool hasDiffusion = true; };
+
 }  // namespace dev
 }  // namespace pda

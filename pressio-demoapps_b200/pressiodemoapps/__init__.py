@@ -20,8 +20,11 @@ from enum import IntEnum as _IntEnum
 __all__ = [
     "CellCenteredUniformMesh", "load_cellcentered_uniform_mesh", "create_full_mesh", "create_sample_mesh", "mesh_from_arrays",
     "InviscidFluxReconstruction", "InviscidFluxScheme", "ViscousFluxReconstruction", "ViscousFluxScheme",
-    "Euler1d", "Euler2d", "Euler3d", "Swe2d", "DiffusionReaction2d", "AdvectionDiffusion2d",
+    "Euler1d", "Euler2d", "Euler3d", "Swe2d", "DiffusionReaction1d", "DiffusionReaction2d", "AdvectionDiffusion2d",
+    "AdvectionDiffusionReaction2d", "Advection1d",
     "create_problem", "create_gray_scott_2d_problem", "create_slip_wall_swe_2d_problem", "create_cross_shock_problem",
+    "create_linear_advection_1d_problem", "create_diffusion_reaction_1d_problem_A", "create_burgers_2d_problem",
+    "create_diffusion_reaction_2d_problem_A", "create_adv_diff_reac_2d_problem_A",
     "advanceRK2", "advanceRK4", "advanceSSP3", "PdaError", "device_count", "BC",
 ]
 
@@ -80,6 +83,7 @@ _sig("pda_mesh_stencil_gids", _C.c_int, _vp, _vp)
 _sig("pda_problem_create", _C.c_int, _vp, _C.c_int, _C.c_int, _C.c_int, _C.c_int, _C.c_int, _vp, _vp, _C.c_int,
      _C.POINTER(_vp))
 _sig("pda_problem_set_bc", _C.c_int, _vp, _C.c_int, _C.c_int, _vp)
+_sig("pda_problem_set_source", _C.c_int, _vp, _vp)
 _sig("pda_problem_free", _C.c_int, _vp)
 _sig("pda_problem_num_dof_per_cell", _C.c_int, _vp)
 _sig("pda_problem_total_dof_sample_mesh", _i32, _vp)
@@ -187,6 +191,18 @@ class AdvectionDiffusion2d(_IntEnum):
     BurgersOutflow = 1
 
 
+class AdvectionDiffusionReaction2d(_IntEnum):
+    ProblemA = 0
+
+
+class Advection1d(_IntEnum):
+    PeriodicLinear = 0
+
+
+class DiffusionReaction1d(_IntEnum):
+    ProblemA = 0
+
+
 class BC(_IntEnum):
     """Device-expressible custom boundary rules (custom_bcs_functions.hpp)."""
     Dirichlet = 0
@@ -194,7 +210,8 @@ class BC(_IntEnum):
     Reflective = 2
 
 
-_FAMILY = {Euler1d: 1, Euler2d: 2, Euler3d: 3, Swe2d: 4, DiffusionReaction2d: 5, AdvectionDiffusion2d: 6}
+_FAMILY = {Euler1d: 1, Euler2d: 2, Euler3d: 3, Swe2d: 4, DiffusionReaction2d: 5, AdvectionDiffusion2d: 6,
+           AdvectionDiffusionReaction2d: 7, Advection1d: 8, DiffusionReaction1d: 9}
 
 
 # ------------------------------------------------------------------------------------------------ mesh
@@ -332,12 +349,41 @@ class Problem:
                                            names, vals, device, _C.byref(h)))
         self._h = h
         self._pattern = None
+        self._source = None      # host functor f(x[,y],t) of the ProblemA families
+        self._source_t = None
 
     def __del__(self):
         h = getattr(self, "_h", None)
         if h:
             _lib.pda_problem_free(h)
             self._h = None
+
+    # ---- source term of the ProblemA families (the reference takes a Python functor: main_binder.cc:313-320,433-438)
+    def setSourceTable(self, values):
+        """per-SAMPLE-cell source values (pda_problem_set_source)"""
+        v = _np.ascontiguousarray(values, dtype=_np.float64)
+        if v.size != self._mesh.sampleMeshSize():
+            raise ValueError("source table has %d entries, expected %d" % (v.size, self._mesh.sampleMeshSize()))
+        _check(_lib.pda_problem_set_source(self._h, v.ctypes.data))
+
+    def _set_source_functor(self, f):
+        self._source = f
+        x, y, _ = self._mesh._coords()
+        c = self._mesh.graph()[:, 0]
+        self._src_xy = (x[c], y[c])
+
+    def _refresh_source(self, time):
+        # the functor is evaluated on the host for every sample cell when the evaluation time changes -- exactly what
+        # the reference's pybind wrapper does per cell (diffusion_reaction1d.hpp:176-181), then handed over as a table
+        if self._source is None or self._source_t == time:
+            return
+        xs, ys = self._src_xy
+        if self._mesh.dimensionality() == 1:
+            tab = [float(self._source(float(a), float(time))) for a in xs]
+        else:
+            tab = [float(self._source(float(a), float(b), float(time))) for a, b in zip(xs, ys)]
+        self.setSourceTable(_np.array(tab))
+        self._source_t = time
 
     # ---- sizes / parameters
     def numDofPerCell(self): return _lib.pda_problem_num_dof_per_cell(self._h)
@@ -398,6 +444,7 @@ class Problem:
     def rightHandSide(self, state, time, V):
         _f64(state, self.totalDofStencilMesh(), "state")
         _f64(V, self.totalDofSampleMesh(), "rhs")
+        self._refresh_source(time)
         _check(_lib.pda_problem_velocity_host(self._h, state.ctypes.data, float(time), V.ctypes.data))
 
     rhs = rightHandSide
@@ -414,6 +461,7 @@ class Problem:
         vals = J.data if hasattr(J, "data") and not isinstance(J, _np.ndarray) else J
         _f64(vals, self.jacobianPattern()[1].size, "jacobian values")
         vp = None if V is None else _f64(V, self.totalDofSampleMesh(), "rhs").ctypes.data
+        self._refresh_source(time)
         _check(_lib.pda_problem_velocity_and_jacobian_host(self._h, state.ctypes.data, float(time), vp,
                                                            vals.ctypes.data))
 
@@ -435,6 +483,7 @@ class Problem:
             if not operand.flags["C_CONTIGUOUS"] or not result.flags["C_CONTIGUOUS"]:
                 raise ValueError("operand/result must be contiguous")
             layout = 1
+        self._refresh_source(time)
         _check(_lib.pda_problem_apply_jacobian_host(self._h, state.ctypes.data, operand.ctypes.data, ncols, layout,
                                                     float(time), result.ctypes.data))
 
@@ -489,14 +538,14 @@ def _make(mesh, family, probEnum, recon, icFlag=1, params=None, device=0):
 
 def create_problem(mesh, probEnum, *args, device=0):
     """Overload set of `create_problem` (src_py/main_binder.cc:255-546, C++ create_problem_eigen):
-       (mesh, Euler1d|Euler3d, recon) ; (mesh, Euler2d|Swe2d, recon[, icFlag][, {name: value}]) ;
-       (mesh, DiffusionReaction2d.GrayScott[, ViscousFluxReconstruction])."""
+       (mesh, Euler1d|Euler3d|Advection1d|AdvectionDiffusionReaction2d, recon) ;
+       (mesh, Euler2d|Swe2d, recon[, icFlag][, {name: value}]) ; (mesh, DiffusionReaction1d) ;
+       (mesh, DiffusionReaction2d[, ViscousFluxReconstruction]) ;
+       (mesh, AdvectionDiffusion2d, recon, ViscousFluxReconstruction[, {name: value}])."""
     fam = _FAMILY.get(type(probEnum))
     if fam is None:
         raise TypeError("create_problem: unknown problem enum %r" % (probEnum,))
-    if fam == 5:
-        if probEnum != DiffusionReaction2d.GrayScott:
-            raise PdaError(5, "DiffusionReaction2d.ProblemA needs a host source functor: not available on the device")
+    if fam in (5, 9):
         return _make(mesh, fam, probEnum, 0, 1, None, device)
     if not args:
         raise TypeError("create_problem: missing reconstruction enum")
@@ -510,6 +559,49 @@ def create_problem(mesh, probEnum, *args, device=0):
         else:
             icFlag = int(a)
     return _make(mesh, fam, probEnum, recon, icFlag, params, device)
+
+
+def create_linear_advection_1d_problem(mesh, recon, *args, ic=1, device=0):
+    """advection1d.hpp:107-152: (mesh, recon, InviscidFluxScheme, velocity) or (mesh, recon, velocity, ic=1)."""
+    if args and isinstance(args[0], InviscidFluxScheme):
+        velocity = float(args[1])
+    else:
+        velocity = float(args[0])
+        if len(args) > 1:
+            ic = int(args[1])
+    return _make(mesh, 8, Advection1d.PeriodicLinear, recon, ic, {"velocity": velocity}, device)
+
+
+def _problem_a(mesh, fam, enum, args, device):
+    # (mesh, diffusion, reaction) or (mesh, sourceFunctor, diffusion, reaction)
+    src = None
+    if callable(args[0]):
+        src, args = args[0], args[1:]
+    p = _make(mesh, fam, enum, 0, 1, {"diffusion": float(args[0]), "reaction": float(args[1])}, device)
+    if src is not None:
+        p._set_source_functor(src)
+    return p
+
+
+def create_diffusion_reaction_1d_problem_A(mesh, *args, device=0):
+    """diffusion_reaction1d.hpp:128-212: (mesh, diffusion, reaction) or (mesh, source(x, t), diffusion, reaction)."""
+    return _problem_a(mesh, 9, DiffusionReaction1d.ProblemA, args, device)
+
+
+def create_diffusion_reaction_2d_problem_A(mesh, viscRecon, *args, device=0):
+    """diffusion_reaction2d.hpp:186-257: (mesh, visc, diffusion, reaction) or (mesh, visc, source(x, y, t), D, k)."""
+    return _problem_a(mesh, 5, DiffusionReaction2d.ProblemA, args, device)
+
+
+def create_burgers_2d_problem(mesh, probEnum, recon, viscRecon, params, device=0):
+    """advection_diffusion2d.hpp:115-152 (custom coefficients through the {name: value} map)."""
+    return _make(mesh, 6, probEnum, recon, 1, dict(params), device)
+
+
+def create_adv_diff_reac_2d_problem_A(mesh, recon, ux, uy, diffusion, sigma, device=0):
+    """advection_diffusion_reaction2d.hpp:140-160."""
+    return _make(mesh, 7, AdvectionDiffusionReaction2d.ProblemA, recon, 1,
+                 {"ux": ux, "uy": uy, "diffusion": diffusion, "sigma": sigma}, device)
 
 
 def create_problem_slab(mesh, probEnum, recon, rank, nranks, device=0):

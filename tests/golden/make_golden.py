@@ -81,6 +81,30 @@ CASES = [
     ("euler3d_smooth_weno3_per_10x8x6", [10, 8, 6], [-1, 1, -1, 1, -1, 1], ("x", "y", "z"), 5, "euler3d", 0, W3, 1, None, 0.0, None),
     ("euler3d_sedovsym_weno3_8", [8, 8, 8], [0, 1, 0, 1, 0, 1], (), 5, "euler3d", 1, W3, 1, None, 0.0, None),
     ("euler3d_sedovsym_fo_7x6x8", [7, 6, 8], [0, 1, 0, 1, 0, 1], (), 3, "euler3d", 1, FO, 1, None, 0.0, None),
+    # the remaining families the north star names: Burgers (tests_cpp/eigen_2d_burgers_*), advection-diffusion-reaction
+    # (eigen_2d_adv_diff_reac_*), 1D linear advection (eigen_1d_linear_adv_*), diffusion-reaction ProblemA
+    # (eigen_{1,2}d_diffusion_reaction_*); "testSource" = a time-dependent analytic source functor (oracle/ref_driver.cc)
+    ("burgers_per_weno5_20x18", [20, 18], [-1, 1, -1, 1], ("x", "y"), 7, "advdiff2d", 0, W5, 1, None, 0.0, None),
+    ("burgers_per_fo_12x10", [12, 10], [-1, 1, -1, 1], ("x", "y"), 3, "advdiff2d", 0, FO, 1, None, 0.0, None),
+    ("burgers_out_weno3_param", [20, 18], [-1, 1, -1, 1], (), 5, "advdiff2d", 1, W3, 1,
+     {"diffusion": 1e-3, "pulseX": 0.1, "pulseMagnitude": 0.6}, 0.0, None),
+    ("burgers_out_weno5_20x18", [20, 18], [-1, 1, -1, 1], (), 7, "advdiff2d", 1, W5, 1, None, 0.0, None),
+    ("burgers_out_fo_16", [16, 16], [-1, 1, -1, 1], (), 3, "advdiff2d", 1, FO, 1, None, 0.0, None),
+    ("burgers_out_weno3_sample", [30, 30], [-1, 1, -1, 1], (), 5, "advdiff2d", 1, W3, 1, None, 0.0, 0.1),
+    ("adr_fo_16x14", [16, 14], [0, 1, 0, 1], (), 3, "advdiffreac2d", 0, FO, 1, None, 0.0, None),
+    ("adr_weno3_16x14", [16, 14], [0, 1, 0, 1], (), 5, "advdiffreac2d", 0, W3, 1, None, 0.0, None),
+    ("adr_weno5_param", [18, 16], [0, 1, 0, 1], (), 7, "advdiffreac2d", 0, W5, 1,
+     {"ux": 0.3, "uy": 0.2, "diffusion": 0.01, "sigma": 2.0}, 0.0, None),
+    ("adr_weno5_sample", [30, 30], [0, 1, 0, 1], (), 7, "advdiffreac2d", 0, W5, 1, None, 0.0, 0.1),
+    ("adv1d_weno5_per50", [50, 1], [-1.0, 1.0], ("x",), 7, "advection1d", 0, W5, 1, None, 0.0, None),
+    ("adv1d_weno3_ic2_vel", [50, 1], [0.0, 4.0], ("x",), 5, "advection1d", 0, W3, 2, {"velocity": 0.5}, 0.0, None),
+    ("adv1d_fo_ic4", [40, 1], [0.0, 4.0], ("x",), 3, "advection1d", 0, FO, 4, None, 0.0, None),
+    ("diffreac1d_a_40", [40, 1], [0.0, 1.0], (), 3, "diffreac1d", 0, FO, 1, None, 0.0, None),
+    ("diffreac1d_a_src_param", [40, 1], [0.0, 1.0], (), 3, "diffreac1d", 0, FO, 1,
+     {"diffusion": 0.02, "reaction": 0.03, "testSource": 1}, 0.3, None),
+    ("diffreac2d_a_16x14", [16, 14], [0, 1, 0, 1], (), 3, "diffreac2d", 0, FO, 1, None, 0.0, None),
+    ("diffreac2d_a_src", [16, 14], [0, 1, 0, 1], (), 3, "diffreac2d", 0, FO, 1, {"testSource": 1}, 0.3, None),
+    ("diffreac2d_a_sample", [30, 30], [0, 1, 0, 1], (), 3, "diffreac2d", 0, FO, 1, None, 0.0, 0.1),
 ]
 
 
@@ -120,6 +144,11 @@ def make_case(case, outdir):
     IC = ref.initialCondition()
     rng = np.random.default_rng(20261017)
     U = IC * (1.0 + 1e-3 * rng.uniform(-1, 1, IC.size))
+    if not np.any(IC):   # families whose initial condition is identically zero: a small random state instead
+        U = 0.1 * rng.uniform(-1, 1, IC.size)
+    if params and "testSource" in params:   # the functor's values at the sample cells (what the binding tabulates)
+        c = ma["graph"][:, 0]
+        extra["src"] = np.sin(ma["x"][c] + t) if fam == "diffreac1d" else np.cos(ma["x"][c] * ma["y"][c] + t)
     V = ref.velocity(U, t)
     V2, Jv = ref.velocityAndJacobian(U, t)
     rowptr, colidx = ref.pattern()

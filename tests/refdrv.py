@@ -12,7 +12,8 @@ import numpy as np
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 REFDIR = os.path.join(ROOT, "oracle", "_ref")
 
-FAM = {"euler1d": 1, "euler2d": 2, "euler3d": 3, "swe2d": 4, "diffreac2d": 5, "advdiff2d": 6}
+FAM = {"euler1d": 1, "euler2d": 2, "euler3d": 3, "swe2d": 4, "diffreac2d": 5, "advdiff2d": 6, "advdiffreac2d": 7,
+       "advection1d": 8, "diffreac1d": 9}
 
 
 def ref_lib_path(omp=False):
@@ -159,6 +160,7 @@ def _oracle(omp=False):
         L.or_create_from_arrays.restype = vp
         L.or_create_from_arrays.argtypes = [ci, ci, C.c_int32, C.c_int32, vp, vp, vp, vp, vp, ci, ci, ci, ci, ci, vp, vp]
         L.or_destroy.argtypes = [vp]
+        L.or_set_source.argtypes = [vp, vp]
         L.or_query.restype = C.c_longlong
         L.or_query.argtypes = [vp, ci]
         L.or_mesh_arrays.argtypes = [vp] * 8
@@ -228,6 +230,11 @@ class OracleProblem:
                               rb.ctypes.data, d.ctypes.data)
         return dict(graph=g, x=x, y=y, z=z, rowsInner=ri[:self.nInner], rowsNearBd=rb[:self.nNearBd], d=d[:3],
                     dInv=d[3:])
+
+    def setSource(self, values):
+        v = np.ascontiguousarray(values, dtype=np.float64)
+        assert v.size == self.nSample
+        self.L.or_set_source(self.h, v.ctypes.data)
 
     def initialCondition(self):
         U = np.zeros(self.nDofStencil)

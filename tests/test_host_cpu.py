@@ -15,7 +15,10 @@ from conftest import ROOT, golden_names
 
 R = pda.InviscidFluxReconstruction
 ENUM = {"euler1d": pda.Euler1d, "euler2d": pda.Euler2d, "euler3d": pda.Euler3d, "swe2d": pda.Swe2d,
-        "diffreac2d": pda.DiffusionReaction2d}
+        "diffreac2d": pda.DiffusionReaction2d, "advdiff2d": pda.AdvectionDiffusion2d,
+        "advdiffreac2d": pda.AdvectionDiffusionReaction2d, "advection1d": pda.Advection1d,
+        "diffreac1d": pda.DiffusionReaction1d}
+VISC = pda.ViscousFluxReconstruction.FirstOrder
 
 
 def make_mesh(g):
@@ -29,6 +32,28 @@ def make_mesh(g):
 def make_problem(g, mesh):
     m = g.meta
     e = ENUM[m["family"]](m["prob"])
+    prm = dict(m["params"] or {})
+    if m["family"] in ("diffreac1d", "diffreac2d") and m["prob"] == 0:
+        # ProblemA through the reference's named factories; "testSource" = the analytic functor of oracle/ref_driver.cc
+        D, k = prm.get("diffusion", 0.01), prm.get("reaction", 0.01)
+        one_d = m["family"] == "diffreac1d"
+        src = ()
+        if "testSource" in prm:
+            import math
+            src = ((lambda x, t: math.sin(x + t)),) if one_d else ((lambda x, y, t: math.cos(x * y + t)),)
+        if not prm:
+            return pda.create_problem(mesh, e) if one_d else pda.create_problem(mesh, e, VISC)
+        if one_d:
+            return pda.create_diffusion_reaction_1d_problem_A(mesh, *src, D, k)
+        return pda.create_diffusion_reaction_2d_problem_A(mesh, VISC, *src, D, k)
+    if m["family"] == "advdiff2d":
+        if prm:
+            return pda.create_burgers_2d_problem(mesh, e, R(m["recon"]), VISC, prm)
+        return pda.create_problem(mesh, e, R(m["recon"]), VISC)
+    if m["family"] == "advdiffreac2d" and prm:
+        return pda.create_adv_diff_reac_2d_problem_A(mesh, R(m["recon"]), prm["ux"], prm["uy"], prm["diffusion"], prm["sigma"])
+    if m["family"] == "advection1d":
+        return pda.create_linear_advection_1d_problem(mesh, R(m["recon"]), prm.get("velocity", 1.0), m["ic"])
     if m["family"] == "diffreac2d":
         if m["params"]:
             p = m["params"]

@@ -121,7 +121,10 @@ def test_oracle_matches_reference_golden(name, load_golden):
     or last-ulp, the restatement keeps the reference's operation order)."""
     g = load_golden(name)
     m = g.meta
-    o = OracleProblem(None, m["family"], m["prob"], m["recon"], m["ic"], m["params"], arrays=oracle_arrays(g))
+    prm = {k: v for k, v in (m["params"] or {}).items() if k != "testSource"}
+    o = OracleProblem(None, m["family"], m["prob"], m["recon"], m["ic"], prm, arrays=oracle_arrays(g))
+    if "src" in g:
+        o.setSource(g["src"])
     assert (o.nSample, o.nStencil, o.ndpc, o.nnz) == (g["graph"].shape[0], g["x"].size, m["ndpc"], m["nnz"])
     ma = o.mesh_arrays()
     assert np.array_equal(ma["rowsInner"], g["rowsInner"])
