@@ -198,6 +198,23 @@ pda_status pda_slab_initial_condition(pda_problem p, double* U_owned);
 pda_status pda_slab_velocity_interior_dev(pda_problem p, const double* dU_local, double t, double* dV_owned, void* stream);
 pda_status pda_slab_velocity_boundary_dev(pda_problem p, const double* dU_local, double t, double* dV_owned, void* stream);
 
+
+/* Peer mode (3D lattices): the halo exchange fused with the evaluation over NVLink peer memory, no collective library
+ * on the data path.  Every rank owns a halo buffer (2 parities x {lower, upper} x halo planes + flags) that its ring
+ * neighbours fill with copy-engine peer copies followed by a flag write; ONE kernel launch evaluates all owned planes
+ * and only the CTAs that touch a halo plane wait for the flag, after the interior chunks have been scheduled.
+ *   1. every rank:  pda_slab_peer_handle()  -> 64-byte cudaIpcMemHandle of its buffer;
+ *   2. all-gather the handles (torch.distributed / MPI / files), then pda_slab_peer_connect(all handles by rank);
+ *      neighbours living in the SAME process connect with pda_slab_peer_connect_local instead;
+ *   3. per evaluation: pda_slab_velocity_peer_dev(dU_owned, t, dV_owned, stream) -- dU_owned holds the owned planes
+ *      only, (k1-k0)*plane_dofs doubles.  Every rank must call it the same number of times (SPMD); work enqueued on
+ *      `stream` after the call (e.g. the update of U) is ordered after the outgoing copies.  Ranks sharing one
+ *      process must use distinct streams. */
+pda_status pda_slab_peer_handle(pda_problem p, unsigned char handle[64]);
+pda_status pda_slab_peer_connect(pda_problem p, const unsigned char* handles /* nranks x 64 bytes */);
+pda_status pda_slab_peer_connect_local(pda_problem p, pda_problem lower, pda_problem upper);
+pda_status pda_slab_velocity_peer_dev(pda_problem p, const double* dU_owned, double t, double* dV_owned, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

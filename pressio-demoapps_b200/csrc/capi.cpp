@@ -279,4 +279,23 @@ pda_status pda_slab_velocity_boundary_dev(pda_problem p, const double* dU, doubl
   return guarded([&] { P(p).slabVelocityDev(dU, t, dV, stream, true); });
 }
 
+pda_status pda_slab_peer_handle(pda_problem p, unsigned char handle[64]) {
+  return guarded([&] {
+    if (!handle) throw pda::Error(pda::kInvalid, "slab_peer_handle: null output");
+    P(p).slabPeerHandle(handle);
+  });
+}
+
+pda_status pda_slab_peer_connect(pda_problem p, const unsigned char* handles) {
+  return guarded([&] { P(p).slabPeerConnect(handles); });
+}
+
+pda_status pda_slab_peer_connect_local(pda_problem p, pda_problem lower, pda_problem upper) {
+  return guarded([&] { P(p).slabPeerConnectLocal(&P(lower), &P(upper)); });
+}
+
+pda_status pda_slab_velocity_peer_dev(pda_problem p, const double* dU, double t, double* dV, void* stream) {
+  return guarded([&] { P(p).slabVelocityPeerDev(dU, t, dV, stream); });
+}
+
 }  // extern "C"

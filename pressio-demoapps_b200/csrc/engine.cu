@@ -184,7 +184,29 @@ struct DeviceState {
     if (sH2D) cudaStreamDestroy(sH2D);
     if (sD2H) cudaStreamDestroy(sD2H);
     for (int i = 0; i < kMaxChunks; ++i) { if (evIn[i]) cudaEventDestroy(evIn[i]); if (evOut[i]) cudaEventDestroy(evOut[i]); }
+    for (int i = 0; i < 2; ++i) {
+      if (peer.opened[i] && peer.remote[i] && !(i == 1 && peer.remote[1] == peer.remote[0])) cudaIpcCloseMemHandle(peer.remote[i]);
+      if (peer.sPush[i]) cudaStreamDestroy(peer.sPush[i]);
+      if (peer.evPushed[i]) cudaEventDestroy(peer.evPushed[i]);
+    }
+    if (peer.evReady) cudaEventDestroy(peer.evReady);
+    if (peer.base) cudaFree(peer.base);
   }
+  // ---- slab peer mode: library-owned halo buffers the ring neighbours push into over NVLink (engine.cu, bottom)
+  struct PeerHalo {
+    unsigned char* base = nullptr;        // [2 parities][lo,hi][h planes] doubles | flags | epoch table
+    size_t haloDoubles = 0;               // h * planeDofs
+    size_t flagsOff = 0, tableOff = 0, bytes = 0;
+    unsigned char* remote[2] = {nullptr, nullptr};   // base of the lower / upper neighbour's buffer (peer-mapped)
+    bool opened[2] = {false, false};      // remote[i] came from cudaIpcOpenMemHandle
+    bool connected = false;
+    cudaStream_t sPush[2] = {nullptr, nullptr};
+    cudaEvent_t evReady = nullptr, evPushed[2] = {nullptr, nullptr};
+    uint32_t epoch = 0;
+    static constexpr size_t kFlagStride = 128, kTableEntries = 65536;
+    double* halo(unsigned char* b, int par, int side) const { return reinterpret_cast<double*>(b) + (size_t)(par * 2 + side) * haloDoubles; }
+    uint32_t* flag(unsigned char* b, int par, int side) const { return reinterpret_cast<uint32_t*>(b + flagsOff + (size_t)(par * 2 + side) * kFlagStride); }
+  } peer;
   dev::GhostView ghostView(int ndpc) const {
     dev::GhostView gv;
     for (int s = 0; s < 6; ++s) gv.g[s] = ghost[s].p;
@@ -1365,6 +1387,7 @@ void Problem::makeSlab(int rank, int nranks) {
   if (per < (S_ - 1) / 2) throw Error(kInvalid, "slab: fewer planes per rank than the stencil halo");
   if (!latticeKernelAvailable(family_, dim_, S_)) throw Error(kUnsupported, "slab: no structured kernel for this problem");
   slab_ = true;
+  slabRank_ = rank; slabRanks_ = nranks;
   slabK0_ = rank * per;
   slabK1_ = slabK0_ + per;
 }
@@ -1444,6 +1467,146 @@ void Problem::slabVelocityDev(const double* dUlocal, double /*t*/, double* dVown
     default: throw Error(kUnsupported, "slab: family not supported");
   }
   PDA_CUDA(cudaGetLastError());
+}
+
+// ----------------------------------------------------------------------------------------------- slab: peer mode
+// The halo exchange without a collective library: every rank owns a halo buffer (two parities x {lower, upper} x h
+// planes) that its ring neighbours fill with copy-engine peer copies over NVLink, each followed by a 4-byte copy of
+// the evaluation's epoch into a flag.  The velocity kernel is ONE launch over all owned planes; only the CTAs whose z
+// chunk touches a halo plane poll the flag (ld.acquire.sys), and they are scheduled so that interior chunks run while
+// the pushes are in flight.  No SM is needed to signal (a signalling kernel could starve behind the polling CTAs).
+// Double buffering by epoch parity makes the buffers race-free without a "done reading" handshake: a neighbour can
+// push epoch e+2 only after its kernel e+1 completed, which needed my push e+1, which my stream ordered after my
+// kernel e -- the last reader of the parity-e buffers.
+namespace {
+void ensurePeerBuffer(DeviceState& ds, size_t haloDoubles) {
+  auto& ph = ds.peer;
+  if (ph.base) return;
+  ph.haloDoubles = haloDoubles;
+  ph.flagsOff = ((4 * haloDoubles * sizeof(double)) + 255) & ~size_t(255);
+  ph.tableOff = ph.flagsOff + 4 * DeviceState::PeerHalo::kFlagStride;
+  ph.bytes = ph.tableOff + DeviceState::PeerHalo::kTableEntries * sizeof(uint32_t);
+  PDA_CUDA(cudaMalloc(&ph.base, ph.bytes));
+  PDA_CUDA(cudaMemset(ph.base + ph.flagsOff, 0, 4 * DeviceState::PeerHalo::kFlagStride));
+  std::vector<uint32_t> table(DeviceState::PeerHalo::kTableEntries);
+  for (size_t i = 0; i < table.size(); ++i) table[i] = (uint32_t)i;
+  PDA_CUDA(cudaMemcpy(ph.base + ph.tableOff, table.data(), table.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
+  for (int i = 0; i < 2; ++i) {
+    PDA_CUDA(cudaStreamCreateWithFlags(&ph.sPush[i], cudaStreamNonBlocking));
+    PDA_CUDA(cudaEventCreateWithFlags(&ph.evPushed[i], cudaEventDisableTiming));
+  }
+  PDA_CUDA(cudaEventCreateWithFlags(&ph.evReady, cudaEventDisableTiming));
+  PDA_CUDA(cudaDeviceSynchronize());
+}
+}  // namespace
+
+void Problem::slabPeerHandle(unsigned char handle[64]) {
+  if (!slab_) throw Error(kInvalid, "not a slab problem");
+  if (dim_ != 3) throw Error(kUnsupported, "slab peer mode: 3D lattices only (2D slabs use the send/recv halo path)");
+  ensureDevice();
+  PDA_CUDA(cudaSetDevice(device_));
+  int64_t planeDofs; int32_t h;
+  slabExtent(nullptr, nullptr, &h, &planeDofs);
+  ensurePeerBuffer(*dev_, (size_t)h * (size_t)planeDofs);
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+  cudaIpcMemHandle_t hd;
+  PDA_CUDA(cudaIpcGetMemHandle(&hd, dev_->peer.base));
+  std::memcpy(handle, &hd, 64);
+}
+
+void Problem::slabPeerConnect(const unsigned char* handles) {
+  if (!handles) throw Error(kInvalid, "slab_peer_connect: null handles");
+  unsigned char mine[64];
+  slabPeerHandle(mine);   // allocates
+  auto& ph = dev_->peer;
+  const int lo = (slabRank_ - 1 + slabRanks_) % slabRanks_, hi = (slabRank_ + 1) % slabRanks_;
+  const int nb[2] = {lo, hi};
+  for (int i = 0; i < 2; ++i) {
+    if (nb[i] == slabRank_) { ph.remote[i] = ph.base; continue; }
+    if (i == 1 && hi == lo) { ph.remote[1] = ph.remote[0]; ph.opened[1] = true; continue; }
+    cudaIpcMemHandle_t hd;
+    std::memcpy(&hd, handles + (size_t)nb[i] * 64, 64);
+    void* ptr = nullptr;
+    PDA_CUDA(cudaIpcOpenMemHandle(&ptr, hd, cudaIpcMemLazyEnablePeerAccess));
+    ph.remote[i] = static_cast<unsigned char*>(ptr);
+    ph.opened[i] = true;
+  }
+  ph.connected = true;
+}
+
+void Problem::slabPeerConnectLocal(Problem* lo, Problem* hi) {
+  if (!lo || !hi) throw Error(kInvalid, "slab_peer_connect_local: null neighbour");
+  unsigned char tmp[64];
+  Problem* nb[2] = {lo, hi};
+  slabPeerHandle(tmp);
+  for (int i = 0; i < 2; ++i) {
+    if (!nb[i]->slab_ || nb[i]->S_ != S_ || nb[i]->mesh_->n[0] != mesh_->n[0] || nb[i]->mesh_->n[1] != mesh_->n[1])
+      throw Error(kInvalid, "slab_peer_connect_local: neighbour is not a slab of the same lattice");
+    nb[i]->slabPeerHandle(tmp);
+    if (nb[i]->device_ != device_) {
+      PDA_CUDA(cudaSetDevice(device_));
+      int can = 0;
+      PDA_CUDA(cudaDeviceCanAccessPeer(&can, device_, nb[i]->device_));
+      if (!can) throw Error(kUnsupported, "slab_peer_connect_local: no peer access between the two devices");
+      const cudaError_t e = cudaDeviceEnablePeerAccess(nb[i]->device_, 0);
+      if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) PDA_CUDA(e);
+      (void)cudaGetLastError();
+    }
+    dev_->peer.remote[i] = nb[i]->dev_->peer.base;
+    dev_->peer.opened[i] = false;
+  }
+  dev_->peer.connected = true;
+}
+
+void Problem::slabVelocityPeerDev(const double* dU, double /*t*/, double* dV, void* streamV) {
+  if (!slab_) throw Error(kInvalid, "not a slab problem");
+  if (!dU || !dV) throw Error(kInvalid, "velocity: null pointer");
+  ensureDevice();
+  if (!dev_->peer.connected) throw Error(kInvalid, "slab peer mode: pda_slab_peer_connect has not been called");
+  if (family_ != F_EULER3D) throw Error(kUnsupported, "slab peer mode: Euler3d only");
+  PDA_CUDA(cudaSetDevice(device_));
+  DeviceState& ds = *dev_;
+  auto& ph = ds.peer;
+  cudaStream_t st = (cudaStream_t)streamV;
+  Mesh& m = *mesh_;
+  const int h = (S_ - 1) / 2;
+  const int32_t nOwned = slabK1_ - slabK0_;
+  if (m.n[0] < 2 * m.halo() || m.n[1] < 2 * m.halo()) throw Error(kUnsupported, "slab peer mode: mesh too small for the tiled kernel");
+  const size_t planeDofs = (size_t)m.n[0] * m.n[1] * ndpc_;
+  const size_t haloBytes = (size_t)h * planeDofs * sizeof(double);
+  ++ph.epoch;
+  const int par = (int)(ph.epoch & 1u);
+  const uint32_t val = ph.epoch & 0xffffu;
+  const unsigned char* valSrc = ph.base + ph.tableOff + sizeof(uint32_t) * val;
+
+  // U as of everything enqueued on `st` so far is what the neighbours receive
+  PDA_CUDA(cudaEventRecord(ph.evReady, st));
+  // [1] my top h planes -> upper neighbour's LOWER halo ; [0] my bottom h planes -> lower neighbour's UPPER halo
+  for (int i = 1; i >= 0; --i) {
+    PDA_CUDA(cudaStreamWaitEvent(ph.sPush[i], ph.evReady, 0));
+    const double* src = (i == 1) ? dU + (size_t)(nOwned - h) * planeDofs : dU;
+    const int side = (i == 1) ? 0 : 1;
+    PDA_CUDA(cudaMemcpyAsync(ph.halo(ph.remote[i], par, side), src, haloBytes, cudaMemcpyDefault, ph.sPush[i]));
+    PDA_CUDA(cudaMemcpyAsync(ph.flag(ph.remote[i], par, side), valSrc, sizeof(uint32_t), cudaMemcpyDefault, ph.sPush[i]));
+    PDA_CUDA(cudaEventRecord(ph.evPushed[i], ph.sPush[i]));
+  }
+
+  dev::Deltas dl{{m.dInv[0], m.dInv[1], m.dInv[2]}};
+  dev::LatticeDesc L;
+  for (int a = 0; a < 3; ++a) { L.n[a] = m.n[a]; L.per[a] = m.periodic[a] ? 1 : 0; }
+  L.n[2] = nOwned;
+  L.planeBegin = 0; L.planeEnd = nOwned; L.haloPlanes = 0; L.slab = 2; L.meshHalo = m.halo();
+  L.haloLo = ph.halo(ph.base, par, 0); L.haloHi = ph.halo(ph.base, par, 1);
+  L.flagLo = ph.flag(ph.base, par, 0); L.flagHi = ph.flag(ph.base, par, 1);
+  L.epoch = val;
+  dispatchScheme(S_, [&](auto sTag) {
+    constexpr int S = decltype(sTag)::value;
+    launchLattice3dTiled<dev::Euler<3>, S>(dev::Euler<3>{gamma_}, L, dl, dU, dV, st);
+    ++launches_;
+  });
+  PDA_CUDA(cudaGetLastError());
+  // the caller may overwrite U once `st` reaches this point: both pushes must have left by then
+  for (int i = 0; i < 2; ++i) PDA_CUDA(cudaStreamWaitEvent(st, ph.evPushed[i], 0));
 }
 
 }  // namespace pda

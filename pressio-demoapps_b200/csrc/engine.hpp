@@ -51,6 +51,11 @@ class Problem {
   void slabExtent(int32_t* k0, int32_t* k1, int32_t* halo, int64_t* planeDofs) const;
   void slabInitialCondition(double* Uowned) const;
   void slabVelocityDev(const double* dUlocal, double t, double* dVowned, void* stream, bool boundary);
+  // peer-memory halo exchange fused with the evaluation (engine.cu, "slab: peer mode")
+  void slabPeerHandle(unsigned char handle[64]);
+  void slabPeerConnect(const unsigned char* handles);           // nranks x 64 bytes, indexed by rank
+  void slabPeerConnectLocal(Problem* lo, Problem* hi);          // same-process neighbours (tests, single-process multi-GPU)
+  void slabVelocityPeerDev(const double* dUowned, double t, double* dVowned, void* stream);
 
  private:
   friend struct DeviceState;
@@ -86,6 +91,7 @@ class Problem {
   // slab
   bool slab_ = false;
   int32_t slabK0_ = 0, slabK1_ = 0;
+  int slabRank_ = 0, slabRanks_ = 1;
 
   int64_t launches_ = 0;
   std::unique_ptr<DeviceState> dev_;

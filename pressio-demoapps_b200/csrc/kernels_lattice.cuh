@@ -20,8 +20,16 @@ struct LatticeDesc {
   int32_t planeBegin;  // slowest-axis planes [planeBegin, planeEnd) are evaluated
   int32_t planeEnd;
   int32_t haloPlanes;  // slab mode: U carries this many extra planes below plane 0 (and above the last)
-  int32_t slab;        // 1: no wrap along the slowest axis, U/V are slab-local
+  int32_t slab;        // 1: no wrap along the slowest axis, U/V are slab-local; 2: peer mode (below)
   int32_t meshHalo;    // (mesh stencil-1)/2: rows this close to a physical boundary are near-boundary rows
+  // peer mode (slab == 2, multi-GPU over NVLink peer memory): U holds the owned planes only; the h planes below plane 0
+  // / above plane n-1 live in library-owned halo buffers that the ring neighbours fill by peer copies, each followed
+  // by a flag write.  A CTA that needs a halo plane spins on the flag until it carries this evaluation's epoch.
+  const double* haloLo;
+  const double* haloHi;
+  const uint32_t* flagLo;
+  const uint32_t* flagHi;
+  uint32_t epoch;
 };
 
 // index of the cell `off` steps away along one axis; -1 if outside a non-periodic axis
@@ -153,6 +161,7 @@ void launchLatticeVelocity(const Phys& phys, const Mesh& m, const dev::Deltas& d
   dev::LatticeDesc L;
   for (int a = 0; a < 3; ++a) { L.n[a] = m.n[a]; L.per[a] = m.periodic[a] ? 1 : 0; }
   L.planeBegin = planeBegin; L.planeEnd = planeEnd; L.haloPlanes = 0; L.slab = 0; L.meshHalo = m.halo();
+  L.haloLo = L.haloHi = nullptr; L.flagLo = L.flagHi = nullptr; L.epoch = 0;
   int64_t planeCells = 1;
   for (int a = 0; a < Phys::dim - 1; ++a) planeCells *= m.n[a];
   const int64_t nwork = planeCells * (planeEnd - planeBegin);
@@ -175,6 +184,7 @@ void launchLatticeVelocitySlab(const Phys& phys, const Mesh& m, const dev::Delta
   for (int a = 0; a < 3; ++a) { L.n[a] = m.n[a]; L.per[a] = m.periodic[a] ? 1 : 0; }
   L.n[Phys::dim - 1] = nOwned;
   L.planeBegin = pBegin; L.planeEnd = pEnd; L.haloPlanes = (S - 1) / 2; L.slab = 1; L.meshHalo = m.halo();
+  L.haloLo = L.haloHi = nullptr; L.flagLo = L.flagHi = nullptr; L.epoch = 0;
   int64_t planeCells = 1;
   for (int a = 0; a < Phys::dim - 1; ++a) planeCells *= m.n[a];
   const int64_t nwork = planeCells * (pEnd - pBegin);

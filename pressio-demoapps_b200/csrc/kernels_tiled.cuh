@@ -216,7 +216,10 @@ k_euler3d_velocity_tiled(double gamma, LatticeDesc L, Deltas dl, const double* _
   const int tid = ty * TX + tx;
   const bool edgeWarp = (ty == TY);
   const int x0 = blockIdx.x * TX, y0 = blockIdx.y * TY;
-  const int k0 = L.planeBegin + blockIdx.z * LZ;
+  // peer mode: z chunks run in reverse order, so the chunk that needs the upper halo (at its END) starts first and
+  // the one that needs the lower halo (at its START) last: the neighbours' pushes land while interior work runs
+  const int zc = (L.slab == 2) ? (int)(gridDim.z - 1 - blockIdx.z) : (int)blockIdx.z;
+  const int k0 = L.planeBegin + zc * LZ;
   const int k1 = min(k0 + LZ, L.planeEnd);
   const int nx = L.n[0], ny = L.n[1], nz = L.n[2];
   const int perZ = L.per[2];
@@ -224,14 +227,32 @@ k_euler3d_velocity_tiled(double gamma, LatticeDesc L, Deltas dl, const double* _
   // storage plane of lattice plane p (slab: halo planes precede plane 0, no wrap)
   auto planeOf = [&](int p) -> int64_t { return L.slab ? (int64_t)(p + L.haloPlanes) : (int64_t)fixIdx(p, nz, perZ); };
   const int64_t rowStride = (int64_t)nx * N, planeStride = (int64_t)nx * ny * N;
+  // base of plane p for the z-column fetches; peer mode: planes outside [0,nz) come from the halo buffers, once the
+  // neighbour's flag carries this evaluation's epoch (lane 0 polls with acquire.sys, the warp follows)
+  auto planeBase = [&](int p) -> const double* {
+    if (L.slab == 2) {
+      if (p >= 0 && p < nz) return U + (int64_t)p * planeStride;
+      const uint32_t* flag = (p < 0) ? L.flagLo : L.flagHi;
+      if (tx == 0) {
+        unsigned seen;
+        do {
+          asm volatile("ld.acquire.sys.global.u32 %0, [%1];\n" : "=r"(seen) : "l"(flag) : "memory");
+          if (seen != L.epoch) __nanosleep(200);
+        } while (seen != L.epoch);
+      }
+      __syncwarp();
+      return (p < 0) ? L.haloLo + (int64_t)(p + h) * planeStride : L.haloHi + (int64_t)(p - nz) * planeStride;
+    }
+    return U + planeOf(p) * planeStride;
+  };
 
   // own column (clamped into the domain for threads of a ragged tile; the edge warp has none)
   const int ci = min(x0 + tx, nx - 1), cj = min(y0 + min(ty, TY - 1), ny - 1);
-  const double* colBase = U + ((int64_t)cj * nx + ci) * N;
+  const int64_t colOff = ((int64_t)cj * nx + ci) * N;
   const int zMine = oZ + (min(ty, TY - 1) * TX + tx) * N;   // + slot*slotStride + d
   // thread-private async copy of this column's cell of plane p into ring slot `slot`
   auto fetchColumn = [&](int p, int slot) {
-    const double* src = colBase + planeOf(p) * planeStride;
+    const double* src = planeBase(p) + colOff;
     const int off = zMine + slot * slotStride;
 #pragma unroll
     for (int d = 0; d < N; ++d) cpAsync8(&smem[off + d], src + d);
@@ -419,6 +440,8 @@ void launchLattice3dTiled(const Phys& phys, const dev::LatticeDesc& L, const dev
   // z chunks: long enough to amortise the ghost step (1/LZ extra z faces), short enough to fill 148 SMs x 2 CTAs
   int LZ = 64;
   while (LZ > 8 && (int64_t)gx * gy * ((planes + LZ - 1) / LZ) < 148 * 2 * 4) LZ /= 2;
+  // peer mode: at least two chunks, so that no CTA needs both halos and the pushes overlap interior work
+  if (L.slab == 2) while (LZ > 8 && (planes + LZ - 1) / LZ < 2) LZ /= 2;
   const int gz = (planes + LZ - 1) / LZ;
   dim3 grid(gx, gy, gz), block(32, TY + 1);
   // TMA rows need 16-byte aligned segments: even cell counts (40-byte cells) and an aligned base

@@ -106,6 +106,10 @@ _sig("pda_slab_extent", _C.c_int, _vp, _C.POINTER(_i32), _C.POINTER(_i32), _C.PO
 _sig("pda_slab_initial_condition", _C.c_int, _vp, _vp)
 _sig("pda_slab_velocity_interior_dev", _C.c_int, _vp, _vp, _dbl, _vp, _vp)
 _sig("pda_slab_velocity_boundary_dev", _C.c_int, _vp, _vp, _dbl, _vp, _vp)
+_sig("pda_slab_peer_handle", _C.c_int, _vp, _vp)
+_sig("pda_slab_peer_connect", _C.c_int, _vp, _vp)
+_sig("pda_slab_peer_connect_local", _C.c_int, _vp, _vp, _vp)
+_sig("pda_slab_velocity_peer_dev", _C.c_int, _vp, _vp, _dbl, _vp, _vp)
 
 
 def _check(status):
@@ -528,6 +532,25 @@ class Problem:
 
     def slabVelocityBoundaryDevice(self, dU, time, dV, stream=0):
         _check(_lib.pda_slab_velocity_boundary_dev(self._h, dU, float(time), dV, stream))
+
+    # peer mode: halo exchange over NVLink peer memory fused with the evaluation (include/pda_b200.h)
+    def peerHandle(self):
+        buf = _C.create_string_buffer(64)
+        _check(_lib.pda_slab_peer_handle(self._h, buf))
+        return buf.raw
+
+    def peerConnect(self, handles):
+        """handles: the 64-byte handles of ALL ranks, in rank order (list of bytes or one bytes object)"""
+        blob = handles if isinstance(handles, (bytes, bytearray)) else b"".join(handles)
+        if len(blob) % 64:
+            raise ValueError("peerConnect: handles must be 64 bytes each")
+        _check(_lib.pda_slab_peer_connect(self._h, _C.c_char_p(bytes(blob))))
+
+    def peerConnectLocal(self, lower, upper):
+        _check(_lib.pda_slab_peer_connect_local(self._h, lower._h, upper._h))
+
+    def slabVelocityPeerDevice(self, dU_owned, time, dV_owned, stream=0):
+        _check(_lib.pda_slab_velocity_peer_dev(self._h, dU_owned, float(time), dV_owned, stream))
 
 
 def _make(mesh, family, probEnum, recon, icFlag=1, params=None, device=0):

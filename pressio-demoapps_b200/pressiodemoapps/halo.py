@@ -42,3 +42,15 @@ def post_halo_exchange(local, halo, plane_dofs, rank, world, group=None):
 def wait_all(works):
     for w in works:
         w.wait()
+
+
+def connect_peer_halo(problem, rank, world, group=None):
+    """Peer mode (include/pda_b200.h): all-gather the ranks' 64-byte IPC handles of their halo buffers and map the two
+    ring neighbours' buffers.  After this, `problem.slabVelocityPeerDevice` needs no collective on the data path."""
+    mine = problem.peerHandle()
+    if world == 1:
+        problem.peerConnect([mine])
+        return
+    handles = [None] * world
+    dist.all_gather_object(handles, mine, group=group)
+    problem.peerConnect(handles)

@@ -298,3 +298,40 @@ def test_slab_decomposition_equals_full(nranks, n):
         p.slabVelocityBoundaryDevice(Ul.data_ptr(), 0.0, Vl.data_ptr(), st)
         torch.cuda.synchronize()
         assert np.array_equal(Vl.cpu().numpy(), Vfull[k0 * pd:k1 * pd])
+
+
+@pytest.mark.parametrize("nranks,n,recon", [(1, (20, 18, 16), "Weno5"), (2, (20, 18, 16), "Weno5"),
+                                            (4, (36, 20, 24), "Weno5"), (4, (36, 20, 48), "Weno3"),
+                                            (2, (64, 48, 160), "Weno5")])
+def test_slab_peer_mode_equals_full(nranks, n, recon):
+    """peer mode (halo exchange fused with the evaluation, include/pda_b200.h) on ONE device: the ranks are slab
+    problems of one process, wired to each other with pda_slab_peer_connect_local (distinct streams, as the header
+    demands).  Each rank's owned planes only are passed in; the neighbours' copy-engine pushes + flags deliver the
+    halos.  Several evaluations with changing states exercise the epoch/parity protocol; every result must equal the
+    full-mesh velocity bit for bit."""
+    import torch
+    scheme = getattr(R, recon)
+    mesh = pda.create_full_mesh(list(n), [-1, 1, -1, 1, -1, 1], 7 if recon == "Weno5" else 5, ("x", "y", "z"))
+    full = pda.create_problem(mesh, pda.Euler3d.PeriodicSmooth, scheme)
+    nz, pd = n[2], n[0] * n[1] * 5
+    probs = [pda.create_problem_slab(mesh, pda.Euler3d.PeriodicSmooth, scheme, r, nranks) for r in range(nranks)]
+    if nranks == 1:
+        probs[0].peerConnect([probs[0].peerHandle()])
+    else:
+        for r, p in enumerate(probs):
+            p.peerConnectLocal(probs[(r - 1) % nranks], probs[(r + 1) % nranks])
+    streams = [torch.cuda.Stream() for _ in range(nranks)]
+    ext = [p.slabExtent() for p in probs]
+    for it in range(5):
+        U = perturbed(full, seed=100 + it)
+        Vfull = full.createRightHandSide()
+        full.rightHandSide(U, 0.0, Vfull)
+        Ug = torch.from_numpy(U).cuda()
+        Us = [Ug[k0 * pd:k1 * pd].clone() for (k0, k1, _, _) in ext]
+        Vs = [torch.zeros((k1 - k0) * pd, dtype=torch.float64, device="cuda") for (k0, k1, _, _) in ext]
+        torch.cuda.synchronize()
+        for r, p in enumerate(probs):
+            p.slabVelocityPeerDevice(Us[r].data_ptr(), 0.0, Vs[r].data_ptr(), streams[r].cuda_stream)
+        torch.cuda.synchronize()
+        for r, (k0, k1, _, _) in enumerate(ext):
+            assert np.array_equal(Vs[r].cpu().numpy(), Vfull[k0 * pd:k1 * pd]), (it, r)
