@@ -14,6 +14,7 @@
 #include "kernels_lattice.cuh"
 #include "kernels_tiled.cuh"
 #include "kernels_jacobian.cuh"
+#include "kernels_jaclattice.cuh"
 
 namespace pda {
 
@@ -164,6 +165,10 @@ struct DeviceState {
   // scratch owned by the problem (host-pointer entry points, applyJacobian)
   DevBuf<double> dU, dV, dJ, dB, dR;
   DevBuf<int32_t> dRowptr, dColidx;
+  // lattice Jacobian kernel: per-cell CSR base and block-slot tables (indexed by gid)
+  DevBuf<int32_t> latBase;
+  DevBuf<uint8_t> latSlots;
+  bool latJacReady = false;
   DevBuf<double> src;          // per-sample-row source table (diffusion-reaction ProblemA, ADR ProblemA)
   bool srcReady = false;
   // host-pointer pipeline (velocityHost on large lattices)
@@ -1045,8 +1050,16 @@ void Problem::evaluateDev(const double* dU, double t, double* dV, double* dJ, vo
   const int nc = m.ncols();
   dev::Deltas dl{{m.dInv[0], m.dInv[1], m.dInv[2]}};
 
+  // inner rows of a 2D full lattice: face-sharing lattice kernel (kernels_jaclattice.cuh); everything else: staged
+  // graph-driven kernel
+  const bool jacLattice = dJ && m.lattice && dim_ == 2 && ds.innerViaLattice && family_ != F_DIFFREAC2D;
   if (dJ) {
     buildPattern();
+    if (jacLattice && !mergedNeighbors_ && !ds.latJacReady) {
+      ds.latBase.upload(cellBase_);
+      ds.latSlots.upload(slots_);
+      ds.latJacReady = true;
+    }
     if (!ds.jacTablesReady) {
       auto fill = [&](DeviceRowSet& rs) {
         std::vector<int32_t> base(rs.n), len(rs.n);
@@ -1058,8 +1071,7 @@ void Problem::evaluateDev(const double* dU, double t, double* dV, double* dJ, vo
         }
         rs.jBase.upload(base); rs.jLen.upload(len); rs.jSlot.upload(sl);
       };
-      ensureInnerRows();
-      fill(ds.inner);
+      if (!(jacLattice && !mergedNeighbors_)) { ensureInnerRows(); fill(ds.inner); }
       fill(ds.nearBd);
       ds.jacTablesReady = true;
     }
@@ -1140,6 +1152,27 @@ void Problem::evaluateDev(const double* dU, double t, double* dV, double* dJ, vo
       if (ds.innerViaLattice && !dJ) {
         launchLatticeVelocity<Phys, S>(phys, m, dl, dU, dV, st, 0, m.n[dim_ - 1], 0);
         ++launches_;
+      } else if (jacLattice && !mergedNeighbors_) {
+        if constexpr (Phys::dim == 2) {
+          using JL = dev::JacLat2d<Phys, S>;
+          auto kern = dev::k_jacobian_lattice2d<Phys, S>;
+          static bool configured = false;
+          if (!configured) {
+            PDA_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)JL::smemBytes));
+            configured = true;
+          }
+          dev::LatticeDesc L;
+          for (int a = 0; a < 3; ++a) { L.n[a] = m.n[a]; L.per[a] = m.periodic[a] ? 1 : 0; }
+          L.planeBegin = 0; L.planeEnd = m.n[1]; L.haloPlanes = 0; L.slab = 0; L.meshHalo = m.halo();
+          L.haloLo = L.haloHi = nullptr; L.flagLo = L.flagHi = nullptr; L.epoch = 0;
+          const int w0 = L.per[0] ? m.n[0] : m.n[0] - 2 * m.halo(), w1 = L.per[1] ? m.n[1] : m.n[1] - 2 * m.halo();
+          if (w0 > 0 && w1 > 0) {
+            dev::JacLatTables jt{ds.latBase.p, ds.latSlots.p, slotCols_, ndpc_ * (1 + dim_ * (S - 1))};
+            dim3 grid((unsigned)((w0 + JL::T - 1) / JL::T), (unsigned)((w1 + JL::T - 1) / JL::T));
+            kern<<<grid, JL::THREADS, JL::smemBytes, st>>>(phys, L, dl, jt, dU, dV, dJ);
+            ++launches_;
+          }
+        }
       } else if (ds.inner.n > 0) {
         if (dJ && !mergedNeighbors_) {
           // staged assembly: every value of the inner rows written once, coalesced (no memset needed for them)

@@ -335,3 +335,40 @@ def test_slab_peer_mode_equals_full(nranks, n, recon):
         torch.cuda.synchronize()
         for r, (k0, k1, _, _) in enumerate(ext):
             assert np.array_equal(Vs[r].cpu().numpy(), Vfull[k0 * pd:k1 * pd]), (it, r)
+
+
+@pytest.mark.parametrize("case", ["euler_weno5", "euler_weno3_per", "swe_weno5", "euler_fo", "burgers_weno5_per"])
+def test_lattice_and_graph_jacobian_kernels_agree(case):
+    """medium-size property: the face-sharing lattice Jacobian kernel (kernels_jaclattice.cuh: full 2D lattices) and
+    the graph-driven staged kernel (same mesh handed over as arrays => not recognised as a lattice) give the same
+    velocity and Jacobian; ragged 31x31 tiles, periodic wrap and scheme stencil < mesh stencil included."""
+    if case == "euler_weno5":
+        n, bounds, st, per = [100, 71], [0, 1, 0, 1], 7, ()
+        mk = lambda m: pda.create_problem(m, pda.Euler2d.Riemann, R.Weno5)
+    elif case == "euler_weno3_per":
+        n, bounds, st, per = [64, 45], [-1, 1, -1, 1], 7, ("x", "y")
+        mk = lambda m: pda.create_problem(m, pda.Euler2d.PeriodicSmooth, R.Weno3)
+    elif case == "swe_weno5":
+        n, bounds, st, per = [70, 66], [-5, 5, -5, 5], 7, ()
+        mk = lambda m: pda.create_problem(m, pda.Swe2d.SlipWall, R.Weno5)
+    elif case == "euler_fo":
+        n, bounds, st, per = [40, 37], [0, 1, 0, 1], 3, ()
+        mk = lambda m: pda.create_problem(m, pda.Euler2d.Riemann, R.FirstOrder)
+    else:
+        n, bounds, st, per = [48, 40], [-1, 1, -1, 1], 7, ("x", "y")
+        mk = lambda m: pda.create_problem(m, pda.AdvectionDiffusion2d.BurgersPeriodic, R.Weno5,
+                                          pda.ViscousFluxReconstruction.FirstOrder)
+    lat = pda.create_full_mesh(n, bounds, st, per)
+    p1 = mk(lat)
+    ma = mesh_arrays(lat)
+    generic = pda.mesh_from_arrays(2, st, ma["d"], ma["x"], ma["y"], ma["z"], ma["graph"], detect_lattice=False)
+    p2 = mk(generic)
+    U = perturbed(p1)
+    V1, V2 = p1.createRightHandSide(), p2.createRightHandSide()
+    J1, J2 = p1.createJacobian(), p2.createJacobian()
+    p1.rightHandSideAndJacobian(U, 0.0, V1, J1)
+    p2.rightHandSideAndJacobian(U, 0.0, V2, J2)
+    assert np.array_equal(J1.indptr, J2.indptr) and np.array_equal(J1.indices, J2.indices)
+    assert scaled_err(V1, V2, field=True) <= 1.0
+    # same formulas, different association of the two faces' products: rounding-level differences only
+    assert scaled_err(J1.data, J2.data, 1e-11, 1e-9) <= 1.0
