@@ -167,7 +167,7 @@ struct DeviceState {
   DevBuf<int32_t> dRowptr, dColidx;
   // lattice Jacobian kernel: per-cell CSR base and block-slot tables (indexed by gid)
   DevBuf<int32_t> latBase;
-  DevBuf<uint8_t> latSlots;
+  DevBuf<uint4> latSlots;
   bool latJacReady = false;
   DevBuf<double> src;          // per-sample-row source table (diffusion-reaction ProblemA, ADR ProblemA)
   bool srcReady = false;
@@ -1057,7 +1057,13 @@ void Problem::evaluateDev(const double* dU, double t, double* dV, double* dJ, vo
     buildPattern();
     if (jacLattice && !mergedNeighbors_ && !ds.latJacReady) {
       ds.latBase.upload(cellBase_);
-      ds.latSlots.upload(slots_);
+      {   // slot table padded to 16 bytes per cell: one vector load per cell in the kernel
+        std::vector<uint4> padded(cellBase_.size(), make_uint4(0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu));
+        if (slotCols_ > 16) throw Error(kUnsupported, "lattice Jacobian: slot table wider than 16 columns");
+        for (size_t r = 0; r < cellBase_.size(); ++r)
+          std::memcpy(&padded[r], &slots_[r * slotCols_], (size_t)slotCols_);
+        ds.latSlots.upload(padded);
+      }
       ds.latJacReady = true;
     }
     if (!ds.jacTablesReady) {
@@ -1167,7 +1173,7 @@ void Problem::evaluateDev(const double* dU, double t, double* dV, double* dJ, vo
           L.haloLo = L.haloHi = nullptr; L.flagLo = L.flagHi = nullptr; L.epoch = 0;
           const int w0 = L.per[0] ? m.n[0] : m.n[0] - 2 * m.halo(), w1 = L.per[1] ? m.n[1] : m.n[1] - 2 * m.halo();
           if (w0 > 0 && w1 > 0) {
-            dev::JacLatTables jt{ds.latBase.p, ds.latSlots.p, slotCols_, ndpc_ * (1 + dim_ * (S - 1))};
+            dev::JacLatTables jt{ds.latBase.p, ds.latSlots.p, ndpc_ * (1 + dim_ * (S - 1))};
             dim3 grid((unsigned)((w0 + JL::T - 1) / JL::T), (unsigned)((w1 + JL::T - 1) / JL::T));
             kern<<<grid, JL::THREADS, JL::smemBytes, st>>>(phys, L, dl, jt, dU, dV, dJ);
             ++launches_;

@@ -7,16 +7,17 @@
 //
 // A lane owns ONE face: the 32 lanes of a warp sit on 32 consecutive faces of one mesh line (a row for the x phase,
 // a column for the y phase), i.e. on the left faces of 32 consecutive cells; lane l also owns cell l of the line
-// (31 cells per warp task: the last lane only supplies the right face of cell 30).  With
+// (the last lane of a line only supplies the right face of the last cell).  With
 //      t[k][m][j] = JN[k][j] * d(uNeg_j)/d(q_m) + JP[k][j] * d(uPos_j)/d(q_m)         (q_m = m-th cell of the face stencil)
 // the block of row-cell c at stencil position P is   hInv * ( t_c[k][P][j] - t_{c+1}[k][P-1][j] ):  the face's own
 // products and its right neighbour's, fetched by ONE warp shuffle -- one set of products per face serves both cells.
 //   * every (row k, position P) is N contiguous doubles (one 32-byte sector for Euler2d): stored straight to the CSR
 //     value array, each entry written once, no shared-memory staging, no memset, no read-modify-write;
-//     the self block alone meets both axes: the x phase stores it, the y phase adds to it (an L2 hit, 1/13 of the data);
+//     the self block alone meets both axes: its x part is parked in shared memory until the y phase completes it;
 //   * flux Jacobians (2 N^2 doubles) live in a thread-private shared-memory column, the row loop over k is rolled:
 //     small code (the instruction cache was the first limiter of the staged kernel) and fewer live registers;
-//   * a CTA = 31 x 31 cell tile: phase x = its 31 rows, barrier, phase y = its 31 columns (same code, other stride).
+//   * a CTA = 15 x 15 cell tile, a warp carries two lines of 16 faces: phase x = the tile's rows, barrier, phase y = its
+//     columns (same code, other stride); the x part of the self blocks and of V waits in shared memory in between.
 #pragma once
 #include "kernels_generic.cuh"
 #include "kernels_lattice.cuh"
@@ -29,98 +30,130 @@ struct JacLat2d {
   static constexpr int N = Phys::ndpc;
   static constexpr int WARPS = 8;
   static constexpr int THREADS = 32 * WARPS;
-  static constexpr int T = 31;                                        // cells per warp task, tile edge
-  static constexpr size_t smemBytes = (size_t)2 * N * N * THREADS * sizeof(double);
+  static constexpr int T = 15;                  // tile edge in cells; a warp carries two lines of 16 faces (15 cells)
+  static constexpr int SELF = N * N + 1;        // padded self-block stride: conflict-free along both tile axes
+  static constexpr int oSelf = 2 * N * N * THREADS;           // [T*T][SELF] x-phase part of the self blocks
+  static constexpr int oV = oSelf + T * T * SELF;             // [T*T][N]    x-phase part of the velocity
+  static constexpr size_t smemBytes = (size_t)(oV + T * T * N) * sizeof(double);
 };
 
 struct JacLatTables {
   const int32_t* cellBase;   // [cells] offset of the cell's first CSR row
-  const uint8_t* cellSlots;  // [cells][nslotCols] block position of graph column c
-  int32_t nslotCols;
+  const uint4* cellSlots;    // [cells] 16 bytes: block position of graph column c (padded copy of the slot table)
   int32_t rowLen;            // entries per CSR row of an inner cell
 };
 
-// one mesh line of one axis: lane l = face between cells (a-1, a), a = a0 + lane, and owner of cell a
+template <int N> PDA_DEVFN void loadCell(const double* __restrict__ p, double* q) {
+  if constexpr (N == 4) {
+    asm volatile("ld.global.nc.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(q[0]), "=d"(q[1]), "=d"(q[2]), "=d"(q[3]) : "l"(p));
+  } else if constexpr (N == 2) {
+    const double2 v = __ldg(reinterpret_cast<const double2*>(p));
+    q[0] = v.x; q[1] = v.y;
+  } else {
+#pragma unroll
+    for (int d = 0; d < N; ++d) q[d] = __ldg(p + d);
+  }
+}
+template <int N> PDA_DEVFN void storeBlockRow(double* __restrict__ dst, const double* v) {
+  if constexpr (N == 4) {   // one full 32-byte sector per store (STG.256)
+    asm volatile("st.global.v4.f64 [%0], {%1,%2,%3,%4};" ::"l"(dst), "d"(v[0]), "d"(v[1]), "d"(v[2]), "d"(v[3]) : "memory");
+  } else if constexpr (N == 2) {
+    *reinterpret_cast<double2*>(dst) = make_double2(v[0], v[1]);
+  } else {
+#pragma unroll
+    for (int j = 0; j < N; ++j) dst[j] = v[j];
+  }
+}
+
+// one mesh line of one axis: lane f of a 16-lane group = face between cells (a-1, a), a = a0 + f, and owner of
+// cell a (f < 15).  `o` = coordinate of the line on the other axis, `cellLocal` = tile-local index of the owned cell.
+// `a` may lie one past the inner region (that lane supplies the right face of the last cell): only stencil
+// coordinates are clamped, never the face position.
 template <class Phys, int S, int AX>
 PDA_DEVFN void jacLatLine(const Phys& phys, const LatticeDesc& L, const JacLatTables& jt, double hInv,
                           const double* __restrict__ U, double* __restrict__ V, double* __restrict__ Jv,
-                          int a0, int hiA, int o, double* __restrict__ sJ /* + tid */, int lane) {
+                          int a, int o, bool owns, int cellLocal, double* __restrict__ sAll, int tid) {
   constexpr int N = Phys::ndpc;
   constexpr int h = (S - 1) / 2;
-  constexpr int THREADS = JacLat2d<Phys, S>::THREADS;
+  using K = JacLat2d<Phys, S>;
+  constexpr int THREADS = K::THREADS;
+  double* sJ = sAll + tid;
   const int nx = L.n[0];
   const int nA = L.n[AX], perA = L.per[AX];
-  const int a = a0 + lane;
-  const bool owns = (lane < 31) && (a < hiA);
 
   // cells of the face stencil: coordinate a-h+m, m = 0..S-2 (wrapped on periodic axes, clamped for idle lanes)
-  int64_t off[S - 1];
+  double q[S - 1][N];
 #pragma unroll
   for (int m = 0; m < S - 1; ++m) {
     int c = a - h + m;
     if (perA) c = (c < 0) ? c + nA : (c >= nA ? c - nA : c);
     else c = (c < 0) ? 0 : (c >= nA ? nA - 1 : c);
     const int64_t gid = (AX == 0) ? (int64_t)o * nx + c : (int64_t)c * nx + o;
-    off[m] = gid * N;
+    loadCell<N>(U + gid * N, q[m]);
   }
+  // owned cell: gid, CSR base, block slots (one 16-byte load)
+  const int64_t gidSelf = (AX == 0) ? (int64_t)o * nx + a : (int64_t)a * nx + o;
+  const uint4 sv = owns ? __ldg(jt.cellSlots + gidSelf) : make_uint4(0, 0, 0, 0);
+  const int32_t base = owns ? __ldg(jt.cellBase + gidSelf) : 0;
+  auto slotOf = [&](int c) -> int {
+    const unsigned w = (c < 4) ? sv.x : (c < 8 ? sv.y : (c < 12 ? sv.z : sv.w));
+    return (int)((w >> (8 * (c & 3))) & 0xffu);
+  };
 
-  // ---- face states, flux, flux Jacobians
+  // ---- face states, flux, flux Jacobians (parked in this thread's shared-memory column)
   double F[N];
   {
     double un[N], up[N];
 #pragma unroll
     for (int d = 0; d < N; ++d) {
-      double q[S - 1];
+      double qd[S - 1];
 #pragma unroll
-      for (int m = 0; m < S - 1; ++m) q[m] = U[off[m] + d];
-      Recon<S>::face(q, un[d], up[d]);
+      for (int m = 0; m < S - 1; ++m) qd[m] = q[m][d];
+      Recon<S>::face(qd, un[d], up[d]);
     }
     double JN[N * N], JP[N * N];
     phys.template flux<AX>(un, up, F);
     phys.template fluxJac<AX>(un, up, JN, JP);
 #pragma unroll
-    for (int e = 0; e < N * N; ++e) { sJ[e * THREADS] = JN[e]; sJ[(N * N + e) * THREADS] = JP[e]; }
+    for (int e = 0; e < N * N; ++e) { sJ[e * THREADS] = hInv * JN[e]; sJ[(N * N + e) * THREADS] = hInv * JP[e]; }
   }
   // ---- reconstruction gradients of every dof
   double gN[N][S - 1], gP[N][S - 1];
 #pragma unroll
   for (int j = 0; j < N; ++j) {
-    double q[S - 1], t0, t1;
+    double qd[S - 1], t0, t1;
 #pragma unroll
-    for (int m = 0; m < S - 1; ++m) q[m] = U[off[m] + j];
-    Recon<S>::faceGrad(q, t0, t1, gN[j], gP[j]);
+    for (int m = 0; m < S - 1; ++m) qd[m] = q[m][j];
+    Recon<S>::faceGrad(qd, t0, t1, gN[j], gP[j]);
   }
 
-  // ---- owned cell: gid, CSR base, slots of its S stencil positions along this axis
-  const int aa = owns ? a : ((a0 < hiA) ? a0 : 0);
-  const int64_t gidSelf = (AX == 0) ? (int64_t)o * nx + aa : (int64_t)aa * nx + o;
-  const uint8_t* slots = jt.cellSlots + gidSelf * jt.nslotCols;
   int sl[S];
-  sl[h] = slots[0];
+  sl[h] = slotOf(0);
 #pragma unroll
   for (int l = 0; l < h; ++l) {
-    sl[h - 1 - l] = slots[gcol<2>(sideMinus<AX>(), l)];
-    sl[h + 1 + l] = slots[gcol<2>(sidePlus<AX>(), l)];
+    sl[h - 1 - l] = slotOf(gcol<2>(sideMinus<AX>(), l));
+    sl[h + 1 + l] = slotOf(gcol<2>(sidePlus<AX>(), l));
   }
-  double* jBase = Jv + jt.cellBase[gidSelf];
+  double* jBase = Jv + base;
   const int rowLen = jt.rowLen;
+  double* sSelf = sAll + K::oSelf + cellLocal * K::SELF;
+  double* sV = sAll + K::oV + cellLocal * N;
 
-  // ---- velocity: hInv (F_left - F_right)
+  // ---- velocity: hInv (F_left - F_right); x phase parks its part in shared memory, y phase completes and stores
   {
     double v[N];
 #pragma unroll
     for (int d = 0; d < N; ++d) v[d] = hInv * (F[d] - __shfl_down_sync(0xffffffffu, F[d], 1));
-    if (owns && V) {
-      double* out = V + gidSelf * N;
+    if (owns) {
       if (AX == 0) {
 #pragma unroll
-        for (int d = 0; d < N; ++d) out[d] = v[d];
+        for (int d = 0; d < N; ++d) sV[d] = v[d];
       } else {
 #pragma unroll
-        for (int d = 0; d < N; ++d) v[d] += out[d];
+        for (int d = 0; d < N; ++d) v[d] += sV[d];
         if constexpr (PhysTraits<Phys>::hasDiffusion) {
           // first-layer neighbours as a graph row (left, front, right, back): inner cells have them all
-          const int i = (int)(gidSelf % nx), jrow = (int)(gidSelf / nx), ny = L.n[1];
+          const int i = o, jrow = a, ny = L.n[1];
           auto wrapI = [&](int c, int n) { return c < 0 ? c + n : (c >= n ? c - n : c); };
           int32_t row5[5];
           row5[0] = (int32_t)gidSelf;
@@ -131,8 +164,11 @@ PDA_DEVFN void jacLatLine(const Phys& phys, const LatticeDesc& L, const JacLatTa
           addDiffusionInner<Phys>(phys, row5, U, v);
         }
         addForcing<Phys>(phys, U + gidSelf * N, v, (int32_t)gidSelf);
+        if (V) {
+          double* out = V + gidSelf * N;
 #pragma unroll
-        for (int d = 0; d < N; ++d) out[d] = v[d];
+          for (int d = 0; d < N; ++d) out[d] = v[d];
+        }
       }
     }
   }
@@ -142,7 +178,7 @@ PDA_DEVFN void jacLatLine(const Phys& phys, const LatticeDesc& L, const JacLatTa
   for (int k = 0; k < N; ++k) {
     double jn[N], jp[N];
 #pragma unroll
-    for (int j = 0; j < N; ++j) { jn[j] = hInv * sJ[(k * N + j) * THREADS]; jp[j] = hInv * sJ[(N * N + k * N + j) * THREADS]; }
+    for (int j = 0; j < N; ++j) { jn[j] = sJ[(k * N + j) * THREADS]; jp[j] = sJ[(N * N + k * N + j) * THREADS]; }
     double* rowp = jBase + (int64_t)k * rowLen;
 #pragma unroll
     for (int P = 0; P < S; ++P) {
@@ -157,27 +193,27 @@ PDA_DEVFN void jacLatLine(const Phys& phys, const LatticeDesc& L, const JacLatTa
         val[j] = mine - got;
       }
       if (owns) {
-        double* dst = rowp + sl[P] * N;
-        if (AX != 0 && P == h) {
+        if (P == h && AX == 0) {   // self block: x part waits in shared memory for the y part (the reference's order)
 #pragma unroll
-          for (int j = 0; j < N; ++j) val[j] += dst[j];
-        }
-        if constexpr (N == 4) {
-          reinterpret_cast<double2*>(dst)[0] = make_double2(val[0], val[1]);
-          reinterpret_cast<double2*>(dst)[1] = make_double2(val[2], val[3]);
-        } else if constexpr (N == 2) {
-          reinterpret_cast<double2*>(dst)[0] = make_double2(val[0], val[1]);
+          for (int j = 0; j < N; ++j) sSelf[k * N + j] = val[j];
         } else {
+          if (P == h) {
 #pragma unroll
-          for (int j = 0; j < N; ++j) dst[j] = val[j];
+            for (int j = 0; j < N; ++j) val[j] += sSelf[k * N + j];
+          }
+          storeBlockRow<N>(rowp + sl[P] * N, val);
         }
       }
     }
   }
-  // ---- point terms and diffusion (after both flux phases: the reference adds them last)
+  // ---- point terms and diffusion (after both flux phases: the reference adds them last); a few entries of rows
+  //      this tile has just written (same thread, or x-phase threads before the barrier): read-modify-write in L2
   if (AX != 0 && owns) {
-    addExtraJacInner<Phys>(phys, U + gidSelf * N, slots, [&](int k, int slot, int j, double val) {
-      jBase[(int64_t)k * rowLen + slot * N + j] += val;
+    uint8_t slots[16];
+#pragma unroll
+    for (int c = 0; c < 16; ++c) slots[c] = (uint8_t)slotOf(c);
+    addExtraJacInner<Phys>(phys, U + gidSelf * N, slots, [&](int k, int slot, int j, double x) {
+      jBase[(int64_t)k * rowLen + slot * N + j] += x;
     });
   }
 }
@@ -187,24 +223,24 @@ __global__ void __launch_bounds__(JacLat2d<Phys, S>::THREADS, 1)
 k_jacobian_lattice2d(Phys phys, LatticeDesc L, Deltas dl, JacLatTables jt, const double* __restrict__ U,
                      double* __restrict__ V, double* __restrict__ Jv) {
   using K = JacLat2d<Phys, S>;
-  extern __shared__ double sJall[];
+  extern __shared__ __align__(16) double sAll[];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  double* sJ = sJall + tid;
+  const int line = 2 * warp + (lane >> 4), f = lane & 15;
   const int lo0 = L.per[0] ? 0 : L.meshHalo, hi0 = L.per[0] ? L.n[0] : L.n[0] - L.meshHalo;
   const int lo1 = L.per[1] ? 0 : L.meshHalo, hi1 = L.per[1] ? L.n[1] : L.n[1] - L.meshHalo;
   const int I0 = lo0 + K::T * blockIdx.x, J0 = lo1 + K::T * blockIdx.y;
-  // phase x: rows J0 .. J0+30
-  for (int task = warp; task < K::T; task += K::WARPS) {
-    const int j = J0 + task;
-    if (j >= hi1) break;
-    jacLatLine<Phys, S, 0>(phys, L, jt, dl.hInv[0], U, V, Jv, I0, hi0, j, sJ, lane);
+  {   // phase x: line = row J0+line, lanes along x
+    const int j = J0 + line, a = I0 + f;
+    const bool owns = (line < K::T) && (f < K::T) && (j < hi1) && (a < hi0);
+    jacLatLine<Phys, S, 0>(phys, L, jt, dl.hInv[0], U, V, Jv, a, min(j, hi1 - 1), owns,
+                           min(line, K::T - 1) * K::T + min(f, K::T - 1), sAll, tid);
   }
-  __syncthreads();   // self blocks and V of the tile are in place (block-scope visibility of the global stores)
-  // phase y: columns I0 .. I0+30
-  for (int task = warp; task < K::T; task += K::WARPS) {
-    const int i = I0 + task;
-    if (i >= hi0) break;
-    jacLatLine<Phys, S, 1>(phys, L, jt, dl.hInv[1], U, V, Jv, J0, hi1, i, sJ, lane);
+  __syncthreads();
+  {   // phase y: line = column I0+line, lanes along y
+    const int i = I0 + line, a = J0 + f;
+    const bool owns = (line < K::T) && (f < K::T) && (i < hi0) && (a < hi1);
+    jacLatLine<Phys, S, 1>(phys, L, jt, dl.hInv[1], U, V, Jv, a, min(i, hi0 - 1), owns,
+                           min(f, K::T - 1) * K::T + min(line, K::T - 1), sAll, tid);
   }
 }
 
