@@ -232,7 +232,7 @@ class CellCenteredUniformMesh:
 
     def __del__(self):
         h = getattr(self, "_h", None)
-        if h:
+        if h and _lib is not None:   # module globals are gone at interpreter shutdown
             _lib.pda_mesh_free(h)
             self._h = None
 
@@ -358,7 +358,7 @@ class Problem:
 
     def __del__(self):
         h = getattr(self, "_h", None)
-        if h:
+        if h and _lib is not None:
             _lib.pda_problem_free(h)
             self._h = None
 

@@ -372,3 +372,22 @@ def test_lattice_and_graph_jacobian_kernels_agree(case):
     assert scaled_err(V1, V2, field=True) <= 1.0
     # same formulas, different association of the two faces' products: rounding-level differences only
     assert scaled_err(J1.data, J2.data, 1e-11, 1e-9) <= 1.0
+
+
+def test_slab_peer_mode_multi_process():
+    """peer mode across PROCESSES (one rank per GPU, IPC-mapped halo buffers, cross-GPU flags): tools/check_peer_multi.py
+    under torchrun on two GPUs; every rank's slab must equal the full-mesh velocity bit for bit.  Skipped on a
+    single-GPU box (the single-process protocol test above still runs there)."""
+    import subprocess
+    import sys
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    import os
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
+                        "--master-addr", "127.0.0.1", "--master-port", "29571",
+                        os.path.join(root, "tools", "check_peer_multi.py"), "--cells", "64"],
+                       capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    assert "mismatching evaluations: 0" in r.stdout
