@@ -385,6 +385,14 @@ def run_b200_arm(args):
                 line["jacobian"] = jacobian_leg(torch, pda, local_rank, n2=args.n2)
             except Exception as e:
                 line["jacobian"] = {"error": str(e)}
+        if world == 1 and not args.no_configs:
+            # the other BASELINE.json configs (cfg 1-4), device-resident: velocity cells/s, Jacobian nnz/s, applyJacobian
+            sys.path.insert(0, os.path.join(ROOT, "tools"))
+            try:
+                import bench_configs
+                line["configs"] = bench_configs.run(hbm_peak, device=local_rank)
+            except Exception as e:
+                line["configs"] = {"error": str(e)}
         print(json.dumps(line), flush=True)
     if dist is not None:
         dist.barrier()
@@ -403,6 +411,7 @@ def main():
                     help="N>1 halo exchange: peer-memory pushes fused with the kernel (default) or NCCL send/recv")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-jacobian", action="store_true")
+    ap.add_argument("--no-configs", action="store_true", help="skip the cfg 1-4 legs (tools/bench_configs.py)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
     if args.impl == "reference":

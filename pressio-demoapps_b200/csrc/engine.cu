@@ -165,6 +165,10 @@ struct DeviceState {
   // scratch owned by the problem (host-pointer entry points, applyJacobian)
   DevBuf<double> dU, dV, dJ, dB, dR;
   DevBuf<int32_t> dRowptr, dColidx;
+  // J*B per cell (k_spmm_cells_rowmajor): per-cell CSR base / row length, lattice visiting order, transposed operands
+  DevBuf<int32_t> dCellBase, dCellLen, dCellOrder;
+  DevBuf<double> dBt, dRt;
+  bool spmmReady = false;
   // lattice Jacobian kernel: per-cell CSR base and block-slot tables (indexed by gid)
   DevBuf<int32_t> latBase;
   DevBuf<uint4> latSlots;
@@ -1381,12 +1385,61 @@ void Problem::applyJacobianDev(const double* dU, const double* dB, int ncols, in
   evaluateDev(dU, t, ds.dV.p, ds.dJ.p, st);
   const int32_t nrows = nDofSample();
   const int64_t nJc = nDofStencil();
-  // row-major: B[r*ncols + c]; col-major: B[c*rows + r]
-  const int64_t ldbRow = (layout == 1) ? ncols : 1, ldbCol = (layout == 1) ? 1 : nJc;
-  const int64_t ldrRow = (layout == 1) ? ncols : 1, ldrCol = (layout == 1) ? 1 : nrows;
-  dev::k_spmm_csr<<<gridFor((int64_t)nrows * 32, 256), 256, 0, st>>>(nrows, ds.dRowptr.p, ds.dColidx.p, ds.dJ.p, dB, ncols,
-                                                                   ldbRow, ldbCol, dR, ldrRow, ldrCol);
-  ++launches_;
+  if (ncols >= 8) {
+    // operands with many columns: per-cell kernel on row-major data (column-major operands are transposed around it)
+    if (!ds.spmmReady) {
+      ds.dCellBase.upload(cellBase_);
+      ds.dCellLen.upload(cellLen_);
+      Mesh& m = *mesh_;
+      if (m.lattice && dim_ >= 2 && m.nSample == m.nStencil) {
+        // tile-major visiting order: the B rows of a cell's stencil neighbours stay in L1 between cells
+        const int32_t nx = m.n[0], ny = m.n[1], nz = (dim_ == 3) ? m.n[2] : 1;
+        const int32_t T = (dim_ == 2) ? 8 : 4, Tz = (dim_ == 3) ? T : 1;
+        std::vector<int32_t> order;
+        order.reserve((size_t)m.nSample);
+        for (int32_t k0 = 0; k0 < nz; k0 += Tz)
+          for (int32_t j0 = 0; j0 < ny; j0 += T)
+            for (int32_t i0 = 0; i0 < nx; i0 += T)
+              for (int32_t k = k0; k < std::min(nz, k0 + Tz); ++k)
+                for (int32_t j = j0; j < std::min(ny, j0 + T); ++j)
+                  for (int32_t i = i0; i < std::min(nx, i0 + T); ++i) order.push_back((k * ny + j) * nx + i);
+        ds.dCellOrder.upload(order);
+      }
+      ds.spmmReady = true;
+    }
+    const double* Bp = dB;
+    double* Rp = dR;
+    auto transpose = [&](const double* in, int64_t rows, int64_t cols, double* out) {
+      const int64_t tiles = ((rows + 31) / 32) * ((cols + 31) / 32);
+      dev::k_transpose<<<(unsigned)tiles, 256, 0, st>>>(in, rows, cols, out);
+      ++launches_;
+    };
+    if (layout != 1) {   // column-major: memory is [ncols][nJc]
+      ds.dBt.alloc((size_t)nJc * ncols);
+      ds.dRt.alloc((size_t)nrows * ncols);
+      transpose(dB, ncols, nJc, ds.dBt.p);
+      Bp = ds.dBt.p; Rp = ds.dRt.p;
+    }
+    const int32_t ncells = mesh_->nSample;
+    const int32_t* order = ds.dCellOrder.p;
+    const unsigned grid = gridFor((int64_t)ncells * 32, 256);
+    switch (ndpc_) {
+      case 1: dev::k_spmm_cells_rowmajor<1><<<grid, 256, 0, st>>>(ncells, order, ds.dCellBase.p, ds.dCellLen.p, ds.dColidx.p, ds.dJ.p, Bp, ncols, Rp); break;
+      case 2: dev::k_spmm_cells_rowmajor<2><<<grid, 256, 0, st>>>(ncells, order, ds.dCellBase.p, ds.dCellLen.p, ds.dColidx.p, ds.dJ.p, Bp, ncols, Rp); break;
+      case 3: dev::k_spmm_cells_rowmajor<3><<<grid, 256, 0, st>>>(ncells, order, ds.dCellBase.p, ds.dCellLen.p, ds.dColidx.p, ds.dJ.p, Bp, ncols, Rp); break;
+      case 4: dev::k_spmm_cells_rowmajor<4><<<grid, 256, 0, st>>>(ncells, order, ds.dCellBase.p, ds.dCellLen.p, ds.dColidx.p, ds.dJ.p, Bp, ncols, Rp); break;
+      default: dev::k_spmm_cells_rowmajor<5><<<grid, 256, 0, st>>>(ncells, order, ds.dCellBase.p, ds.dCellLen.p, ds.dColidx.p, ds.dJ.p, Bp, ncols, Rp); break;
+    }
+    ++launches_;
+    if (layout != 1) transpose(ds.dRt.p, nrows, ncols, dR);
+  } else {
+    // row-major: B[r*ncols + c]; col-major: B[c*rows + r]
+    const int64_t ldbRow = (layout == 1) ? ncols : 1, ldbCol = (layout == 1) ? 1 : nJc;
+    const int64_t ldrRow = (layout == 1) ? ncols : 1, ldrCol = (layout == 1) ? 1 : nrows;
+    dev::k_spmm_rows_fewcols<<<gridFor((int64_t)nrows * 32, 256), 256, 0, st>>>(nrows, ds.dRowptr.p, ds.dColidx.p, ds.dJ.p, dB,
+                                                                              ncols, ldbRow, ldbCol, dR, ldrRow, ldrCol);
+    ++launches_;
+  }
   PDA_CUDA(cudaGetLastError());
 }
 

@@ -537,21 +537,106 @@ k_gray_scott_lattice(GrayScottParams gp, int32_t nx, int32_t ny, const double2* 
 }
 
 // ------------------------------------------------------------------------------------------------ J * B
-// applyJacobian (adapter_cpp.hpp:231-259): R = J * B with the fixed CSR pattern; one warp per row, lanes over
-// the row's entries, B row-major [ncol_J][nB] or col-major (ldb = rows).
-__global__ void k_spmm_csr(int32_t nrows, const int32_t* __restrict__ rowptr, const int32_t* __restrict__ colidx,
-                           const double* __restrict__ vals, const double* __restrict__ B, int nB, int64_t ldbRow,
-                           int64_t ldbCol, double* __restrict__ R, int64_t ldrRow, int64_t ldrCol) {
-  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+// applyJacobian (adapter_cpp.hpp:231-259): R = J * B with the fixed CSR pattern.  The N rows of a cell share one
+// column pattern made of N-wide blocks (entry (k, block b, j) at base + k*len + b*N + j, column id_b*N + j), so the
+// product is done per CELL:
+//   * row-major operands with >= 8 columns: one warp per cell, LANES ACROSS THE OPERAND COLUMNS -- every B row is one
+//     coalesced read shared by the N rows of the cell, J entries are warp-uniform (vector) loads, no reduction;
+//     cells are visited in a tile-major order on lattices so that the B rows of stencil neighbours hit in L1;
+//   * everything else (vectors, few columns): one warp per row, lanes across the row's entries, J read once for up
+//     to 8 columns, shuffle reduction.  Column-major operands with many columns are transposed around kernel 1.
+template <int N>
+__global__ void __launch_bounds__(256)
+k_spmm_cells_rowmajor(int32_t ncells, const int32_t* __restrict__ order, const int32_t* __restrict__ cellBase,
+                      const int32_t* __restrict__ cellLen, const int32_t* __restrict__ colidx,
+                      const double* __restrict__ vals, const double* __restrict__ B, int nB, double* __restrict__ R) {
+  const int w = (int)(((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
+  const int lane = threadIdx.x & 31;
+  if (w >= ncells) return;
+  const int32_t cell = order ? order[w] : w;
+  const int64_t base = cellBase[cell];
+  const int32_t len = cellLen[cell];
+  const int nblk = len / N;
+  for (int c0 = 0; c0 < nB; c0 += 32) {
+    const int c = c0 + lane;
+    const bool active = c < nB;
+    double acc[N];
+#pragma unroll
+    for (int k = 0; k < N; ++k) acc[k] = 0.0;
+    for (int b = 0; b < nblk; ++b) {
+      const int32_t col0 = colidx[base + b * N];
+      double bv[N];
+#pragma unroll
+      for (int j = 0; j < N; ++j) bv[j] = active ? B[(int64_t)(col0 + j) * nB + c] : 0.0;
+#pragma unroll
+      for (int k = 0; k < N; ++k) {
+        const double* jv = vals + base + (int64_t)k * len + b * N;
+        double a[N];
+        if constexpr (N == 4) {
+          asm volatile("ld.global.nc.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(a[0]), "=d"(a[1]), "=d"(a[2]), "=d"(a[3]) : "l"(jv));
+        } else if constexpr (N == 2) {
+          const double2 t = __ldg(reinterpret_cast<const double2*>(jv));
+          a[0] = t.x; a[1] = t.y;
+        } else {
+#pragma unroll
+          for (int j = 0; j < N; ++j) a[j] = __ldg(jv + j);
+        }
+#pragma unroll
+        for (int j = 0; j < N; ++j) acc[k] += a[j] * bv[j];
+      }
+    }
+    if (active) {
+#pragma unroll
+      for (int k = 0; k < N; ++k) R[((int64_t)cell * N + k) * nB + c] = acc[k];
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256)
+k_spmm_rows_fewcols(int32_t nrows, const int32_t* __restrict__ rowptr, const int32_t* __restrict__ colidx,
+                    const double* __restrict__ vals, const double* __restrict__ B, int nB, int64_t ldbRow,
+                    int64_t ldbCol, double* __restrict__ R, int64_t ldrRow, int64_t ldrCol) {
+  const int warp = (int)(((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
   const int lane = threadIdx.x & 31;
   if (warp >= nrows) return;
   const int32_t b = rowptr[warp], e = rowptr[warp + 1];
-  for (int c = 0; c < nB; ++c) {
-    double acc = 0.0;
-    for (int32_t p = b + lane; p < e; p += 32) acc += vals[p] * B[(int64_t)colidx[p] * ldbRow + c * ldbCol];
+  for (int c0 = 0; c0 < nB; c0 += 8) {
+    const int nb = min(8, nB - c0);
+    double acc[8];
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
-    if (lane == 0) R[(int64_t)warp * ldrRow + c * ldrCol] = acc;
+    for (int c = 0; c < 8; ++c) acc[c] = 0.0;
+    for (int32_t p = b + lane; p < e; p += 32) {
+      const double v = vals[p];
+      const double* brow = B + (int64_t)colidx[p] * ldbRow + (int64_t)c0 * ldbCol;
+#pragma unroll
+      for (int c = 0; c < 8; ++c) if (c < nb) acc[c] += v * brow[c * ldbCol];
+    }
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+      if (c < nb) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) acc[c] += __shfl_xor_sync(0xffffffffu, acc[c], o);
+        if (lane == 0) R[(int64_t)warp * ldrRow + (int64_t)(c0 + c) * ldrCol] = acc[c];
+      }
+    }
+  }
+}
+
+// out[c][r] <- in[r][c]  (in: rows x cols row-major); 32x32 tiles through shared memory, linear tile index
+__global__ void __launch_bounds__(256)
+k_transpose(const double* __restrict__ in, int64_t rows, int64_t cols, double* __restrict__ out) {
+  __shared__ double tile[32][33];
+  const int64_t tilesC = (cols + 31) / 32;
+  const int64_t r0 = ((int64_t)blockIdx.x / tilesC) * 32, c0 = ((int64_t)blockIdx.x % tilesC) * 32;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  for (int i = ty; i < 32; i += 8) {
+    const int64_t r = r0 + i, c = c0 + tx;
+    if (r < rows && c < cols) tile[i][tx] = in[r * cols + c];
+  }
+  __syncthreads();
+  for (int i = ty; i < 32; i += 8) {
+    const int64_t c = c0 + i, r = r0 + tx;
+    if (r < rows && c < cols) out[c * rows + r] = tile[tx][i];
   }
 }
 

@@ -418,6 +418,11 @@ class Problem:
     createRhs = createRightHandSide
     createVelocity = createRightHandSide
 
+    def jacobianNnz(self):
+        nnz = _i64()
+        _check(_lib.pda_problem_jacobian_nnz(self._h, _C.byref(nnz)))
+        return int(nnz.value)
+
     def jacobianPattern(self):
         if self._pattern is None:
             nnz = _i64()

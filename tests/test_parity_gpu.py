@@ -391,3 +391,34 @@ def test_slab_peer_mode_multi_process():
                        capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
     assert "mismatching evaluations: 0" in r.stdout
+
+
+@pytest.mark.parametrize("case", ["euler2d_lattice", "swe_sample", "euler3d", "burgers"])
+@pytest.mark.parametrize("ncols", [8, 25, 40])
+def test_apply_jacobian_many_columns(case, ncols):
+    """operands with >= 8 columns take the per-cell J*B kernel (lanes across operand columns; column-major operands
+    transposed around it; lattices visited in tile-major order): every layout must equal J @ B of the assembled
+    Jacobian (tests_perf/main.py:37-48 uses 25 columns)"""
+    if case == "euler2d_lattice":
+        mesh = pda.create_full_mesh([37, 29], [0, 1, 0, 1], 7)
+        p = pda.create_problem(mesh, pda.Euler2d.Riemann, R.Weno5)
+    elif case == "swe_sample":
+        full = pda.create_full_mesh([30, 30], [-5, 5, -5, 5], 5)
+        gids = np.sort(np.random.default_rng(5).choice(900, 200, replace=False)).astype(np.int32)
+        p = pda.create_problem(pda.create_sample_mesh(full, gids), pda.Swe2d.SlipWall, R.Weno3)
+    elif case == "euler3d":
+        mesh = pda.create_full_mesh([10, 9, 8], [-1, 1, -1, 1, -1, 1], 5, ("x", "y", "z"))
+        p = pda.create_problem(mesh, pda.Euler3d.PeriodicSmooth, R.Weno3)
+    else:
+        mesh = pda.create_full_mesh([20, 18], [-1, 1, -1, 1], 5, ("x", "y"))
+        p = pda.create_problem(mesh, pda.AdvectionDiffusion2d.BurgersPeriodic, R.Weno3,
+                               pda.ViscousFluxReconstruction.FirstOrder)
+    U = perturbed(p)
+    J = p.createJacobian()
+    p.jacobian(U, 0.0, J)
+    rng = np.random.default_rng(11)
+    for order in ("C", "F"):
+        B = np.asarray(rng.uniform(-1, 1, (U.size, ncols)), order=order)
+        Rm = p.createApplyJacobianResult(B)
+        p.applyJacobian(U, B, 0.0, Rm)
+        assert scaled_err(Rm, J @ B, 1e-11, 1e-9) <= 1.0

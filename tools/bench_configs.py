@@ -1,0 +1,123 @@
+"""Device-resident throughput of every BASELINE.json config on one B200 (the headline cfg 5 is bench.py's own line):
+cfg 1 (1D Sod WENO5 1000), cfg 2 (2D Riemann WENO5 2048^2), cfg 3 (SWE slip wall first-order / WENO3 and Gray-Scott,
+4096^2), cfg 4 (double Mach reflection 4096x1024, 5 % sample mesh).  Velocity cells/s, velocity+Jacobian nnz/s and
+applyJacobian (25 columns, like tests_perf/main.py:37-48), each with its HBM roofline fraction
+(bytes: SURVEY 8(d): 2*ndpc*8 per cell for the velocity, + 8 per stored nnz for the Jacobian).
+
+    python tools/bench_configs.py [--small]        # one JSON object on stdout
+bench.py embeds the same object as "configs" (N=1 runs).
+"""
+import json
+import os
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(ROOT, "pressio-demoapps_b200"))
+
+
+def _time(fn, reps, warm=2):
+    import torch
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(reps):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / reps
+
+
+def measure(p, hbm_gbs, jac=True, apply_cols=0, reps=5, t=0.0):
+    import torch
+    st = torch.cuda.current_stream().cuda_stream
+    ndpc = p.numDofPerCell()
+    ncell = p.totalDofSampleMesh() // ndpc
+    U = torch.from_numpy(p.initialCondition()).cuda()
+    V = torch.empty(p.totalDofSampleMesh(), dtype=torch.float64, device="cuda")
+    out = {"cells": ncell, "ndpc": ndpc}
+    l0 = p.launchCount()
+    ms = _time(lambda: p.rightHandSideDevice(U.data_ptr(), t, V.data_ptr(), st), reps)
+    out["velocity"] = {"ms": ms, "cells_per_s": ncell / (ms * 1e-3),
+                       "hbm_frac": 2 * ndpc * 8.0 * ncell / (ms * 1e-3) * 1e-9 / hbm_gbs}
+    if jac:
+        t0 = time.time()
+        nnz = int(p.jacobianNnz())
+        out["pattern_build_s"] = time.time() - t0
+        Jv = torch.empty(nnz, dtype=torch.float64, device="cuda")
+        ms = _time(lambda: p.rightHandSideAndJacobianDevice(U.data_ptr(), t, V.data_ptr(), Jv.data_ptr(), st), reps)
+        by = nnz * 8.0 + 2 * ndpc * 8.0 * ncell
+        out["jacobian"] = {"ms": ms, "nnz": nnz, "nnz_per_s": nnz / (ms * 1e-3), "hbm_frac": by / (ms * 1e-3) * 1e-9 / hbm_gbs}
+        if apply_cols:
+            del Jv
+            B = torch.rand(p.totalDofStencilMesh(), apply_cols, dtype=torch.float64, device="cuda")
+            Rm = torch.empty(p.totalDofSampleMesh(), apply_cols, dtype=torch.float64, device="cuda")
+            ms = _time(lambda: p.applyJacobianDevice(U.data_ptr(), B.data_ptr(), apply_cols, 1, t, Rm.data_ptr(), st), max(2, reps // 2))
+            out["apply_jacobian"] = {"ms": ms, "cols": apply_cols, "layout": "row-major",
+                                     "nnz_cols_per_s": nnz * apply_cols / (ms * 1e-3)}
+    out["gpu_launches"] = int(p.launchCount() - l0)
+    return out
+
+
+def run(hbm_gbs, small=False, device=0):
+    import numpy as np
+    import torch
+    import pressiodemoapps as pda
+    R = pda.InviscidFluxReconstruction
+    res = {}
+
+    def guarded(name, fn):
+        try:
+            res[name] = fn()
+        except Exception as e:   # a config that fails is reported, not hidden
+            res[name] = {"error": "%s: %s" % (type(e).__name__, e)}
+        torch.cuda.empty_cache()
+
+    def cfg1():
+        mesh = pda.create_full_mesh([1000], [-0.5, 0.5], 7)
+        p = pda.create_problem(mesh, pda.Euler1d.Sod, R.Weno5, device=device)
+        return dict(workload="1D Euler Sod WENO5 1000 cells (launch-latency bound)", **measure(p, hbm_gbs, reps=50))
+
+    def cfg2():
+        n = 512 if small else 2048
+        mesh = pda.create_full_mesh([n, n], [0, 1, 0, 1], 7)
+        p = pda.create_problem(mesh, pda.Euler2d.Riemann, R.Weno5, device=device)
+        return dict(workload="2D Euler Riemann WENO5 %dx%d full mesh" % (n, n), **measure(p, hbm_gbs, apply_cols=25))
+
+    def cfg3(kind):
+        n = 512 if small else 4096
+        if kind == "gs":
+            mesh = pda.create_full_mesh([n, n], [-1.25, 1.25, -1.25, 1.25], 3, ("x", "y"))
+            p = pda.create_problem(mesh, pda.DiffusionReaction2d.GrayScott, pda.ViscousFluxReconstruction.FirstOrder, device=device)
+            return dict(workload="2D Gray-Scott %dx%d periodic" % (n, n), **measure(p, hbm_gbs))
+        rec, st = (R.FirstOrder, 3) if kind == "swe_fo" else (R.Weno3, 5)
+        mesh = pda.create_full_mesh([n, n], [-5, 5, -5, 5], st)
+        p = pda.create_problem(mesh, pda.Swe2d.SlipWall, rec, device=device)
+        return dict(workload="2D SWE slip wall %s %dx%d (reflective BCs)" % (rec.name, n, n), **measure(p, hbm_gbs))
+
+    def cfg4(rec, st):
+        nx, ny = (512, 128) if small else (4096, 1024)
+        full = pda.create_full_mesh([nx, ny], [0, 4, 0, 1], st)
+        rng = np.random.default_rng(20261017)
+        gids = np.sort(rng.choice(nx * ny, (nx * ny) // 20, replace=False)).astype(np.int32)
+        sm = pda.create_sample_mesh(full, gids)
+        p = pda.create_problem(sm, pda.Euler2d.DoubleMachReflection, rec, device=device)
+        return dict(workload="2D Euler double Mach reflection %s %dx%d, 5%% sample mesh (%d cells, stencil mesh %d)"
+                             % (rec.name, nx, ny, gids.size, sm.stencilMeshSize()), **measure(p, hbm_gbs, t=0.1))
+
+    guarded("cfg1_euler1d_sod_weno5", cfg1)
+    guarded("cfg2_euler2d_riemann_weno5", cfg2)
+    guarded("cfg3_swe_firstorder", lambda: cfg3("swe_fo"))
+    guarded("cfg3_swe_weno3", lambda: cfg3("swe_w3"))
+    guarded("cfg3_gray_scott", lambda: cfg3("gs"))
+    guarded("cfg4_dmr_sample_weno3", lambda: cfg4(R.Weno3, 5))
+    guarded("cfg4_dmr_sample_weno5", lambda: cfg4(R.Weno5, 7))
+    return res
+
+
+if __name__ == "__main__":
+    peaks = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    hbm = float(json.load(open(peaks))["hbm_gbs"]) if os.path.exists(peaks) else 6650.0
+    print(json.dumps(run(hbm, small="--small" in sys.argv), indent=1))
