@@ -169,6 +169,7 @@ struct DeviceState {
   DevBuf<int32_t> dCellBase, dCellLen, dCellOrder;
   DevBuf<double> dBt, dRt;
   bool spmmReady = false;
+  int32_t spmmMaxLen = 0;
   // lattice Jacobian kernel: per-cell CSR base and block-slot tables (indexed by gid)
   DevBuf<int32_t> latBase;
   DevBuf<uint4> latSlots;
@@ -1422,13 +1423,24 @@ void Problem::applyJacobianDev(const double* dU, const double* dB, int ncols, in
     }
     const int32_t ncells = mesh_->nSample;
     const int32_t* order = ds.dCellOrder.p;
-    const unsigned grid = gridFor((int64_t)ncells * 32, 256);
+    const unsigned grid = (unsigned)gridFor(ncells, 64);   // 64 cells (one tile of the visiting order) per CTA
+    // shared memory: two chunk slots per warp, sized for the longest row block of this problem
+    int32_t maxLen = 0;
+    if (ds.spmmMaxLen == 0) { for (int32_t l : cellLen_) maxLen = std::max(maxLen, l); ds.spmmMaxLen = maxLen; }
+    const int slotDoubles = (ndpc_ * ds.spmmMaxLen + 1) & ~1;
+    const size_t smem = (size_t)16 * slotDoubles * sizeof(double);
+    auto launch = [&](auto nTag) {
+      constexpr int NN = decltype(nTag)::value;
+      auto kern = dev::k_spmm_cells_rowmajor<NN>;
+      PDA_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      kern<<<grid, 256, smem, st>>>(ncells, order, ds.dCellBase.p, ds.dCellLen.p, ds.dColidx.p, ds.dJ.p, Bp, ncols, Rp, slotDoubles);
+    };
     switch (ndpc_) {
-      case 1: dev::k_spmm_cells_rowmajor<1><<<grid, 256, 0, st>>>(ncells, order, ds.dCellBase.p, ds.dCellLen.p, ds.dColidx.p, ds.dJ.p, Bp, ncols, Rp); break;
-      case 2: dev::k_spmm_cells_rowmajor<2><<<grid, 256, 0, st>>>(ncells, order, ds.dCellBase.p, ds.dCellLen.p, ds.dColidx.p, ds.dJ.p, Bp, ncols, Rp); break;
-      case 3: dev::k_spmm_cells_rowmajor<3><<<grid, 256, 0, st>>>(ncells, order, ds.dCellBase.p, ds.dCellLen.p, ds.dColidx.p, ds.dJ.p, Bp, ncols, Rp); break;
-      case 4: dev::k_spmm_cells_rowmajor<4><<<grid, 256, 0, st>>>(ncells, order, ds.dCellBase.p, ds.dCellLen.p, ds.dColidx.p, ds.dJ.p, Bp, ncols, Rp); break;
-      default: dev::k_spmm_cells_rowmajor<5><<<grid, 256, 0, st>>>(ncells, order, ds.dCellBase.p, ds.dCellLen.p, ds.dColidx.p, ds.dJ.p, Bp, ncols, Rp); break;
+      case 1: launch(std::integral_constant<int, 1>{}); break;
+      case 2: launch(std::integral_constant<int, 2>{}); break;
+      case 3: launch(std::integral_constant<int, 3>{}); break;
+      case 4: launch(std::integral_constant<int, 4>{}); break;
+      default: launch(std::integral_constant<int, 5>{}); break;
     }
     ++launches_;
     if (layout != 1) transpose(ds.dRt.p, nrows, ncols, dR);

@@ -545,51 +545,91 @@ k_gray_scott_lattice(GrayScottParams gp, int32_t nx, int32_t ny, const double2* 
 //     cells are visited in a tile-major order on lattices so that the B rows of stencil neighbours hit in L1;
 //   * everything else (vectors, few columns): one warp per row, lanes across the row's entries, J read once for up
 //     to 8 columns, shuffle reduction.  Column-major operands with many columns are transposed around kernel 1.
+// smem: per warp two slots of `slotDoubles` doubles (the J chunk of the current cell and of the next one in flight)
 template <int N>
 __global__ void __launch_bounds__(256)
 k_spmm_cells_rowmajor(int32_t ncells, const int32_t* __restrict__ order, const int32_t* __restrict__ cellBase,
                       const int32_t* __restrict__ cellLen, const int32_t* __restrict__ colidx,
-                      const double* __restrict__ vals, const double* __restrict__ B, int nB, double* __restrict__ R) {
-  const int w = (int)(((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
-  const int lane = threadIdx.x & 31;
-  if (w >= ncells) return;
-  const int32_t cell = order ? order[w] : w;
-  const int64_t base = cellBase[cell];
-  const int32_t len = cellLen[cell];
-  const int nblk = len / N;
-  for (int c0 = 0; c0 < nB; c0 += 32) {
-    const int c = c0 + lane;
-    const bool active = c < nB;
-    double acc[N];
-#pragma unroll
-    for (int k = 0; k < N; ++k) acc[k] = 0.0;
-    for (int b = 0; b < nblk; ++b) {
-      const int32_t col0 = colidx[base + b * N];
-      double bv[N];
-#pragma unroll
-      for (int j = 0; j < N; ++j) bv[j] = active ? B[(int64_t)(col0 + j) * nB + c] : 0.0;
-#pragma unroll
-      for (int k = 0; k < N; ++k) {
-        const double* jv = vals + base + (int64_t)k * len + b * N;
-        double a[N];
-        if constexpr (N == 4) {
-          asm volatile("ld.global.nc.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(a[0]), "=d"(a[1]), "=d"(a[2]), "=d"(a[3]) : "l"(jv));
-        } else if constexpr (N == 2) {
-          const double2 t = __ldg(reinterpret_cast<const double2*>(jv));
-          a[0] = t.x; a[1] = t.y;
-        } else {
-#pragma unroll
-          for (int j = 0; j < N; ++j) a[j] = __ldg(jv + j);
-        }
-#pragma unroll
-        for (int j = 0; j < N; ++j) acc[k] += a[j] * bv[j];
+                      const double* __restrict__ vals, const double* __restrict__ B, int nB, double* __restrict__ R,
+                      int slotDoubles) {
+  // a CTA owns 64 consecutive cells of the visiting order (one 8x8 lattice tile): warp w takes cells w, w+8, ...
+  // The cell's J chunk (N rows x len, contiguous in the CSR value array) streams into shared memory with cp.async,
+  // one cell ahead of the arithmetic; the arithmetic then reads it as warp-uniform (broadcast) shared loads.
+  extern __shared__ __align__(16) double sChunks[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  double* const slot0 = sChunks + (size_t)(2 * warp) * slotDoubles;
+  constexpr int PIECE = (N % 2 == 0) ? 2 : 1;   // doubles per cp.async (16-byte pieces need an even chunk offset)
+
+  auto cellOf = [&](int t) -> int32_t {
+    const int64_t w = (int64_t)blockIdx.x * 64 + t * 8 + warp;
+    if (t >= 8 || w >= ncells) return -1;
+    return order ? order[w] : (int32_t)w;
+  };
+  auto prefetch = [&](int32_t cell, double* dst) {
+    if (cell >= 0) {
+      const double* src = vals + cellBase[cell];
+      const int n = N * cellLen[cell];
+      for (int e = lane * PIECE; e < n; e += 32 * PIECE) {
+        const unsigned sa = (unsigned)__cvta_generic_to_shared(dst + e);
+        if constexpr (PIECE == 2) asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(sa), "l"(src + e) : "memory");
+        else asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"(sa), "l"(src + e) : "memory");
       }
     }
-    if (active) {
+    asm volatile("cp.async.commit_group;\n" ::: "memory");
+  };
+
+  int32_t cell = cellOf(0);
+  prefetch(cell, slot0);
+  for (int t = 0; t < 8 && cell >= 0; ++t) {
+    const int32_t next = cellOf(t + 1);
+    prefetch(next, slot0 + ((t + 1) & 1) * slotDoubles);
+    const int64_t base = cellBase[cell];
+    const int32_t len = cellLen[cell];
+    const int nblk = len / N;
+    // first column of every block: one load by the first nblk lanes, broadcast by shuffle (nblk <= 19)
+    const int32_t myCol = (lane < nblk) ? __ldg(colidx + base + lane * N) : 0;
+    asm volatile("cp.async.wait_group 1;\n" ::: "memory");   // this cell's chunk has landed (the next one may be in flight)
+    __syncwarp();
+    const double* sj = slot0 + (t & 1) * slotDoubles;
+    for (int c0 = 0; c0 < nB; c0 += 32) {
+      const int c = c0 + lane;
+      const bool active = c < nB;
+      const double* Bc = B + (active ? c : 0);
+      double acc[N];
 #pragma unroll
-      for (int k = 0; k < N; ++k) R[((int64_t)cell * N + k) * nB + c] = acc[k];
+      for (int k = 0; k < N; ++k) acc[k] = 0.0;
+#pragma unroll 4
+      for (int b = 0; b < nblk; ++b) {
+        const int32_t col0 = __shfl_sync(0xffffffffu, myCol, b);
+        const double* bp = Bc + (int64_t)col0 * nB;
+        double bv[N];
+#pragma unroll
+        for (int j = 0; j < N; ++j) bv[j] = __ldg(bp + (int64_t)j * nB);
+#pragma unroll
+        for (int k = 0; k < N; ++k) {
+          const double* jv = sj + k * len + b * N;
+          if constexpr (N % 2 == 0) {   // even N: the block row is 16-byte aligned in the slot -> LDS.128
+#pragma unroll
+            for (int j = 0; j < N; j += 2) {
+              const double2 a = *reinterpret_cast<const double2*>(jv + j);
+              acc[k] += a.x * bv[j];
+              acc[k] += a.y * bv[j + 1];
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < N; ++j) acc[k] += jv[j] * bv[j];
+          }
+        }
+      }
+      if (active) {
+#pragma unroll
+        for (int k = 0; k < N; ++k) R[((int64_t)cell * N + k) * nB + c] = acc[k];
+      }
     }
+    __syncwarp();   // everyone is done with this slot before the prefetch two cells ahead overwrites it
+    cell = next;
   }
+  asm volatile("cp.async.wait_group 0;\n" ::: "memory");
 }
 
 __global__ void __launch_bounds__(256)
