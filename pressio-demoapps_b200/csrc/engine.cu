@@ -15,6 +15,7 @@
 #include "kernels_tiled.cuh"
 #include "kernels_jacobian.cuh"
 #include "kernels_jaclattice.cuh"
+#include "kernels_march2d.cuh"
 
 namespace pda {
 

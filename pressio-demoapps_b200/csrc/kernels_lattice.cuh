@@ -155,6 +155,11 @@ template <class Phys, int S>
 void launchLattice3dTiled(const Phys& phys, const dev::LatticeDesc& L, const dev::Deltas& dl, const double* dU,
                           double* dV, cudaStream_t st);
 
+// 2D: y-marching, face-sharing kernel (kernels_march2d.cuh)
+template <class Phys, int S>
+void launchMarch2d(const Phys& phys, const dev::LatticeDesc& L, const dev::Deltas& dl, const double* dU, double* dV,
+                   cudaStream_t st);
+
 template <class Phys, int S>
 void launchLatticeVelocity(const Phys& phys, const Mesh& m, const dev::Deltas& dl, const double* dU, double* dV,
                            cudaStream_t st, int32_t planeBegin, int32_t planeEnd, int /*flags*/) {
@@ -171,6 +176,10 @@ void launchLatticeVelocity(const Phys& phys, const Mesh& m, const dev::Deltas& d
       launchLattice3dTiled<Phys, S>(phys, L, dl, dU, dV, st);
       return;
     }
+  }
+  if constexpr (Phys::dim == 2) {
+    launchMarch2d<Phys, S>(phys, L, dl, dU, dV, st);
+    return;
   }
   const int block = 128;
   dev::k_velocity_lattice_v1<Phys, S><<<(unsigned)((nwork + block - 1) / block), block, 0, st>>>(phys, L, dl, dU, dV);
@@ -194,6 +203,10 @@ void launchLatticeVelocitySlab(const Phys& phys, const Mesh& m, const dev::Delta
       launchLattice3dTiled<Phys, S>(phys, L, dl, dUlocal, dVowned, st);
       return;
     }
+  }
+  if constexpr (Phys::dim == 2) {
+    launchMarch2d<Phys, S>(phys, L, dl, dUlocal, dVowned, st);
+    return;
   }
   const int block = 128;
   dev::k_velocity_lattice_v1<Phys, S><<<(unsigned)((nwork + block - 1) / block), block, 0, st>>>(phys, L, dl, dUlocal, dVowned);

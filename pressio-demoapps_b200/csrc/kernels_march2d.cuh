@@ -1,0 +1,194 @@
+// kernels_march2d.cuh -- structured 2D velocity with every face flux computed ONCE, registers and shuffles only.
+//
+// Replaces the reference's inner-cell velocity loops on full 2D meshes (euler_2d_prob_class.hpp:991-1044,
+// swe_2d_prob_class.hpp:928-981, advection_diffusion_2d_prob_class.hpp inner loop), which evaluate both faces of
+// both axes per cell (each face flux twice).
+//
+// A warp owns a strip of 32 columns and MARCHES along y:
+//   * lane l holds column x0-h+l; the y stencil of that column is a register ring of 2h+1 rows (rows j-h..j+h), one
+//     new row per step fetched one step ahead with a single coalesced (AoS, 256-bit for 4 dofs) load per lane;
+//   * the front y-face flux of row j is the back flux of row j+1 (registers) -> y faces once;
+//   * the x stencil of row j comes from the neighbouring lanes by warp shuffle; each lane computes the LEFT face of
+//     its cell, the right face is lane+1's left face (one more shuffle) -> x faces once.  The 2h edge lanes of a warp
+//     only feed stencils (32-2h output cells per warp and step);
+//   * no shared memory, no barrier; V written once per cell, coalesced.
+// Euler uses the branch-free reciprocal / square root arithmetic of the 3D kernel (kernels_tiled.cuh).
+// Works for scheme stencils 3/5/7, periodic or not per axis (cells whose MESH stencil leaves a non-periodic domain
+// belong to the near-boundary kernel), diffusion / point terms of the advection-diffusion families, and slab-local
+// storage (2D multi-GPU slabs).
+#pragma once
+#include "kernels_lattice.cuh"
+#include "kernels_tiled.cuh"
+#include "kernels_jaclattice.cuh"
+
+namespace pda {
+namespace dev {
+
+// Rusanov flux of the DIM-dimensional Euler equations along AX with the fast reciprocal / square root
+// (impl/euler_rusanov_flux_values_function.hpp:54-208)
+template <int DIM, int AX>
+PDA_DEVFN void eulerFluxFast(double gamma, const double* qL, const double* qR, double* F) {
+  constexpr int N = DIM + 2;
+  const double gm1 = gamma - 1.0;
+  const double rL = qL[0], rR = qR[0];
+  const double iL = rcpFast(rL), iR = rcpFast(rR);
+  double vL[DIM], vR[DIM];
+  double kL = 0.0, kR = 0.0;
+#pragma unroll
+  for (int m = 0; m < DIM; ++m) {
+    vL[m] = qL[1 + m] * iL; vR[m] = qR[1 + m] * iR;
+    kL = fma(vL[m], vL[m], kL); kR = fma(vR[m], vR[m], kR);
+  }
+  const double pL = gm1 * fma(-0.5 * rL, kL, qL[N - 1]);
+  const double pR = gm1 * fma(-0.5 * rR, kR, qR[N - 1]);
+  const double HL = (qL[N - 1] + pL) * iL;
+  const double HR = (qR[N - 1] + pR) * iR;
+  const double mL = rL * vL[AX], mR = rR * vR[AX];
+  const double RT = sqrtFast(rR * iL);
+  const double iRT = rcpFast(1.0 + RT);
+  double k = 0.0;
+#pragma unroll
+  for (int m = 0; m < DIM; ++m) { const double v = fma(RT, vR[m], vL[m]) * iRT; k = fma(v, v, k); }
+  const double H = fma(RT, HR, HL) * iRT;
+  const double a = sqrtFast(gm1 * fma(-0.5, k, H));
+  const double smax = sqrtFast(k) + a;
+  const double pS = pL + pR;
+  F[0] = 0.5 * fma(smax, rL - rR, mL + mR);
+#pragma unroll
+  for (int m = 0; m < DIM; ++m)
+    F[1 + m] = 0.5 * (fma(smax, qL[1 + m] - qR[1 + m], fma(mL, vL[m], mR * vR[m])) + ((m == AX) ? pS : 0.0));
+  F[N - 1] = 0.5 * fma(smax, qL[N - 1] - qR[N - 1], fma(mL, HL, mR * HR));
+}
+
+template <class Phys, int AX>
+PDA_DEVFN void faceFlux2d(const Phys& phys, const double* uN, const double* uP, double* F) {
+  if constexpr (std::is_same<Phys, Euler<2>>::value) eulerFluxFast<2, AX>(phys.gamma, uN, uP, F);
+  else phys.template flux<AX>(uN, uP, F);
+}
+
+template <class Phys, int S>
+__global__ void __launch_bounds__(128)
+k_velocity_march2d(Phys phys, LatticeDesc L, Deltas dl, const double* __restrict__ U, double* __restrict__ V, int LY) {
+  constexpr int N = Phys::ndpc;
+  constexpr int h = (S - 1) / 2;
+  constexpr int W = 32 - 2 * h;      // output cells per warp and step
+  constexpr int R = 2 * h + 1;       // ring rows j-h .. j+h
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int nx = L.n[0], ny = L.n[1];
+  const int lo0 = L.per[0] ? 0 : L.meshHalo, hi0 = L.per[0] ? nx : nx - L.meshHalo;
+  int yb = L.planeBegin, ye = L.planeEnd;
+  if (!L.slab && !L.per[1]) { yb = max(yb, L.meshHalo); ye = min(ye, ny - L.meshHalo); }
+  const int nStrips = (hi0 - lo0 + W - 1) / W;
+  const int wid = blockIdx.x * 4 + warp;
+  const int strip = wid % nStrips, chunk = wid / nStrips;
+  const int j0 = yb + chunk * LY;
+  if (j0 >= ye) return;
+  const int j1 = min(j0 + LY, ye);
+  const int x = lo0 + strip * W - h + lane;
+  int xc = x;
+  if (L.per[0]) { xc %= nx; if (xc < 0) xc += nx; }   // edge lanes of tiny periodic meshes may wrap more than once
+  else xc = (xc < 0) ? 0 : (xc >= nx ? nx - 1 : xc);
+  const bool outLane = (lane >= h) && (lane <= 31 - h) && (x < hi0);
+
+  auto rowPtr = [&](int r) -> const double* {
+    int sr;
+    if (L.slab) sr = r + L.haloPlanes;
+    else if (L.per[1]) { sr = r % ny; if (sr < 0) sr += ny; }
+    else sr = (r < 0) ? 0 : (r >= ny ? ny - 1 : r);
+    return U + ((int64_t)sr * nx + xc) * N;
+  };
+  auto yFace = [&](const double (*q)[N], double* F) {   // q[0..2h-1] = rows around the face
+    double uN[N], uP[N];
+#pragma unroll
+    for (int d = 0; d < N; ++d) {
+      double s[2 * h];
+#pragma unroll
+      for (int o = 0; o < 2 * h; ++o) s[o] = q[o][d];
+      reconFaceFast<S>(s, uN[d], uP[d]);
+    }
+    faceFlux2d<Phys, 1>(phys, uN, uP, F);
+  };
+
+  double q[R][N];
+#pragma unroll
+  for (int i = 0; i < R; ++i) loadCell<N>(rowPtr(j0 - h + i), q[i]);
+  double FyB[N];
+  yFace(q, FyB);
+
+  for (int j = j0; j < j1; ++j) {
+    double nxt[N];
+    const bool more = (j + 1 < j1);
+    if (more) loadCell<N>(rowPtr(j + 1 + h), nxt);   // lands while this row is computed
+    // ---- front y face (j+1/2): rows j-h+1 .. j+h
+    double FyF[N];
+    yFace(q + 1, FyF);
+    // ---- x left face of this lane's cell from the neighbouring lanes' row-j values
+    double Fx[N];
+    {
+      double uN[N], uP[N];
+#pragma unroll
+      for (int d = 0; d < N; ++d) {
+        double s[2 * h];
+#pragma unroll
+        for (int o = 0; o < 2 * h; ++o)
+          s[o] = (o == h) ? q[h][d] : __shfl_sync(0xffffffffu, q[h][d], (lane + o - h) & 31);
+        reconFaceFast<S>(s, uN[d], uP[d]);
+      }
+      faceFlux2d<Phys, 0>(phys, uN, uP, Fx);
+    }
+    double v[N];
+#pragma unroll
+    for (int d = 0; d < N; ++d) {
+      const double FxR = __shfl_down_sync(0xffffffffu, Fx[d], 1);
+      v[d] = dl.hInv[0] * (Fx[d] - FxR);
+      v[d] += dl.hInv[1] * (FyB[d] - FyF[d]);
+      FyB[d] = FyF[d];
+    }
+    if constexpr (PhysTraits<Phys>::hasDiffusion) {
+      // dD[ax] * (u+ - 2u + u-), x then y, after the flux balances (advection_diffusion_2d_prob_class.hpp:1167-1201)
+#pragma unroll
+      for (int d = 0; d < N; ++d) {
+        const double uL = __shfl_sync(0xffffffffu, q[h][d], (lane - 1) & 31);
+        const double uR = __shfl_sync(0xffffffffu, q[h][d], (lane + 1) & 31);
+        v[d] += phys.dD[0] * (uR - 2.0 * q[h][d] + uL);
+      }
+#pragma unroll
+      for (int d = 0; d < N; ++d) v[d] += phys.dD[1] * (q[h + 1][d] - 2.0 * q[h][d] + q[h - 1][d]);
+    }
+    if (outLane) {
+      const int64_t vIdx = (int64_t)j * nx + x;
+      addForcing<Phys>(phys, q[h], v, (int32_t)vIdx);
+      storeBlockRow<N>(V + vIdx * N, v);
+    }
+    // ---- rotate the ring
+#pragma unroll
+    for (int i = 0; i < R - 1; ++i)
+#pragma unroll
+      for (int d = 0; d < N; ++d) q[i][d] = q[i + 1][d];
+    if (more) {
+#pragma unroll
+      for (int d = 0; d < N; ++d) q[R - 1][d] = nxt[d];
+    }
+  }
+}
+
+}  // namespace dev
+
+template <class Phys, int S>
+void launchMarch2d(const Phys& phys, const dev::LatticeDesc& L, const dev::Deltas& dl, const double* dU, double* dV,
+                   cudaStream_t st) {
+  static_assert(Phys::dim == 2, "2D kernel");
+  constexpr int h = (S - 1) / 2, W = 32 - 2 * h;
+  const int lo0 = L.per[0] ? 0 : L.meshHalo, hi0 = L.per[0] ? L.n[0] : L.n[0] - L.meshHalo;
+  int yb = L.planeBegin, ye = L.planeEnd;
+  if (!L.slab && !L.per[1]) { yb = std::max(yb, L.meshHalo); ye = std::min(ye, L.n[1] - L.meshHalo); }
+  if (hi0 <= lo0 || ye <= yb) return;
+  const int64_t nStrips = (hi0 - lo0 + W - 1) / W;
+  // y chunks: long enough to amortise the ring fill (2h+1 rows, one extra y face), short enough for >= 4 waves
+  int LY = 64;
+  while (LY > 8 && nStrips * ((ye - yb + LY - 1) / LY) < (int64_t)148 * 16 * 4) LY /= 2;
+  const int64_t tasks = nStrips * ((ye - yb + LY - 1) / LY);
+  dev::k_velocity_march2d<Phys, S><<<(unsigned)((tasks + 3) / 4), 128, 0, st>>>(phys, L, dl, dU, dV, LY);
+}
+
+}  // namespace pda
