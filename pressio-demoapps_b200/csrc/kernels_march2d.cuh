@@ -60,9 +60,29 @@ PDA_DEVFN void eulerFluxFast(double gamma, const double* qL, const double* qR, d
   F[N - 1] = 0.5 * fma(smax, qL[N - 1] - qR[N - 1], fma(mL, HL, mR * HR));
 }
 
+// shallow-water Rusanov flux (impl/swe_rusanov_flux_values_function.hpp:54-97) with the fast reciprocal / square
+// root: depths are positive normal numbers, the 1e-30 guards of the reference vanish in double precision next to them
+template <int AX>
+PDA_DEVFN void sweFluxFast(double g, const double* qL, const double* qR, double* F) {
+  const double hL = qL[0], hR = qR[0];
+  const double iL = rcpFast(hL), iR = rcpFast(hR);
+  const double uL = qL[1] * iL, vL = qL[2] * iL;
+  const double uR = qR[1] * iR, vR = qR[2] * iR;
+  const double unL = (AX == 0) ? uL : vL, unR = (AX == 0) ? uR : vR;
+  const double pS = 0.5 * g * fma(hL, hL, hR * hR);
+  const double sL = sqrtFast(hL), sR = sqrtFast(hR);
+  const double um = fma(unL, sL, unR * sR) * rcpFast(sL + sR);
+  const double smax = fabs(um) + sqrtFast(g * (0.5 * (hL + hR)));
+  const double mL = hL * unL, mR = hR * unR;
+  F[0] = 0.5 * fma(smax, qL[0] - qR[0], mL + mR);
+  F[1] = 0.5 * (fma(smax, qL[1] - qR[1], fma(mL, uL, mR * uR)) + ((AX == 0) ? pS : 0.0));
+  F[2] = 0.5 * (fma(smax, qL[2] - qR[2], fma(mL, vL, mR * vR)) + ((AX == 1) ? pS : 0.0));
+}
+
 template <class Phys, int AX>
 PDA_DEVFN void faceFlux2d(const Phys& phys, const double* uN, const double* uP, double* F) {
   if constexpr (std::is_same<Phys, Euler<2>>::value) eulerFluxFast<2, AX>(phys.gamma, uN, uP, F);
+  else if constexpr (std::is_same<Phys, Swe2d>::value) sweFluxFast<AX>(phys.g, uN, uP, F);
   else phys.template flux<AX>(uN, uP, F);
 }
 

@@ -118,8 +118,26 @@ PDA_DEVFN void weno5FaceFast(const double* q, double& uNeg, double& uPos) {
   uPos = Np * (Dn * r);
 }
 
+// WENO3 at one face from the four cells around it (impl/weno3.hpp:56-114), both sides with ONE reciprocal
+PDA_DEVFN void weno3FaceFast(const double* q, double& uNeg, double& uPos) {
+  const double b = q[0], c = q[1], d = q[2], e = q[3];
+  const double dbc = b - c, dcd = c - d, dde = d - e;
+  const double Eb = fma(dbc, dbc, kWenoEps), Ec = fma(dcd, dcd, kWenoEps), Ed = fma(dde, dde, kWenoEps);
+  const double Gb = Eb * Eb, Gc = Ec * Ec, Gd = Ed * Ed;
+  const double pm = 0.5 * (c + d);
+  const double p0 = 0.5 * fma(3.0, c, -b), p1 = 0.5 * fma(3.0, d, -e);
+  // neg: w0 = Gc/(Gc + 2 Gb) on p0, rest on pm ; pos: w0 = 2 Gd/(2 Gd + Gc) on pm, rest on p1
+  const double Dn = fma(2.0, Gb, Gc), Dp = fma(2.0, Gd, Gc);
+  const double Nn = fma(Gc, p0, 2.0 * Gb * pm);
+  const double Np = fma(2.0 * Gd, pm, Gc * p1);
+  const double r = rcpFast(Dn * Dp);
+  uNeg = Nn * (Dp * r);
+  uPos = Np * (Dn * r);
+}
+
 template <int S> PDA_DEVFN void reconFaceFast(const double* q, double& uNeg, double& uPos) {
   if constexpr (S == 7) weno5FaceFast(q, uNeg, uPos);
+  else if constexpr (S == 5) weno3FaceFast(q, uNeg, uPos);
   else Recon<S>::face(q, uNeg, uPos);
 }
 
