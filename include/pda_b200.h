@@ -176,6 +176,15 @@ pda_status pda_problem_velocity_and_jacobian_dev(pda_problem p, const double* dU
 pda_status pda_problem_apply_jacobian_dev(pda_problem p, const double* dU, const double* dB, int ncols, int layout,
                                           double t, double* dR, void* stream);
 
+/* Explicit time stepping with the state resident in HBM: `nsteps` steps of size dt from t0, U updated in place, no
+ * host round trip between evaluations.  Stage arithmetic of the steppers the reference's tests drive the problems with
+ * (tests_cpp/pressio/include/pressio/ode/impl/ode_explicit_stepper_without_mass_matrix.hpp: ForwardEuler :168-186,
+ * SSPRungeKutta3 :230-281, RungeKutta4 :284-340) and of the Python module's advanceRK2 (pressiodemoapps/__init__.py:90-113).
+ * Full meshes only (sample mesh == stencil mesh). */
+enum { PDA_STEPPER_FORWARD_EULER = 0, PDA_STEPPER_RK2 = 1, PDA_STEPPER_RK4 = 2, PDA_STEPPER_SSPRK3 = 3 };
+pda_status pda_problem_advance_dev(pda_problem p, int stepper, double* dU, double t0, double dt, int32_t nsteps, void* stream);
+pda_status pda_problem_advance_host(pda_problem p, int stepper, double* U, double t0, double dt, int32_t nsteps);
+
 /* test hooks = viewGhostLeft/Front/Right/Back (euler_2d_prob_class.hpp:205-210): ghost rows after the last
  * evaluation, [numCellsNearBd][ndpc*(stencil-1)/2] */
 pda_status pda_problem_ghosts(pda_problem p, int side, double* out);

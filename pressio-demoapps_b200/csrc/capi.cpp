@@ -246,6 +246,14 @@ pda_status pda_problem_apply_jacobian_dev(pda_problem p, const double* dU, const
   return guarded([&] { P(p).applyJacobianDev(dU, dB, ncols, layout, t, dR, stream); });
 }
 
+pda_status pda_problem_advance_dev(pda_problem p, int stepper, double* dU, double t0, double dt, int32_t nsteps, void* stream) {
+  return guarded([&] { P(p).advanceDev(stepper, dU, t0, dt, nsteps, stream); });
+}
+
+pda_status pda_problem_advance_host(pda_problem p, int stepper, double* U, double t0, double dt, int32_t nsteps) {
+  return guarded([&] { P(p).advanceHost(stepper, U, t0, dt, nsteps); });
+}
+
 pda_status pda_problem_ghosts(pda_problem p, int side, double* out) {
   return guarded([&] { P(p).ghosts(side, out); });
 }

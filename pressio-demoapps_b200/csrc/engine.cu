@@ -166,6 +166,7 @@ struct DeviceState {
   // scratch owned by the problem (host-pointer entry points, applyJacobian)
   DevBuf<double> dU, dV, dJ, dB, dR;
   DevBuf<int32_t> dRowptr, dColidx;
+  DevBuf<double> stAux, stK[4];   // stepper work vectors
   // J*B per cell (k_spmm_cells_rowmajor): per-cell CSR base / row length, lattice visiting order, transposed operands
   DevBuf<int32_t> dCellBase, dCellLen, dCellOrder;
   DevBuf<double> dBt, dRt;
@@ -1468,6 +1469,105 @@ void Problem::applyJacobianHost(const double* U, const double* B, int ncols, int
   PDA_CUDA(cudaMemcpyAsync(ds.dB.p, B, nU * ncols * sizeof(double), cudaMemcpyHostToDevice, ds.stream));
   applyJacobianDev(ds.dU.p, ds.dB.p, ncols, layout, t, ds.dR.p, ds.stream);
   PDA_CUDA(cudaMemcpyAsync(R, ds.dR.p, nR * ncols * sizeof(double), cudaMemcpyDeviceToHost, ds.stream));
+  PDA_CUDA(cudaStreamSynchronize(ds.stream));
+}
+
+// ----------------------------------------------------------------------------------------------- steppers
+// Explicit time stepping with the state resident in HBM.  Same stage arithmetic as the steppers the
+// reference's tests use (tests_cpp/pressio/include/pressio/ode/impl/ode_explicit_stepper_without_mass_matrix.hpp:
+// ForwardEuler :168-186, SSPRungeKutta3 :230-281, RungeKutta4 :284-340) and the RK2 of the reference's Python module
+// (pressiodemoapps/__init__.py:90-113), so the reference's gold files are reproduced end to end on the GPU.
+namespace {
+__global__ void k_lincomb3(int64_t n, double* __restrict__ out, double a, const double* __restrict__ x, double b,
+                           const double* __restrict__ y, double c, const double* __restrict__ z) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  double r = a * x[i] + b * y[i];
+  if (z) r += c * z[i];
+  out[i] = r;
+}
+__global__ void k_rk4_combine(int64_t n, double* __restrict__ y, double c1, const double* __restrict__ k1, double c2,
+                              const double* __restrict__ k2, const double* __restrict__ k3, const double* __restrict__ k4) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  y[i] = y[i] + c1 * k1[i] + c2 * k2[i] + c2 * k3[i] + c1 * k4[i];
+}
+}  // namespace
+
+void Problem::advanceDev(int scheme, double* dU, double t0, double dt, int32_t nsteps, void* streamV) {
+  if (!dU) throw Error(kInvalid, "advance: null pointer");
+  if (scheme < 0 || scheme > 3) throw Error(kInvalid, "advance: invalid stepper enum");
+  if (nsteps < 0) throw Error(kInvalid, "advance: negative step count");
+  if (mesh_->nSample != mesh_->nStencil) throw Error(kInvalid, "advance: time stepping needs a full mesh (sample mesh == stencil mesh)");
+  ensureDevice();
+  PDA_CUDA(cudaSetDevice(device_));
+  DeviceState& ds = *dev_;
+  cudaStream_t st = (cudaStream_t)streamV;
+  const int64_t n = nDofStencil();
+  ds.stAux.alloc((size_t)n);
+  for (int i = 0; i < (scheme == 2 ? 4 : 1); ++i) ds.stK[i].alloc((size_t)n);
+  const unsigned grid = (unsigned)((n + 255) / 256);
+  auto lin = [&](double* out, double a, const double* x, double b, const double* y, double c, const double* z) {
+    k_lincomb3<<<grid, 256, 0, st>>>(n, out, a, x, b, y, c, z);
+    ++launches_;
+  };
+  double* aux = ds.stAux.p;
+  double* k1 = ds.stK[0].p;
+  double t = t0;
+  for (int32_t s = 0; s < nsteps; ++s, t += dt) {   // time accumulates like ode_advance_n_steps.hpp:114
+    switch (scheme) {
+      case 0:   // forward Euler: y += dt f(y, t)
+        evaluateDev(dU, t, k1, nullptr, st);
+        lin(dU, 1.0, dU, dt, k1, 0.0, nullptr);
+        break;
+      case 1: { // RK2 (Heun) of the Python module
+        evaluateDev(dU, t, k1, nullptr, st);
+        lin(aux, 1.0, dU, dt, k1, 0.0, nullptr);
+        double* k2 = aux;   // f(aux) may not alias its input: use a second buffer
+        ds.stK[1].alloc((size_t)n);
+        k2 = ds.stK[1].p;
+        evaluateDev(aux, t + dt, k2, nullptr, st);
+        lin(dU, 1.0, dU, 0.5 * dt, k2, 0.5 * dt, k1);
+        break;
+      }
+      case 2: { // RK4
+        double *k2 = ds.stK[1].p, *k3 = ds.stK[2].p, *k4 = ds.stK[3].p;
+        const double half = dt / 2.0;
+        evaluateDev(dU, t, k1, nullptr, st);
+        lin(aux, 1.0, dU, half, k1, 0.0, nullptr);
+        evaluateDev(aux, t + half, k2, nullptr, st);
+        lin(aux, 1.0, dU, half, k2, 0.0, nullptr);
+        evaluateDev(aux, t + half, k3, nullptr, st);
+        lin(aux, 1.0, dU, dt, k3, 0.0, nullptr);
+        evaluateDev(aux, t + dt, k4, nullptr, st);
+        k_rk4_combine<<<grid, 256, 0, st>>>(n, dU, dt / 6.0, k1, dt / 3.0, k2, k3, k4);
+        ++launches_;
+        break;
+      }
+      default: { // SSPRK3
+        evaluateDev(dU, t, k1, nullptr, st);
+        lin(aux, 1.0, dU, dt, k1, 0.0, nullptr);                       // u1 = u + dt f(u, t)
+        evaluateDev(aux, t + dt, k1, nullptr, st);
+        lin(aux, 0.25, aux, 0.75, dU, 0.25 * dt, k1);                  // u2 = 1/4 u1 + 3/4 u + 1/4 dt f(u1, t+dt)
+        evaluateDev(aux, t + dt / 2.0, k1, nullptr, st);
+        lin(dU, 1.0 / 3.0, dU, 2.0 / 3.0, aux, (2.0 / 3.0) * dt, k1);  // u = 1/3 u + 2/3 u2 + 2/3 dt f(u2, t+dt/2)
+        break;
+      }
+    }
+  }
+  PDA_CUDA(cudaGetLastError());
+}
+
+void Problem::advanceHost(int scheme, double* U, double t0, double dt, int32_t nsteps) {
+  if (!U) throw Error(kInvalid, "advance: null pointer");
+  ensureDevice();
+  PDA_CUDA(cudaSetDevice(device_));
+  DeviceState& ds = *dev_;
+  const size_t n = (size_t)nDofStencil();
+  ds.dU.alloc(n);
+  PDA_CUDA(cudaMemcpyAsync(ds.dU.p, U, n * sizeof(double), cudaMemcpyHostToDevice, ds.stream));
+  advanceDev(scheme, ds.dU.p, t0, dt, nsteps, ds.stream);
+  PDA_CUDA(cudaMemcpyAsync(U, ds.dU.p, n * sizeof(double), cudaMemcpyDeviceToHost, ds.stream));
   PDA_CUDA(cudaStreamSynchronize(ds.stream));
 }
 

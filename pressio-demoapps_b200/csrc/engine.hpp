@@ -43,6 +43,9 @@ class Problem {
   void velocityDev(const double* dU, double t, double* dV, void* stream);
   void velocityAndJacobianDev(const double* dU, double t, double* dV, double* dJ, void* stream);
   void applyJacobianDev(const double* dU, const double* dB, int ncols, int layout, double t, double* dR, void* stream);
+  // device-resident explicit time stepping (U never leaves HBM between evaluations): engine.cu "steppers"
+  void advanceDev(int scheme, double* dU, double t0, double dt, int32_t nsteps, void* stream);
+  void advanceHost(int scheme, double* U, double t0, double dt, int32_t nsteps);
   void ghosts(int side, double* out);
   int64_t launchCount() const { return launches_; }
 

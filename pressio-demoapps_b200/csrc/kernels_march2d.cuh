@@ -51,7 +51,7 @@ PDA_DEVFN void eulerFluxFast(double gamma, const double* qL, const double* qR, d
   for (int m = 0; m < DIM; ++m) { const double v = fma(RT, vR[m], vL[m]) * iRT; k = fma(v, v, k); }
   const double H = fma(RT, HR, HL) * iRT;
   const double a = sqrtFast(gm1 * fma(-0.5, k, H));
-  const double smax = sqrtFast(k) + a;
+  const double smax = sqrtFastTiny(k) + a;
   const double pS = pL + pR;
   F[0] = 0.5 * fma(smax, rL - rR, mL + mR);
 #pragma unroll

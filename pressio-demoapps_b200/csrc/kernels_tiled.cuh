@@ -74,6 +74,16 @@ PDA_DEVFN double sqrtFast(double x) {
   return (x == 0.0) ? 0.0 : s;   // x == 0: the seed is inf and the chain NaN; x < 0 stays NaN like sqrt()
 }
 
+// sqrtFast for arguments that may be arbitrarily small (|v_roe|^2 of gas almost at rest: far from a blast the
+// velocities are numerical dust, and their squares reach the denormal range where the ftz seed is inf).  Tiny
+// arguments are scaled by an exact power of four around the Newton chain; still branch-free.
+PDA_DEVFN double sqrtFastTiny(double x) {
+  const bool tiny = x < 1.0e-200;
+  const double xs = tiny ? x * 0x1p+400 : x;
+  const double s = sqrtFast(xs);
+  return tiny ? s * 0x1p-200 : s;
+}
+
 // ---------------------------------------------------------------------------------------------------------------
 // WENO5 (Jiang-Shu) at one face from the six cells around it, both sides (impl/weno5.hpp:56-178):
 // q = (a,b,c,d,e,f) = cells i-3..i+2, face between c and d; uNeg from (a..e), uPos from (b..f).
@@ -165,7 +175,7 @@ PDA_DEVFN void eulerFlux3dFast(double gamma, int ax, const double* qL, const dou
   const double H = fma(RT, HR, HL) * iRT;
   const double k = fma(w, w, fma(v, v, u * u));
   const double a = sqrtFast(gm1 * fma(-0.5, k, H));
-  const double smax = sqrtFast(k) + a;
+  const double smax = sqrtFastTiny(k) + a;
   const double pS = pL + pR;
   F[0] = 0.5 * fma(smax, rL - rR, mL + mR);
   F[1] = 0.5 * (fma(smax, qL[1] - qR[1], fma(mL, uL, mR * uR)) + ((ax == 0) ? pS : 0.0));

@@ -32,6 +32,9 @@ _HERE = _os.path.dirname(_os.path.abspath(__file__))
 _LIBPATH = _os.path.join(_os.path.dirname(_HERE), "lib", "libpda_b200.so")
 
 
+_STEPPERS = {"euler": 0, "rk2": 1, "rk4": 2, "ssprk3": 3}
+
+
 class PdaError(RuntimeError):
     """Raised where the reference throws std::runtime_error (or calls exit())."""
 
@@ -106,6 +109,8 @@ _sig("pda_slab_extent", _C.c_int, _vp, _C.POINTER(_i32), _C.POINTER(_i32), _C.PO
 _sig("pda_slab_initial_condition", _C.c_int, _vp, _vp)
 _sig("pda_slab_velocity_interior_dev", _C.c_int, _vp, _vp, _dbl, _vp, _vp)
 _sig("pda_slab_velocity_boundary_dev", _C.c_int, _vp, _vp, _dbl, _vp, _vp)
+_sig("pda_problem_advance_dev", _C.c_int, _vp, _C.c_int, _vp, _dbl, _dbl, _C.c_int32, _vp)
+_sig("pda_problem_advance_host", _C.c_int, _vp, _C.c_int, _vp, _dbl, _dbl, _C.c_int32)
 _sig("pda_slab_peer_handle", _C.c_int, _vp, _vp)
 _sig("pda_slab_peer_connect", _C.c_int, _vp, _vp)
 _sig("pda_slab_peer_connect_local", _C.c_int, _vp, _vp, _vp)
@@ -519,6 +524,16 @@ class Problem:
 
     def launchCount(self):
         return int(_lib.pda_problem_launch_count(self._h))
+
+    # ---- device-resident explicit time stepping (include/pda_b200.h: pda_problem_advance_*)
+    def advance(self, stepper, state, dt, nsteps, startTime=0.0):
+        """`nsteps` steps of `stepper` ("euler", "rk2", "rk4", "ssprk3") on the GPU; `state` (numpy, updated in place)
+        crosses PCIe once each way"""
+        _f64(state, self.totalDofStencilMesh(), "state")
+        _check(_lib.pda_problem_advance_host(self._h, _STEPPERS[stepper], state.ctypes.data, float(startTime), float(dt), int(nsteps)))
+
+    def advanceDevice(self, stepper, dU, dt, nsteps, startTime=0.0, stream=0):
+        _check(_lib.pda_problem_advance_dev(self._h, _STEPPERS[stepper], dU, float(startTime), float(dt), int(nsteps), stream))
 
     # ---- slab decomposition (one process per GPU)
     def slabExtent(self):

@@ -1,0 +1,31 @@
+"""Converts the gold files of the reference's own explicit-run regression tests (tests_cpp/*/[scheme/]*gold*.txt)
+into ONE compressed fixture, tests/golden/refgold/refgold.npz, keyed "<case>/<scheme>/<check>" (tests/refgold_cases.py).
+Run in the build container (needs /root/reference); the GPU box only sees the fixture.
+    python tests/golden/make_refgold.py
+"""
+import os
+import sys
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.dirname(HERE))
+from refgold_cases import CASES, gold_key   # noqa: E402
+
+REF = "/root/reference/tests_cpp"
+out = {}
+for name, c in CASES.items():
+    for scheme in c["schemes"]:
+        for check, fname in c["checks"].items():
+            if check == "rho_linf":
+                continue   # a constant asserted by compare.py; lives in refgold_cases.py
+            if c["subdirs"] is False:
+                path = os.path.join(REF, c["ref_dir"], fname)
+            elif c["subdirs"]:
+                path = os.path.join(REF, c["ref_dir"], c["subdirs"].format(scheme=scheme), fname)
+            else:
+                path = os.path.join(REF, c["ref_dir"], scheme, fname)
+            out[gold_key(name, scheme, check)] = np.loadtxt(path)
+os.makedirs(os.path.join(HERE, "refgold"), exist_ok=True)
+np.savez_compressed(os.path.join(HERE, "refgold", "refgold.npz"), **out)
+print("wrote %d gold vectors, %d values" % (len(out), sum(v.size for v in out.values())))
