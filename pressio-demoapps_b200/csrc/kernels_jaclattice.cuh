@@ -19,6 +19,7 @@
 //   * a CTA = 15 x 15 cell tile, a warp carries two lines of 16 faces: phase x = the tile's rows, barrier, phase y = its
 //     columns (same code, other stride); the x part of the self blocks and of V waits in shared memory in between.
 #pragma once
+#include "fastmath.cuh"
 #include "kernels_generic.cuh"
 #include "kernels_lattice.cuh"
 
@@ -109,11 +110,11 @@ PDA_DEVFN void jacLatLine(const Phys& phys, const LatticeDesc& L, const JacLatTa
       double qd[S - 1];
 #pragma unroll
       for (int m = 0; m < S - 1; ++m) qd[m] = q[m][d];
-      Recon<S>::face(qd, un[d], up[d]);
+      reconFaceFast<S>(qd, un[d], up[d]);
     }
     double JN[N * N], JP[N * N];
-    phys.template flux<AX>(un, up, F);
-    phys.template fluxJac<AX>(un, up, JN, JP);
+    faceFlux2d<Phys, AX>(phys, un, up, F);
+    faceFluxJac2d<Phys, AX>(phys, un, up, JN, JP);
 #pragma unroll
     for (int e = 0; e < N * N; ++e) { sJ[e * THREADS] = hInv * JN[e]; sJ[(N * N + e) * THREADS] = hInv * JP[e]; }
   }
@@ -121,10 +122,10 @@ PDA_DEVFN void jacLatLine(const Phys& phys, const LatticeDesc& L, const JacLatTa
   double gN[N][S - 1], gP[N][S - 1];
 #pragma unroll
   for (int j = 0; j < N; ++j) {
-    double qd[S - 1], t0, t1;
+    double qd[S - 1];
 #pragma unroll
     for (int m = 0; m < S - 1; ++m) qd[m] = q[m][j];
-    Recon<S>::faceGrad(qd, t0, t1, gN[j], gP[j]);
+    reconFaceGradFast<S>(qd, gN[j], gP[j]);
   }
 
   int sl[S];

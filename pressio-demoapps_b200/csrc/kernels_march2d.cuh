@@ -17,74 +17,12 @@
 // belong to the near-boundary kernel), diffusion / point terms of the advection-diffusion families, and slab-local
 // storage (2D multi-GPU slabs).
 #pragma once
+#include "fastmath.cuh"
 #include "kernels_lattice.cuh"
-#include "kernels_tiled.cuh"
 #include "kernels_jaclattice.cuh"
 
 namespace pda {
 namespace dev {
-
-// Rusanov flux of the DIM-dimensional Euler equations along AX with the fast reciprocal / square root
-// (impl/euler_rusanov_flux_values_function.hpp:54-208)
-template <int DIM, int AX>
-PDA_DEVFN void eulerFluxFast(double gamma, const double* qL, const double* qR, double* F) {
-  constexpr int N = DIM + 2;
-  const double gm1 = gamma - 1.0;
-  const double rL = qL[0], rR = qR[0];
-  const double iL = rcpFast(rL), iR = rcpFast(rR);
-  double vL[DIM], vR[DIM];
-  double kL = 0.0, kR = 0.0;
-#pragma unroll
-  for (int m = 0; m < DIM; ++m) {
-    vL[m] = qL[1 + m] * iL; vR[m] = qR[1 + m] * iR;
-    kL = fma(vL[m], vL[m], kL); kR = fma(vR[m], vR[m], kR);
-  }
-  const double pL = gm1 * fma(-0.5 * rL, kL, qL[N - 1]);
-  const double pR = gm1 * fma(-0.5 * rR, kR, qR[N - 1]);
-  const double HL = (qL[N - 1] + pL) * iL;
-  const double HR = (qR[N - 1] + pR) * iR;
-  const double mL = rL * vL[AX], mR = rR * vR[AX];
-  const double RT = sqrtFast(rR * iL);
-  const double iRT = rcpFast(1.0 + RT);
-  double k = 0.0;
-#pragma unroll
-  for (int m = 0; m < DIM; ++m) { const double v = fma(RT, vR[m], vL[m]) * iRT; k = fma(v, v, k); }
-  const double H = fma(RT, HR, HL) * iRT;
-  const double a = sqrtFast(gm1 * fma(-0.5, k, H));
-  const double smax = sqrtFastTiny(k) + a;
-  const double pS = pL + pR;
-  F[0] = 0.5 * fma(smax, rL - rR, mL + mR);
-#pragma unroll
-  for (int m = 0; m < DIM; ++m)
-    F[1 + m] = 0.5 * (fma(smax, qL[1 + m] - qR[1 + m], fma(mL, vL[m], mR * vR[m])) + ((m == AX) ? pS : 0.0));
-  F[N - 1] = 0.5 * fma(smax, qL[N - 1] - qR[N - 1], fma(mL, HL, mR * HR));
-}
-
-// shallow-water Rusanov flux (impl/swe_rusanov_flux_values_function.hpp:54-97) with the fast reciprocal / square
-// root: depths are positive normal numbers, the 1e-30 guards of the reference vanish in double precision next to them
-template <int AX>
-PDA_DEVFN void sweFluxFast(double g, const double* qL, const double* qR, double* F) {
-  const double hL = qL[0], hR = qR[0];
-  const double iL = rcpFast(hL), iR = rcpFast(hR);
-  const double uL = qL[1] * iL, vL = qL[2] * iL;
-  const double uR = qR[1] * iR, vR = qR[2] * iR;
-  const double unL = (AX == 0) ? uL : vL, unR = (AX == 0) ? uR : vR;
-  const double pS = 0.5 * g * fma(hL, hL, hR * hR);
-  const double sL = sqrtFast(hL), sR = sqrtFast(hR);
-  const double um = fma(unL, sL, unR * sR) * rcpFast(sL + sR);
-  const double smax = fabs(um) + sqrtFast(g * (0.5 * (hL + hR)));
-  const double mL = hL * unL, mR = hR * unR;
-  F[0] = 0.5 * fma(smax, qL[0] - qR[0], mL + mR);
-  F[1] = 0.5 * (fma(smax, qL[1] - qR[1], fma(mL, uL, mR * uR)) + ((AX == 0) ? pS : 0.0));
-  F[2] = 0.5 * (fma(smax, qL[2] - qR[2], fma(mL, vL, mR * vR)) + ((AX == 1) ? pS : 0.0));
-}
-
-template <class Phys, int AX>
-PDA_DEVFN void faceFlux2d(const Phys& phys, const double* uN, const double* uP, double* F) {
-  if constexpr (std::is_same<Phys, Euler<2>>::value) eulerFluxFast<2, AX>(phys.gamma, uN, uP, F);
-  else if constexpr (std::is_same<Phys, Swe2d>::value) sweFluxFast<AX>(phys.g, uN, uP, F);
-  else phys.template flux<AX>(uN, uP, F);
-}
 
 template <class Phys, int S>
 __global__ void __launch_bounds__(128)

@@ -25,6 +25,7 @@
 #pragma once
 #include <cstdint>
 
+#include "fastmath.cuh"
 #include "kernels_lattice.cuh"
 
 namespace pda {
@@ -40,115 +41,6 @@ PDA_DEVFN void cpAsyncWaitAll() { asm volatile("cp.async.wait_group 0;\n" ::: "m
 PDA_DEVFN int32_t fixIdx(int32_t idx, int32_t n, int32_t periodic) {
   if (periodic) return idx < 0 ? idx + n : (idx >= n ? idx - n : idx);
   return idx < 0 ? 0 : (idx >= n ? n - 1 : idx);
-}
-
-// ---------------------------------------------------------------------------------------------------------------
-// Branch-free FP64 reciprocal and square root: MUFU seed (>= 20 good bits) + Newton steps; relative error ~2 ulp.
-// Arguments are positive normal numbers here (densities, Roe averages, sums of squared smoothness indicators >=
-// eps^2), so the IEEE slow paths (denormals, inf, signed zero) that make `/` and sqrt() a subroutine call with a
-// divergent branch are not needed.  The reference's tolerance (1e-12) is four orders above this error.
-// ---------------------------------------------------------------------------------------------------------------
-PDA_DEVFN double rcpFast(double x) {
-  double r;
-  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
-  double e = fma(-x, r, 1.0);
-  r = fma(r, e, r);
-  e = fma(-x, r, 1.0);
-  r = fma(r, e, r);
-  return r;
-}
-PDA_DEVFN double sqrtFast(double x) {
-  double y;
-  asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
-  // two Newton steps on y ~ x^-1/2:  y <- y + y*(1 - x*y*y)/2
-  double t = x * y;
-  double e = fma(-t, y, 1.0);
-  y = fma(0.5 * y, e, y);
-  t = x * y;
-  e = fma(-t, y, 1.0);
-  y = fma(0.5 * y, e, y);
-  // s = x*y with one residual correction
-  double s = x * y;
-  const double r = fma(-s, s, x);
-  s = fma(r, 0.5 * y, s);
-  return (x == 0.0) ? 0.0 : s;   // x == 0: the seed is inf and the chain NaN; x < 0 stays NaN like sqrt()
-}
-
-// sqrtFast for arguments that may be arbitrarily small (|v_roe|^2 of gas almost at rest: far from a blast the
-// velocities are numerical dust, and their squares reach the denormal range where the ftz seed is inf).  Tiny
-// arguments are scaled by an exact power of four around the Newton chain; still branch-free.
-PDA_DEVFN double sqrtFastTiny(double x) {
-  const bool tiny = x < 1.0e-200;
-  const double xs = tiny ? x * 0x1p+400 : x;
-  const double s = sqrtFast(xs);
-  return tiny ? s * 0x1p-200 : s;
-}
-
-// ---------------------------------------------------------------------------------------------------------------
-// WENO5 (Jiang-Shu) at one face from the six cells around it, both sides (impl/weno5.hpp:56-178):
-// q = (a,b,c,d,e,f) = cells i-3..i+2, face between c and d; uNeg from (a..e), uPos from (b..f).
-//   * smoothness indicators from first/second differences; E_k = 4*(eps + B_k), the common factor 16 cancels in the
-//     weights: w_k = c_k/E_k^2 / sum;  multiplied through by E_0^2 E_1^2 E_2^2 -> no division per weight;
-//   * candidate polynomials in difference form around c / d (fewer operations, less cancellation);
-//   * uNeg = Nn/Dn, uPos = Np/Dp with ONE reciprocal: r = 1/(Dn*Dp).
-// ~75 FP64 instructions per (face, dof) instead of ~135.
-// ---------------------------------------------------------------------------------------------------------------
-PDA_DEVFN void weno5FaceFast(const double* q, double& uNeg, double& uPos) {
-  constexpr double k133 = 13.0 / 3.0, eps4 = 4.0e-6, s6 = 1.0 / 6.0;
-  const double c = q[2], d = q[3];
-  const double d0 = q[1] - q[0], d1 = c - q[1], d2 = d - c, d3 = q[4] - d, d4 = q[5] - q[4];
-  const double tb = d1 - d0, tc = d2 - d1, td = d3 - d2, te = d4 - d3;
-  const double tb2 = tb * tb, tc2 = tc * tc, td2 = td * td, te2 = te * te;
-  // neg side: s0 = a-4b+3c = 3 d1 - d0 ; s1 = b-d = -(d1+d2) ; s2 = 3c-4d+e = d3 - 3 d2
-  const double sn0 = fma(3.0, d1, -d0), sn1 = d1 + d2, sn2 = fma(-3.0, d2, d3);
-  // pos side: s0 = b-4c+3d = 3 d2 - d1 ; s1 = c-e = -(d2+d3) ; s2 = 3d-4e+f = d4 - 3 d3
-  const double sp0 = fma(3.0, d2, -d1), sp1 = d2 + d3, sp2 = fma(-3.0, d3, d4);
-  const double En0 = fma(sn0, sn0, fma(k133, tb2, eps4));
-  const double En1 = fma(sn1, sn1, fma(k133, tc2, eps4));
-  const double En2 = fma(sn2, sn2, fma(k133, td2, eps4));
-  const double Ep0 = fma(sp0, sp0, fma(k133, tc2, eps4));
-  const double Ep1 = fma(sp1, sp1, fma(k133, td2, eps4));
-  const double Ep2 = fma(sp2, sp2, fma(k133, te2, eps4));
-  const double Gn0 = En0 * En0, Gn1 = En1 * En1, Gn2 = En2 * En2;
-  const double Gp0 = Ep0 * Ep0, Gp1 = Ep1 * Ep1, Gp2 = Ep2 * Ep2;
-  // candidates: p(a,b,c) = c + (5 d1 - 2 d0)/6 ; p(b,c,d) = c + (2 d2 + d1)/6 ; p(c,d,e) = d - (2 d2 + d3)/6 ;
-  //             p(d,e,f) = d + (2 d4 - 5 d3)/6
-  const double pabc = fma(s6, fma(5.0, d1, -2.0 * d0), c);
-  const double pbcd = fma(s6, fma(2.0, d2, d1), c);
-  const double pcde = fma(-s6, fma(2.0, d2, d3), d);
-  const double pdef = fma(s6, fma(2.0, d4, -5.0 * d3), d);
-  // neg: linear weights (1,6,3)/10 ; pos: (3,6,1)/10
-  const double n0 = Gn1 * Gn2, n1 = 6.0 * (Gn0 * Gn2), n2 = 3.0 * (Gn0 * Gn1);
-  const double m0 = 3.0 * (Gp1 * Gp2), m1 = 6.0 * (Gp0 * Gp2), m2 = Gp0 * Gp1;
-  const double Dn = n0 + (n1 + n2), Dp = m0 + (m1 + m2);
-  const double Nn = fma(n0, pabc, fma(n1, pbcd, n2 * pcde));
-  const double Np = fma(m0, pbcd, fma(m1, pcde, m2 * pdef));
-  const double r = rcpFast(Dn * Dp);
-  uNeg = Nn * (Dp * r);
-  uPos = Np * (Dn * r);
-}
-
-// WENO3 at one face from the four cells around it (impl/weno3.hpp:56-114), both sides with ONE reciprocal
-PDA_DEVFN void weno3FaceFast(const double* q, double& uNeg, double& uPos) {
-  const double b = q[0], c = q[1], d = q[2], e = q[3];
-  const double dbc = b - c, dcd = c - d, dde = d - e;
-  const double Eb = fma(dbc, dbc, kWenoEps), Ec = fma(dcd, dcd, kWenoEps), Ed = fma(dde, dde, kWenoEps);
-  const double Gb = Eb * Eb, Gc = Ec * Ec, Gd = Ed * Ed;
-  const double pm = 0.5 * (c + d);
-  const double p0 = 0.5 * fma(3.0, c, -b), p1 = 0.5 * fma(3.0, d, -e);
-  // neg: w0 = Gc/(Gc + 2 Gb) on p0, rest on pm ; pos: w0 = 2 Gd/(2 Gd + Gc) on pm, rest on p1
-  const double Dn = fma(2.0, Gb, Gc), Dp = fma(2.0, Gd, Gc);
-  const double Nn = fma(Gc, p0, 2.0 * Gb * pm);
-  const double Np = fma(2.0 * Gd, pm, Gc * p1);
-  const double r = rcpFast(Dn * Dp);
-  uNeg = Nn * (Dp * r);
-  uPos = Np * (Dn * r);
-}
-
-template <int S> PDA_DEVFN void reconFaceFast(const double* q, double& uNeg, double& uPos) {
-  if constexpr (S == 7) weno5FaceFast(q, uNeg, uPos);
-  else if constexpr (S == 5) weno3FaceFast(q, uNeg, uPos);
-  else Recon<S>::face(q, uNeg, uPos);
 }
 
 // 3D Euler Rusanov flux along axis `ax` (runtime), impl/euler_rusanov_flux_values_function.hpp:151-208:
