@@ -38,6 +38,16 @@ FLOPS_PER_CELL = 2673.0    # 3*(5*152+116)+45, each face once
 BYTES_PER_CELL = 80.0      # 2*ndpc*8
 
 
+def load_traffic(kernel_key):
+    """DRAM bytes per launch (dram__bytes_read.sum + dram__bytes_write.sum) of the dominant kernels from the committed
+    `ncu --set full` captures (profiles/ncu_traffic_r01.json, written by tools/ncu_summary.py --traffic)"""
+    p = os.path.join(ROOT, "profiles", "ncu_traffic_r01.json")
+    if not os.path.exists(p):
+        return None
+    with open(p) as f:
+        return json.load(f).get(kernel_key)
+
+
 def load_peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -214,7 +224,9 @@ def jacobian_leg(torch, pda, dev, n2=2048, steps=3, warmup=1):
             "workload": "2D Euler Riemann WENO5 %dx%d velocity+Jacobian (cfg 2)" % (n2, n2),
             "gpu_launches": p.launchCount() - l0,
             "roofline": {"bound": "hbm", "achieved": bytes_per_eval / (ms * 1e-3) * 1e-9, "peak": peak, "unit": "GB/s",
-                         "frac": bytes_per_eval / (ms * 1e-3) * 1e-9 / peak}}
+                         "frac": bytes_per_eval / (ms * 1e-3) * 1e-9 / peak, "kernel": "k_jacobian_lattice2d<Euler<2>,7>",
+                         "traffic": load_traffic("k_jacobian_lattice2d<Euler<2>,7>@2048^2") if n2 == 2048 else None,
+                         "algorithmic_bytes": bytes_per_eval}}
 
 
 def run_b200_arm(args):
@@ -352,7 +364,8 @@ def run_b200_arm(args):
     e2e_s = max_over_ranks(time.perf_counter() - t0) / K
     e2e = {"value": ncells / e2e_s, "unit": UNIT, "h2d_bytes_per_step": int(hU.numel() * 8 * world),
            "d2h_bytes_per_step": int(hV.numel() * 8 * world), "ms_per_step": e2e_s * 1e3,
-           "api": "pda_problem_velocity_host" if world == 1 else "slab: H2D + halo exchange + pda_slab_velocity_*_dev + D2H"}
+           "api": "pda_problem_velocity_host" if world == 1 else
+           ("slab: H2D + pda_slab_velocity_peer_dev + D2H" if args.halo == "peer" else "slab: H2D + halo exchange + pda_slab_velocity_*_dev + D2H")}
 
     if rank == 0:
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
@@ -365,8 +378,11 @@ def run_b200_arm(args):
                            "l2": "inputs larger than L2 (state %.2f GB per GPU)" % (ncells * 40e-9 / world)},
                 "gpu_launches": int(launches), "clocks": clocks, "e2e": e2e,
                 "roofline": {"bound": "hbm", "achieved": ach_gbs, "peak": hbm_peak, "unit": "GB/s",
-                             "frac": ach_gbs / hbm_peak, "traffic": None, "peak_source": peak_src,
-                             "kernel": "k_velocity_lattice", "kernel_ms": k_ms, "binding": "fp64",
+                             "frac": ach_gbs / hbm_peak,
+                             "traffic": (load_traffic("k_euler3d_velocity_tiled<7,7>@512^3") if (world == 1 and n == 512) else None),
+                             "traffic_unit": "bytes per launch (ncu --set full, profiles/ncu_traffic_r01.json)",
+                             "algorithmic_bytes": kernel_cells * BYTES_PER_CELL, "peak_source": peak_src,
+                             "kernel": "k_euler3d_velocity_tiled<7,7>", "kernel_ms": k_ms, "binding": "fp64",
                              "fp64": {"achieved": ach_tf, "peak": fp64_peak, "unit": "TFLOP/s",
                                       "frac": ach_tf / fp64_peak if fp64_peak else None,
                                       "peak_source": "measured DFMA loop (pda_measure_fp64_peak), same process",

@@ -392,9 +392,61 @@ PDA_DEVFN void eulerFluxJacFast(double gamma, const double* qL, const double* qR
   }
 }
 
+// shallow-water Rusanov flux Jacobians (impl/swe_rusanov_flux_jacobian_function.hpp:54-136; same terms as
+// Swe2d::fluxJac in physics.cuh): 1/h, 1/sqrt(h), 1/(sL+sR) and 1/sqrt(g(hL+hR)) once each, no IEEE division
+template <int AX>
+PDA_DEVFN void sweFluxJacFast(double g, const double* qL, const double* qR, double* JL, double* JR) {
+  constexpr double nx = (AX == 0) ? 1.0 : 0.0, ny = (AX == 1) ? 1.0 : 0.0;
+  const double hL = qL[0], hR = qR[0];
+  const double iL = rcpFast(hL), iR = rcpFast(hR);
+  const double uL = qL[1] * iL, vL = qL[2] * iL, uR = qR[1] * iR, vR = qR[2] * iR;
+  const double unL = (AX == 0) ? uL : vL, unR = (AX == 0) ? uR : vR;
+  const double sL = sqrtFast(hL), sR = sqrtFast(hR);
+  const double isL = sL * iL, isR = sR * iR;            // 1/sqrt(h)
+  const double ss = sL + sR;
+  const double iss = rcpFast(ss);
+  const double hsun = sL * unL + sR * unR + kEs;
+  const double ahs = fabs(hsun);
+  const double sgn = (hsun < 0.0) ? -1.0 : 1.0;         // hsun/|hsun|
+  const double um = (unL * sL + unR * sR) * iss;
+  const double smax = fabs(um) + sqrtFast(g * (0.5 * (hL + hR)));
+  const double termL = unL * iL, termR = unR * iR;      // (n.q)/h^2
+  const double gterm = g * rsqrtFast(g * (hL + hR)) * 0.35355339059327373;   // g / (2^(3/2) sqrt(g (hL+hR)))
+  const double iss2 = iss * iss;
+  double dL[3], dR[3];
+  dL[0] = -0.5 * ahs * isL * iss2 + (0.5 * unL * isL - sL * termL) * sgn * iss + gterm;
+  dL[1] = nx * sgn * isL * iss;
+  dL[2] = ny * sgn * isL * iss;
+  dR[0] = -0.5 * ahs * isR * iss2 + (0.5 * unR * isR - sR * termR) * sgn * iss + gterm;
+  dR[1] = nx * sgn * isR * iss;
+  dR[2] = ny * sgn * isR * iss;
+  const double d0 = qR[0] - qL[0], d1 = qR[1] - qL[1], d2 = qR[2] - qL[2];
+
+  JL[0] = -0.5 * dL[0] * d0 + 0.5 * (nx * uL + ny * vL - qL[0] * termL) + 0.5 * smax;
+  JL[1] = 0.5 * nx - 0.5 * dL[1] * d0;
+  JL[2] = 0.5 * ny - 0.5 * dL[2] * d0;
+  JL[3] = 0.5 * (g * nx * qL[0] - qL[1] * termL) - 0.5 * dL[0] * d1;
+  JL[4] = nx * uL + 0.5 * ny * vL + 0.5 * smax - 0.5 * dL[1] * d1;
+  JL[5] = 0.5 * ny * uL - 0.5 * dL[2] * d1;
+  JL[6] = 0.5 * (g * ny * qL[0] - qL[2] * termL) - 0.5 * dL[0] * d2;
+  JL[7] = 0.5 * nx * vL - 0.5 * dL[1] * d2;
+  JL[8] = ny * vL + 0.5 * nx * uL + 0.5 * smax - 0.5 * dL[2] * d2;
+
+  JR[0] = -0.5 * dR[0] * d0 + 0.5 * (nx * uR + ny * vR - qR[0] * termR) - 0.5 * smax;
+  JR[1] = 0.5 * nx - 0.5 * dR[1] * d0;
+  JR[2] = 0.5 * ny - 0.5 * dR[2] * d0;
+  JR[3] = 0.5 * (g * nx * qR[0] - qR[1] * termR) - 0.5 * dR[0] * d1;
+  JR[4] = nx * uR + 0.5 * ny * vR - 0.5 * smax - 0.5 * dR[1] * d1;
+  JR[5] = 0.5 * ny * uR - 0.5 * dR[2] * d1;
+  JR[6] = 0.5 * (g * ny * qR[0] - qR[2] * termR) - 0.5 * dR[0] * d2;
+  JR[7] = 0.5 * nx * vR - 0.5 * dR[1] * d2;
+  JR[8] = ny * vR + 0.5 * nx * uR - 0.5 * smax - 0.5 * dR[2] * d2;
+}
+
 template <class Phys, int AX>
 PDA_DEVFN void faceFluxJac2d(const Phys& phys, const double* uN, const double* uP, double* JN, double* JP) {
   if constexpr (std::is_same<Phys, Euler<2>>::value) eulerFluxJacFast<2, AX>(phys.gamma, uN, uP, JN, JP);
+  else if constexpr (std::is_same<Phys, Swe2d>::value) sweFluxJacFast<AX>(phys.g, uN, uP, JN, JP);
   else phys.template fluxJac<AX>(uN, uP, JN, JP);
 }
 

@@ -36,6 +36,8 @@ struct JacLat2d {
   static constexpr int oSelf = 2 * N * N * THREADS;           // [T*T][SELF] x-phase part of the self blocks
   static constexpr int oV = oSelf + T * T * SELF;             // [T*T][N]    x-phase part of the velocity
   static constexpr size_t smemBytes = (size_t)(oV + T * T * N) * sizeof(double);
+  // small systems fit two CTAs per SM in 128 registers; Euler (4 dofs, WENO5: 96 gradient registers) does not
+  static constexpr int MIN_CTAS = (N <= 2 || (N == 3 && S <= 5)) ? 2 : 1;
 };
 
 struct JacLatTables {
@@ -220,7 +222,7 @@ PDA_DEVFN void jacLatLine(const Phys& phys, const LatticeDesc& L, const JacLatTa
 }
 
 template <class Phys, int S>
-__global__ void __launch_bounds__(JacLat2d<Phys, S>::THREADS, 1)
+__global__ void __launch_bounds__(JacLat2d<Phys, S>::THREADS, JacLat2d<Phys, S>::MIN_CTAS)
 k_jacobian_lattice2d(Phys phys, LatticeDesc L, Deltas dl, JacLatTables jt, const double* __restrict__ U,
                      double* __restrict__ V, double* __restrict__ Jv) {
   using K = JacLat2d<Phys, S>;

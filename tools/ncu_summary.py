@@ -12,6 +12,30 @@ KEYS = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum
         "l1tex__t_bytes_pipe_lsu_mem_global_op_ld.sum", "l1tex__t_bytes_pipe_lsu_mem_global_op_st.sum"]
 STALL = "smsp__average_warps_issue_stalled_"
 
+def raw_rows(rep):
+    out = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    rows = list(csv.reader(io.StringIO(out)))
+    return rows[0], rows[1], rows[2:]
+
+
+def to_bytes(val, unit):
+    mult = {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "Tbyte": 1e12}[unit]
+    return float(val.replace(",", "")) * mult
+
+
+if len(sys.argv) > 1 and sys.argv[1] == "--traffic":
+    # python tools/ncu_summary.py --traffic "kernel key=report.ncu-rep" ... > profiles/ncu_traffic_r01.json
+    import json
+    res = {}
+    for arg in sys.argv[2:]:
+        key, rep = arg.rsplit("=", 1)
+        hdr, units, rows = raw_rows(rep)
+        d, u = dict(zip(hdr, rows[0])), dict(zip(hdr, units))
+        res[key] = to_bytes(d["dram__bytes_read.sum"], u["dram__bytes_read.sum"]) + \
+            to_bytes(d["dram__bytes_write.sum"], u["dram__bytes_write.sum"])
+    print(json.dumps(res, indent=1))
+    sys.exit(0)
+
 for rep in sys.argv[1:]:
     out = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
     rows = list(csv.reader(io.StringIO(out)))
