@@ -31,13 +31,26 @@ struct JacLat2d {
   static constexpr int N = Phys::ndpc;
   static constexpr int WARPS = 8;
   static constexpr int THREADS = 32 * WARPS;
-  static constexpr int T = 15;                  // tile edge in cells; a warp carries two lines of 16 faces (15 cells)
-  static constexpr int SELF = N * N + 1;        // padded self-block stride: conflict-free along both tile axes
-  static constexpr int oSelf = 2 * N * N * THREADS;           // [T*T][SELF] x-phase part of the self blocks
-  static constexpr int oV = oSelf + T * T * SELF;             // [T*T][N]    x-phase part of the velocity
+  static constexpr int NBLK = 1 + 2 * (S - 1);
+  static constexpr int ROWLEN = N * NBLK;        // entries per CSR row of an inner cell
+  static constexpr int CHUNK = N * ROWLEN;       // doubles per cell (its N rows are consecutive in the CSR arrays)
+  // 4 dofs: a block row is one aligned 32-byte sector -> stored straight to HBM (STG.256).  Other sizes (24-, 16-,
+  // 8-byte block rows) would turn into partial-sector writes (4x the L2 write transactions): the cell chunks are
+  // STAGED in shared memory and streamed out coalesced, a tile row of cells being one contiguous range of the CSR
+  // value array.
+  static constexpr bool STAGE = (N != 4);
+  static constexpr int CSTRIDE = CHUNK | 1;      // odd stride: conflict-free across lanes
+  static constexpr size_t kBudget = 200 * 1024;
+  static constexpr size_t stagedBytes(int t) { return (size_t)(2 * N * N * THREADS + t * t * CSTRIDE + t * t * N) * sizeof(double); }
+  // tile edge in cells; a warp carries two lines of 16 faces (<= 15 cells each)
+  static constexpr int T = !STAGE ? 15 : (stagedBytes(15) <= kBudget ? 15 : (stagedBytes(11) <= kBudget ? 11 : 7));
+  static constexpr int SELF = N * N + 1;        // (direct mode) padded self-block stride: conflict-free along both tile axes
+  static constexpr int oSelf = 2 * N * N * THREADS;           // direct: [T*T][SELF] x-phase part of the self blocks
+  static constexpr int oChunk = oSelf;                        // staged: [T*T][CSTRIDE] the cells' chunks
+  static constexpr int oV = oSelf + T * T * (STAGE ? CSTRIDE : SELF);   // [T*T][N] x-phase part of the velocity
   static constexpr size_t smemBytes = (size_t)(oV + T * T * N) * sizeof(double);
-  // small systems fit two CTAs per SM in 128 registers; Euler (4 dofs, WENO5: 96 gradient registers) does not
-  static constexpr int MIN_CTAS = (N <= 2 || (N == 3 && S <= 5)) ? 2 : 1;
+  // small systems in direct mode fit two CTAs per SM in 128 registers; Euler (96 gradient registers) does not
+  static constexpr int MIN_CTAS = 1;
 };
 
 struct JacLatTables {
@@ -140,6 +153,7 @@ PDA_DEVFN void jacLatLine(const Phys& phys, const LatticeDesc& L, const JacLatTa
   double* jBase = Jv + base;
   const int rowLen = jt.rowLen;
   double* sSelf = sAll + K::oSelf + cellLocal * K::SELF;
+  double* sChunk = sAll + K::oChunk + cellLocal * K::CSTRIDE;
   double* sV = sAll + K::oV + cellLocal * N;
 
   // ---- velocity: hInv (F_left - F_right); x phase parks its part in shared memory, y phase completes and stores
@@ -196,7 +210,16 @@ PDA_DEVFN void jacLatLine(const Phys& phys, const LatticeDesc& L, const JacLatTa
         val[j] = mine - got;
       }
       if (owns) {
-        if (P == h && AX == 0) {   // self block: x part waits in shared memory for the y part (the reference's order)
+        if constexpr (K::STAGE) {
+          double* dst = sChunk + k * K::ROWLEN + sl[P] * N;
+          if (P == h && AX != 0) {
+#pragma unroll
+            for (int j = 0; j < N; ++j) dst[j] += val[j];   // self block: x part already there (x, then y)
+          } else {
+#pragma unroll
+            for (int j = 0; j < N; ++j) dst[j] = val[j];
+          }
+        } else if (P == h && AX == 0) {   // self block: x part waits in shared memory for the y part (the reference's order)
 #pragma unroll
           for (int j = 0; j < N; ++j) sSelf[k * N + j] = val[j];
         } else {
@@ -216,7 +239,8 @@ PDA_DEVFN void jacLatLine(const Phys& phys, const LatticeDesc& L, const JacLatTa
 #pragma unroll
     for (int c = 0; c < 16; ++c) slots[c] = (uint8_t)slotOf(c);
     addExtraJacInner<Phys>(phys, U + gidSelf * N, slots, [&](int k, int slot, int j, double x) {
-      jBase[(int64_t)k * rowLen + slot * N + j] += x;
+      if constexpr (K::STAGE) sChunk[k * K::ROWLEN + slot * N + j] += x;
+      else jBase[(int64_t)k * rowLen + slot * N + j] += x;
     });
   }
 }
@@ -244,6 +268,22 @@ k_jacobian_lattice2d(Phys phys, LatticeDesc L, Deltas dl, JacLatTables jt, const
     const bool owns = (line < K::T) && (f < K::T) && (i < hi0) && (a < hi1);
     jacLatLine<Phys, S, 1>(phys, L, jt, dl.hInv[1], U, V, Jv, a, min(i, hi0 - 1), owns,
                            min(f, K::T - 1) * K::T + min(line, K::T - 1), sAll, tid);
+  }
+  if constexpr (K::STAGE) {
+    // stream the staged chunks out: the cells of a tile row are consecutive inner cells, i.e. ONE contiguous range of
+    // the CSR value array -> lanes across it, coalesced, every value written once
+    __syncthreads();
+    const int nvalid = min(K::T, hi0 - I0);
+    for (int r = warp; r < K::T; r += K::WARPS) {
+      const int j = J0 + r;
+      if (j >= hi1) break;
+      double* dst = Jv + jt.cellBase[(int64_t)j * L.n[0] + I0];
+      const double* src = sAll + K::oChunk + (size_t)(r * K::T) * K::CSTRIDE;
+      for (int e = lane; e < nvalid * K::CHUNK; e += 32) {
+        const int c = e / K::CHUNK, w = e - c * K::CHUNK;
+        dst[e] = src[c * K::CSTRIDE + w];
+      }
+    }
   }
 }
 

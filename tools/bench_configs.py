@@ -107,6 +107,14 @@ def run(hbm_gbs, small=False, device=0):
         return dict(workload="2D Euler double Mach reflection %s %dx%d, 5%% sample mesh (%d cells, stencil mesh %d)"
                              % (rec.name, nx, ny, gids.size, sm.stencilMeshSize()), **measure(p, hbm_gbs, t=0.1))
 
+    def cfg5_jac(rec, st, n):
+        # the headline problem's Jacobian at the largest size whose nnz fits the reference's int32 index type
+        n = 32 if small else n
+        mesh = pda.create_full_mesh([n, n, n], [-1, 1, -1, 1, -1, 1], st, ("x", "y", "z"))
+        p = pda.create_problem(mesh, pda.Euler3d.PeriodicSmooth, rec, device=device)
+        return dict(workload="3D Euler PeriodicSmooth %s %d^3 (Jacobian: nnz must fit int32 like the reference's "
+                             "SparseMatrix<double,RowMajor,int32_t>)" % (rec.name, n), **measure(p, hbm_gbs, reps=3))
+
     guarded("cfg1_euler1d_sod_weno5", cfg1)
     guarded("cfg2_euler2d_riemann_weno5", cfg2)
     guarded("cfg3_swe_firstorder", lambda: cfg3("swe_fo"))
@@ -114,6 +122,8 @@ def run(hbm_gbs, small=False, device=0):
     guarded("cfg3_gray_scott", lambda: cfg3("gs"))
     guarded("cfg4_dmr_sample_weno3", lambda: cfg4(R.Weno3, 5))
     guarded("cfg4_dmr_sample_weno5", lambda: cfg4(R.Weno5, 7))
+    guarded("cfg5_euler3d_weno3_jacobian", lambda: cfg5_jac(R.Weno3, 5, 160))   # 160^3 * 325 = 1.33 G nnz
+    guarded("cfg5_euler3d_weno5_jacobian", lambda: cfg5_jac(R.Weno5, 7, 128))   # 128^3 * 475 = 1.00 G nnz
     return res
 
 
