@@ -177,7 +177,8 @@ PDA_DEVFN void sweFluxFast(double g, const double* qL, const double* qR, double*
 
 template <class Phys, int AX>
 PDA_DEVFN void faceFlux2d(const Phys& phys, const double* uN, const double* uP, double* F) {
-  if constexpr (std::is_same<Phys, Euler<2>>::value) eulerFluxFast<2, AX>(phys.gamma, uN, uP, F);
+  if constexpr (std::is_same<Phys, Euler<1>>::value || std::is_same<Phys, Euler<2>>::value || std::is_same<Phys, Euler<3>>::value)
+    eulerFluxFast<Phys::dim, AX>(phys.gamma, uN, uP, F);
   else if constexpr (std::is_same<Phys, Swe2d>::value) sweFluxFast<AX>(phys.g, uN, uP, F);
   else phys.template flux<AX>(uN, uP, F);
 }
@@ -445,7 +446,8 @@ PDA_DEVFN void sweFluxJacFast(double g, const double* qL, const double* qR, doub
 
 template <class Phys, int AX>
 PDA_DEVFN void faceFluxJac2d(const Phys& phys, const double* uN, const double* uP, double* JN, double* JP) {
-  if constexpr (std::is_same<Phys, Euler<2>>::value) eulerFluxJacFast<2, AX>(phys.gamma, uN, uP, JN, JP);
+  if constexpr (std::is_same<Phys, Euler<1>>::value || std::is_same<Phys, Euler<2>>::value || std::is_same<Phys, Euler<3>>::value)
+    eulerFluxJacFast<Phys::dim, AX>(phys.gamma, uN, uP, JN, JP);
   else if constexpr (std::is_same<Phys, Swe2d>::value) sweFluxJacFast<AX>(phys.g, uN, uP, JN, JP);
   else phys.template fluxJac<AX>(uN, uP, JN, JP);
 }

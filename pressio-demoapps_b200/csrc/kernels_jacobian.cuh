@@ -18,6 +18,7 @@
 // Requires the regular inner-row pattern (no coincident neighbours); tiny periodic meshes whose neighbours merge keep
 // the read-modify-write kernel (k_jacobian_inner_rows).
 #pragma once
+#include "fastmath.cuh"
 #include "kernels_generic.cuh"
 
 namespace pda {
@@ -63,11 +64,11 @@ PDA_DEVFN void jacobianFaceRole(const Phys& phys, const int32_t* __restrict__ ro
     double q[S - 1];
 #pragma unroll
     for (int p = 0; p < S - 1; ++p) q[p] = U[(int64_t)cells[p + face] * N + d];
-    Recon<S>::face(q, un[d], up[d]);
+    reconFaceFast<S>(q, un[d], up[d]);
   }
   double F[N], JN[N * N], JP[N * N];
-  phys.template flux<AX>(un, up, F);
-  phys.template fluxJac<AX>(un, up, JN, JP);
+  faceFlux2d<Phys, AX>(phys, un, up, F);
+  faceFluxJac2d<Phys, AX>(phys, un, up, JN, JP);
 #pragma unroll
   for (int d = 0; d < N; ++d) {
     const double other = __shfl_xor_sync(0xffffffffu, F[d], 1);
@@ -77,10 +78,10 @@ PDA_DEVFN void jacobianFaceRole(const Phys& phys, const int32_t* __restrict__ ro
   // positions 0..h, the R lane h+1..S-1; position p receives the L face's column m = p and the R face's m = p-1.
 #pragma unroll
   for (int j = 0; j < N; ++j) {
-    double q[S - 1], gN[S - 1], gP[S - 1], t0, t1;
+    double q[S - 1], gN[S - 1], gP[S - 1];
 #pragma unroll
     for (int p = 0; p < S - 1; ++p) q[p] = U[(int64_t)cells[p + face] * N + j];
-    Recon<S>::faceGrad(q, t0, t1, gN, gP);
+    reconFaceGradFast<S>(q, gN, gP);
 #pragma unroll
     for (int s = 0; s <= h; ++s) {
       constexpr int dummy = 0; (void)dummy;
