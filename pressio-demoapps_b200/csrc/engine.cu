@@ -1062,7 +1062,8 @@ void Problem::evaluateDev(const double* dU, double t, double* dV, double* dJ, vo
   const bool jacLattice = dJ && m.lattice && dim_ == 2 && ds.innerViaLattice && family_ != F_DIFFREAC2D;
   if (dJ) {
     buildPattern();
-    if (jacLattice && !mergedNeighbors_ && !ds.latJacReady) {
+    const bool gsLat = family_ == F_DIFFREAC2D && probId_ == 1 && ds.innerViaLattice && m.fullyPeriodic;
+    if (((jacLattice || gsLat) && !mergedNeighbors_) && !ds.latJacReady) {
       ds.latBase.upload(cellBase_);
       {   // slot table padded to 16 bytes per cell: one vector load per cell in the kernel
         std::vector<uint4> padded(cellBase_.size(), make_uint4(0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu));
@@ -1084,12 +1085,14 @@ void Problem::evaluateDev(const double* dU, double t, double* dV, double* dJ, vo
         }
         rs.jBase.upload(base); rs.jLen.upload(len); rs.jSlot.upload(sl);
       };
-      if (!(jacLattice && !mergedNeighbors_)) { ensureInnerRows(); fill(ds.inner); }
+      if (!((jacLattice || gsLat) && !mergedNeighbors_)) { ensureInnerRows(); fill(ds.inner); }
       fill(ds.nearBd);
       ds.jacTablesReady = true;
     }
     // the staged inner-row kernel writes every value once; only rows assembled by read-modify-write need zeros
-    if (family_ == F_DIFFREAC2D || family_ == F_DIFFREAC1D || mergedNeighbors_) {
+    if (gsLat && !mergedNeighbors_) {
+      // the Gray-Scott lattice kernel writes every value once
+    } else if (family_ == F_DIFFREAC2D || family_ == F_DIFFREAC1D || mergedNeighbors_) {
       PDA_CUDA(cudaMemsetAsync(dJ, 0, colidx_.size() * sizeof(double), st));
     } else if (ds.nearBd.n > 0) {
       dev::k_zero_cell_chunks<<<gridFor((int64_t)ds.nearBd.n * 32, 256), 256, 0, st>>>(ds.nearBd.jBase.p, ds.nearBd.jLen.p,
@@ -1102,7 +1105,11 @@ void Problem::evaluateDev(const double* dU, double t, double* dV, double* dJ, vo
   if (family_ == F_DIFFREAC2D && probId_ == 1) {
     dev::GrayScottParams gp{gs_[0], gs_[1], gs_[2], gs_[3], m.dInv[0] * m.dInv[0], m.dInv[1] * m.dInv[1]};
     if (!m.fullyPeriodic) throw Error(kInvalid, "GrayScott requires a periodic mesh");
-    if (ds.innerViaLattice && !dJ) {
+    if (ds.innerViaLattice && dJ && !mergedNeighbors_) {
+      const int64_t ncell = (int64_t)m.n[0] * m.n[1];
+      dev::k_gray_scott_lattice_jac<<<(unsigned)((ncell + 127) / 128), 128, 0, st>>>(
+          gp, m.n[0], m.n[1], reinterpret_cast<const double2*>(dU), reinterpret_cast<double2*>(dV), dJ, ds.latBase.p, ds.latSlots.p);
+    } else if (ds.innerViaLattice && !dJ) {
       dim3 grid((unsigned)((m.n[0] + 127) / 128), (unsigned)m.n[1]);
       dev::k_gray_scott_lattice<<<grid, 128, 0, st>>>(gp, m.n[0], m.n[1], reinterpret_cast<const double2*>(dU),
                                                      reinterpret_cast<double2*>(dV));

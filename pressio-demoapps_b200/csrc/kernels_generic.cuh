@@ -536,6 +536,59 @@ k_gray_scott_lattice(GrayScottParams gp, int32_t nx, int32_t ny, const double2* 
   V[(int64_t)j * nx + i] = out;
 }
 
+// Gray-Scott velocity + Jacobian on a periodic full lattice: one thread per cell, 128 consecutive cells per CTA.  The
+// 20 stored entries of a cell (2 rows x 5 blocks x 2, explicit zeros included) are assembled in shared memory at
+// their sorted block positions and the CTA streams its 128 chunks -- one contiguous 20 KB range of the CSR value
+// array -- out coalesced: every value written once, no memset, no read-modify-write.
+__global__ void __launch_bounds__(128)
+k_gray_scott_lattice_jac(GrayScottParams gp, int32_t nx, int32_t ny, const double2* __restrict__ U,
+                         double2* __restrict__ V, double* __restrict__ Jv, const int32_t* __restrict__ cellBase,
+                         const uint4* __restrict__ cellSlots) {
+  constexpr int CH = 20, STR = 21;
+  __shared__ double sJ[128 * STR];
+  const int64_t ncell = (int64_t)nx * ny;
+  const int64_t gid0 = (int64_t)blockIdx.x * 128;
+  const int64_t gid = gid0 + threadIdx.x;
+  if (gid < ncell) {
+    const int32_t i = (int32_t)(gid % nx), j = (int32_t)(gid / nx);
+    const int32_t il = (i == 0) ? nx - 1 : i - 1, ir = (i == nx - 1) ? 0 : i + 1;
+    const int32_t jb = (j == 0) ? ny - 1 : j - 1, jf = (j == ny - 1) ? 0 : j + 1;
+    const double2 c = U[gid];
+    const double2 l = U[(int64_t)j * nx + il], rt = U[(int64_t)j * nx + ir];
+    const double2 b = U[(int64_t)jb * nx + i], f = U[(int64_t)jf * nx + i];
+    const double uDx = gp.Du * gp.dxInvSq, uDy = gp.Du * gp.dyInvSq;
+    const double vDx = gp.Dv * gp.dxInvSq, vDy = gp.Dv * gp.dyInvSq;
+    const double u = c.x, w = c.y;
+    const double uvv = u * w * w;
+    if (V) {
+      double2 out;
+      out.x = gp.F * (1.0 - u) - uvv + uDx * (rt.x - 2.0 * u + l.x) + uDy * (b.x - 2.0 * u + f.x);
+      out.y = -(gp.F + gp.k) * w + uvv + vDx * (rt.y - 2.0 * w + l.y) + vDy * (b.y - 2.0 * w + f.y);
+      V[gid] = out;
+    }
+    const uint4 sv = __ldg(cellSlots + gid);   // graph columns: 0 self, 1 left, 2 front (j+1), 3 right, 4 back (j-1)
+    const int s0 = sv.x & 0xff, sl = (sv.x >> 8) & 0xff, sf = (sv.x >> 16) & 0xff, sr = (sv.x >> 24) & 0xff, sb = sv.y & 0xff;
+    double* r0 = sJ + threadIdx.x * STR;
+    double* r1 = r0 + 10;
+    // the reference accumulates into zeroed entries: 0 + x (diffusion_reaction_2d_prob_class.hpp:486-527)
+    r0[2 * s0] = -2.0 * uDx - 2.0 * uDy - w * w - gp.F;
+    r0[2 * s0 + 1] = -(2.0 * u * w);
+    r1[2 * s0] = w * w;
+    r1[2 * s0 + 1] = -2.0 * vDx - 2.0 * vDy + 2.0 * u * w - (gp.F + gp.k);
+    r0[2 * sl] = uDx; r0[2 * sl + 1] = 0.0; r1[2 * sl] = 0.0; r1[2 * sl + 1] = vDx;
+    r0[2 * sr] = uDx; r0[2 * sr + 1] = 0.0; r1[2 * sr] = 0.0; r1[2 * sr + 1] = vDx;
+    r0[2 * sf] = uDy; r0[2 * sf + 1] = 0.0; r1[2 * sf] = 0.0; r1[2 * sf + 1] = vDy;
+    r0[2 * sb] = uDy; r0[2 * sb + 1] = 0.0; r1[2 * sb] = 0.0; r1[2 * sb + 1] = vDy;
+  }
+  __syncthreads();
+  const int nvalid = (int)min((int64_t)128, ncell - gid0);
+  double* dst = Jv + cellBase[gid0];
+  for (int e = threadIdx.x; e < nvalid * CH; e += 128) {
+    const int cc = e / CH, w = e - cc * CH;
+    dst[e] = sJ[cc * STR + w];
+  }
+}
+
 // ------------------------------------------------------------------------------------------------ J * B
 // applyJacobian (adapter_cpp.hpp:231-259): R = J * B with the fixed CSR pattern.  The N rows of a cell share one
 // column pattern made of N-wide blocks (entry (k, block b, j) at base + k*len + b*N + j, column id_b*N + j), so the
