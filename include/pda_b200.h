@@ -223,6 +223,9 @@ pda_status pda_slab_peer_handle(pda_problem p, unsigned char handle[64]);
 pda_status pda_slab_peer_connect(pda_problem p, const unsigned char* handles /* nranks x 64 bytes */);
 pda_status pda_slab_peer_connect_local(pda_problem p, pda_problem lower, pda_problem upper);
 pda_status pda_slab_velocity_peer_dev(pda_problem p, const double* dU_owned, double t, double* dV_owned, void* stream);
+/* host-pointer flavour (owned planes only, pinned buffers recommended): chunks of planes flow H2D -> kernel -> D2H on
+ * three streams; the boundary chunks go first so the pushes to the neighbours overlap the interior uploads */
+pda_status pda_slab_velocity_peer_host(pda_problem p, const double* U_owned, double t, double* V_owned);
 
 #ifdef __cplusplus
 }

@@ -306,4 +306,8 @@ pda_status pda_slab_velocity_peer_dev(pda_problem p, const double* dU, double t,
   return guarded([&] { P(p).slabVelocityPeerDev(dU, t, dV, stream); });
 }
 
+pda_status pda_slab_velocity_peer_host(pda_problem p, const double* U, double t, double* V) {
+  return guarded([&] { P(p).slabVelocityPeerHost(U, t, V); });
+}
+
 }  // extern "C"

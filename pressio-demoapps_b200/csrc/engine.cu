@@ -1770,55 +1770,131 @@ void Problem::slabPeerConnectLocal(Problem* lo, Problem* hi) {
   dev_->peer.connected = true;
 }
 
-void Problem::slabVelocityPeerDev(const double* dU, double /*t*/, double* dV, void* streamV) {
-  if (!slab_) throw Error(kInvalid, "not a slab problem");
-  if (!dU || !dV) throw Error(kInvalid, "velocity: null pointer");
-  ensureDevice();
-  if (!dev_->peer.connected) throw Error(kInvalid, "slab peer mode: pda_slab_peer_connect has not been called");
-  if (family_ != F_EULER3D) throw Error(kUnsupported, "slab peer mode: Euler3d only");
-  PDA_CUDA(cudaSetDevice(device_));
+// one evaluation = one epoch: enqueue the pushes of my boundary planes (copy engine, after `ready` fired) ...
+void Problem::peerPush(const double* dU, void* readyEvent0, void* readyEvent1) {
   DeviceState& ds = *dev_;
   auto& ph = ds.peer;
-  cudaStream_t st = (cudaStream_t)streamV;
   Mesh& m = *mesh_;
   const int h = (S_ - 1) / 2;
   const int32_t nOwned = slabK1_ - slabK0_;
-  if (m.n[0] < 2 * m.halo() || m.n[1] < 2 * m.halo()) throw Error(kUnsupported, "slab peer mode: mesh too small for the tiled kernel");
   const size_t planeDofs = (size_t)m.n[0] * m.n[1] * ndpc_;
   const size_t haloBytes = (size_t)h * planeDofs * sizeof(double);
   ++ph.epoch;
   const int par = (int)(ph.epoch & 1u);
   const uint32_t val = ph.epoch & 0xffffu;
   const unsigned char* valSrc = ph.base + ph.tableOff + sizeof(uint32_t) * val;
-
-  // U as of everything enqueued on `st` so far is what the neighbours receive
-  PDA_CUDA(cudaEventRecord(ph.evReady, st));
   // [1] my top h planes -> upper neighbour's LOWER halo ; [0] my bottom h planes -> lower neighbour's UPPER halo
   for (int i = 1; i >= 0; --i) {
-    PDA_CUDA(cudaStreamWaitEvent(ph.sPush[i], ph.evReady, 0));
+    PDA_CUDA(cudaStreamWaitEvent(ph.sPush[i], (cudaEvent_t)readyEvent0, 0));
+    if (readyEvent1) PDA_CUDA(cudaStreamWaitEvent(ph.sPush[i], (cudaEvent_t)readyEvent1, 0));
     const double* src = (i == 1) ? dU + (size_t)(nOwned - h) * planeDofs : dU;
     const int side = (i == 1) ? 0 : 1;
     PDA_CUDA(cudaMemcpyAsync(ph.halo(ph.remote[i], par, side), src, haloBytes, cudaMemcpyDefault, ph.sPush[i]));
     PDA_CUDA(cudaMemcpyAsync(ph.flag(ph.remote[i], par, side), valSrc, sizeof(uint32_t), cudaMemcpyDefault, ph.sPush[i]));
     PDA_CUDA(cudaEventRecord(ph.evPushed[i], ph.sPush[i]));
   }
+}
 
+// ... and launch the kernel over owned planes [p0, p1) of the current epoch
+void Problem::peerLaunch(const double* dU, double* dV, void* streamV, int32_t p0, int32_t p1) {
+  DeviceState& ds = *dev_;
+  auto& ph = ds.peer;
+  cudaStream_t st = (cudaStream_t)streamV;
+  Mesh& m = *mesh_;
+  const int32_t nOwned = slabK1_ - slabK0_;
+  const int par = (int)(ph.epoch & 1u);
   dev::Deltas dl{{m.dInv[0], m.dInv[1], m.dInv[2]}};
   dev::LatticeDesc L;
   for (int a = 0; a < 3; ++a) { L.n[a] = m.n[a]; L.per[a] = m.periodic[a] ? 1 : 0; }
   L.n[2] = nOwned;
-  L.planeBegin = 0; L.planeEnd = nOwned; L.haloPlanes = 0; L.slab = 2; L.meshHalo = m.halo();
+  L.planeBegin = p0; L.planeEnd = p1; L.haloPlanes = 0; L.slab = 2; L.meshHalo = m.halo();
   L.haloLo = ph.halo(ph.base, par, 0); L.haloHi = ph.halo(ph.base, par, 1);
   L.flagLo = ph.flag(ph.base, par, 0); L.flagHi = ph.flag(ph.base, par, 1);
-  L.epoch = val;
+  L.epoch = ph.epoch & 0xffffu;
   dispatchScheme(S_, [&](auto sTag) {
     constexpr int S = decltype(sTag)::value;
     launchLattice3dTiled<dev::Euler<3>, S>(dev::Euler<3>{gamma_}, L, dl, dU, dV, st);
     ++launches_;
   });
   PDA_CUDA(cudaGetLastError());
+}
+
+void Problem::peerCheck() {
+  if (!slab_) throw Error(kInvalid, "not a slab problem");
+  ensureDevice();
+  if (!dev_->peer.connected) throw Error(kInvalid, "slab peer mode: pda_slab_peer_connect has not been called");
+  if (family_ != F_EULER3D) throw Error(kUnsupported, "slab peer mode: Euler3d only");
+  Mesh& m = *mesh_;
+  if (m.n[0] < 2 * m.halo() || m.n[1] < 2 * m.halo()) throw Error(kUnsupported, "slab peer mode: mesh too small for the tiled kernel");
+  PDA_CUDA(cudaSetDevice(device_));
+}
+
+void Problem::slabVelocityPeerDev(const double* dU, double /*t*/, double* dV, void* streamV) {
+  if (!dU || !dV) throw Error(kInvalid, "velocity: null pointer");
+  peerCheck();
+  auto& ph = dev_->peer;
+  cudaStream_t st = (cudaStream_t)streamV;
+  // U as of everything enqueued on `st` so far is what the neighbours receive
+  PDA_CUDA(cudaEventRecord(ph.evReady, st));
+  peerPush(dU, ph.evReady, nullptr);
+  peerLaunch(dU, dV, streamV, 0, slabK1_ - slabK0_);
   // the caller may overwrite U once `st` reaches this point: both pushes must have left by then
   for (int i = 0; i < 2; ++i) PDA_CUDA(cudaStreamWaitEvent(st, ph.evPushed[i], 0));
+}
+
+// host-pointer flavour: chunks of owned planes flow H2D -> kernel -> D2H on three streams like velocityHost; the two
+// boundary chunks are uploaded first so that the pushes to the neighbours leave while the interior chunks stream in
+void Problem::slabVelocityPeerHost(const double* U, double t, double* V) {
+  if (!U || !V) throw Error(kInvalid, "velocity: null pointer");
+  peerCheck();
+  DeviceState& ds = *dev_;
+  auto& ph = ds.peer;
+  Mesh& m = *mesh_;
+  const int h = (S_ - 1) / 2;
+  const int32_t nOwned = slabK1_ - slabK0_;
+  const size_t planeDofs = (size_t)m.n[0] * m.n[1] * ndpc_;
+  const size_t n = (size_t)nOwned * planeDofs;
+  ds.dU.alloc(n); ds.dV.alloc(n);
+  ds.ensurePipeline();
+  const int nChunks = (int)std::min<int64_t>(DeviceState::kMaxChunks, nOwned / std::max(8, 2 * h));
+  // the previous call's kernels / pushes must be done before dU is overwritten
+  PDA_CUDA(cudaEventRecord(ds.evOut[0], ds.stream));
+  PDA_CUDA(cudaStreamWaitEvent(ds.sH2D, ds.evOut[0], 0));
+  if (ph.epoch > 0) for (int i = 0; i < 2; ++i) PDA_CUDA(cudaStreamWaitEvent(ds.sH2D, ph.evPushed[i], 0));
+  if (nChunks < 3) {
+    PDA_CUDA(cudaMemcpyAsync(ds.dU.p, U, n * sizeof(double), cudaMemcpyHostToDevice, ds.sH2D));
+    PDA_CUDA(cudaEventRecord(ds.evIn[0], ds.sH2D));
+    PDA_CUDA(cudaStreamWaitEvent(ds.stream, ds.evIn[0], 0));
+    slabVelocityPeerDev(ds.dU.p, t, ds.dV.p, ds.stream);
+    PDA_CUDA(cudaMemcpyAsync(V, ds.dV.p, n * sizeof(double), cudaMemcpyDeviceToHost, ds.stream));
+    PDA_CUDA(cudaStreamSynchronize(ds.stream));
+    return;
+  }
+  auto c0 = [&](int c) { return (int32_t)((int64_t)nOwned * c / nChunks); };
+  auto h2d = [&](int c) {
+    const size_t off = (size_t)c0(c) * planeDofs, cnt = (size_t)(c0(c + 1) - c0(c)) * planeDofs;
+    PDA_CUDA(cudaMemcpyAsync(ds.dU.p + off, U + off, cnt * sizeof(double), cudaMemcpyHostToDevice, ds.sH2D));
+    PDA_CUDA(cudaEventRecord(ds.evIn[c], ds.sH2D));
+  };
+  auto compute = [&](int c) {
+    for (int w = std::max(0, c - 1); w <= std::min(nChunks - 1, c + 1); ++w) PDA_CUDA(cudaStreamWaitEvent(ds.stream, ds.evIn[w], 0));
+    peerLaunch(ds.dU.p, ds.dV.p, ds.stream, c0(c), c0(c + 1));
+    PDA_CUDA(cudaEventRecord(ds.evOut[c], ds.stream));
+    PDA_CUDA(cudaStreamWaitEvent(ds.sD2H, ds.evOut[c], 0));
+    const size_t off = (size_t)c0(c) * planeDofs, cnt = (size_t)(c0(c + 1) - c0(c)) * planeDofs;
+    PDA_CUDA(cudaMemcpyAsync(V + off, ds.dV.p + off, cnt * sizeof(double), cudaMemcpyDeviceToHost, ds.sD2H));
+  };
+  h2d(nChunks - 1);
+  h2d(0);
+  peerPush(ds.dU.p, ds.evIn[nChunks - 1], ds.evIn[0]);   // boundary planes are on the device: send them off
+  for (int c = 1; c < nChunks - 1; ++c) {
+    h2d(c);
+    compute(c - 1);
+  }
+  compute(nChunks - 2);
+  compute(nChunks - 1);
+  PDA_CUDA(cudaStreamSynchronize(ds.sD2H));
+  PDA_CUDA(cudaStreamSynchronize(ds.stream));
 }
 
 }  // namespace pda

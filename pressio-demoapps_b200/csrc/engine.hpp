@@ -59,6 +59,7 @@ class Problem {
   void slabPeerConnect(const unsigned char* handles);           // nranks x 64 bytes, indexed by rank
   void slabPeerConnectLocal(Problem* lo, Problem* hi);          // same-process neighbours (tests, single-process multi-GPU)
   void slabVelocityPeerDev(const double* dUowned, double t, double* dVowned, void* stream);
+  void slabVelocityPeerHost(const double* Uowned, double t, double* Vowned);
 
  private:
   friend struct DeviceState;
@@ -69,6 +70,9 @@ class Problem {
   void ensureSource();
   void evaluateDev(const double* dU, double t, double* dV, double* dJ, void* stream);
   void evaluatePlanes(const double* dU, double t, double* dV, void* stream, int32_t p0, int32_t p1);
+  void peerCheck();
+  void peerPush(const double* dU, void* readyEvent0, void* readyEvent1);
+  void peerLaunch(const double* dU, double* dV, void* stream, int32_t p0, int32_t p1);
 
   Mesh* mesh_;
   int family_, probId_, recon_, icFlag_;

@@ -115,6 +115,7 @@ _sig("pda_slab_peer_handle", _C.c_int, _vp, _vp)
 _sig("pda_slab_peer_connect", _C.c_int, _vp, _vp)
 _sig("pda_slab_peer_connect_local", _C.c_int, _vp, _vp, _vp)
 _sig("pda_slab_velocity_peer_dev", _C.c_int, _vp, _vp, _dbl, _vp, _vp)
+_sig("pda_slab_velocity_peer_host", _C.c_int, _vp, _vp, _dbl, _vp)
 
 
 def _check(status):
@@ -568,6 +569,10 @@ class Problem:
 
     def peerConnectLocal(self, lower, upper):
         _check(_lib.pda_slab_peer_connect_local(self._h, lower._h, upper._h))
+
+    def slabVelocityPeer(self, U_owned, time, V_owned):
+        """host-pointer flavour: numpy (ideally pinned) arrays of the owned planes"""
+        _check(_lib.pda_slab_velocity_peer_host(self._h, U_owned.ctypes.data, float(time), V_owned.ctypes.data))
 
     def slabVelocityPeerDevice(self, dU_owned, time, dV_owned, stream=0):
         _check(_lib.pda_slab_velocity_peer_dev(self._h, dU_owned, float(time), dV_owned, stream))

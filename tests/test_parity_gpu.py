@@ -391,6 +391,24 @@ def test_lattice_and_graph_jacobian_kernels_agree(case):
     assert scaled_err(J1.data, J2.data, 1e-11, 1e-9) <= 1.0
 
 
+def test_slab_peer_mode_host_pipeline_single_rank():
+    """pda_slab_velocity_peer_host with one rank (its own ring neighbour): chunked H2D -> kernel -> D2H pipeline, pushes
+    issued after the two boundary chunks; equals the full-mesh velocity bit for bit over several calls.  (More ranks
+    need one thread or process each -- the call is synchronous -- see the multi-process test below.)"""
+    n = (24, 20, 96)
+    mesh = pda.create_full_mesh(list(n), [-1, 1, -1, 1, -1, 1], 7, ("x", "y", "z"))
+    full = pda.create_problem(mesh, pda.Euler3d.PeriodicSmooth, R.Weno5)
+    p = pda.create_problem_slab(mesh, pda.Euler3d.PeriodicSmooth, R.Weno5, 0, 1)
+    p.peerConnect([p.peerHandle()])
+    for it in range(3):
+        U = perturbed(full, seed=300 + it)
+        Vfull = full.createRightHandSide()
+        full.rightHandSide(U, 0.0, Vfull)
+        V = np.zeros_like(U)
+        p.slabVelocityPeer(U, 0.0, V)
+        assert np.array_equal(V, Vfull), it
+
+
 def test_slab_peer_mode_multi_process():
     """peer mode across PROCESSES (one rank per GPU, IPC-mapped halo buffers, cross-GPU flags): tools/check_peer_multi.py
     under torchrun on two GPUs; every rank's slab must equal the full-mesh velocity bit for bit.  Skipped on a

@@ -42,6 +42,12 @@ for it in range(a.iters):
     torch.cuda.synchronize()
     ok = torch.equal(dV, Vf[k0 * pd:k1 * pd])
     bad += 0 if ok else 1
+    # host-pointer flavour (chunked H2D -> kernel -> D2H pipeline, pushes after the boundary chunks)
+    hU = Uo.cpu().pin_memory()
+    hV = torch.zeros_like(hU).pin_memory()
+    p.slabVelocityPeer(hU.numpy(), 0.0, hV.numpy())
+    ok = torch.equal(hV, Vf[k0 * pd:k1 * pd].cpu())
+    bad += 0 if ok else 1
 t = torch.tensor([bad], device="cuda")
 dist.all_reduce(t)
 if rank == 0:
