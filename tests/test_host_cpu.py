@@ -178,3 +178,24 @@ def test_cabi_exports_every_declared_symbol():
     assert not missing, missing
     lib.pda_version.restype = C.c_char_p
     assert b"sm_100a" in lib.pda_version()
+
+
+def _build_c_demo(tmp_path):
+    """examples/c_abi_demo.c compiled as C99 against include/pda_b200.h: the boundary is a C ABI, not a C++ one"""
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    lib = os.path.join(root, "pressio-demoapps_b200", "lib")
+    exe = os.path.join(str(tmp_path), "c_abi_demo")
+    r = subprocess.run(["gcc", "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-I" + os.path.join(root, "include"),
+                        os.path.join(root, "examples", "c_abi_demo.c"), "-L" + lib, "-lpda_b200", "-Wl,-rpath," + lib, "-lm",
+                        "-o", exe], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    return exe
+
+
+def test_c_abi_demo_host_part(tmp_path):
+    import subprocess
+    exe = _build_c_demo(tmp_path)
+    r = subprocess.run([exe], capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "c_abi_demo ok" in r.stdout

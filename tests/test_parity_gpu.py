@@ -457,3 +457,13 @@ def test_apply_jacobian_many_columns(case, ncols):
         Rm = p.createApplyJacobianResult(B)
         p.applyJacobian(U, B, 0.0, Rm)
         assert scaled_err(Rm, J @ B, 1e-11, 1e-9) <= 1.0
+
+
+def test_c_abi_demo_on_gpu(tmp_path):
+    """the plain-C client of include/pda_b200.h (examples/c_abi_demo.c): velocity + Jacobian + 10 SSPRK3 steps"""
+    import subprocess
+    from test_host_cpu import _build_c_demo
+    exe = _build_c_demo(tmp_path)
+    r = subprocess.run([exe], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "max|V|" in r.stdout and "c_abi_demo ok" in r.stdout
