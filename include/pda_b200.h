@@ -70,7 +70,7 @@ enum { PDA_FIRST_ORDER = 0, PDA_WENO3 = 1, PDA_WENO5 = 2 };
 /* ghost sides, in the reference's graph-column order (GhostRelativeLocation, ghost_relative_locations.hpp) */
 enum { PDA_SIDE_LEFT = 0, PDA_SIDE_FRONT = 1, PDA_SIDE_RIGHT = 2, PDA_SIDE_BACK = 3, PDA_SIDE_BOTTOM = 4, PDA_SIDE_TOP = 5 };
 /* device-expressible custom boundary conditions (custom_bc_holder.hpp / custom_bcs_functions.hpp) */
-enum { PDA_BC_DIRICHLET = 0, PDA_BC_HOMOG_NEUMANN = 1, PDA_BC_REFLECTIVE = 2 };
+enum { PDA_BC_DIRICHLET = 0, PDA_BC_HOMOG_NEUMANN = 1, PDA_BC_REFLECTIVE = 2, PDA_BC_HOST_CALLBACK = 3 };
 /* operand layout for apply_jacobian (adapter_cpp.hpp:231-259: vector, col-major, row-major) */
 enum { PDA_LAYOUT_COL_MAJOR = 0, PDA_LAYOUT_ROW_MAJOR = 1 };
 
@@ -145,6 +145,17 @@ pda_status pda_problem_set_source(pda_problem p, const double* values);
 /* custom BCs (Swe2d::CustomBCs, Euler2d Riemann/NormalShock and AdvectionDiffusion2d custom-BC overloads): one device-expressible rule per side.
  * values: ndpc doubles (Dirichlet ghost state); ignored otherwise.  (custom_bcs_functions.hpp:60-164) */
 pda_status pda_problem_set_bc(pda_problem p, int side, int kind, const double* values);
+/* Arbitrary HOST functors for one side -- the reference's custom-BC functor contract, one-to-one
+ * (custom_bcs_functions.hpp:107-164 ghost fill, :60-103 Jacobian factors; tests_cpp/eigen_2d_swe_custom_bcs/main.cc:6-58):
+ *   ghost(user, nearBdRowId, graphRow, cellX, cellY, U (whole state, host copy), ndpc, cellWidth, ghostValues)
+ *   factors(user, graphRow, cellX, cellY, ndpc, factors)            (may be NULL: factors stay 1)
+ * This is the SLOW path kept for generality: every evaluation copies the state to the host, runs the functor for the
+ * boundary cells of that side and uploads the ghost rows.  Device-expressible rules (pda_problem_set_bc) never leave HBM. */
+typedef void (*pda_bc_ghost_fn)(void* user, int32_t near_bd_row, const int32_t* graph_row, double cell_x, double cell_y,
+                                const double* U, int ndpc, double cell_width, double* ghost_values);
+typedef void (*pda_bc_factor_fn)(void* user, const int32_t* graph_row, double cell_x, double cell_y, int ndpc,
+                                 double* factors);
+pda_status pda_problem_set_bc_callback(pda_problem p, int side, pda_bc_ghost_fn ghost, pda_bc_factor_fn factors, void* user);
 pda_status pda_problem_free(pda_problem p);
 
 int     pda_problem_num_dof_per_cell(pda_problem p);       /* numDofPerCell()        adapter_cpp.hpp:93-95   */

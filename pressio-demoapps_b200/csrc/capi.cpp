@@ -185,6 +185,10 @@ pda_status pda_problem_set_bc(pda_problem p, int side, int kind, const double* v
   return guarded([&] { P(p).setBc(side, kind, values); });
 }
 
+pda_status pda_problem_set_bc_callback(pda_problem p, int side, pda_bc_ghost_fn ghost, pda_bc_factor_fn factors, void* user) {
+  return guarded([&] { P(p).setBcCallback(side, ghost, factors, user); });
+}
+
 pda_status pda_problem_free(pda_problem p) {
   if (p) { delete p->p; delete p; }
   return PDA_OK;

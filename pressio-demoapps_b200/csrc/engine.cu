@@ -70,7 +70,7 @@ enum { F_EULER1D = 1, F_EULER2D = 2, F_EULER3D = 3, F_SWE2D = 4, F_DIFFREAC2D = 
        F_ADVDIFFREAC2D = 7, F_ADVECTION1D = 8, F_DIFFREAC1D = 9 };
 enum { E2_PERIODIC = 0, E2_KH = 1, E2_SEDOV_FULL = 2, E2_SEDOV_SYM = 3, E2_RIEMANN = 4, E2_NORMAL_SHOCK = 5,
        E2_DMR = 6, E2_CROSS_SHOCK = 7, E2_NEUMANN = 8 };
-enum { BC_DIRICHLET = 0, BC_NEUMANN = 1, BC_REFLECTIVE = 2 };
+enum { BC_DIRICHLET = 0, BC_NEUMANN = 1, BC_REFLECTIVE = 2, BC_CALLBACK = 3 };
 
 // Euler2d parameter indices (impl/euler_2d_parametrization_helpers.hpp:59-72)
 enum { icNormalShockMach = 0, icCrossDensity = 1, icCrossInletX = 2, icCrossBottomY = 3, icRiem1TRP = 4,
@@ -167,6 +167,7 @@ struct DeviceState {
   DevBuf<double> dU, dV, dJ, dB, dR;
   DevBuf<int32_t> dRowptr, dColidx;
   DevBuf<double> stAux, stK[4];   // stepper work vectors
+  PinnedBuf<double> hostU, hostGhost[4];   // host-functor boundary conditions (slow path)
   // J*B per cell (k_spmm_cells_rowmajor): per-cell CSR base / row length, lattice visiting order, transposed operands
   DevBuf<int32_t> dCellBase, dCellLen, dCellOrder;
   DevBuf<double> dBt, dRt;
@@ -393,11 +394,28 @@ void Problem::setBc(int side, int kind, const double* values) {
     throw Error(kInvalid, "custom BCs only valid for Swe2d::CustomBCs, Euler2d::{Riemann, NormalShock} and AdvectionDiffusion2d");
   if (side < 0 || side > 3) throw Error(kInvalid, "set_bc: invalid side");
   if (kind < 0 || kind > 2) throw Error(kInvalid, "set_bc: invalid kind");
+  bc_[side] = BcRule{};
   bc_[side].kind = kind;
   if (kind == BC_DIRICHLET) {
     if (!values) throw Error(kInvalid, "set_bc: Dirichlet needs ndpc values");
     for (int d = 0; d < ndpc_; ++d) bc_[side].values[d] = values[d];
   }
+  customBcs_ = true;
+  if (dev_) { dev_->haveGhosts = false; dev_->jacTablesReady = false; }
+}
+
+void Problem::setBcCallback(int side, BcGhostFn ghost, BcFactorFn factors, void* user) {
+  const bool ok = (family_ == F_SWE2D && probId_ == 1) || family_ == F_ADVDIFF2D ||
+                  (family_ == F_EULER2D && (probId_ == E2_RIEMANN || probId_ == E2_NORMAL_SHOCK));
+  if (!ok)
+    throw Error(kInvalid, "custom BCs only valid for Swe2d::CustomBCs, Euler2d::{Riemann, NormalShock} and AdvectionDiffusion2d");
+  if (side < 0 || side > 3) throw Error(kInvalid, "set_bc_callback: invalid side");
+  if (!ghost) throw Error(kInvalid, "set_bc_callback: null ghost functor");
+  bc_[side] = BcRule{};
+  bc_[side].kind = BC_CALLBACK;
+  bc_[side].ghostFn = ghost;
+  bc_[side].factorFn = factors;
+  bc_[side].user = user;
   customBcs_ = true;
   if (dev_) { dev_->haveGhosts = false; dev_->jacTablesReady = false; }
 }
@@ -964,6 +982,7 @@ void Problem::buildGhostRecipes() {
           }
         }
         if (src < 0) src = self;   // degenerate (mesh narrower than the stencil): the reference reads out of bounds
+        if (style == CUSTOM && bc_[side].kind == BC_CALLBACK) continue;   // filled on the host (runHostBcCallbacks)
         g.src = src;
         g.kind = 0;
         g.mode = (int16_t)sideMode[side];
@@ -993,6 +1012,10 @@ void Problem::buildGhostRecipes() {
         for (int s : {sm, sp}) {
           if (!hasBd(s)) continue;
           const int k = bc_[s].kind;
+          if (k == BC_CALLBACK) {
+            if (bc_[s].factorFn) bc_[s].factorFn(bc_[s].user, row, cxv, cyv, ndpc_, f);
+            continue;
+          }
           for (int d = 0; d < ndpc_; ++d) f[d] = (k == BC_DIRICHLET) ? 0.0 : 1.0;
           if (k == BC_REFLECTIVE) f[1 + ax] = -1.0;
         }
@@ -1152,6 +1175,11 @@ void Problem::evaluateDev(const double* dU, double t, double* dV, double* dJ, vo
       case 5: launchGhost(std::integral_constant<int, 5>{}); break;
     }
     ++launches_;
+    if (customBcs_) {
+      bool anyCb = false;
+      for (int sd = 0; sd < 4; ++sd) anyCb = anyCb || bc_[sd].kind == BC_CALLBACK;
+      if (anyCb) runHostBcCallbacks(dU, st);
+    }
   }
 
   auto run = [&](auto phys) {
@@ -1234,6 +1262,46 @@ void Problem::evaluateDev(const double* dU, double t, double* dV, double* dJ, vo
     default: throw Error(kUnsupported, "family not supported on device");
   }
   PDA_CUDA(cudaGetLastError());
+}
+
+// Host-functor boundary conditions (PDA_BC_HOST_CALLBACK): the reference's fillGhostsUseCustomFunctors
+// (custom_bcs_functions.hpp:107-164) with the functor running on the host over a copy of the state.  Slow path by
+// construction (state D2H + ghost rows H2D per evaluation); the device-expressible rules never leave HBM.
+void Problem::runHostBcCallbacks(const double* dU, void* streamV) {
+  DeviceState& ds = *dev_;
+  cudaStream_t st = (cudaStream_t)streamV;
+  Mesh& m = *mesh_;
+  const int nc = m.ncols();
+  const int h = ds.hS;
+  const std::vector<int32_t>& nb = ds.nearBd.hostRowIds;
+  const int32_t nNb = (int32_t)nb.size();
+  const size_t nU = (size_t)nDofStencil();
+  ds.hostU.alloc(nU);
+  PDA_CUDA(cudaMemcpyAsync(ds.hostU.p, dU, nU * sizeof(double), cudaMemcpyDeviceToHost, st));
+  PDA_CUDA(cudaStreamSynchronize(st));
+  const size_t rowLen = (size_t)h * ndpc_;
+  std::vector<int32_t> rowBuf(nc);
+  for (int side = 0; side < 4; ++side) {
+    if (bc_[side].kind != BC_CALLBACK) continue;
+    ds.hostGhost[side].alloc((size_t)std::max<int32_t>(nNb, 1) * rowLen);
+    std::memset(ds.hostGhost[side].p, 0, (size_t)std::max<int32_t>(nNb, 1) * rowLen * sizeof(double));
+    const double width = (side == 0 || side == 2) ? m.d[0] : m.d[1];
+    for (int32_t r = 0; r < nNb; ++r) {
+      const int32_t* row;
+      if (m.haveGraph) row = &m.graph[(size_t)nb[r] * nc];
+      else { m.latticeRow(nb[r], rowBuf.data()); row = rowBuf.data(); }
+      bool hasBd = false;
+      for (int L = 0; L < m.halo(); ++L) hasBd = hasBd || row[graphCol(dim_, side, L)] == -1;
+      if (!hasBd) continue;
+      const int32_t self = row[0];
+      double cxv, cyv;
+      if (m.haveCoords) { cxv = m.x[self]; cyv = m.y[self]; }
+      else { cxv = m.latticeCoord(0, self % m.n[0]); cyv = m.latticeCoord(1, (self / m.n[0]) % m.n[1]); }
+      bc_[side].ghostFn(bc_[side].user, r, row, cxv, cyv, ds.hostU.p, ndpc_, width, ds.hostGhost[side].p + (size_t)r * rowLen);
+    }
+    PDA_CUDA(cudaMemcpyAsync(ds.ghost[side].p, ds.hostGhost[side].p, (size_t)nNb * rowLen * sizeof(double),
+                             cudaMemcpyHostToDevice, st));
+  }
 }
 
 // per-row source table f(x[,y]) of the ProblemA families: the reference's default functors

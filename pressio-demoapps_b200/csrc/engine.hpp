@@ -13,9 +13,15 @@ namespace pda {
 
 struct DeviceState;   // everything that lives in HBM (engine.cu)
 
+using BcGhostFn = void (*)(void*, int32_t, const int32_t*, double, double, const double*, int, double, double*);
+using BcFactorFn = void (*)(void*, const int32_t*, double, double, int, double*);
+
 struct BcRule {
   int kind = -1;               // PDA_BC_* or -1 (unset)
   double values[5] = {0, 0, 0, 0, 0};
+  BcGhostFn ghostFn = nullptr;     // kind 3 (host callback)
+  BcFactorFn factorFn = nullptr;
+  void* user = nullptr;
 };
 
 class Problem {
@@ -32,6 +38,7 @@ class Problem {
   double queryParameter(const std::string& name) const;
   void initialCondition(double* U) const;
   void setBc(int side, int kind, const double* values);
+  void setBcCallback(int side, BcGhostFn ghost, BcFactorFn factors, void* user);
   void setSource(const double* values);   // nSample doubles (host)
 
   int64_t jacobianNnz();
@@ -68,6 +75,7 @@ class Problem {
   void ensureInnerRows();
   void buildGhostRecipes();
   void ensureSource();
+  void runHostBcCallbacks(const double* dU, void* stream);
   void evaluateDev(const double* dU, double t, double* dV, double* dJ, void* stream);
   void evaluatePlanes(const double* dU, double t, double* dV, void* stream, int32_t p0, int32_t p1);
   void peerCheck();

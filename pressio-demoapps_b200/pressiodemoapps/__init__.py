@@ -33,6 +33,10 @@ _LIBPATH = _os.path.join(_os.path.dirname(_HERE), "lib", "libpda_b200.so")
 
 
 _STEPPERS = {"euler": 0, "rk2": 1, "rk4": 2, "ssprk3": 3}
+_GHOST_FN = _C.CFUNCTYPE(None, _C.c_void_p, _C.c_int32, _C.POINTER(_C.c_int32), _C.c_double, _C.c_double,
+                         _C.POINTER(_C.c_double), _C.c_int, _C.c_double, _C.POINTER(_C.c_double))
+_FACTOR_FN = _C.CFUNCTYPE(None, _C.c_void_p, _C.POINTER(_C.c_int32), _C.c_double, _C.c_double, _C.c_int,
+                          _C.POINTER(_C.c_double))
 
 
 class PdaError(RuntimeError):
@@ -109,6 +113,7 @@ _sig("pda_slab_extent", _C.c_int, _vp, _C.POINTER(_i32), _C.POINTER(_i32), _C.PO
 _sig("pda_slab_initial_condition", _C.c_int, _vp, _vp)
 _sig("pda_slab_velocity_interior_dev", _C.c_int, _vp, _vp, _dbl, _vp, _vp)
 _sig("pda_slab_velocity_boundary_dev", _C.c_int, _vp, _vp, _dbl, _vp, _vp)
+_sig("pda_problem_set_bc_callback", _C.c_int, _vp, _C.c_int, _GHOST_FN, _FACTOR_FN, _vp)
 _sig("pda_problem_advance_dev", _C.c_int, _vp, _C.c_int, _vp, _dbl, _dbl, _C.c_int32, _vp)
 _sig("pda_problem_advance_host", _C.c_int, _vp, _C.c_int, _vp, _dbl, _dbl, _C.c_int32)
 _sig("pda_slab_peer_handle", _C.c_int, _vp, _vp)
@@ -358,6 +363,7 @@ class Problem:
             _check(_lib.pda_problem_create(mesh._h, family, int(problemId), int(recon), int(icFlag), len(params),
                                            names, vals, device, _C.byref(h)))
         self._h = h
+        self._recon = int(recon)
         self._pattern = None
         self._source = None      # host functor f(x[,y],t) of the ProblemA families
         self._source_t = None
@@ -412,6 +418,34 @@ class Problem:
     def setBC(self, side, kind, values=None):
         v = None if values is None else _np.ascontiguousarray(values, dtype=_np.float64)
         _check(_lib.pda_problem_set_bc(self._h, int(side), int(kind), None if v is None else v.ctypes.data))
+
+    def setBCFunctor(self, side, ghost, factors=None):
+        """Arbitrary host functors for one side (pda_problem_set_bc_callback; the reference's C++ functor contract,
+        custom_bcs_functions.hpp:107-164 / :60-103) -- the slow, fully general path:
+            ghost(nearBdRowId, graphRow, cellX, cellY, U, ndpc, cellWidth, ghostValues)   # numpy views; fill ghostValues
+            factors(graphRow, cellX, cellY, ndpc, factorsOut)                              # optional"""
+        ncols = self._mesh.graph().shape[1]
+        nU = self.totalDofStencilMesh()
+        ndpc = self.numDofPerCell()
+        h = self._recon + 1   # ghost layers = (scheme stencil - 1)/2, scheme stencil = 3 + 2*recon
+
+        def _ghost(user, row_id, grow, x, y, U, nd, width, out):
+            g = _np.ctypeslib.as_array(grow, shape=(ncols,))
+            u = _np.ctypeslib.as_array(U, shape=(nU,))
+            o = _np.ctypeslib.as_array(out, shape=(h * ndpc,))
+            ghost(int(row_id), g, float(x), float(y), u, int(nd), float(width), o)
+
+        cg = _GHOST_FN(_ghost)
+        cf = _FACTOR_FN()
+        if factors is not None:
+            def _fac(user, grow, x, y, nd, out):
+                g = _np.ctypeslib.as_array(grow, shape=(ncols,))
+                o = _np.ctypeslib.as_array(out, shape=(ndpc,))
+                factors(g, float(x), float(y), int(nd), o)
+            cf = _FACTOR_FN(_fac)
+        self._bc_keepalive = getattr(self, "_bc_keepalive", {})
+        self._bc_keepalive[int(side)] = (cg, cf)
+        _check(_lib.pda_problem_set_bc_callback(self._h, int(side), cg, cf, None))
 
     # ---- creators
     def initialCondition(self):

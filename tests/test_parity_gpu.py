@@ -467,3 +467,49 @@ def test_c_abi_demo_on_gpu(tmp_path):
     r = subprocess.run([exe], capture_output=True, text=True, timeout=300)
     assert r.returncode == 0, r.stdout + r.stderr
     assert "max|V|" in r.stdout and "c_abi_demo ok" in r.stdout
+
+
+def test_custom_bcs_host_functors_equal_device_rules():
+    """PDA_BC_HOST_CALLBACK: the reference's functor contract (tests_cpp/eigen_2d_swe_custom_bcs/main.cc:6-58: Dirichlet
+    on the left, homogeneous Neumann elsewhere, with their Jacobian-factor overloads) through host callbacks gives the
+    same ghosts, velocity and Jacobian as the device-expressible rules -- bit for bit."""
+    mesh = pda.create_full_mesh([30, 26], [-5, 5, -5, 5], 3)
+    dirich = np.array([0.00001, 0.004, 0.001])
+
+    def make(kind):
+        p = pda.create_problem(mesh, pda.Swe2d.CustomBCs, R.FirstOrder)
+        if kind == "device":
+            p.setBC(0, pda.BC.Dirichlet, dirich)
+            for s in (1, 2, 3):
+                p.setBC(s, pda.BC.HomogNeumann)
+            return p
+
+        def g_dirichlet(row_id, grow, x, y, U, ndpc, width, out):
+            out[:3] = dirich
+
+        def f_dirichlet(grow, x, y, ndpc, fac):
+            fac[:] = 0.0
+
+        def g_neumann(row_id, grow, x, y, U, ndpc, width, out):
+            c = grow[0] * ndpc
+            out[:3] = U[c:c + 3]
+
+        def f_neumann(grow, x, y, ndpc, fac):
+            fac[:] = 1.0
+        p.setBCFunctor(0, g_dirichlet, f_dirichlet)
+        for s in (1, 2, 3):
+            p.setBCFunctor(s, g_neumann, f_neumann)
+        return p
+    pd_, ph = make("device"), make("host")
+    U = perturbed(pd_)
+    Vd, Vh = pd_.createRightHandSide(), ph.createRightHandSide()
+    Jd, Jh = pd_.createJacobian(), ph.createJacobian()
+    pd_.rightHandSideAndJacobian(U, 0.0, Vd, Jd)
+    ph.rightHandSideAndJacobian(U, 0.0, Vh, Jh)
+    for s in range(4):
+        assert np.array_equal(pd_.viewGhost(s), ph.viewGhost(s)), s
+    assert np.array_equal(Vd, Vh)
+    assert np.array_equal(Jd.data, Jh.data)
+    V2 = ph.createRightHandSide()
+    ph.rightHandSide(U, 0.0, V2)
+    assert np.array_equal(V2, Vd)
