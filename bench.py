@@ -195,6 +195,30 @@ def run_reference_arm(args):
     print(json.dumps(line), flush=True)
 
 
+def ref_jacobian_leg(n2_cpu=512, target_s=6.0):
+    """the UNMODIFIED reference (OpenMP build) on cfg 2's problem at a bounded size: 2D Euler Riemann WENO5
+    velocity+Jacobian, stored nnz per second on the host cores"""
+    from refdrv import RefProblem, have_ref
+    import pressiodemoapps as pda
+    if not have_ref(omp=True):
+        return {"unavailable": "oracle/_ref/libpda_ref_omp.so did not travel with the snapshot"}
+    import shutil
+    d = tempfile.mkdtemp(prefix="bench_mesh2d_")
+    try:
+        mesh = pda.create_full_mesh([n2_cpu, n2_cpu], [0, 1, 0, 1], 7)
+        mesh.write(d)
+        r = RefProblem(d, "euler2d", 4, 2, omp=True)
+        U = r.initialCondition()
+        t1 = r.time_jacobian(U, 0.0, 1, 1)
+        reps = int(max(2, min(100, target_s / max(t1, 1e-6))))
+        sec = r.time_jacobian(U, 0.0, 0, reps)
+        return dict(value=r.nnz / sec, unit="nnz/s", cores=r.num_threads(), kind="reference",
+                    sample="%dx%d 2D Euler Riemann WENO5 velocity+Jacobian (unmodified reference, OpenMP), %d evals, "
+                           "%.3f s/eval, nnz %d" % (n2_cpu, n2_cpu, reps, sec, r.nnz))
+    finally:
+        shutil.rmtree(d, ignore_errors=True)
+
+
 # ------------------------------------------------------------------------------------------------ B200 arm
 def jacobian_leg(torch, pda, dev, n2=2048, steps=3, warmup=1):
     """cfg 2: 2D Euler Riemann WENO5 n2^2 full mesh, velocity + Jacobian on one GPU -> stored nnz per second"""
@@ -406,6 +430,11 @@ def run_b200_arm(args):
             torch.cuda.empty_cache()
             try:
                 line["jacobian"] = jacobian_leg(torch, pda, local_rank, n2=args.n2)
+                if not args.no_cpu:
+                    try:
+                        line["jacobian"]["cpu_baseline"] = ref_jacobian_leg()
+                    except Exception as e:
+                        line["jacobian"]["cpu_baseline"] = {"unavailable": str(e)}
             except Exception as e:
                 line["jacobian"] = {"error": str(e)}
         if world == 1 and not args.no_configs:
