@@ -510,6 +510,7 @@ def test_custom_bcs_host_functors_equal_device_rules():
         assert np.array_equal(pd_.viewGhost(s), ph.viewGhost(s)), s
     assert np.array_equal(Vd, Vh)
     assert np.array_equal(Jd.data, Jh.data)
-    V2 = ph.createRightHandSide()
-    ph.rightHandSide(U, 0.0, V2)
-    assert np.array_equal(V2, Vd)
+    V2, V3 = ph.createRightHandSide(), pd_.createRightHandSide()
+    ph.rightHandSide(U, 0.0, V2)      # velocity-only path (other inner-cell kernel than the Jacobian path)
+    pd_.rightHandSide(U, 0.0, V3)
+    assert np.array_equal(V2, V3)
