@@ -10,6 +10,7 @@
 
 #include <type_traits>
 
+#include "fastmath.cuh"
 #include "physics.cuh"
 
 namespace pda {
@@ -121,13 +122,20 @@ PDA_DEVFN void axisVelocity(const Phys& phys, const int32_t* __restrict__ row, c
       const int side = (p < h) ? sideMinus<AX>() : sidePlus<AX>();
       q[p] = stencilVal<N, NEARBD>(U, cells[p], gv, nbRow, side, layer, d);
     }
-    Recon<S>::face(q, uLn[d], uLp[d]);
-    Recon<S>::face(q + 1, uRn[d], uRp[d]);
+    // inner rows: division-free leaf arithmetic (fastmath.cuh); near-boundary rows (< 1 % of the cells, ghost states
+    // in the stencil) keep the reference's operation order
+    if constexpr (NEARBD) { Recon<S>::face(q, uLn[d], uLp[d]); Recon<S>::face(q + 1, uRn[d], uRp[d]); }
+    else { reconFaceFast<S>(q, uLn[d], uLp[d]); reconFaceFast<S>(q + 1, uRn[d], uRp[d]); }
     if constexpr (PhysTraits<Phys>::hasDiffusion) dterm[d] = phys.dD[AX] * (q[h + 1] - 2.0 * q[h] + q[h - 1]);
   }
   double FL[N], FR[N];
-  phys.template flux<AX>(uLn, uLp, FL);
-  phys.template flux<AX>(uRn, uRp, FR);
+  if constexpr (NEARBD) {
+    phys.template flux<AX>(uLn, uLp, FL);
+    phys.template flux<AX>(uRn, uRp, FR);
+  } else {
+    faceFlux2d<Phys, AX>(phys, uLn, uLp, FL);
+    faceFlux2d<Phys, AX>(phys, uRn, uRp, FR);
+  }
 #pragma unroll
   for (int d = 0; d < N; ++d) {
     v[d] += hInv * (FL[d] - FR[d]);
