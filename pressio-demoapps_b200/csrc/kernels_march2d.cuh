@@ -50,7 +50,7 @@ k_velocity_march2d(Phys phys, LatticeDesc L, Deltas dl, const double* __restrict
 
   auto rowPtr = [&](int r) -> const double* {
     int sr;
-    if (L.slab) sr = r + L.haloPlanes;
+    if (L.slab) sr = max(r + L.haloPlanes, 0);   // the ghost step's lowest row is loaded but never used
     else if (L.per[1]) { sr = r % ny; if (sr < 0) sr += ny; }
     else sr = (r < 0) ? 0 : (r >= ny ? ny - 1 : r);
     return U + ((int64_t)sr * nx + xc) * N;
@@ -67,19 +67,36 @@ k_velocity_march2d(Phys phys, LatticeDesc L, Deltas dl, const double* __restrict
     faceFlux2d<Phys, 1>(phys, uN, uP, F);
   };
 
+  // the march starts one row early ("ghost" step: only the y face below the first row), so that EVERY y face comes
+  // from the same code -> a row's result does not depend on where chunks / slabs are cut (bit-exact decompositions)
   double q[R][N];
 #pragma unroll
-  for (int i = 0; i < R; ++i) loadCell<N>(rowPtr(j0 - h + i), q[i]);
+  for (int i = 0; i < R; ++i) loadCell<N>(rowPtr(j0 - 1 - h + i), q[i]);
   double FyB[N];
-  yFace(q, FyB);
+#pragma unroll
+  for (int d = 0; d < N; ++d) FyB[d] = 0.0;
 
-  for (int j = j0; j < j1; ++j) {
+  for (int j = j0 - 1; j < j1; ++j) {
+    const bool ghost = (j < j0);
     double nxt[N];
     const bool more = (j + 1 < j1);
     if (more) loadCell<N>(rowPtr(j + 1 + h), nxt);   // lands while this row is computed
     // ---- front y face (j+1/2): rows j-h+1 .. j+h
     double FyF[N];
     yFace(q + 1, FyF);
+    if (ghost) {
+#pragma unroll
+      for (int d = 0; d < N; ++d) FyB[d] = FyF[d];
+#pragma unroll
+      for (int i = 0; i < R - 1; ++i)
+#pragma unroll
+        for (int d = 0; d < N; ++d) q[i][d] = q[i + 1][d];
+      if (more) {
+#pragma unroll
+        for (int d = 0; d < N; ++d) q[R - 1][d] = nxt[d];
+      }
+      continue;
+    }
     // ---- x left face of this lane's cell from the neighbouring lanes' row-j values
     double Fx[N];
     {

@@ -514,3 +514,30 @@ def test_custom_bcs_host_functors_equal_device_rules():
     ph.rightHandSide(U, 0.0, V2)      # velocity-only path (other inner-cell kernel than the Jacobian path)
     pd_.rightHandSide(U, 0.0, V3)
     assert np.array_equal(V2, V3)
+
+
+@pytest.mark.parametrize("nranks,n,recon,sten", [(2, (70, 48), "Weno5", 7), (3, (33, 60), "Weno3", 5), (4, (40, 32), "FirstOrder", 3)])
+def test_slab_decomposition_2d_equals_full(nranks, n, recon, sten):
+    """2D y-slabs (send/recv layout: [halo rows | owned rows | halo rows]) through the y-marching kernel reproduce the
+    full-mesh velocity bit for bit"""
+    import torch
+    scheme = getattr(R, recon)
+    mesh = pda.create_full_mesh(list(n), [-1, 1, -1, 1], sten, ("x", "y"))
+    full = pda.create_problem(mesh, pda.Euler2d.PeriodicSmooth, scheme)
+    U = perturbed(full)
+    Vfull = full.createRightHandSide()
+    full.rightHandSide(U, 0.0, Vfull)
+    ny, pd = n[1], n[0] * 4
+    Ug = torch.from_numpy(U).cuda().reshape(ny, pd)
+    st = torch.cuda.current_stream().cuda_stream
+    for r in range(nranks):
+        p = pda.create_problem_slab(mesh, pda.Euler2d.PeriodicSmooth, scheme, r, nranks)
+        k0, k1, h, pdofs = p.slabExtent()
+        assert pdofs == pd and h == (sten - 1) // 2
+        rows = [(k % ny) for k in range(k0 - h, k1 + h)]
+        Ul = Ug[rows].contiguous().reshape(-1)
+        Vl = torch.zeros((k1 - k0) * pd, dtype=torch.float64, device="cuda")
+        p.slabVelocityInteriorDevice(Ul.data_ptr(), 0.0, Vl.data_ptr(), st)
+        p.slabVelocityBoundaryDevice(Ul.data_ptr(), 0.0, Vl.data_ptr(), st)
+        torch.cuda.synchronize()
+        assert np.array_equal(Vl.cpu().numpy(), Vfull[k0 * pd:k1 * pd]), r
