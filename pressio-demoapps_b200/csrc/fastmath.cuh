@@ -43,14 +43,12 @@ PDA_DEVFN double sqrtFast(double x) {
   return (x == 0.0) ? 0.0 : s;   // x == 0: the seed is inf and the chain NaN; x < 0 stays NaN like sqrt()
 }
 
-// sqrtFast for arguments that may be arbitrarily small (|v_roe|^2 of gas almost at rest: far from a blast the
-// velocities are numerical dust, and their squares reach the denormal range where the ftz seed is inf).  Tiny
-// arguments are scaled by an exact power of four around the Newton chain; still branch-free.
+// sqrt(k) for the wave speed smax = sqrt(|v_roe|^2) + a, where k may be arbitrarily small (gas almost at rest: far
+// from a blast the velocities are numerical dust and their squares reach the denormal range, where the ftz seed of
+// sqrtFast is inf and the Newton chain NaN).  Below 1e-200 the square root is < 1e-100 and vanishes next to the sound
+// speed a in double precision, so such arguments are treated as zero: one compare + select, still branch-free.
 PDA_DEVFN double sqrtFastTiny(double x) {
-  const bool tiny = x < 1.0e-200;
-  const double xs = tiny ? x * 0x1p+400 : x;
-  const double s = sqrtFast(xs);
-  return tiny ? s * 0x1p-200 : s;
+  return sqrtFast((x < 1.0e-200) ? 0.0 : x);
 }
 
 // ---------------------------------------------------------------------------------------------------------------

@@ -114,7 +114,7 @@ struct Tile3dSmem {
 // All shared-memory tiles are AoS ([..][cell][dof], 40-byte cells): a lane stride of 40 bytes is conflict-free for
 // 8-byte accesses, the dof index becomes an immediate offset, and a row of the plane tile is ONE contiguous range
 // of the AoS state in HBM -> one cp.async.bulk per row (two where the periodic wrap splits it).
-template <int S, int TY>
+template <int S, int TY, bool PEER>
 __global__ void __launch_bounds__(32 * (TY + 1), (TY <= 7 ? 2 : 1))
 k_euler3d_velocity_tiled(double gamma, LatticeDesc L, Deltas dl, const double* __restrict__ U, double* __restrict__ V,
                          int LZ, int useTma) {
@@ -138,7 +138,7 @@ k_euler3d_velocity_tiled(double gamma, LatticeDesc L, Deltas dl, const double* _
   const int x0 = blockIdx.x * TX, y0 = blockIdx.y * TY;
   // peer mode: z chunks run in reverse order, so the chunk that needs the upper halo (at its END) starts first and
   // the one that needs the lower halo (at its START) last: the neighbours' pushes land while interior work runs
-  const int zc = (L.slab == 2) ? (int)(gridDim.z - 1 - blockIdx.z) : (int)blockIdx.z;
+  const int zc = PEER ? (int)(gridDim.z - 1 - blockIdx.z) : (int)blockIdx.z;
   const int k0 = L.planeBegin + zc * LZ;
   const int k1 = min(k0 + LZ, L.planeEnd);
   const int nx = L.n[0], ny = L.n[1], nz = L.n[2];
@@ -150,7 +150,7 @@ k_euler3d_velocity_tiled(double gamma, LatticeDesc L, Deltas dl, const double* _
   // base of plane p for the z-column fetches; peer mode: planes outside [0,nz) come from the halo buffers, once the
   // neighbour's flag carries this evaluation's epoch (lane 0 polls with acquire.sys, the warp follows)
   auto planeBase = [&](int p) -> const double* {
-    if (L.slab == 2) {
+    if constexpr (PEER) {
       if (p >= 0 && p < nz) return U + (int64_t)p * planeStride;
       const uint32_t* flag = (p < 0) ? L.flagLo : L.flagHi;
       if (tx == 0) {
@@ -347,11 +347,13 @@ void launchLattice3dTiled(const Phys& phys, const dev::LatticeDesc& L, const dev
   constexpr int TY = 7;   // 7 cell warps + 1 edge warp = 256 threads, 2 CTAs per SM at 128 registers
   using T = dev::Tile3dSmem<S, TY>;
   constexpr size_t smem = T::template bytes<5>();
-  auto kern = dev::k_euler3d_velocity_tiled<S, TY>;
+  auto kern = (L.slab == 2) ? dev::k_euler3d_velocity_tiled<S, TY, true> : dev::k_euler3d_velocity_tiled<S, TY, false>;
   static bool configured = false;
   if (!configured) {
-    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+    for (auto k : {dev::k_euler3d_velocity_tiled<S, TY, true>, dev::k_euler3d_velocity_tiled<S, TY, false>}) {
+      cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      cudaFuncSetAttribute(k, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+    }
     configured = true;
   }
   const int planes = L.planeEnd - L.planeBegin;
