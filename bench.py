@@ -219,6 +219,56 @@ def ref_jacobian_leg(n2_cpu=512, target_s=6.0):
         shutil.rmtree(d, ignore_errors=True)
 
 
+class numa_local:
+    """Context manager: while active, the calling THREAD runs on the CPUs of the NUMA node its GPU hangs off (sysfs
+    local_cpulist of the GPU's PCI function), so that pinned host buffers allocated and first-touched inside are
+    placed on that node and host<->device copies do not cross the socket interconnect.  The mask is restored on exit
+    (the OpenMP legs of the CPU baseline must see all cores).  `info` describes the binding for the JSON line."""
+
+    def __init__(self, torch, device_index, enabled=True):
+        self.info = None
+        self.saved = None
+        self.cpus = None
+        if not enabled:
+            return
+        try:
+            pr = torch.cuda.get_device_properties(device_index)
+            bdf = "%04x:%02x:%02x.0" % (pr.pci_domain_id, pr.pci_bus_id, pr.pci_device_id)
+            base = "/sys/bus/pci/devices/" + bdf
+            with open(base + "/local_cpulist") as f:
+                spec = f.read().strip()
+            cpus = set()
+            for part in spec.split(","):
+                if "-" in part:
+                    lo, hi = part.split("-")
+                    cpus.update(range(int(lo), int(hi) + 1))
+                elif part:
+                    cpus.add(int(part))
+            cpus &= os.sched_getaffinity(0)
+            node = None
+            try:
+                with open(base + "/numa_node") as f:
+                    node = int(f.read().strip())
+            except Exception:
+                pass
+            if cpus:
+                self.cpus = cpus
+                self.info = {"pci": bdf, "numa_node": node, "cpus": len(cpus)}
+        except Exception:
+            pass
+
+    def __enter__(self):
+        if self.cpus:
+            self.saved = os.sched_getaffinity(0)
+            os.sched_setaffinity(0, self.cpus)
+        return self
+
+    def __exit__(self, *exc):
+        if self.saved is not None:
+            os.sched_setaffinity(0, self.saved)
+        return False
+
+
 # ------------------------------------------------------------------------------------------------ B200 arm
 def jacobian_leg(torch, pda, dev, n2=2048, steps=3, warmup=1):
     """cfg 2: 2D Euler Riemann WENO5 n2^2 full mesh, velocity + Jacobian on one GPU -> stored nnz per second"""
@@ -266,6 +316,8 @@ def run_b200_arm(args):
     if pda.device_count() < 1:
         raise SystemExit("bench.py: no CUDA device (the engine has no CPU fallback)")
     torch.cuda.set_device(local_rank)
+    numa_ctx = numa_local(torch, local_rank, enabled=not args.no_numa_bind)
+    numa = numa_ctx.info
     dist = None
     if world > 1:
         import torch.distributed as dist
@@ -297,8 +349,9 @@ def run_b200_arm(args):
 
     if world == 1:
         p = pda.create_problem(mesh, pda.Euler3d.PeriodicSmooth, R.Weno5, device=local_rank)
-        hU = torch.empty(p.totalDofStencilMesh(), dtype=torch.float64, pin_memory=True)
-        hV = torch.empty(p.totalDofSampleMesh(), dtype=torch.float64, pin_memory=True)
+        with numa_ctx:   # pinned buffers on the GPU's NUMA node
+            hU = torch.empty(p.totalDofStencilMesh(), dtype=torch.float64, pin_memory=True).zero_()
+            hV = torch.empty(p.totalDofSampleMesh(), dtype=torch.float64, pin_memory=True).zero_()
         hU.numpy()[:] = p.initialCondition()
         dU = hU.cuda()
         dV = torch.empty_like(dU)
@@ -313,8 +366,9 @@ def run_b200_arm(args):
         p = pda.create_problem_slab(mesh, pda.Euler3d.PeriodicSmooth, R.Weno5, rank, world, device=local_rank)
         k0, k1, h, pd = p.slabExtent()
         nown = (k1 - k0) * pd
-        hU = torch.empty(nown, dtype=torch.float64, pin_memory=True)
-        hV = torch.empty(nown, dtype=torch.float64, pin_memory=True)
+        with numa_ctx:   # pinned buffers on the GPU's NUMA node
+            hU = torch.empty(nown, dtype=torch.float64, pin_memory=True).zero_()
+            hV = torch.empty(nown, dtype=torch.float64, pin_memory=True).zero_()
         hU.numpy()[:] = p.slabInitialCondition()
         dUl = torch.empty(nown + 2 * h * pd, dtype=torch.float64, device="cuda")
         dUl[h * pd: h * pd + nown].copy_(hU)
@@ -406,7 +460,8 @@ def run_b200_arm(args):
                            "partition": ("z-slabs x%d, halo 3 planes/side: %s" % (world, "copy-engine peer pushes over NVLink + "
                                          "flags, fused into one kernel launch (no collective)" if args.halo == "peer" else
                                          "NCCL send/recv, interior/boundary launches")) if world > 1 else "single GPU",
-                           "l2": "inputs larger than L2 (state %.2f GB per GPU)" % (ncells * 40e-9 / world)},
+                           "l2": "inputs larger than L2 (state %.2f GB per GPU)" % (ncells * 40e-9 / world),
+                           "host_numa_binding": numa},
                 "gpu_launches": int(launches), "clocks": clocks, "e2e": e2e,
                 "roofline": {"bound": "hbm", "achieved": ach_gbs, "peak": hbm_peak, "unit": "GB/s",
                              "frac": ach_gbs / hbm_peak,
@@ -461,6 +516,7 @@ def main():
     ap.add_argument("--n2", type=int, default=2048, help="cells per axis of the 2D Jacobian mesh (BASELINE: 2048)")
     ap.add_argument("--halo", default="peer", choices=["peer", "nccl"],
                     help="N>1 halo exchange: peer-memory pushes fused with the kernel (default) or NCCL send/recv")
+    ap.add_argument("--no-numa-bind", action="store_true", help="do not pin the process to its GPU's NUMA node")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-jacobian", action="store_true")
     ap.add_argument("--no-configs", action="store_true", help="skip the cfg 1-4 legs (tools/bench_configs.py)")
