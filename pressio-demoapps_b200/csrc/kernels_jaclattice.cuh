@@ -50,7 +50,7 @@ struct JacLat2d {
   static constexpr int oV = oSelf + T * T * (STAGE ? CSTRIDE : SELF);   // [T*T][N] x-phase part of the velocity
   static constexpr size_t smemBytes = (size_t)(oV + T * T * N) * sizeof(double);
   // small systems in direct mode fit two CTAs per SM in 128 registers; Euler (96 gradient registers) does not
-  static constexpr int MIN_CTAS = 1;
+  static constexpr int MIN_CTAS = (N == 4) ? 2 : 1;
 };
 
 struct JacLatTables {
