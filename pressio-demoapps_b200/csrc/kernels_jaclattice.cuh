@@ -102,7 +102,7 @@ PDA_DEVFN void jacLatLine(const Phys& phys, const LatticeDesc& L, const JacLatTa
 #pragma unroll
   for (int m = 0; m < S - 1; ++m) {
     int c = a - h + m;
-    if (perA) c = (c < 0) ? c + nA : (c >= nA ? c - nA : c);
+    if (perA) { c %= nA; if (c < 0) c += nA; }   // idle lanes of a ragged tile on a small mesh may wrap twice
     else c = (c < 0) ? 0 : (c >= nA ? nA - 1 : c);
     const int64_t gid = (AX == 0) ? (int64_t)o * nx + c : (int64_t)c * nx + o;
     loadCell<N>(U + gid * N, q[m]);

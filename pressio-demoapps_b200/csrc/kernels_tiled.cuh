@@ -38,8 +38,14 @@ PDA_DEVFN void cpAsync8(void* smemDst, const void* gmemSrc) {
 PDA_DEVFN void cpAsyncCommit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
 PDA_DEVFN void cpAsyncWaitAll() { asm volatile("cp.async.wait_group 0;\n" ::: "memory"); }
 
-PDA_DEVFN int32_t fixIdx(int32_t idx, int32_t n, int32_t periodic) {
+PDA_DEVFN int32_t fixIdx(int32_t idx, int32_t n, int32_t periodic) {   // |idx| may exceed n by less than n
   if (periodic) return idx < 0 ? idx + n : (idx >= n ? idx - n : idx);
+  return idx < 0 ? 0 : (idx >= n ? n - 1 : idx);
+}
+// x/y halo of a ragged tile on a small periodic mesh may wrap more than once (the values only feed lanes that do not
+// store, but the address must stay inside the allocation)
+PDA_DEVFN int32_t wrapIdx(int32_t idx, int32_t n, int32_t periodic) {
+  if (periodic) { idx %= n; return idx < 0 ? idx + n : idx; }
   return idx < 0 ? 0 : (idx >= n ? n - 1 : idx);
 }
 
@@ -209,7 +215,7 @@ k_euler3d_velocity_tiled(double gamma, LatticeDesc L, Deltas dl, const double* _
       if (tx == 0) mbarArriveExpectTx(bar, total);
       __syncwarp();
       if (tx < PY) {
-        const int gy = fixIdx(y0 - h + tx, ny, L.per[1]);
+        const int gy = wrapIdx(y0 - h + tx, ny, L.per[1]);
         for (int sI = 0; sI < nseg; ++sI)
           bulkCopyG2S(&smem[oP + (tx * PX + segD[sI]) * N], src + (int64_t)gy * rowStride + (int64_t)segG[sI] * N,
                       (unsigned)segL[sI] * (N * 8), bar);
@@ -220,8 +226,8 @@ k_euler3d_velocity_tiled(double gamma, LatticeDesc L, Deltas dl, const double* _
         const int rem = e - r * ((TX + 2 * h) * N);
         const int cc = rem / N;
         const int d = rem - cc * N;
-        const int gy = fixIdx(y0 - h + r, ny, L.per[1]);
-        const int gx = fixIdx(x0 - h + cc, nx, L.per[0]);
+        const int gy = wrapIdx(y0 - h + r, ny, L.per[1]);
+        const int gx = wrapIdx(x0 - h + cc, nx, L.per[0]);
         cpAsync8(&smem[oP + (r * PX + (HX - h) + cc) * N + d], src + (int64_t)gy * rowStride + (int64_t)gx * N + d);
       }
       cpAsyncCommit();
