@@ -110,7 +110,7 @@ struct Tile3dSmem {
   static constexpr int PX = TX + 2 * HX, PY = TY + 2 * h;
   static constexpr int R = 2 * h + 1;              // z ring: planes k-h+1 .. k+h in use, k+h+1 in flight
   template <int N> static constexpr size_t bytes() {
-    return sizeof(double) * (size_t)(N * PY * PX + R * N * TY * TX + N * (TY + 1) * TX + N * TY + 2);
+    return sizeof(double) * (size_t)(N * PY * PX + R * N * TY * TX + 2 * (N * (TY + 1) * TX + N * TY) + 2);
   }
 };
 
@@ -130,9 +130,11 @@ k_euler3d_velocity_tiled(double gamma, LatticeDesc L, Deltas dl, const double* _
   constexpr int NT = TX * (TY + 1);
   constexpr int oP = 0;                        // [PY][PX][N]      current plane with x/y halo
   constexpr int oZ = oP + N * PY * PX;         // [R][TY][TX][N]   thread-private z columns
-  constexpr int oFy = oZ + R * N * TY * TX;    // [TY+1][TX][N]    y-face fluxes
-  constexpr int oXe = oFy + N * (TY + 1) * TX; // [TY][N]          tile-edge x-face fluxes
-  constexpr int oBar = oXe + N * TY;           // mbarrier (8 bytes)
+  // flux exchange buffers, DOUBLE-BUFFERED by step parity: a warp may run a whole step ahead of the neighbour that still
+  // reads its previous flux (only one barrier per step), so consecutive steps must not share a buffer
+  constexpr int kFx = N * (TY + 1) * TX + N * TY;  // one exchange buffer: [TY+1][TX][N] y-face + [TY][N] tile-edge x-face fluxes
+  constexpr int oFy0 = oZ + R * N * TY * TX;
+  constexpr int oBar = oFy0 + 2 * kFx;         // mbarrier (8 bytes)
   constexpr int slotStride = N * TY * TX;
 
   extern __shared__ __align__(16) double smem[];
@@ -256,6 +258,8 @@ k_euler3d_velocity_tiled(double gamma, LatticeDesc L, Deltas dl, const double* _
 
   for (int k = k0 - 1; k < k1; ++k) {
     const bool ghost = (k < k0);
+    const int oFy = oFy0 + (k & 1) * kFx;
+    const int oXe = oFy + N * (TY + 1) * TX;
     if (!edgeWarp) {
       cpAsyncWaitAll();   // this thread's column cell of plane k+h (fetched one step ago) has landed
       // prefetch the plane the NEXT z face needs into the free slot (slot0 + 2h) mod R
