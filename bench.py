@@ -480,9 +480,38 @@ def run_b200_arm(args):
                 line["cpu_reference_weno3"] = ref_weno3_leg(128, 5.0)
             except Exception as e:   # the compiled reference is optional on the GPU box
                 line["cpu_reference_weno3"] = {"unavailable": str(e)}
-        if world == 1 and not args.no_jacobian:
+        if world == 1:
             del dU, dV
             torch.cuda.empty_cache()
+            # the reference-pinned twin of the headline: 3D Euler WENO3 (the reference implements it; its 3D WENO5
+            # does not exist), same mesh size, device resident; the unmodified reference's CPU number sits beside it
+            try:
+                mesh3 = pda.create_full_mesh([n, n, n], [-1, 1, -1, 1, -1, 1], 5, ("x", "y", "z"))
+                p3 = pda.create_problem(mesh3, pda.Euler3d.PeriodicSmooth, R.Weno3, device=local_rank)
+                U3 = torch.from_numpy(p3.initialCondition()).cuda()
+                V3 = torch.empty_like(U3)
+                for _ in range(3):
+                    p3.rightHandSideDevice(U3.data_ptr(), 0.0, V3.data_ptr(), st)
+                torch.cuda.synchronize()
+                a3, b3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                a3.record()
+                for _ in range(K):
+                    p3.rightHandSideDevice(U3.data_ptr(), 0.0, V3.data_ptr(), st)
+                b3.record()
+                torch.cuda.synchronize()
+                ms3 = a3.elapsed_time(b3) / K
+                fl3 = 3 * (5 * 56 + 116) + 45   # WENO3 ~56 flop per (face, dof)
+                line["weno3_reference_pinned"] = {
+                    "workload": "3D Euler PeriodicSmooth WENO3 %d^3 velocity" % n, "ms_per_step": ms3,
+                    "value": ncells / (ms3 * 1e-3), "unit": UNIT, "flops_per_cell": fl3,
+                    "fp64_frac": ncells * fl3 / (ms3 * 1e-3) * 1e-12 / fp64_peak if fp64_peak else None,
+                    "hbm_frac": ncells * BYTES_PER_CELL / (ms3 * 1e-3) * 1e-9 / hbm_peak,
+                    "cpu_reference": line.get("cpu_reference_weno3")}
+                del U3, V3, p3, mesh3
+                torch.cuda.empty_cache()
+            except Exception as e:
+                line["weno3_reference_pinned"] = {"error": str(e)}
+        if world == 1 and not args.no_jacobian:
             try:
                 line["jacobian"] = jacobian_leg(torch, pda, local_rank, n2=args.n2)
                 if not args.no_cpu:
