@@ -535,7 +535,26 @@ def run_b200_arm(args):
         dist.destroy_process_group()
 
 
+def ensure_built():
+    """the built libraries travel with the snapshot; on a fresh checkout (artefacts are git-ignored) build them once:
+    rank 0 runs __graft_entry__.build(), the other ranks wait for the files"""
+    lib = os.path.join(ROOT, "pressio-demoapps_b200", "lib", "libpda_b200.so")
+    ora = os.path.join(ROOT, "oracle", "_ref", "libpda_oracle_omp.so")
+    if os.path.exists(lib) and os.path.exists(ora):
+        return
+    if int(os.environ.get("LOCAL_RANK", "0")) == 0:
+        sys.path.insert(0, ROOT)
+        import __graft_entry__
+        __graft_entry__.build()
+    else:
+        t_end = time.time() + 900
+        while time.time() < t_end and not (os.path.exists(lib) and os.path.exists(ora)):
+            time.sleep(2.0)
+        time.sleep(2.0)
+
+
 def main():
+    ensure_built()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
