@@ -1,0 +1,205 @@
+// pda_b200_eigen.hpp -- the C++ shim of INTEGRATION.md as a real header: the public surface of the reference's
+// PublicProblemEigenMixinCpp (include/pressiodemoapps/adapter_cpp.hpp:59-264) and of load_cellcentered_uniform_mesh_eigen
+// (mesh.hpp:87-91) on top of the C-ABI include/pda_b200.h.  Needs Eigen 3.4 on the include path (the reference
+// vendors it under tpls/eigen3).  A user of the reference switches namespace `pressiodemoapps` -> `pressiodemoapps_b200`.
+#pragma once
+#include <Eigen/Core>
+#include <Eigen/Sparse>
+
+#include <stdexcept>
+#include <string>
+#include <unordered_map>
+#include <vector>
+
+#include "pda_b200.h"
+
+namespace pressiodemoapps_b200 {
+
+// enumerator order = the reference's (euler1d.hpp:64-69, euler2d.hpp:66-76, euler3d.hpp:65-68, swe2d.hpp:65-68, ...)
+enum class InviscidFluxReconstruction { FirstOrder = 0, Weno3 = 1, Weno5 = 2 };
+enum class Euler1d { PeriodicSmooth = 0, Sod, Lax, ShuOsher };
+enum class Euler2d { PeriodicSmooth = 0, KelvinHelmholtz, SedovFull, SedovSymmetry, Riemann, NormalShock,
+                     DoubleMachReflection, CrossShock, testingonlyneumann };
+enum class Euler3d { PeriodicSmooth = 0, SedovSymmetry };
+enum class Swe2d { SlipWall = 0, CustomBCs };
+enum class DiffusionReaction2d { ProblemA = 0, GrayScott };
+enum class AdvectionDiffusion2d { BurgersPeriodic = 0, BurgersOutflow };
+enum class AdvectionDiffusionReaction2d { ProblemA = 0 };
+enum class Advection1d { PeriodicLinear = 0 };
+enum class DiffusionReaction1d { ProblemA = 0 };
+
+namespace impl {
+inline void check(pda_status s) { if (s != PDA_OK) throw std::runtime_error(pda_last_error()); }
+template <class E> struct family_of;
+template <> struct family_of<Euler1d> { static constexpr int value = PDA_FAMILY_EULER1D; };
+template <> struct family_of<Euler2d> { static constexpr int value = PDA_FAMILY_EULER2D; };
+template <> struct family_of<Euler3d> { static constexpr int value = PDA_FAMILY_EULER3D; };
+template <> struct family_of<Swe2d> { static constexpr int value = PDA_FAMILY_SWE2D; };
+template <> struct family_of<DiffusionReaction2d> { static constexpr int value = PDA_FAMILY_DIFFUSION_REACTION2D; };
+template <> struct family_of<AdvectionDiffusion2d> { static constexpr int value = PDA_FAMILY_ADVECTION_DIFFUSION2D; };
+template <> struct family_of<AdvectionDiffusionReaction2d> { static constexpr int value = PDA_FAMILY_ADVECTION_DIFFUSION_REACTION2D; };
+template <> struct family_of<Advection1d> { static constexpr int value = PDA_FAMILY_ADVECTION1D; };
+template <> struct family_of<DiffusionReaction1d> { static constexpr int value = PDA_FAMILY_DIFFUSION_REACTION1D; };
+}  // namespace impl
+
+// CellCenteredUniformMesh look-alike (impl/mesh_ccu.hpp:115-159)
+class Mesh {
+ public:
+  using scalar_type = double;
+  using index_t = int32_t;
+  using graph_t = Eigen::Matrix<int32_t, Eigen::Dynamic, Eigen::Dynamic, Eigen::RowMajor>;
+  explicit Mesh(const std::string& dir) { impl::check(pda_mesh_load(dir.c_str(), &h_)); }
+  Mesh(const Mesh&) = delete;
+  Mesh& operator=(const Mesh&) = delete;
+  Mesh(Mesh&& o) noexcept : h_(o.h_) { o.h_ = nullptr; }
+  ~Mesh() { if (h_) pda_mesh_free(h_); }
+  int dimensionality() const { return pda_mesh_dimensionality(h_); }
+  int stencilSize() const { return pda_mesh_stencil_size(h_); }
+  index_t stencilMeshSize() const { return pda_mesh_stencil_mesh_size(h_); }
+  index_t sampleMeshSize() const { return pda_mesh_sample_mesh_size(h_); }
+  index_t numCellsInner() const { return pda_mesh_num_cells_inner(h_); }
+  index_t numCellsNearBd() const { return pda_mesh_num_cells_near_bd(h_); }
+  bool isFullyPeriodic() const { return pda_mesh_is_fully_periodic(h_) != 0; }
+  double dx() const { return deltas_(0); }
+  double dy() const { return deltas_(1); }
+  double dz() const { return deltas_(2); }
+  double dxInv() const { return deltas_(3); }
+  double dyInv() const { return deltas_(4); }
+  double dzInv() const { return deltas_(5); }
+  graph_t graph() const {
+    graph_t g(sampleMeshSize(), pda_mesh_graph_cols(h_));
+    impl::check(pda_mesh_graph(h_, g.data()));
+    return g;
+  }
+  Eigen::VectorXd viewX() const { return coord_(0); }
+  Eigen::VectorXd viewY() const { return coord_(1); }
+  Eigen::VectorXd viewZ() const { return coord_(2); }
+  std::vector<index_t> graphRowsOfCellsAwayFromBd() const {
+    std::vector<index_t> r((size_t)numCellsInner());
+    if (!r.empty()) impl::check(pda_mesh_rows_inner(h_, r.data()));
+    return r;
+  }
+  std::vector<index_t> graphRowsOfCellsNearBd() const {
+    std::vector<index_t> r((size_t)numCellsNearBd());
+    if (!r.empty()) impl::check(pda_mesh_rows_near_bd(h_, r.data()));
+    return r;
+  }
+  pda_mesh handle() const { return h_; }
+
+ private:
+  double deltas_(int i) const {
+    double d[3], di[3];
+    impl::check(pda_mesh_deltas(h_, d, di));
+    return i < 3 ? d[i] : di[i - 3];
+  }
+  Eigen::VectorXd coord_(int axis) const {
+    const auto n = stencilMeshSize();
+    Eigen::VectorXd x(n), y(n), z(n);
+    impl::check(pda_mesh_coordinates(h_, x.data(), y.data(), z.data()));
+    return axis == 0 ? x : (axis == 1 ? y : z);
+  }
+  pda_mesh h_ = nullptr;
+};
+
+inline Mesh load_cellcentered_uniform_mesh_eigen(const std::string& dir) { return Mesh(dir); }
+
+// PublicProblemEigenMixinCpp look-alike (adapter_cpp.hpp:59-264).  The mesh must outlive the problem, like in the
+// reference (std::reference_wrapper, euler_2d_prob_class.hpp:1277).
+class Problem {
+ public:
+  using scalar_type = double;
+  using independent_variable_type = double;
+  using state_type = Eigen::VectorXd;
+  using rhs_type = Eigen::VectorXd;
+  using right_hand_side_type = Eigen::VectorXd;
+  using jacobian_type = Eigen::SparseMatrix<double, Eigen::RowMajor, int32_t>;
+
+  Problem(const Mesh& m, int family, int id, int recon, int icFlag,
+          const std::unordered_map<std::string, double>& params, int device) {
+    std::vector<const char*> names;
+    std::vector<double> vals;
+    for (auto& kv : params) { names.push_back(kv.first.c_str()); vals.push_back(kv.second); }
+    impl::check(pda_problem_create(m.handle(), family, id, recon, icFlag, (int)names.size(),
+                                   names.empty() ? nullptr : names.data(), vals.empty() ? nullptr : vals.data(), device, &h_));
+  }
+  Problem(const Problem&) = delete;
+  Problem& operator=(const Problem&) = delete;
+  Problem(Problem&& o) noexcept : h_(o.h_) { o.h_ = nullptr; }
+  ~Problem() { if (h_) pda_problem_free(h_); }
+
+  int numDofPerCell() const { return pda_problem_num_dof_per_cell(h_); }
+  int32_t totalDofSampleMesh() const { return pda_problem_total_dof_sample_mesh(h_); }
+  int32_t totalDofStencilMesh() const { return pda_problem_total_dof_stencil_mesh(h_); }
+  double queryParameter(const std::string& name) const {
+    double v;
+    impl::check(pda_problem_query_parameter(h_, name.c_str(), &v));
+    return v;
+  }
+  double gamma() const { return queryParameter("gamma"); }
+  double gravity() const { return queryParameter("gravity"); }
+  double coriolis() const { return queryParameter("coriolis"); }
+
+  state_type initialCondition() const {
+    state_type u(totalDofStencilMesh());
+    impl::check(pda_problem_initial_condition(h_, u.data()));
+    return u;
+  }
+  state_type createState() const { return state_type::Zero(totalDofStencilMesh()); }
+  rhs_type createRightHandSide() const { return rhs_type::Zero(totalDofSampleMesh()); }
+  rhs_type createRhs() const { return createRightHandSide(); }
+  jacobian_type createJacobian() const {   // fixed pattern, explicit zeros kept, like the reference
+    int64_t nnz = 0;
+    impl::check(pda_problem_jacobian_nnz(h_, &nnz));
+    jacobian_type J(totalDofSampleMesh(), totalDofStencilMesh());
+    J.resizeNonZeros(nnz);
+    impl::check(pda_problem_jacobian_pattern(h_, J.outerIndexPtr(), J.innerIndexPtr()));
+    std::fill(J.valuePtr(), J.valuePtr() + nnz, 0.0);
+    return J;
+  }
+  template <class Operand>
+  Operand createApplyJacobianResult(const Operand& B) const { return Operand::Zero(totalDofSampleMesh(), B.cols()); }
+  template <class Operand>
+  Operand createResultOfJacobianActionOn(const Operand& B) const { return createApplyJacobianResult(B); }
+
+  void rightHandSide(const state_type& U, double t, rhs_type& V) const {
+    impl::check(pda_problem_velocity_host(h_, U.data(), t, V.data()));
+  }
+  void rhs(const state_type& U, double t, rhs_type& V) const { rightHandSide(U, t, V); }
+  void operator()(const state_type& U, double t, rhs_type& V) const { rightHandSide(U, t, V); }
+  void rightHandSideAndJacobian(const state_type& U, double t, rhs_type& V, jacobian_type& J) const {
+    impl::check(pda_problem_velocity_and_jacobian_host(h_, U.data(), t, V.data(), J.valuePtr()));
+  }
+  void operator()(const state_type& U, double t, rhs_type& V, jacobian_type& J, bool computeJac) const {
+    if (computeJac) rightHandSideAndJacobian(U, t, V, J); else rightHandSide(U, t, V);
+  }
+  void jacobian(const state_type& U, double t, jacobian_type& J) const {
+    impl::check(pda_problem_velocity_and_jacobian_host(h_, U.data(), t, nullptr, J.valuePtr()));
+  }
+  template <class Operand>   // Eigen vector or matrix (col- or row-major)
+  void applyJacobian(const state_type& U, const Operand& B, double t, Operand& R) const {
+    impl::check(pda_problem_apply_jacobian_host(h_, U.data(), B.data(), (int)B.cols(),
+                                                Operand::IsRowMajor ? PDA_LAYOUT_ROW_MAJOR : PDA_LAYOUT_COL_MAJOR, t, R.data()));
+  }
+  // explicit time stepping with the state resident in HBM (no reference counterpart: its tests borrow pressio's steppers)
+  void advance(int stepper, state_type& U, double t0, double dt, int32_t nsteps) const {
+    impl::check(pda_problem_advance_host(h_, stepper, U.data(), t0, dt, nsteps));
+  }
+  pda_problem handle() const { return h_; }
+
+ private:
+  pda_problem h_ = nullptr;
+};
+
+// create_problem_eigen(mesh, <enum>, recon[, icFlag][, {name: value}])  (euler1d.hpp:82-99, euler2d.hpp:88-186, ...)
+template <class ProbEnum>
+Problem create_problem_eigen(const Mesh& m, ProbEnum e, InviscidFluxReconstruction r, int icFlag = 1,
+                             const std::unordered_map<std::string, double>& params = {}, int device = 0) {
+  return Problem(m, impl::family_of<ProbEnum>::value, static_cast<int>(e), static_cast<int>(r), icFlag, params, device);
+}
+template <class ProbEnum>
+Problem create_problem_eigen(const Mesh& m, ProbEnum e, InviscidFluxReconstruction r,
+                             const std::unordered_map<std::string, double>& params, int device = 0) {
+  return Problem(m, impl::family_of<ProbEnum>::value, static_cast<int>(e), static_cast<int>(r), 1, params, device);
+}
+
+}  // namespace pressiodemoapps_b200

@@ -199,3 +199,32 @@ def test_c_abi_demo_host_part(tmp_path):
     r = subprocess.run([exe], capture_output=True, text=True, timeout=120)
     assert r.returncode == 0, r.stdout + r.stderr
     assert "c_abi_demo ok" in r.stdout
+
+
+def _eigen_include():
+    for d in ("/root/reference/tpls/eigen3", "/usr/include/eigen3", "/usr/local/include/eigen3"):
+        if os.path.exists(os.path.join(d, "Eigen", "Core")):
+            return d
+    return None
+
+
+def test_cpp_eigen_shim_compiles_and_runs_host_part(tmp_path):
+    """include/pda_b200_eigen.hpp (the C++ shim of INTEGRATION.md: Mesh / Problem with the reference's public surface and
+    Eigen types) + examples/cpp_shim_demo.cc written like the reference's tests_cpp mains.  Needs Eigen (the reference
+    vendors it; absent on the GPU box -> skipped there)."""
+    import subprocess
+    eig = _eigen_include()
+    if eig is None:
+        pytest.skip("Eigen headers not available")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    lib = os.path.join(root, "pressio-demoapps_b200", "lib")
+    exe = os.path.join(str(tmp_path), "cpp_shim_demo")
+    r = subprocess.run(["g++", "-std=c++17", "-O1", "-Wall", "-I" + os.path.join(root, "include"), "-I" + eig,
+                        os.path.join(root, "examples", "cpp_shim_demo.cc"), "-L" + lib, "-lpda_b200", "-Wl,-rpath," + lib,
+                        "-o", exe], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr[-3000:]
+    mdir = os.path.join(str(tmp_path), "mesh")
+    pda.create_full_mesh([20, 20], [0, 1, 0, 1], 7).write(mdir)
+    r = subprocess.run([exe, mdir], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "dofs 1600 nnz 55808" in r.stdout and "cpp_shim_demo ok" in r.stdout
