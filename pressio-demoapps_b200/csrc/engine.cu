@@ -171,7 +171,7 @@ struct DeviceState {
   // J*B per cell (k_spmm_cells_rowmajor): per-cell CSR base / row length, lattice visiting order, transposed operands
   DevBuf<int32_t> dCellBase, dCellLen, dCellOrder;
   DevBuf<double> dBt, dRt;
-  bool spmmReady = false;
+  bool spmmReady = false, spmmFewReady = false;
   int32_t spmmMaxLen = 0;
   // lattice Jacobian kernel: per-cell CSR base and block-slot tables (indexed by gid)
   DevBuf<int32_t> latBase;
@@ -1525,9 +1525,28 @@ void Problem::applyJacobianDev(const double* dU, const double* dB, int ncols, in
     // row-major: B[r*ncols + c]; col-major: B[c*rows + r]
     const int64_t ldbRow = (layout == 1) ? ncols : 1, ldbCol = (layout == 1) ? 1 : nJc;
     const int64_t ldrRow = (layout == 1) ? ncols : 1, ldrCol = (layout == 1) ? 1 : nrows;
-    dev::k_spmm_rows_fewcols<<<gridFor((int64_t)nrows * 32, 256), 256, 0, st>>>(nrows, ds.dRowptr.p, ds.dColidx.p, ds.dJ.p, dB,
-                                                                              ncols, ldbRow, ldbCol, dR, ldrRow, ldrCol);
-    ++launches_;
+    if (!ds.spmmFewReady) { ds.dCellBase.upload(cellBase_); ds.dCellLen.upload(cellLen_); ds.spmmFewReady = true; }
+    const int32_t ncells = mesh_->nSample;
+    const unsigned grid = (unsigned)gridFor((int64_t)ncells * 32, 256);
+    auto launch = [&](auto nTag) {
+      constexpr int NN = decltype(nTag)::value;
+      // columns in groups of 4, 2, 1 (J is re-read per group: operands with >= 8 columns take the other kernel)
+      int c0 = 0;
+      while (c0 < ncols) {
+        const int left = ncols - c0;
+        if (left >= 4) { dev::k_spmm_cells_fewcols<NN, 4><<<grid, 256, 0, st>>>(ncells, ds.dCellBase.p, ds.dCellLen.p, ds.dColidx.p, ds.dJ.p, dB, c0, ldbRow, ldbCol, dR, ldrRow, ldrCol); c0 += 4; }
+        else if (left >= 2) { dev::k_spmm_cells_fewcols<NN, 2><<<grid, 256, 0, st>>>(ncells, ds.dCellBase.p, ds.dCellLen.p, ds.dColidx.p, ds.dJ.p, dB, c0, ldbRow, ldbCol, dR, ldrRow, ldrCol); c0 += 2; }
+        else { dev::k_spmm_cells_fewcols<NN, 1><<<grid, 256, 0, st>>>(ncells, ds.dCellBase.p, ds.dCellLen.p, ds.dColidx.p, ds.dJ.p, dB, c0, ldbRow, ldbCol, dR, ldrRow, ldrCol); c0 += 1; }
+        ++launches_;
+      }
+    };
+    switch (ndpc_) {
+      case 1: launch(std::integral_constant<int, 1>{}); break;
+      case 2: launch(std::integral_constant<int, 2>{}); break;
+      case 3: launch(std::integral_constant<int, 3>{}); break;
+      case 4: launch(std::integral_constant<int, 4>{}); break;
+      default: launch(std::integral_constant<int, 5>{}); break;
+    }
   }
   PDA_CUDA(cudaGetLastError());
 }

@@ -723,6 +723,67 @@ k_spmm_rows_fewcols(int32_t nrows, const int32_t* __restrict__ rowptr, const int
   }
 }
 
+// Few operand columns (J*v of Newton-Krylov solvers): one warp per CELL.  The cell's N rows are one contiguous chunk
+// of N*len values: lanes stride over the chunk (coalesced, every J value and column index read once) in batches of
+// four independent entries (all loads of a batch in flight together); entry e belongs to row e / len (compares, no
+// division); per-row partial sums in registers, one shuffle reduction per row and column.
+template <int N, int NB>
+__global__ void __launch_bounds__(256)
+k_spmm_cells_fewcols(int32_t ncells, const int32_t* __restrict__ cellBase, const int32_t* __restrict__ cellLen,
+                     const int32_t* __restrict__ colidx, const double* __restrict__ vals, const double* __restrict__ B,
+                     int c0, int64_t ldbRow, int64_t ldbCol, double* __restrict__ R, int64_t ldrRow, int64_t ldrCol) {
+  const int cell = (int)(((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
+  const int lane = threadIdx.x & 31;
+  if (cell >= ncells) return;
+  const int64_t base = cellBase[cell];
+  const int32_t len = cellLen[cell];
+  const int n = N * len;
+  const double* Bc = B + (int64_t)c0 * ldbCol;
+  double acc[N][NB];
+#pragma unroll
+  for (int k = 0; k < N; ++k)
+#pragma unroll
+    for (int c = 0; c < NB; ++c) acc[k][c] = 0.0;
+  for (int e0 = lane; e0 < n; e0 += 128) {
+    double v[4];
+    int32_t col[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int e = e0 + 32 * u;
+      const bool ok = e < n;
+      v[u] = ok ? __ldg(vals + base + e) : 0.0;
+      col[u] = ok ? __ldg(colidx + base + e) : 0;
+    }
+    double bv[4][NB];
+#pragma unroll
+    for (int u = 0; u < 4; ++u)
+#pragma unroll
+      for (int c = 0; c < NB; ++c) bv[u][c] = __ldg(Bc + (int64_t)col[u] * ldbRow + c * ldbCol);
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int e = e0 + 32 * u;
+      int k = 0;
+#pragma unroll
+      for (int kk = 1; kk < N; ++kk) k += (e >= kk * len) ? 1 : 0;
+#pragma unroll
+      for (int kk = 0; kk < N; ++kk) {
+        const double w = (kk == k) ? v[u] : 0.0;
+#pragma unroll
+        for (int c = 0; c < NB; ++c) acc[kk][c] = fma(w, bv[u][c], acc[kk][c]);
+      }
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < N; ++k)
+#pragma unroll
+    for (int c = 0; c < NB; ++c) {
+      double a = acc[k][c];
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
+      if (lane == 0) R[((int64_t)cell * N + k) * ldrRow + (int64_t)(c0 + c) * ldrCol] = a;
+    }
+}
+
 // out[c][r] <- in[r][c]  (in: rows x cols row-major); 32x32 tiles through shared memory, linear tile index
 __global__ void __launch_bounds__(256)
 k_transpose(const double* __restrict__ in, int64_t rows, int64_t cols, double* __restrict__ out) {

@@ -57,6 +57,10 @@ def measure(p, hbm_gbs, jac=True, apply_cols=0, reps=5, t=0.0):
             ms = _time(lambda: p.applyJacobianDevice(U.data_ptr(), B.data_ptr(), apply_cols, 1, t, Rm.data_ptr(), st), max(2, reps // 2))
             out["apply_jacobian"] = {"ms": ms, "cols": apply_cols, "layout": "row-major",
                                      "nnz_cols_per_s": nnz * apply_cols / (ms * 1e-3)}
+            b1 = torch.rand(p.totalDofStencilMesh(), dtype=torch.float64, device="cuda")
+            r1 = torch.empty(p.totalDofSampleMesh(), dtype=torch.float64, device="cuda")
+            ms = _time(lambda: p.applyJacobianDevice(U.data_ptr(), b1.data_ptr(), 1, 1, t, r1.data_ptr(), st), max(2, reps // 2))
+            out["apply_jacobian_vector"] = {"ms": ms, "cols": 1, "nnz_per_s": nnz / (ms * 1e-3)}
     out["gpu_launches"] = int(p.launchCount() - l0)
     return out
 
