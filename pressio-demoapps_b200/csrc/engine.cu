@@ -16,6 +16,7 @@
 #include "kernels_jacobian.cuh"
 #include "kernels_jaclattice.cuh"
 #include "kernels_march2d.cuh"
+#include "kernels_applylattice.cuh"
 
 namespace pda {
 
@@ -1068,6 +1069,7 @@ void dispatchScheme(int S, F&& f) {
 }
 
 inline int gridFor(int64_t n, int block) { return (int)((n + block - 1) / block); }
+constexpr int kFusedApplyMaxCols = 8;   // operands up to this many columns take the matrix-free inner-row kernel
 
 }  // namespace
 
@@ -1214,7 +1216,7 @@ void Problem::evaluateDev(const double* dU, double t, double* dV, double* dJ, vo
           L.planeBegin = 0; L.planeEnd = m.n[1]; L.haloPlanes = 0; L.slab = 0; L.meshHalo = m.halo();
           L.haloLo = L.haloHi = nullptr; L.flagLo = L.flagHi = nullptr; L.epoch = 0;
           const int w0 = L.per[0] ? m.n[0] : m.n[0] - 2 * m.halo(), w1 = L.per[1] ? m.n[1] : m.n[1] - 2 * m.halo();
-          if (w0 > 0 && w1 > 0) {
+          if (w0 > 0 && w1 > 0 && !skipInnerJacobian_) {
             dev::JacLatTables jt{ds.latBase.p, ds.latSlots.p, ndpc_ * (1 + dim_ * (S - 1))};
             dim3 grid((unsigned)((w0 + JL::T - 1) / JL::T), (unsigned)((w1 + JL::T - 1) / JL::T));
             kern<<<grid, JL::THREADS, JL::smemBytes, st>>>(phys, L, dl, jt, dU, dV, dJ);
@@ -1454,15 +1456,84 @@ void Problem::applyJacobianDev(const double* dU, const double* dB, int ncols, in
   if (ncols < 1) throw Error(kInvalid, "applyJacobian: ncols must be >= 1");
   ensureDevice();
   PDA_CUDA(cudaSetDevice(device_));
-  buildPattern();
   DeviceState& ds = *dev_;
   cudaStream_t st = (cudaStream_t)streamV;   // NULL = the legacy default stream (CUDA convention)
-  ds.dV.alloc((size_t)nDofSample());
-  ds.dJ.alloc(colidx_.size());
-  if (!ds.dRowptr.p) { ds.dRowptr.upload(rowptr_); ds.dColidx.upload(colidx_); }
-  evaluateDev(dU, t, ds.dV.p, ds.dJ.p, st);
   const int32_t nrows = nDofSample();
   const int64_t nJc = nDofStencil();
+  Mesh& mm = *mesh_;
+  const bool fused = mm.lattice && dim_ == 2 && ds.innerViaLattice && ncols <= kFusedApplyMaxCols &&
+                     (family_ == F_EULER2D || family_ == F_SWE2D || family_ == F_ADVDIFF2D || family_ == F_ADVDIFFREAC2D);
+  // the assembled Jacobian (pattern, values scratch) is needed unless every row is matrix-free (periodic lattices)
+  if (!(fused && ds.nearBd.n == 0)) {
+    buildPattern();
+    ds.dV.alloc((size_t)nDofSample());
+    ds.dJ.alloc(colidx_.size());
+    if (!ds.dRowptr.p) { ds.dRowptr.upload(rowptr_); ds.dColidx.upload(colidx_); }
+  }
+  if (fused) {
+    // ---- matrix-free inner rows (kernels_applylattice.cuh); near-boundary rows through the assembled path
+    const int64_t ldbRow = (layout == 1) ? ncols : 1, ldbCol = (layout == 1) ? 1 : nJc;
+    const int64_t ldrRow = (layout == 1) ? ncols : 1, ldrCol = (layout == 1) ? 1 : nrows;
+    if (ds.nearBd.n > 0) {
+      skipInnerJacobian_ = true;
+      try { evaluateDev(dU, t, ds.dV.p, ds.dJ.p, st); } catch (...) { skipInnerJacobian_ = false; throw; }
+      skipInnerJacobian_ = false;
+      if (!ds.spmmFewReady) { ds.dCellBase.upload(cellBase_); ds.dCellLen.upload(cellLen_); ds.spmmFewReady = true; }
+      const unsigned gridNb = (unsigned)gridFor((int64_t)ds.nearBd.n * 32, 256);
+      auto nbLaunch = [&](auto nTag) {
+        constexpr int NN = decltype(nTag)::value;
+        for (int c0 = 0; c0 < ncols; ++c0) {
+          dev::k_spmm_cells_fewcols<NN, 1><<<gridNb, 256, 0, st>>>(ds.nearBd.n, ds.nearBd.rowIds.p, ds.dCellBase.p, ds.dCellLen.p,
+                                                                   ds.dColidx.p, ds.dJ.p, dB, c0, ldbRow, ldbCol, dR, ldrRow, ldrCol);
+          ++launches_;
+        }
+      };
+      switch (ndpc_) {
+        case 1: nbLaunch(std::integral_constant<int, 1>{}); break;
+        case 2: nbLaunch(std::integral_constant<int, 2>{}); break;
+        case 3: nbLaunch(std::integral_constant<int, 3>{}); break;
+        default: nbLaunch(std::integral_constant<int, 4>{}); break;
+      }
+    }
+    dev::Deltas dl{{mm.dInv[0], mm.dInv[1], mm.dInv[2]}};
+    dev::LatticeDesc L;
+    for (int a = 0; a < 3; ++a) { L.n[a] = mm.n[a]; L.per[a] = mm.periodic[a] ? 1 : 0; }
+    L.planeBegin = 0; L.planeEnd = mm.n[1]; L.haloPlanes = 0; L.slab = 0; L.meshHalo = mm.halo();
+    L.haloLo = L.haloHi = nullptr; L.flagLo = L.flagHi = nullptr; L.epoch = 0;
+    const int w0 = L.per[0] ? mm.n[0] : mm.n[0] - 2 * mm.halo(), w1 = L.per[1] ? mm.n[1] : mm.n[1] - 2 * mm.halo();
+    if (w0 > 0 && w1 > 0) {
+      auto runPhys = [&](auto phys) {
+        using Phys = decltype(phys);
+        dispatchScheme(S_, [&](auto sTag) {
+          constexpr int S = decltype(sTag)::value;
+          constexpr int NC = 4;
+          using AK = dev::ApplyLat2d<Phys, NC>;
+          auto kern = dev::k_applyjac_lattice2d<Phys, S, NC>;
+          PDA_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)AK::smemBytes));
+          dim3 grid((unsigned)((w0 + AK::T - 1) / AK::T), (unsigned)((w1 + AK::T - 1) / AK::T));
+          for (int c0 = 0; c0 < ncols; c0 += NC) {
+            kern<<<grid, AK::THREADS, AK::smemBytes, st>>>(phys, L, dl, dU, dB, ncols, c0, ldbRow, ldbCol, dR, ldrRow, ldrCol);
+            ++launches_;
+          }
+        });
+      };
+      switch (family_) {
+        case F_EULER2D: runPhys(dev::Euler<2>{gamma_}); break;
+        case F_SWE2D: runPhys(dev::Swe2d{physParams_[0], physParams_[1]}); break;
+        case F_ADVDIFF2D:
+          runPhys(dev::Burgers2d{{physParams_[0] * (mm.dInv[0] * mm.dInv[0]), physParams_[0] * (mm.dInv[1] * mm.dInv[1])}});
+          break;
+        default: {
+          const double D = physParams_[2];
+          runPhys(dev::LinAdv<2>{{physParams_[0], physParams_[1]}, {D * (mm.dInv[0] * mm.dInv[0]), D * (mm.dInv[1] * mm.dInv[1])},
+                                 physParams_[3], 1.0, nullptr});
+        }
+      }
+    }
+    PDA_CUDA(cudaGetLastError());
+    return;
+  }
+  evaluateDev(dU, t, ds.dV.p, ds.dJ.p, st);
   if (ncols >= 8) {
     // operands with many columns: per-cell kernel on row-major data (column-major operands are transposed around it)
     if (!ds.spmmReady) {
@@ -1534,9 +1605,9 @@ void Problem::applyJacobianDev(const double* dU, const double* dB, int ncols, in
       int c0 = 0;
       while (c0 < ncols) {
         const int left = ncols - c0;
-        if (left >= 4) { dev::k_spmm_cells_fewcols<NN, 4><<<grid, 256, 0, st>>>(ncells, ds.dCellBase.p, ds.dCellLen.p, ds.dColidx.p, ds.dJ.p, dB, c0, ldbRow, ldbCol, dR, ldrRow, ldrCol); c0 += 4; }
-        else if (left >= 2) { dev::k_spmm_cells_fewcols<NN, 2><<<grid, 256, 0, st>>>(ncells, ds.dCellBase.p, ds.dCellLen.p, ds.dColidx.p, ds.dJ.p, dB, c0, ldbRow, ldbCol, dR, ldrRow, ldrCol); c0 += 2; }
-        else { dev::k_spmm_cells_fewcols<NN, 1><<<grid, 256, 0, st>>>(ncells, ds.dCellBase.p, ds.dCellLen.p, ds.dColidx.p, ds.dJ.p, dB, c0, ldbRow, ldbCol, dR, ldrRow, ldrCol); c0 += 1; }
+        if (left >= 4) { dev::k_spmm_cells_fewcols<NN, 4><<<grid, 256, 0, st>>>(ncells, nullptr, ds.dCellBase.p, ds.dCellLen.p, ds.dColidx.p, ds.dJ.p, dB, c0, ldbRow, ldbCol, dR, ldrRow, ldrCol); c0 += 4; }
+        else if (left >= 2) { dev::k_spmm_cells_fewcols<NN, 2><<<grid, 256, 0, st>>>(ncells, nullptr, ds.dCellBase.p, ds.dCellLen.p, ds.dColidx.p, ds.dJ.p, dB, c0, ldbRow, ldbCol, dR, ldrRow, ldrCol); c0 += 2; }
+        else { dev::k_spmm_cells_fewcols<NN, 1><<<grid, 256, 0, st>>>(ncells, nullptr, ds.dCellBase.p, ds.dCellLen.p, ds.dColidx.p, ds.dJ.p, dB, c0, ldbRow, ldbCol, dR, ldrRow, ldrCol); c0 += 1; }
         ++launches_;
       }
     };

@@ -108,6 +108,7 @@ class Problem {
   int32_t slabK0_ = 0, slabK1_ = 0;
   int slabRank_ = 0, slabRanks_ = 1;
 
+  bool skipInnerJacobian_ = false;   // applyJacobian, matrix-free inner rows: assemble the near-boundary rows only
   int64_t launches_ = 0;
   std::unique_ptr<DeviceState> dev_;
 };

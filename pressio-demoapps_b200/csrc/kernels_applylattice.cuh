@@ -1,0 +1,154 @@
+// kernels_applylattice.cuh -- matrix-free applyJacobian on 2D full lattices: R = J(U) * B without ever storing J.
+//
+// Replaces adapter_cpp.hpp:231-259 (evaluate J into a scratch SparseMatrix, then J*B) for the inner rows.  With
+//   D_f[k] = sum_j JN[k][j] * dN[j] + JP[k][j] * dP[j],   dN[j] = sum_m d(uNeg_j)/d(q_m) * b_m[j]   (dP alike)
+// -- the directional derivative of face f's flux along the operand column b -- the row block of cell c is
+//   R_c[k] = sum_axes hInv * (D_c[k] - D_{c+1}[k])  (+ point / diffusion terms),
+// so a face contributes ONE N-vector per operand column: no CSR values, no 1.7 kB/cell of stores, no second pass
+// reading them back.  Same lane layout as k_jacobian_lattice2d (a lane owns one face, 16-lane lines, 15x15 tiles, x
+// phase then y phase, the x part of R parked in shared memory); up to NC operand columns per pass share the
+// reconstruction gradients and flux Jacobians.  Near-boundary rows (first-order Jacobian with ghost factors) go
+// through the assembled path restricted to those rows.
+#pragma once
+#include "kernels_jaclattice.cuh"
+
+namespace pda {
+namespace dev {
+
+template <class Phys, int NC>
+struct ApplyLat2d {
+  static constexpr int N = Phys::ndpc;
+  static constexpr int WARPS = 8, THREADS = 32 * WARPS, T = 15;
+  static constexpr int RS = N * NC + 1;                       // padded per-cell stride of the parked x part
+  static constexpr size_t smemBytes = (size_t)T * T * RS * sizeof(double);
+};
+
+template <class Phys, int S, int AX, int NC>
+PDA_DEVFN void applyLatLine(const Phys& phys, const LatticeDesc& L, double hInv, const double* __restrict__ U,
+                            const double* __restrict__ B, int ncols, int c0, int64_t ldbRow, int64_t ldbCol,
+                            double* __restrict__ R, int64_t ldrRow, int64_t ldrCol, int a, int o, bool owns,
+                            int cellLocal, double* __restrict__ sR) {
+  constexpr int N = Phys::ndpc;
+  constexpr int h = (S - 1) / 2;
+  using K = ApplyLat2d<Phys, NC>;
+  const int nx = L.n[0], ny = L.n[1];
+  const int nA = L.n[AX], perA = L.per[AX];
+  const int nc = min(NC, ncols - c0);
+
+  int64_t off[S - 1];
+  double q[S - 1][N];
+#pragma unroll
+  for (int m = 0; m < S - 1; ++m) {
+    int c = a - h + m;
+    if (perA) { c %= nA; if (c < 0) c += nA; }
+    else c = (c < 0) ? 0 : (c >= nA ? nA - 1 : c);
+    const int64_t gid = (AX == 0) ? (int64_t)o * nx + c : (int64_t)c * nx + o;
+    off[m] = gid * N;
+    loadCell<N>(U + off[m], q[m]);
+  }
+  // face states + directional derivatives of the reconstructions along every operand column
+  double un[N], up[N], dN[NC][N], dP[NC][N];
+#pragma unroll
+  for (int j = 0; j < N; ++j) {
+    double qd[S - 1], gN[S - 1], gP[S - 1];
+#pragma unroll
+    for (int m = 0; m < S - 1; ++m) qd[m] = q[m][j];
+    reconFaceFast<S>(qd, un[j], up[j]);
+    reconFaceGradFast<S>(qd, gN, gP);
+#pragma unroll
+    for (int c = 0; c < NC; ++c) {
+      double sN = 0.0, sP = 0.0;
+      if (c < nc) {
+#pragma unroll
+        for (int m = 0; m < S - 1; ++m) {
+          const double b = __ldg(B + (off[m] + j) * ldbRow + (int64_t)(c0 + c) * ldbCol);
+          sN = fma(gN[m], b, sN);
+          sP = fma(gP[m], b, sP);
+        }
+      }
+      dN[c][j] = sN; dP[c][j] = sP;
+    }
+  }
+  double JN[N * N], JP[N * N];
+  faceFluxJac2d<Phys, AX>(phys, un, up, JN, JP);
+  double r[NC][N];
+#pragma unroll
+  for (int c = 0; c < NC; ++c)
+#pragma unroll
+    for (int k = 0; k < N; ++k) {
+      double d = 0.0;
+#pragma unroll
+      for (int j = 0; j < N; ++j) d += JN[k * N + j] * dN[c][j] + JP[k * N + j] * dP[c][j];
+      r[c][k] = hInv * (d - __shfl_down_sync(0xffffffffu, d, 1));
+    }
+  if (!owns) return;
+  double* mine = sR + cellLocal * K::RS;
+  if (AX == 0) {
+#pragma unroll
+    for (int c = 0; c < NC; ++c)
+#pragma unroll
+      for (int k = 0; k < N; ++k) mine[c * N + k] = r[c][k];
+    return;
+  }
+  const int64_t gidSelf = (int64_t)a * nx + o;   // y phase: a = row, o = column
+#pragma unroll
+  for (int c = 0; c < NC; ++c)
+#pragma unroll
+    for (int k = 0; k < N; ++k) r[c][k] += mine[c * N + k];
+  if constexpr (std::is_same<Phys, Swe2d>::value || PhysTraits<Phys>::hasDiffusion || std::is_same<Phys, LinAdv<2>>::value) {
+    // point terms and diffusion: the same entries addExtraJacInner adds to J, applied to the operand.  The "slot"
+    // handed to it is the graph column itself (0 self, 1 left, 2 front, 3 right, 4 back).
+    auto wrapI = [&](int v, int n) { return v < 0 ? v + n : (v >= n ? v - n : v); };
+    const int i = o, jr = a;
+    int64_t nb[5];
+    nb[0] = gidSelf;
+    nb[1] = (int64_t)jr * nx + wrapI(i - 1, nx);
+    nb[2] = (int64_t)wrapI(jr + 1, ny) * nx + i;
+    nb[3] = (int64_t)jr * nx + wrapI(i + 1, nx);
+    nb[4] = (int64_t)wrapI(jr - 1, ny) * nx + i;
+    uint8_t ident[16];
+#pragma unroll
+    for (int c = 0; c < 16; ++c) ident[c] = (uint8_t)c;
+    addExtraJacInner<Phys>(phys, U + gidSelf * N, ident, [&](int k, int col, int j, double x) {
+#pragma unroll
+      for (int c = 0; c < NC; ++c)
+        if (c < nc) r[c][k] += x * __ldg(B + (nb[col] * N + j) * ldbRow + (int64_t)(c0 + c) * ldbCol);
+    });
+  }
+#pragma unroll
+  for (int c = 0; c < NC; ++c)
+    if (c < nc) {
+#pragma unroll
+      for (int k = 0; k < N; ++k) R[(gidSelf * N + k) * ldrRow + (int64_t)(c0 + c) * ldrCol] = r[c][k];
+    }
+}
+
+template <class Phys, int S, int NC>
+__global__ void __launch_bounds__(ApplyLat2d<Phys, NC>::THREADS)
+k_applyjac_lattice2d(Phys phys, LatticeDesc L, Deltas dl, const double* __restrict__ U, const double* __restrict__ B,
+                     int ncols, int c0, int64_t ldbRow, int64_t ldbCol, double* __restrict__ R, int64_t ldrRow,
+                     int64_t ldrCol) {
+  using K = ApplyLat2d<Phys, NC>;
+  extern __shared__ __align__(16) double sR[];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int line = 2 * warp + (lane >> 4), f = lane & 15;
+  const int lo0 = L.per[0] ? 0 : L.meshHalo, hi0 = L.per[0] ? L.n[0] : L.n[0] - L.meshHalo;
+  const int lo1 = L.per[1] ? 0 : L.meshHalo, hi1 = L.per[1] ? L.n[1] : L.n[1] - L.meshHalo;
+  const int I0 = lo0 + K::T * blockIdx.x, J0 = lo1 + K::T * blockIdx.y;
+  {
+    const int j = J0 + line, a = I0 + f;
+    const bool owns = (line < K::T) && (f < K::T) && (j < hi1) && (a < hi0);
+    applyLatLine<Phys, S, 0, NC>(phys, L, dl.hInv[0], U, B, ncols, c0, ldbRow, ldbCol, R, ldrRow, ldrCol, a,
+                                 min(j, hi1 - 1), owns, min(line, K::T - 1) * K::T + min(f, K::T - 1), sR);
+  }
+  __syncthreads();
+  {
+    const int i = I0 + line, a = J0 + f;
+    const bool owns = (line < K::T) && (f < K::T) && (i < hi0) && (a < hi1);
+    applyLatLine<Phys, S, 1, NC>(phys, L, dl.hInv[1], U, B, ncols, c0, ldbRow, ldbCol, R, ldrRow, ldrCol, a,
+                                 min(i, hi0 - 1), owns, min(f, K::T - 1) * K::T + min(line, K::T - 1), sR);
+  }
+}
+
+}  // namespace dev
+}  // namespace pda

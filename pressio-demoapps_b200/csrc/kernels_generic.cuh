@@ -729,12 +729,14 @@ k_spmm_rows_fewcols(int32_t nrows, const int32_t* __restrict__ rowptr, const int
 // division); per-row partial sums in registers, one shuffle reduction per row and column.
 template <int N, int NB>
 __global__ void __launch_bounds__(256)
-k_spmm_cells_fewcols(int32_t ncells, const int32_t* __restrict__ cellBase, const int32_t* __restrict__ cellLen,
-                     const int32_t* __restrict__ colidx, const double* __restrict__ vals, const double* __restrict__ B,
+k_spmm_cells_fewcols(int32_t ncells, const int32_t* __restrict__ order, const int32_t* __restrict__ cellBase,
+                     const int32_t* __restrict__ cellLen, const int32_t* __restrict__ colidx,
+                     const double* __restrict__ vals, const double* __restrict__ B,
                      int c0, int64_t ldbRow, int64_t ldbCol, double* __restrict__ R, int64_t ldrRow, int64_t ldrCol) {
-  const int cell = (int)(((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
+  const int w = (int)(((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
   const int lane = threadIdx.x & 31;
-  if (cell >= ncells) return;
+  if (w >= ncells) return;
+  const int cell = order ? order[w] : w;   // `order`: optional list of cells (e.g. the near-boundary rows only)
   const int64_t base = cellBase[cell];
   const int32_t len = cellLen[cell];
   const int n = N * len;

@@ -541,3 +541,39 @@ def test_slab_decomposition_2d_equals_full(nranks, n, recon, sten):
         p.slabVelocityBoundaryDevice(Ul.data_ptr(), 0.0, Vl.data_ptr(), st)
         torch.cuda.synchronize()
         assert np.array_equal(Vl.cpu().numpy(), Vfull[k0 * pd:k1 * pd]), r
+
+
+@pytest.mark.parametrize("case", ["euler_riemann_weno5", "euler_per_weno3", "swe_weno5", "burgers_per_weno5", "adr_weno3",
+                                  "euler_tiny_per"])
+def test_matrix_free_apply_jacobian_equals_assembled(case):
+    """operands with <= 8 columns on 2D lattices take the matrix-free inner-row kernel (kernels_applylattice.cuh: the
+    directional derivative of every face flux, no CSR values stored); result must equal J @ B of the assembled Jacobian
+    for vectors and both matrix layouts, incl. point / diffusion terms, periodic wrap and tiny meshes"""
+    V = pda.ViscousFluxReconstruction.FirstOrder
+    if case == "euler_riemann_weno5":
+        p = pda.create_problem(pda.create_full_mesh([47, 33], [0, 1, 0, 1], 7), pda.Euler2d.Riemann, R.Weno5)
+    elif case == "euler_per_weno3":
+        p = pda.create_problem(pda.create_full_mesh([40, 31], [-1, 1, -1, 1], 7, ("x", "y")), pda.Euler2d.PeriodicSmooth, R.Weno3)
+    elif case == "swe_weno5":
+        p = pda.create_problem(pda.create_full_mesh([36, 40], [-5, 5, -5, 5], 7), pda.Swe2d.SlipWall, R.Weno5)
+    elif case == "burgers_per_weno5":
+        p = pda.create_problem(pda.create_full_mesh([30, 32], [-1, 1, -1, 1], 7, ("x", "y")),
+                               pda.AdvectionDiffusion2d.BurgersPeriodic, R.Weno5, V)
+    elif case == "adr_weno3":
+        p = pda.create_problem(pda.create_full_mesh([26, 22], [0, 1, 0, 1], 5), pda.AdvectionDiffusionReaction2d.ProblemA, R.Weno3)
+    else:
+        p = pda.create_problem(pda.create_full_mesh([6, 5], [-1, 1, -1, 1], 7, ("x", "y")), pda.Euler2d.PeriodicSmooth, R.Weno5)
+    U = perturbed(p)
+    J = p.createJacobian()
+    p.jacobian(U, 0.0, J)
+    rng = np.random.default_rng(21)
+    b = rng.uniform(-1, 1, U.size)
+    r = p.createApplyJacobianResult(b)
+    p.applyJacobian(U, b, 0.0, r)
+    assert scaled_err(r, J @ b, 1e-11, 1e-9) <= 1.0
+    for ncols in (3, 8):
+        for order in ("C", "F"):
+            B = np.asarray(rng.uniform(-1, 1, (U.size, ncols)), order=order)
+            Rm = p.createApplyJacobianResult(B)
+            p.applyJacobian(U, B, 0.0, Rm)
+            assert scaled_err(Rm, J @ B, 1e-11, 1e-9) <= 1.0
