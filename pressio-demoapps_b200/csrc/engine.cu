@@ -6,6 +6,7 @@
 
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 
@@ -1069,7 +1070,11 @@ void dispatchScheme(int S, F&& f) {
 }
 
 inline int gridFor(int64_t n, int block) { return (int)((n + block - 1) / block); }
-constexpr int kFusedApplyMaxCols = 8;   // operands up to this many columns take the matrix-free inner-row kernel
+// operands up to this many columns take the matrix-free inner-row kernel (PDA_FUSED_APPLY_MAX_COLS overrides: tuning)
+inline int fusedApplyMaxCols() {
+  static const int v = [] { const char* e = std::getenv("PDA_FUSED_APPLY_MAX_COLS"); return e ? std::atoi(e) : 12; }();
+  return v;
+}
 
 }  // namespace
 
@@ -1461,7 +1466,7 @@ void Problem::applyJacobianDev(const double* dU, const double* dB, int ncols, in
   const int32_t nrows = nDofSample();
   const int64_t nJc = nDofStencil();
   Mesh& mm = *mesh_;
-  const bool fused = mm.lattice && dim_ == 2 && ds.innerViaLattice && ncols <= kFusedApplyMaxCols &&
+  const bool fused = mm.lattice && dim_ == 2 && ds.innerViaLattice && ncols <= fusedApplyMaxCols() &&
                      (family_ == F_EULER2D || family_ == F_SWE2D || family_ == F_ADVDIFF2D || family_ == F_ADVDIFFREAC2D);
   // the assembled Jacobian (pattern, values scratch) is needed unless every row is matrix-free (periodic lattices)
   if (!(fused && ds.nearBd.n == 0)) {

@@ -34,6 +34,8 @@ PDA_DEVFN void applyLatLine(const Phys& phys, const LatticeDesc& L, double hInv,
   const int nx = L.n[0], ny = L.n[1];
   const int nA = L.n[AX], perA = L.per[AX];
   const int nc = min(NC, ncols - c0);
+  const bool vec4 = (ldbCol == 1) && ((ldbRow & 3) == 0) && ((c0 & 3) == 0) && (nc == 4) &&
+                    ((reinterpret_cast<uintptr_t>(B) & 31) == 0);
 
   int64_t off[S - 1];
   double q[S - 1][N];
@@ -55,18 +57,32 @@ PDA_DEVFN void applyLatLine(const Phys& phys, const LatticeDesc& L, double hInv,
     for (int m = 0; m < S - 1; ++m) qd[m] = q[m][j];
     reconFaceFast<S>(qd, un[j], up[j]);
     reconFaceGradFast<S>(qd, gN, gP);
+    if (NC == 4 && vec4) {
+      // row-major operand, 4 aligned columns: the 4 values of a (cell, dof) are one 32-byte sector -> LDG.256
+      double sN[4] = {0.0, 0.0, 0.0, 0.0}, sP[4] = {0.0, 0.0, 0.0, 0.0};
 #pragma unroll
-    for (int c = 0; c < NC; ++c) {
-      double sN = 0.0, sP = 0.0;
-      if (c < nc) {
+      for (int m = 0; m < S - 1; ++m) {
+        double b[4];
+        loadCell<4>(B + (off[m] + j) * ldbRow + c0, b);
 #pragma unroll
-        for (int m = 0; m < S - 1; ++m) {
-          const double b = __ldg(B + (off[m] + j) * ldbRow + (int64_t)(c0 + c) * ldbCol);
-          sN = fma(gN[m], b, sN);
-          sP = fma(gP[m], b, sP);
-        }
+        for (int c = 0; c < 4; ++c) { sN[c] = fma(gN[m], b[c], sN[c]); sP[c] = fma(gP[m], b[c], sP[c]); }
       }
-      dN[c][j] = sN; dP[c][j] = sP;
+#pragma unroll
+      for (int c = 0; c < NC; ++c) { dN[c][j] = sN[c & 3]; dP[c][j] = sP[c & 3]; }
+    } else {
+#pragma unroll
+      for (int c = 0; c < NC; ++c) {
+        double sN = 0.0, sP = 0.0;
+        if (c < nc) {
+#pragma unroll
+          for (int m = 0; m < S - 1; ++m) {
+            const double b = __ldg(B + (off[m] + j) * ldbRow + (int64_t)(c0 + c) * ldbCol);
+            sN = fma(gN[m], b, sN);
+            sP = fma(gP[m], b, sP);
+          }
+        }
+        dN[c][j] = sN; dP[c][j] = sP;
+      }
     }
   }
   double JN[N * N], JP[N * N];

@@ -546,7 +546,7 @@ def test_slab_decomposition_2d_equals_full(nranks, n, recon, sten):
 @pytest.mark.parametrize("case", ["euler_riemann_weno5", "euler_per_weno3", "swe_weno5", "burgers_per_weno5", "adr_weno3",
                                   "euler_tiny_per"])
 def test_matrix_free_apply_jacobian_equals_assembled(case):
-    """operands with <= 8 columns on 2D lattices take the matrix-free inner-row kernel (kernels_applylattice.cuh: the
+    """operands with <= 12 columns on 2D lattices take the matrix-free inner-row kernel (kernels_applylattice.cuh: the
     directional derivative of every face flux, no CSR values stored); result must equal J @ B of the assembled Jacobian
     for vectors and both matrix layouts, incl. point / diffusion terms, periodic wrap and tiny meshes"""
     V = pda.ViscousFluxReconstruction.FirstOrder
@@ -571,7 +571,7 @@ def test_matrix_free_apply_jacobian_equals_assembled(case):
     r = p.createApplyJacobianResult(b)
     p.applyJacobian(U, b, 0.0, r)
     assert scaled_err(r, J @ b, 1e-11, 1e-9) <= 1.0
-    for ncols in (3, 8):
+    for ncols in (3, 8, 12):
         for order in ("C", "F"):
             B = np.asarray(rng.uniform(-1, 1, (U.size, ncols)), order=order)
             Rm = p.createApplyJacobianResult(B)
