@@ -166,6 +166,21 @@ def test_no_cpu_fallback():
     with pytest.raises(pda.PdaError) as e:
         p.rightHandSide(U, 0.0, V)
     assert e.value.code == 3   # PDA_ERR_NO_DEVICE
+    # every evaluation entry point refuses the same way: Jacobian, applyJacobian (assembled and matrix-free paths),
+    # time stepping, slab / peer mode
+    J = p.createJacobian()
+    for call in (lambda: p.rightHandSideAndJacobian(U, 0.0, V, J), lambda: p.jacobian(U, 0.0, J),
+                 lambda: p.applyJacobian(U, U.copy(), 0.0, p.createApplyJacobianResult(U)),
+                 lambda: p.applyJacobian(U, np.zeros((U.size, 25)), 0.0, np.zeros((V.size, 25))),
+                 lambda: p.advance("rk4", U, 1e-3, 2)):
+        with pytest.raises(pda.PdaError) as e:
+            call()
+        assert e.value.code == 3
+    m3 = pda.create_full_mesh([8, 8, 8], [-1, 1, -1, 1, -1, 1], 7, ("x", "y", "z"))
+    ps = pda.create_problem_slab(m3, pda.Euler3d.PeriodicSmooth, R.Weno5, 0, 2)
+    with pytest.raises(pda.PdaError) as e:
+        ps.peerHandle()
+    assert e.value.code == 3
 
 
 def test_cabi_exports_every_declared_symbol():
