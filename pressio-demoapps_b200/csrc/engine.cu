@@ -1228,7 +1228,7 @@ void Problem::evaluateDev(const double* dU, double t, double* dV, double* dJ, vo
             ++launches_;
           }
         }
-      } else if (ds.inner.n > 0) {
+      } else if (ds.inner.n > 0 && !(skipInnerJacobian_ && dJ)) {
         if (dJ && !mergedNeighbors_) {
           // staged assembly: every value of the inner rows written once, coalesced (no memset needed for them)
           using JS = dev::JacStage<Phys, S>;
@@ -1466,8 +1466,11 @@ void Problem::applyJacobianDev(const double* dU, const double* dB, int ncols, in
   const int32_t nrows = nDofSample();
   const int64_t nJc = nDofStencil();
   Mesh& mm = *mesh_;
-  const bool fused = mm.lattice && dim_ == 2 && ds.innerViaLattice && ncols <= fusedApplyMaxCols() &&
-                     (family_ == F_EULER2D || family_ == F_SWE2D || family_ == F_ADVDIFF2D || family_ == F_ADVDIFFREAC2D);
+  const bool fused3d = mm.lattice && dim_ == 3 && ds.innerViaLattice && family_ == F_EULER3D &&
+                       mm.n[0] >= 2 * mm.halo() && mm.n[1] >= 2 * mm.halo() && mm.n[2] >= 2 * mm.halo();
+  const bool fused = fused3d ||
+                     (mm.lattice && dim_ == 2 && ds.innerViaLattice && ncols <= fusedApplyMaxCols() &&
+                      (family_ == F_EULER2D || family_ == F_SWE2D || family_ == F_ADVDIFF2D || family_ == F_ADVDIFFREAC2D));
   // the assembled Jacobian (pattern, values scratch) is needed unless every row is matrix-free (periodic lattices)
   if (!(fused && ds.nearBd.n == 0)) {
     buildPattern();
@@ -1497,16 +1500,33 @@ void Problem::applyJacobianDev(const double* dU, const double* dB, int ncols, in
         case 1: nbLaunch(std::integral_constant<int, 1>{}); break;
         case 2: nbLaunch(std::integral_constant<int, 2>{}); break;
         case 3: nbLaunch(std::integral_constant<int, 3>{}); break;
-        default: nbLaunch(std::integral_constant<int, 4>{}); break;
+        case 4: nbLaunch(std::integral_constant<int, 4>{}); break;
+        default: nbLaunch(std::integral_constant<int, 5>{}); break;
       }
     }
     dev::Deltas dl{{mm.dInv[0], mm.dInv[1], mm.dInv[2]}};
     dev::LatticeDesc L;
     for (int a = 0; a < 3; ++a) { L.n[a] = mm.n[a]; L.per[a] = mm.periodic[a] ? 1 : 0; }
-    L.planeBegin = 0; L.planeEnd = mm.n[1]; L.haloPlanes = 0; L.slab = 0; L.meshHalo = mm.halo();
+    L.planeBegin = 0; L.planeEnd = mm.n[dim_ - 1]; L.haloPlanes = 0; L.slab = 0; L.meshHalo = mm.halo();
     L.haloLo = L.haloHi = nullptr; L.flagLo = L.flagHi = nullptr; L.epoch = 0;
     const int w0 = L.per[0] ? mm.n[0] : mm.n[0] - 2 * mm.halo(), w1 = L.per[1] ? mm.n[1] : mm.n[1] - 2 * mm.halo();
-    if (w0 > 0 && w1 > 0) {
+    if (fused3d) {
+      const int w2 = L.per[2] ? mm.n[2] : mm.n[2] - 2 * mm.halo();
+      if (w0 > 0 && w1 > 0 && w2 > 0) {
+        dispatchScheme(S_, [&](auto sTag) {
+          constexpr int S = decltype(sTag)::value;
+          constexpr int NC = 2;
+          using AK = dev::ApplyLat3d<NC>;
+          auto kern = dev::k_applyjac_lattice3d<S, NC>;
+          PDA_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)AK::smemBytes));
+          dim3 grid((unsigned)((w0 + AK::T - 1) / AK::T), (unsigned)((w1 + AK::T - 1) / AK::T), (unsigned)((w2 + AK::T - 1) / AK::T));
+          for (int c0 = 0; c0 < ncols; c0 += NC) {
+            kern<<<grid, AK::THREADS, AK::smemBytes, st>>>(gamma_, L, dl, dU, dB, ncols, c0, ldbRow, ldbCol, dR, ldrRow, ldrCol);
+            ++launches_;
+          }
+        });
+      }
+    } else if (w0 > 0 && w1 > 0) {
       auto runPhys = [&](auto phys) {
         using Phys = decltype(phys);
         dispatchScheme(S_, [&](auto sTag) {

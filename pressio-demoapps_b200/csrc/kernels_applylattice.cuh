@@ -166,5 +166,148 @@ k_applyjac_lattice2d(Phys phys, LatticeDesc L, Deltas dl, const double* __restri
   }
 }
 
+
+// ---------------------------------------------------------------------------------------------------------------
+// 3D: the same directional-derivative formulation on full 3D lattices (Euler3d).  There is no assembled alternative
+// at scale: the Jacobian of a 512^3 WENO5 problem has 6.4e10 stored entries (0.5 TB, beyond the reference's int32
+// indexing), while J*v needs the state, the operand and the result only.
+// Tile = 7 x 7 x 7 cells; a line (7 cells + the closing face) occupies 8 lanes, a warp carries 4 lines; phases x, y, z
+// with the partial result parked in shared memory in between.
+// ---------------------------------------------------------------------------------------------------------------
+template <int NC>
+struct ApplyLat3d {
+  static constexpr int N = 5, T = 7, THREADS = 256;
+  static constexpr int RS = N * NC + 1;
+  static constexpr size_t smemBytes = (size_t)T * T * T * RS * sizeof(double);
+};
+
+template <int S, int AX, int NC>
+PDA_DEVFN void applyLatLine3(double gamma, const LatticeDesc& L, double hInv, const double* __restrict__ U,
+                             const double* __restrict__ B, int ncols, int c0, int64_t ldbRow, int64_t ldbCol,
+                             double* __restrict__ R, int64_t ldrRow, int64_t ldrCol, int a, int o1, int o2, bool owns,
+                             int cellLocal, double* __restrict__ sR) {
+  constexpr int N = 5;
+  constexpr int h = (S - 1) / 2;
+  using K = ApplyLat3d<NC>;
+  const int64_t nx = L.n[0], ny = L.n[1];
+  const int nA = L.n[AX], perA = L.per[AX];
+  const int nc = min(NC, ncols - c0);
+  // (a, o1, o2) -> (x, y, z): AX = 0: a = x, (o1, o2) = (y, z); AX = 1: a = y, (o1, o2) = (x, z); AX = 2: a = z, (x, y)
+  auto gidOf = [&](int c) -> int64_t {
+    if (AX == 0) return ((int64_t)o2 * ny + o1) * nx + c;
+    if (AX == 1) return ((int64_t)o2 * ny + c) * nx + o1;
+    return ((int64_t)c * ny + o2) * nx + o1;
+  };
+  int64_t off[S - 1];
+  double q[S - 1][N];
+#pragma unroll
+  for (int m = 0; m < S - 1; ++m) {
+    int c = a - h + m;
+    if (perA) { c %= nA; if (c < 0) c += nA; }
+    else c = (c < 0) ? 0 : (c >= nA ? nA - 1 : c);
+    off[m] = gidOf(c) * N;
+    loadCell<N>(U + off[m], q[m]);
+  }
+  double un[N], up[N], dN[NC][N], dP[NC][N];
+#pragma unroll
+  for (int j = 0; j < N; ++j) {
+    double qd[S - 1], gN[S - 1], gP[S - 1];
+#pragma unroll
+    for (int m = 0; m < S - 1; ++m) qd[m] = q[m][j];
+    reconFaceFast<S>(qd, un[j], up[j]);
+    reconFaceGradFast<S>(qd, gN, gP);
+#pragma unroll
+    for (int c = 0; c < NC; ++c) {
+      double sN = 0.0, sP = 0.0;
+      if (c < nc) {
+#pragma unroll
+        for (int m = 0; m < S - 1; ++m) {
+          const double b = __ldg(B + (off[m] + j) * ldbRow + (int64_t)(c0 + c) * ldbCol);
+          sN = fma(gN[m], b, sN);
+          sP = fma(gP[m], b, sP);
+        }
+      }
+      dN[c][j] = sN; dP[c][j] = sP;
+    }
+  }
+  double JN[N * N], JP[N * N];
+  eulerFluxJacFast<3, AX>(gamma, un, up, JN, JP);
+  double r[NC][N];
+#pragma unroll
+  for (int c = 0; c < NC; ++c)
+#pragma unroll
+    for (int k = 0; k < N; ++k) {
+      double d = 0.0;
+#pragma unroll
+      for (int j = 0; j < N; ++j) d += JN[k * N + j] * dN[c][j] + JP[k * N + j] * dP[c][j];
+      r[c][k] = hInv * (d - __shfl_down_sync(0xffffffffu, d, 1));
+    }
+  if (!owns) return;
+  double* mine = sR + cellLocal * K::RS;
+  if (AX == 0) {
+#pragma unroll
+    for (int c = 0; c < NC; ++c)
+#pragma unroll
+      for (int k = 0; k < N; ++k) mine[c * N + k] = r[c][k];
+  } else if (AX == 1) {
+#pragma unroll
+    for (int c = 0; c < NC; ++c)
+#pragma unroll
+      for (int k = 0; k < N; ++k) mine[c * N + k] += r[c][k];
+  } else {
+    const int64_t gidSelf = gidOf(a);
+#pragma unroll
+    for (int c = 0; c < NC; ++c)
+      if (c < nc) {
+#pragma unroll
+        for (int k = 0; k < N; ++k)
+          R[(gidSelf * N + k) * ldrRow + (int64_t)(c0 + c) * ldrCol] = mine[c * N + k] + r[c][k];   // (x + y) + z
+      }
+  }
+}
+
+template <int S, int NC>
+__global__ void __launch_bounds__(ApplyLat3d<NC>::THREADS)
+k_applyjac_lattice3d(double gamma, LatticeDesc L, Deltas dl, const double* __restrict__ U, const double* __restrict__ B,
+                     int ncols, int c0, int64_t ldbRow, int64_t ldbCol, double* __restrict__ R, int64_t ldrRow,
+                     int64_t ldrCol) {
+  using K = ApplyLat3d<NC>;
+  constexpr int T = K::T;
+  extern __shared__ __align__(16) double sR3[];
+  const int tid = threadIdx.x;
+  const int grp = tid >> 3, f = tid & 7;   // 32 lines of 8 lanes per round
+  int lo[3], hi[3];
+#pragma unroll
+  for (int ax = 0; ax < 3; ++ax) {
+    lo[ax] = L.per[ax] ? 0 : L.meshHalo;
+    hi[ax] = L.per[ax] ? L.n[ax] : L.n[ax] - L.meshHalo;
+  }
+  const int O[3] = {lo[0] + T * (int)blockIdx.x, lo[1] + T * (int)blockIdx.y, lo[2] + T * (int)blockIdx.z};
+#pragma unroll
+  for (int ax = 0; ax < 3; ++ax) {
+    const int a1 = (ax == 0) ? 1 : 0, a2 = (ax == 2) ? 1 : 2;   // the two other axes (ascending)
+#pragma unroll 1
+    for (int round = 0; round < 2; ++round) {
+      const int l = round * 32 + grp;            // line index in the tile: (u, v) offsets along a1, a2
+      const int u = l % T, v = l / T;
+      const int a = O[ax] + f;
+      const int c1 = O[a1] + u, c2 = O[a2] + v;
+      const bool owns = (l < T * T) && (f < T) && (a < hi[ax]) && (c1 < hi[a1]) && (c2 < hi[a2]);
+      const int cc1 = min(c1, hi[a1] - 1), cc2 = min(c2, hi[a2] - 1);
+      const int uu = min(u, T - 1), vv = min(v, T - 1), ff = min(f, T - 1);
+      // tile-local linear index (z*T + y)*T + x
+      int lx, ly, lz;
+      if (ax == 0) { lx = ff; ly = uu; lz = vv; }
+      else if (ax == 1) { lx = uu; ly = ff; lz = vv; }
+      else { lx = uu; ly = vv; lz = ff; }
+      const int cellLocal = (lz * T + ly) * T + lx;
+      if (ax == 0) applyLatLine3<S, 0, NC>(gamma, L, dl.hInv[0], U, B, ncols, c0, ldbRow, ldbCol, R, ldrRow, ldrCol, a, cc1, cc2, owns, cellLocal, sR3);
+      else if (ax == 1) applyLatLine3<S, 1, NC>(gamma, L, dl.hInv[1], U, B, ncols, c0, ldbRow, ldbCol, R, ldrRow, ldrCol, a, cc1, cc2, owns, cellLocal, sR3);
+      else applyLatLine3<S, 2, NC>(gamma, L, dl.hInv[2], U, B, ncols, c0, ldbRow, ldbCol, R, ldrRow, ldrCol, a, cc1, cc2, owns, cellLocal, sR3);
+    }
+    __syncthreads();
+  }
+}
+
 }  // namespace dev
 }  // namespace pda

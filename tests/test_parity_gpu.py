@@ -577,3 +577,30 @@ def test_matrix_free_apply_jacobian_equals_assembled(case):
             Rm = p.createApplyJacobianResult(B)
             p.applyJacobian(U, B, 0.0, Rm)
             assert scaled_err(Rm, J @ B, 1e-11, 1e-9) <= 1.0
+
+
+@pytest.mark.parametrize("case", ["per_weno5", "per_weno3", "sedov_weno3", "per_fo_ragged"])
+def test_matrix_free_apply_jacobian_3d(case):
+    """3D lattices: applyJacobian never assembles the inner rows (k_applyjac_lattice3d, 7^3 tiles, x/y/z phases); equals
+    J @ B of the assembled Jacobian, incl. near-boundary rows (Sedov symmetry walls) and ragged tiles"""
+    if case == "per_weno5":
+        p = pda.create_problem(pda.create_full_mesh([10, 9, 8], [-1, 1, -1, 1, -1, 1], 7, ("x", "y", "z")), pda.Euler3d.PeriodicSmooth, R.Weno5)
+    elif case == "per_weno3":
+        p = pda.create_problem(pda.create_full_mesh([16, 15, 9], [-1, 1, -1, 1, -1, 1], 5, ("x", "y", "z")), pda.Euler3d.PeriodicSmooth, R.Weno3)
+    elif case == "sedov_weno3":
+        p = pda.create_problem(pda.create_full_mesh([12, 11, 10], [0, 1, 0, 1, 0, 1], 5), pda.Euler3d.SedovSymmetry, R.Weno3)
+    else:
+        p = pda.create_problem(pda.create_full_mesh([8, 15, 6], [-1, 1, -1, 1, -1, 1], 3, ("x", "y", "z")), pda.Euler3d.PeriodicSmooth, R.FirstOrder)
+    U = perturbed(p, amp=1e-2)
+    J = p.createJacobian()
+    p.jacobian(U, 0.0, J)
+    rng = np.random.default_rng(31)
+    b = rng.uniform(-1, 1, U.size)
+    r = p.createApplyJacobianResult(b)
+    p.applyJacobian(U, b, 0.0, r)
+    assert scaled_err(r, J @ b, 1e-11, 1e-9) <= 1.0
+    for order in ("C", "F"):
+        B = np.asarray(rng.uniform(-1, 1, (U.size, 3)), order=order)
+        Rm = p.createApplyJacobianResult(B)
+        p.applyJacobian(U, B, 0.0, Rm)
+        assert scaled_err(Rm, J @ B, 1e-11, 1e-9) <= 1.0
