@@ -1515,15 +1515,18 @@ void Problem::applyJacobianDev(const double* dU, const double* dB, int ncols, in
       if (w0 > 0 && w1 > 0 && w2 > 0) {
         dispatchScheme(S_, [&](auto sTag) {
           constexpr int S = decltype(sTag)::value;
-          constexpr int NC = 2;
-          using AK = dev::ApplyLat3d<NC>;
-          auto kern = dev::k_applyjac_lattice3d<S, NC>;
-          PDA_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)AK::smemBytes));
-          dim3 grid((unsigned)((w0 + AK::T - 1) / AK::T), (unsigned)((w1 + AK::T - 1) / AK::T), (unsigned)((w2 + AK::T - 1) / AK::T));
-          for (int c0 = 0; c0 < ncols; c0 += NC) {
+          auto pass = [&](auto ncTag, int c0) {
+            constexpr int NC = decltype(ncTag)::value;
+            using AK = dev::ApplyLat3d<NC>;
+            auto kern = dev::k_applyjac_lattice3d<S, NC>;
+            PDA_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)AK::smemBytes));
+            dim3 grid((unsigned)((w0 + AK::T - 1) / AK::T), (unsigned)((w1 + AK::T - 1) / AK::T), (unsigned)((w2 + AK::T - 1) / AK::T));
             kern<<<grid, AK::THREADS, AK::smemBytes, st>>>(gamma_, L, dl, dU, dB, ncols, c0, ldbRow, ldbCol, dR, ldrRow, ldrCol);
             ++launches_;
-          }
+          };
+          int c0 = 0;
+          for (; c0 + 2 <= ncols; c0 += 2) pass(std::integral_constant<int, 2>{}, c0);
+          if (c0 < ncols) pass(std::integral_constant<int, 1>{}, c0);
         });
       }
     } else if (w0 > 0 && w1 > 0) {

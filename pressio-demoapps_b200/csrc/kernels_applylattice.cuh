@@ -176,7 +176,8 @@ k_applyjac_lattice2d(Phys phys, LatticeDesc L, Deltas dl, const double* __restri
 // ---------------------------------------------------------------------------------------------------------------
 template <int NC>
 struct ApplyLat3d {
-  static constexpr int N = 5, T = 7, THREADS = 256;
+  static constexpr int N = 5, T = 7, THREADS = 224;   // 28 lines of 8 lanes per round, 49 lines per phase: 2 rounds
+  static constexpr int GROUPS = THREADS / 8;
   static constexpr int RS = N * NC + 1;
   static constexpr size_t smemBytes = (size_t)T * T * T * RS * sizeof(double);
 };
@@ -267,7 +268,7 @@ PDA_DEVFN void applyLatLine3(double gamma, const LatticeDesc& L, double hInv, co
 }
 
 template <int S, int NC>
-__global__ void __launch_bounds__(ApplyLat3d<NC>::THREADS)
+__global__ void __launch_bounds__(ApplyLat3d<NC>::THREADS, (NC == 1 ? 2 : 1))
 k_applyjac_lattice3d(double gamma, LatticeDesc L, Deltas dl, const double* __restrict__ U, const double* __restrict__ B,
                      int ncols, int c0, int64_t ldbRow, int64_t ldbCol, double* __restrict__ R, int64_t ldrRow,
                      int64_t ldrCol) {
@@ -275,7 +276,7 @@ k_applyjac_lattice3d(double gamma, LatticeDesc L, Deltas dl, const double* __res
   constexpr int T = K::T;
   extern __shared__ __align__(16) double sR3[];
   const int tid = threadIdx.x;
-  const int grp = tid >> 3, f = tid & 7;   // 32 lines of 8 lanes per round
+  const int grp = tid >> 3, f = tid & 7;   // K::GROUPS lines of 8 lanes per round
   int lo[3], hi[3];
 #pragma unroll
   for (int ax = 0; ax < 3; ++ax) {
@@ -288,7 +289,7 @@ k_applyjac_lattice3d(double gamma, LatticeDesc L, Deltas dl, const double* __res
     const int a1 = (ax == 0) ? 1 : 0, a2 = (ax == 2) ? 1 : 2;   // the two other axes (ascending)
 #pragma unroll 1
     for (int round = 0; round < 2; ++round) {
-      const int l = round * 32 + grp;            // line index in the tile: (u, v) offsets along a1, a2
+      const int l = round * K::GROUPS + grp;     // line index in the tile: (u, v) offsets along a1, a2
       const int u = l % T, v = l / T;
       const int a = O[ax] + f;
       const int c1 = O[a1] + u, c2 = O[a2] + v;
