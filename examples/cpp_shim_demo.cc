@@ -1,6 +1,7 @@
 // The reference's usage pattern (tests_cpp/eigen_2d_euler_riemann_explicit/main.cc) against the B200 engine through
 // include/pda_b200_eigen.hpp: load a mesh directory, create a problem, initial condition, Jacobian with the fixed
 // pattern; evaluate when a GPU is present.  argv[1] = mesh directory written by create_full_mesh.py / pda_mesh_write.
+#include <cmath>
 #include <cstdio>
 
 #include "pda_b200_eigen.hpp"
@@ -28,6 +29,32 @@ int main(int argc, char** argv) {
   } else {
     try { appObj.rightHandSide(state, 0.0, V); return 5; }   // must refuse: no CPU fallback
     catch (const std::runtime_error& e) { std::printf("no device: %s\n", e.what()); }
+  }
+  // boundary-face gradients, written like tests_cpp/gradients/main.cc:24-97
+  {
+    const auto x = meshObj.viewX();
+    const auto y = meshObj.viewY();
+    Eigen::VectorXd f(meshObj.stencilMeshSize());
+    for (int i = 0; i < x.size(); ++i) f(i) = std::sin(M_PI * x(i) * y(i));
+    pda::GradientEvaluator<pda::Mesh> grads(meshObj);
+    const auto G = meshObj.graph();
+    int count = 0;
+    double err = 0.0;
+    if (pda_device_count() > 0) {
+      grads(f);
+      for (auto rowInd : meshObj.graphRowsOfCellsStrictlyOnBd()) {
+        if (!meshObj.cellHasLeftFaceOnBoundary2d(rowInd)) continue;
+        const auto& face = grads.queryFace(G(rowInd, 0), pda::FacePosition::Left);
+        const double gold = face.centerCoordinates[1] * M_PI * std::cos(M_PI * face.centerCoordinates[0] * face.centerCoordinates[1]);
+        err += (face.normalGradient - gold) * (face.normalGradient - gold);
+        ++count;
+      }
+      std::printf("left-wall faces %d, rmse of the one-sided normal gradient %.3e\n", count, std::sqrt(err / std::max(count, 1)));
+      if (count == 0 || !(std::sqrt(err / count) < 0.5)) return 6;
+    } else {
+      try { grads(f); return 7; }
+      catch (const std::runtime_error& e) { std::printf("gradients, no device: %s\n", e.what()); }
+    }
   }
   std::printf("cpp_shim_demo ok\n");
   return 0;

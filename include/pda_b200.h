@@ -27,6 +27,7 @@ extern "C" {
 
 typedef struct pda_mesh_s*    pda_mesh;
 typedef struct pda_problem_s* pda_problem;
+typedef struct pda_gradient_s* pda_gradient;
 typedef int pda_status;
 
 enum {
@@ -119,6 +120,10 @@ pda_status pda_mesh_coordinates(pda_mesh m, double* x, double* y, double* z);   
 pda_status pda_mesh_graph(pda_mesh m, int32_t* graph);                                  /* graph()               */
 pda_status pda_mesh_rows_inner(pda_mesh m, int32_t* rows);                   /* graphRowsOfCellsAwayFromBd()     */
 pda_status pda_mesh_rows_near_bd(pda_mesh m, int32_t* rows);                 /* graphRowsOfCellsNearBd()         */
+/* graphRowsOfCellsStrictlyOnBd() (impl/mesh_ccu.hpp:153-155, filled at :441-447 for 2D meshes only): near-boundary
+ * rows whose cell has at least one face on the domain boundary; count = -1 for a null handle, 0 for 1D / 3D meshes */
+int32_t pda_mesh_num_cells_strictly_on_bd(pda_mesh m);
+pda_status pda_mesh_rows_strictly_on_bd(pda_mesh m, int32_t* rows);
 /* sample mesh only: full-mesh gid of every stencil-mesh cell (stencil_mesh_gids.dat) */
 pda_status pda_mesh_stencil_gids(pda_mesh m, int32_t* gids);
 
@@ -237,6 +242,32 @@ pda_status pda_slab_velocity_peer_dev(pda_problem p, const double* dU_owned, dou
 /* host-pointer flavour (owned planes only, pinned buffers recommended): chunks of planes flow H2D -> kernel -> D2H on
  * three streams; the boundary chunks go first so the pushes to the neighbours overlap the interior uploads */
 pda_status pda_slab_velocity_peer_host(pda_problem p, const double* U_owned, double t, double* V_owned);
+
+/* ------------------------------------------------------------------ boundary-face gradients --------------------- */
+/* GradientEvaluator<Mesh, MaxNumDofPerCell>(mesh)  (gradient.hpp:61-121, impl/gradient_2d.hpp:141-293): normal
+ * gradient of a cell-centred field at every face on the domain boundary, by one-sided finite differences whose width
+ * follows the mesh stencil (two points for stencil 3, three points for 5 and 7: gradient_2d.hpp:179-196).  2D only
+ * (PDA_ERR_UNSUPPORTED with the reference's message otherwise, gradient.hpp:71-73).  The mesh must outlive the
+ * evaluator only during this call: the face list is copied.
+ * Faces are numbered in creation order: rows of graphRowsOfCellsStrictlyOnBd(), then Left, Front, Right, Back
+ * (gradient_2d.hpp:243-284; the reference keeps them in an unordered_map keyed by (cellGID, FacePosition)). */
+pda_status pda_gradient_create(pda_mesh mesh, int max_num_dof_per_cell, pda_gradient* out);
+pda_status pda_gradient_free(pda_gradient g);
+int32_t pda_gradient_num_faces(pda_gradient g);
+/* the Face records (gradient_2d.hpp:109-130); any output may be NULL.  position = FacePosition (schemes_info.hpp:112-114:
+ * 0 Left, 1 Front, 2 Right, 3 Back), normal_direction 1 = x, 2 = y, centers = centerCoordinates [num_faces][3] */
+pda_status pda_gradient_faces(pda_gradient g, int32_t* cell_gid, int32_t* position, int32_t* parent_graph_row,
+                              int32_t* normal_direction, double* centers);
+/* queryFace(cellGID, FacePosition) (gradient.hpp:115-117): index of that face; PDA_ERR_INVALID when the mesh has no
+ * such boundary face (the reference asserts) */
+pda_status pda_gradient_query_face(pda_gradient g, int32_t cell_gid, int position, int32_t* face_index);
+/* operator()(field[, numDofPerCell]) (gradient.hpp:77-93): field = [stencilMeshSize][num_dof_per_cell] row-major,
+ * normal_grad = [num_faces][num_dof_per_cell].  num_dof_per_cell > max_num_dof_per_cell is refused with the
+ * reference's message.  Host-pointer (staged copies, synchronous) and device-pointer + stream flavours; no CPU path. */
+pda_status pda_gradient_compute_host(pda_gradient g, const double* field, int num_dof_per_cell, double* normal_grad);
+pda_status pda_gradient_compute_dev(pda_gradient g, const double* d_field, int num_dof_per_cell, double* d_normal_grad,
+                                    void* stream);
+int64_t pda_gradient_launch_count(pda_gradient g);
 
 #ifdef __cplusplus
 }

@@ -6,8 +6,11 @@
 #include <Eigen/Core>
 #include <Eigen/Sparse>
 
+#include <algorithm>
+#include <array>
 #include <stdexcept>
 #include <string>
+#include <type_traits>
 #include <unordered_map>
 #include <vector>
 
@@ -27,6 +30,7 @@ enum class AdvectionDiffusion2d { BurgersPeriodic = 0, BurgersOutflow };
 enum class AdvectionDiffusionReaction2d { ProblemA = 0 };
 enum class Advection1d { PeriodicLinear = 0 };
 enum class DiffusionReaction1d { ProblemA = 0 };
+enum class FacePosition { Left = 0, Front, Right, Back, Bottom, Top };   // schemes_info.hpp:112-114
 
 namespace impl {
 inline void check(pda_status s) { if (s != PDA_OK) throw std::runtime_error(pda_last_error()); }
@@ -84,9 +88,24 @@ class Mesh {
     if (!r.empty()) impl::check(pda_mesh_rows_near_bd(h_, r.data()));
     return r;
   }
+  // impl/mesh_ccu.hpp:153-155 and 298-326 (2D)
+  std::vector<index_t> graphRowsOfCellsStrictlyOnBd() const {
+    std::vector<index_t> r((size_t)std::max<index_t>(0, pda_mesh_num_cells_strictly_on_bd(h_)));
+    if (!r.empty()) impl::check(pda_mesh_rows_strictly_on_bd(h_, r.data()));
+    return r;
+  }
+  bool cellHasLeftFaceOnBoundary2d(index_t rowInd) const { return firstLayer_(rowInd, 1) == -1; }
+  bool cellHasFrontFaceOnBoundary2d(index_t rowInd) const { return firstLayer_(rowInd, 2) == -1; }
+  bool cellHasRightFaceOnBoundary2d(index_t rowInd) const { return firstLayer_(rowInd, 3) == -1; }
+  bool cellHasBackFaceOnBoundary2d(index_t rowInd) const { return firstLayer_(rowInd, 4) == -1; }
   pda_mesh handle() const { return h_; }
 
  private:
+  index_t firstLayer_(index_t rowInd, int col) const {
+    if (graphCache_.size() == 0) graphCache_ = graph();
+    return graphCache_(rowInd, col);
+  }
+  mutable graph_t graphCache_;
   double deltas_(int i) const {
     double d[3], di[3];
     impl::check(pda_mesh_deltas(h_, d, di));
@@ -102,6 +121,52 @@ class Mesh {
 };
 
 inline Mesh load_cellcentered_uniform_mesh_eigen(const std::string& dir) { return Mesh(dir); }
+
+// GradientEvaluator<MeshType, MaxNumDofPerCell> look-alike (gradient.hpp:61-121): normal gradients at the faces on the
+// domain boundary of a 2D mesh, computed on the GPU by pda_gradient_compute_host.
+template <class MeshType = Mesh, std::size_t MaxNumDofPerCell = 1>
+class GradientEvaluator {
+ public:
+  struct Face {   // the exposition-only struct of gradient.hpp:95-113
+    std::array<double, 3> centerCoordinates = {};
+    std::conditional_t<MaxNumDofPerCell == 1, double, std::array<double, MaxNumDofPerCell>> normalGradient = {};
+    int normalDirection = {};   // 1 = x, 2 = y
+  };
+  explicit GradientEvaluator(const MeshType& mesh) {
+    impl::check(pda_gradient_create(mesh.handle(), (int)MaxNumDofPerCell, &h_));
+    const auto n = (size_t)pda_gradient_num_faces(h_);
+    faces_.resize(n);
+    std::vector<int32_t> dir(n);
+    std::vector<double> cen(3 * n);
+    impl::check(pda_gradient_faces(h_, nullptr, nullptr, nullptr, dir.data(), cen.data()));
+    for (size_t k = 0; k < n; ++k) {
+      faces_[k].centerCoordinates = {cen[3 * k], cen[3 * k + 1], cen[3 * k + 2]};
+      faces_[k].normalDirection = dir[k];
+    }
+  }
+  GradientEvaluator(const GradientEvaluator&) = delete;
+  GradientEvaluator& operator=(const GradientEvaluator&) = delete;
+  ~GradientEvaluator() { if (h_) pda_gradient_free(h_); }
+  template <class FieldType> void operator()(const FieldType& field) { compute_(field, 1); }
+  template <class FieldType> void operator()(const FieldType& field, int numDofPerCell) { compute_(field, numDofPerCell); }
+  const Face& queryFace(int32_t cellGID, FacePosition fp) const {
+    int32_t k = -1;
+    impl::check(pda_gradient_query_face(h_, cellGID, static_cast<int>(fp), &k));
+    return faces_[(size_t)k];
+  }
+
+ private:
+  template <class FieldType> void compute_(const FieldType& field, int nd) {
+    std::vector<double> g(faces_.size() * (size_t)std::max(nd, 1));
+    impl::check(pda_gradient_compute_host(h_, field.data(), nd, g.data()));   // refuses nd > MaxNumDofPerCell
+    for (size_t k = 0; k < faces_.size(); ++k) {
+      if constexpr (MaxNumDofPerCell == 1) faces_[k].normalGradient = g[k];
+      else for (int j = 0; j < nd; ++j) faces_[k].normalGradient[(size_t)j] = g[k * (size_t)nd + (size_t)j];
+    }
+  }
+  pda_gradient h_ = nullptr;
+  std::vector<Face> faces_;
+};
 
 // PublicProblemEigenMixinCpp look-alike (adapter_cpp.hpp:59-264).  The mesh must outlive the problem, like in the
 // reference (std::reference_wrapper, euler_2d_prob_class.hpp:1277).

@@ -1540,3 +1540,64 @@ double or_time_velocity(or_problem* p, const double* U, double t, int warmup, in
   free(V);
   return ((double)(b.tv_sec - a.tv_sec) + 1e-9 * (double)(b.tv_nsec - a.tv_nsec)) / reps;
 }
+
+/* ------------------------------------------------------------------------------------------------------------
+ * GradientEvaluator (gradient.hpp:61-121): normal gradients at the faces on the domain boundary, 2D.
+ * ------------------------------------------------------------------------------------------------------------ */
+int64_t or_gradient_faces(int stencil, const int32_t* graph, const int32_t* rowsNearBd, int32_t nNearBd, const double* x,
+                          const double* y, const double* z, double dx, double dy, int32_t* cellGid, int32_t* position,
+                          int32_t* parentRow, int32_t* normalDir, double* centers) {
+  /* initializeForStoringNormalGradsAtBoundaryFaces, gradient_2d.hpp:233-286 */
+  const int nc = (stencil - 1) * 2 + 1;
+  const double dxHalf = dx * 0.5, dyHalf = dy * 0.5;
+  int64_t k = 0;
+  for (int32_t it = 0; it < nNearBd; ++it) {
+    const int32_t row = rowsNearBd[it];
+    const int32_t* cc = graph + (size_t)row * nc;
+    for (int pos = 0; pos < 4; ++pos) {       /* Left, Front, Right, Back = columns 1..4 */
+      if (cc[1 + pos] != -1) continue;
+      const int32_t gid = cc[0];
+      if (cellGid) cellGid[k] = gid;
+      if (position) position[k] = pos;
+      if (parentRow) parentRow[k] = row;
+      if (normalDir) normalDir[k] = (pos == 0 || pos == 2) ? 1 : 2;
+      if (centers) {
+        centers[3 * k + 0] = (pos == 0) ? x[gid] - dxHalf : ((pos == 2) ? x[gid] + dxHalf : x[gid]);
+        centers[3 * k + 1] = (pos == 1) ? y[gid] + dyHalf : ((pos == 3) ? y[gid] - dyHalf : y[gid]);
+        centers[3 * k + 2] = z[gid];
+      }
+      ++k;
+    }
+  }
+  return k;
+}
+
+void or_gradient_eval(int stencil, const int32_t* graph, int64_t nFaces, const int32_t* position,
+                      const int32_t* parentRow, double dx, double dy, const double* f, int ndpc, double* grad) {
+  /* normalGradBoundaryFacesOneSidedFdAutoStencil (gradient_2d.hpp:164-229) calling
+   * face_normal_gradient_for_cell_centered_function_2d (gradient_2d.hpp:62-104) */
+  const int nc = (stencil - 1) * 2 + 1;
+  for (int64_t k = 0; k < nFaces; ++k) {
+    const int32_t* cc = graph + (size_t)parentRow[k] * nc;
+    const int pos = position[k];
+    const int alongX = (pos == 0 || pos == 2);
+    const int rightSided = (pos == 0 || pos == 3);   /* Left and Back faces use the forward formula */
+    const double h = alongX ? dx : dy;
+    const int32_t i05 = cc[0];
+    const int32_t ip15 = alongX ? cc[3] : cc[2];
+    const int32_t im15 = alongX ? cc[1] : cc[4];
+    const int32_t ip30 = (nc >= 9) ? (alongX ? cc[7] : cc[6]) : -1;
+    const int32_t im30 = (nc >= 9) ? (alongX ? cc[5] : cc[8]) : -1;
+    for (int j = 0; j < ndpc; ++j) {
+      const double f05 = f[(size_t)i05 * ndpc + j];
+      const double fp15 = (ip15 != -1) ? f[(size_t)ip15 * ndpc + j] : 0;
+      const double fm15 = (im15 != -1) ? f[(size_t)im15 * ndpc + j] : 0;
+      const double fp30 = (ip30 != -1) ? f[(size_t)ip30 * ndpc + j] : 0;
+      const double fm30 = (im30 != -1) ? f[(size_t)im30 * ndpc + j] : 0;
+      double g;
+      if (stencil == 3) g = rightSided ? (-f05 + fp15) / h : (f05 - fm15) / h;
+      else g = rightSided ? (-2 * f05 + 3 * fp15 - 1 * fp30) / h : (2 * f05 - 3 * fm15 + 1 * fm30) / h;
+      grad[k * ndpc + j] = g;
+    }
+  }
+}

@@ -50,6 +50,16 @@ void or_euler_flux_jac(int ndpc, double* JL, double* JR, const double* qL, const
 void or_swe_flux(double* F, const double* qL, const double* qR, const double* n, double g);
 void or_swe_flux_jac(double* JL, double* JR, const double* qL, const double* qR, const double* n, double g);
 
+/* GradientEvaluator restated (gradient.hpp:61-121, impl/gradient_2d.hpp:62-104, 164-286), on mesh arrays (2D):
+ * or_gradient_faces lists the boundary faces -- rows with a first-layer neighbour missing among rowsNearBd
+ * (mesh_ccu.hpp:298-326, 441-447), then Left, Front, Right, Back -- and returns their number (outputs may be NULL);
+ * or_gradient_eval fills grad[face][dof] for field[stencilCell][dof]. */
+int64_t or_gradient_faces(int stencil, const int32_t* graph, const int32_t* rowsNearBd, int32_t nNearBd, const double* x,
+                          const double* y, const double* z, double dx, double dy, int32_t* cellGid, int32_t* position,
+                          int32_t* parentRow, int32_t* normalDir, double* centers);
+void or_gradient_eval(int stencil, const int32_t* graph, int64_t nFaces, const int32_t* position,
+                      const int32_t* parentRow, double dx, double dy, const double* field, int ndpc, double* grad);
+
 #ifdef __cplusplus
 }
 #endif

@@ -10,10 +10,12 @@
 #include "../../include/pda_b200.h"
 #include "common.hpp"
 #include "engine.hpp"
+#include "gradient.hpp"
 #include "mesh.hpp"
 
 struct pda_mesh_s { pda::Mesh m; };
 struct pda_problem_s { pda::Problem* p; };
+struct pda_gradient_s { pda::GradientEvaluator* g; };
 
 namespace {
 thread_local std::string g_lastError;
@@ -45,6 +47,10 @@ pda::Mesh& M(pda_mesh m) {
 pda::Problem& P(pda_problem p) {
   if (!p || !p->p) throw pda::Error(pda::kInvalid, "null problem handle");
   return *p->p;
+}
+pda::GradientEvaluator& GE(pda_gradient g) {
+  if (!g || !g->g) throw pda::Error(pda::kInvalid, "null gradient evaluator handle");
+  return *g->g;
 }
 }  // namespace
 
@@ -156,6 +162,25 @@ pda_status pda_mesh_rows_near_bd(pda_mesh m, int32_t* rows) {
     pda::Mesh& mm = M(m);
     mm.ensureRows();
     if (rows && !mm.rowsNearBd.empty()) std::memcpy(rows, mm.rowsNearBd.data(), sizeof(int32_t) * mm.rowsNearBd.size());
+  });
+}
+
+int32_t pda_mesh_num_cells_strictly_on_bd(pda_mesh m) {
+  if (!m) return -1;
+  int32_t n = -1;
+  guarded([&] {
+    std::vector<int32_t> rows;
+    m->m.strictlyOnBdRows(rows);
+    n = (int32_t)rows.size();
+  });
+  return n;
+}
+
+pda_status pda_mesh_rows_strictly_on_bd(pda_mesh m, int32_t* rows) {
+  return guarded([&] {
+    std::vector<int32_t> r;
+    M(m).strictlyOnBdRows(r);
+    if (rows && !r.empty()) std::memcpy(rows, r.data(), sizeof(int32_t) * r.size());
   });
 }
 
@@ -312,6 +337,54 @@ pda_status pda_slab_velocity_peer_dev(pda_problem p, const double* dU, double t,
 
 pda_status pda_slab_velocity_peer_host(pda_problem p, const double* U, double t, double* V) {
   return guarded([&] { P(p).slabVelocityPeerHost(U, t, V); });
+}
+
+// ------------------------------------------------------------------ boundary-face gradients
+pda_status pda_gradient_create(pda_mesh mesh, int max_num_dof_per_cell, pda_gradient* out) {
+  return guarded([&] {
+    if (!out) throw pda::Error(pda::kInvalid, "gradient_create: null output");
+    *out = new pda_gradient_s{new pda::GradientEvaluator(M(mesh), max_num_dof_per_cell)};
+  });
+}
+
+pda_status pda_gradient_free(pda_gradient g) {
+  if (g) { delete g->g; delete g; }
+  return PDA_OK;
+}
+
+int32_t pda_gradient_num_faces(pda_gradient g) { return (g && g->g) ? g->g->numFaces() : -1; }
+int64_t pda_gradient_launch_count(pda_gradient g) { return (g && g->g) ? g->g->launchCount() : -1; }
+
+pda_status pda_gradient_faces(pda_gradient g, int32_t* cell_gid, int32_t* position, int32_t* parent_graph_row,
+                              int32_t* normal_direction, double* centers) {
+  return guarded([&] {
+    pda::GradientEvaluator& e = GE(g);
+    const size_t n = (size_t)e.numFaces();
+    if (n == 0) return;
+    if (cell_gid) std::memcpy(cell_gid, e.cellGid().data(), n * sizeof(int32_t));
+    if (position) std::memcpy(position, e.position().data(), n * sizeof(int32_t));
+    if (parent_graph_row) std::memcpy(parent_graph_row, e.parentRow().data(), n * sizeof(int32_t));
+    if (normal_direction) std::memcpy(normal_direction, e.normalDirection().data(), n * sizeof(int32_t));
+    if (centers) std::memcpy(centers, e.centers().data(), 3 * n * sizeof(double));
+  });
+}
+
+pda_status pda_gradient_query_face(pda_gradient g, int32_t cell_gid, int position, int32_t* face_index) {
+  return guarded([&] {
+    if (!face_index) throw pda::Error(pda::kInvalid, "gradient_query_face: null output");
+    const int32_t i = GE(g).findFace(cell_gid, position);
+    if (i < 0) throw pda::Error(pda::kInvalid, "gradient_query_face: the mesh has no such boundary face");
+    *face_index = i;
+  });
+}
+
+pda_status pda_gradient_compute_host(pda_gradient g, const double* field, int num_dof_per_cell, double* normal_grad) {
+  return guarded([&] { GE(g).computeHost(field, num_dof_per_cell, normal_grad); });
+}
+
+pda_status pda_gradient_compute_dev(pda_gradient g, const double* d_field, int num_dof_per_cell, double* d_normal_grad,
+                                    void* stream) {
+  return guarded([&] { GE(g).computeDev(d_field, num_dof_per_cell, d_normal_grad, stream); });
 }
 
 }  // extern "C"

@@ -119,6 +119,28 @@ void Mesh::nearBdRows(std::vector<int32_t>& out) const {
   }
 }
 
+void Mesh::graphRow(int32_t r, int32_t* row) const {
+  if (haveGraph) {
+    const int nc = ncols();
+    for (int c = 0; c < nc; ++c) row[c] = graph[(size_t)r * nc + c];
+    return;
+  }
+  if (!lattice) throw Error(kInvalid, "mesh: graph not available");
+  latticeRow(r, row);
+}
+
+void Mesh::strictlyOnBdRows(std::vector<int32_t>& out) const {
+  out.clear();
+  if (dim != 2) return;
+  std::vector<int32_t> nb;
+  nearBdRows(nb);
+  int32_t row[32];
+  for (int32_t r : nb) {
+    graphRow(r, row);
+    if (row[1] == -1 || row[2] == -1 || row[3] == -1 || row[4] == -1) out.push_back(r);   // mesh_ccu.hpp:298-326
+  }
+}
+
 void Mesh::ensureCoords() {
   if (haveCoords) return;
   if (!lattice) throw Error(kInvalid, "mesh: coordinates not available");

@@ -55,6 +55,11 @@ struct Mesh {
   bool rowIsNearBd(const int32_t* row) const;
   // list of near-boundary rows in ascending row order (lattice: computed analytically)
   void nearBdRows(std::vector<int32_t>& out) const;
+  // graph row r (ncols() entries): from the stored graph, or synthesised for a lattice that has none
+  void graphRow(int32_t r, int32_t* row) const;
+  // graphRowsOfCellsStrictlyOnBd (mesh_ccu.hpp:153-155, 441-447): the near-boundary rows with a first-layer
+  // neighbour missing, ascending; 2D only (the reference fills the list for 2D meshes only)
+  void strictlyOnBdRows(std::vector<int32_t>& out) const;
 
   static Mesh makeLattice(int dim, const int32_t n[3], const double bounds[6], const int32_t periodic[3], int stencil);
   static Mesh load(const std::string& dir);

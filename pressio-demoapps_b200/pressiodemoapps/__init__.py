@@ -26,6 +26,7 @@ __all__ = [
     "create_linear_advection_1d_problem", "create_diffusion_reaction_1d_problem_A", "create_burgers_2d_problem",
     "create_diffusion_reaction_2d_problem_A", "create_adv_diff_reac_2d_problem_A",
     "advanceRK2", "advanceRK4", "advanceSSP3", "PdaError", "device_count", "BC",
+    "FacePosition", "GradientEvaluator",
 ]
 
 _HERE = _os.path.dirname(_os.path.abspath(__file__))
@@ -87,6 +88,16 @@ _sig("pda_mesh_graph", _C.c_int, _vp, _vp)
 _sig("pda_mesh_rows_inner", _C.c_int, _vp, _vp)
 _sig("pda_mesh_rows_near_bd", _C.c_int, _vp, _vp)
 _sig("pda_mesh_stencil_gids", _C.c_int, _vp, _vp)
+_sig("pda_mesh_num_cells_strictly_on_bd", _i32, _vp)
+_sig("pda_mesh_rows_strictly_on_bd", _C.c_int, _vp, _vp)
+_sig("pda_gradient_create", _C.c_int, _vp, _C.c_int, _C.POINTER(_vp))
+_sig("pda_gradient_free", _C.c_int, _vp)
+_sig("pda_gradient_num_faces", _i32, _vp)
+_sig("pda_gradient_launch_count", _i64, _vp)
+_sig("pda_gradient_faces", _C.c_int, _vp, _vp, _vp, _vp, _vp, _vp)
+_sig("pda_gradient_query_face", _C.c_int, _vp, _i32, _C.c_int, _C.POINTER(_i32))
+_sig("pda_gradient_compute_host", _C.c_int, _vp, _vp, _C.c_int, _vp)
+_sig("pda_gradient_compute_dev", _C.c_int, _vp, _vp, _C.c_int, _vp, _vp)
 _sig("pda_problem_create", _C.c_int, _vp, _C.c_int, _C.c_int, _C.c_int, _C.c_int, _C.c_int, _vp, _vp, _C.c_int,
      _C.POINTER(_vp))
 _sig("pda_problem_set_bc", _C.c_int, _vp, _C.c_int, _C.c_int, _vp)
@@ -292,6 +303,12 @@ class CellCenteredUniformMesh:
     def graphRowsOfCellsNearBd(self):
         r = _np.zeros(self.numCellsNearBd(), dtype=_np.int32)
         _check(_lib.pda_mesh_rows_near_bd(self._h, r.ctypes.data))
+        return r
+
+    def graphRowsOfCellsStrictlyOnBd(self):
+        """impl/mesh_ccu.hpp:153-155: rows of the cells with at least one face on the domain boundary (2D meshes)."""
+        r = _np.zeros(max(0, _lib.pda_mesh_num_cells_strictly_on_bd(self._h)), dtype=_np.int32)
+        _check(_lib.pda_mesh_rows_strictly_on_bd(self._h, r.ctypes.data))
         return r
 
     def stencilMeshGids(self):
@@ -710,6 +727,83 @@ def create_cross_shock_problem(mesh, recon, density, inletXVel, bottomYVel, devi
     return _make(mesh, 2, Euler2d.CrossShock, recon, 1,
                  {"crossShockDensity": density, "crossShockInletXVel": inletXVel,
                   "crossShockBottomYVel": bottomYVel}, device)
+
+
+# ------------------------------------------------------------------------------------- boundary-face gradients
+class FacePosition(_IntEnum):
+    """schemes_info.hpp:112-114."""
+    Left = 0
+    Front = 1
+    Right = 2
+    Back = 3
+    Bottom = 4
+    Top = 5
+
+
+class _Face:
+    """What queryFace returns (gradient.hpp:95-113): centerCoordinates, normalGradient (a float when the evaluator
+    was made for one dof per cell, an array of MaxNumDofPerCell entries otherwise), normalDirection (1 = x, 2 = y)."""
+    __slots__ = ("centerCoordinates", "normalGradient", "normalDirection", "parentCellGraphRow")
+
+    def __init__(self, c, g, d, r):
+        self.centerCoordinates, self.normalGradient, self.normalDirection, self.parentCellGraphRow = c, g, d, r
+
+
+class GradientEvaluator:
+    """GradientEvaluator<MeshType, MaxNumDofPerCell>(mesh) of the reference (gradient.hpp:61-121): normal gradients of
+    a cell-centred field at the faces on the domain boundary (2D), computed on the GPU (pda_gradient_*)."""
+
+    def __init__(self, mesh, maxNumDofPerCell=1):
+        h = _vp()
+        _check(_lib.pda_gradient_create(mesh._h, int(maxNumDofPerCell), _C.byref(h)))
+        self._h = h
+        self._max = int(maxNumDofPerCell)
+        self._nStencil = mesh.stencilMeshSize()
+        n = _lib.pda_gradient_num_faces(self._h)
+        self.cellGIDs = _np.zeros(n, dtype=_np.int32)
+        self.positions = _np.zeros(n, dtype=_np.int32)
+        self.parentRows = _np.zeros(n, dtype=_np.int32)
+        self.normalDirections = _np.zeros(n, dtype=_np.int32)
+        self.centers = _np.zeros((n, 3))
+        _check(_lib.pda_gradient_faces(self._h, self.cellGIDs.ctypes.data, self.positions.ctypes.data,
+                                       self.parentRows.ctypes.data, self.normalDirections.ctypes.data,
+                                       self.centers.ctypes.data))
+        self.normalGradients = _np.zeros((n, self._max))   # like the reference's faces: zero until evaluated
+
+    def __del__(self):
+        h = getattr(self, "_h", None)
+        if h:
+            _lib.pda_gradient_free(h)
+            self._h = None
+
+    def numFaces(self):
+        return int(self.cellGIDs.size)
+
+    def __call__(self, field, numDofPerCell=1):
+        """operator()(field) / operator()(field, numDofPerCell), gradient.hpp:77-93."""
+        nd = int(numDofPerCell)
+        if nd > self._max or nd < 1:   # let the library produce the reference's message
+            _check(_lib.pda_gradient_compute_host(self._h, None, nd, None))
+        field = _f64(field, self._nStencil * nd, "field")
+        out = _np.zeros((self.numFaces(), nd))
+        _check(_lib.pda_gradient_compute_host(self._h, _np.ascontiguousarray(field).ctypes.data, nd, out.ctypes.data))
+        self.normalGradients[:, :nd] = out
+        return out
+
+    def computeDevice(self, dField, numDofPerCell, dNormalGrad, stream=0):
+        """device pointers (ints), asynchronous on `stream`; dNormalGrad = [numFaces][numDofPerCell]"""
+        _check(_lib.pda_gradient_compute_dev(self._h, dField, int(numDofPerCell), dNormalGrad, stream))
+
+    def queryFace(self, cellGID, facePosition):
+        """gradient.hpp:115-117."""
+        i = _i32()
+        _check(_lib.pda_gradient_query_face(self._h, int(cellGID), int(facePosition), _C.byref(i)))
+        k = i.value
+        g = float(self.normalGradients[k, 0]) if self._max == 1 else self.normalGradients[k].copy()
+        return _Face(self.centers[k].copy(), g, int(self.normalDirections[k]), int(self.parentRows[k]))
+
+    def launchCount(self):
+        return int(_lib.pda_gradient_launch_count(self._h))
 
 
 # ------------------------------------------------------------------------------------------------ time loops

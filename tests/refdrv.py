@@ -304,3 +304,83 @@ def exact_velocity_and_jacobian(meshDir, family, probEnum, recon, icFlag, params
     L.or_velocity_and_jacobian(h, Ul.ctypes.data, C.c_longdouble(t), V.ctypes.data, J.ctypes.data)
     L.or_destroy(h)
     return V.astype(np.float64), J.astype(np.float64)
+
+
+# ------------------------------------------------------------------------------------ boundary-face gradients
+def ref_grad_lib_path():
+    return os.path.join(REFDIR, "libpda_ref_grad.so")
+
+
+def have_ref_grad():
+    return os.path.exists(ref_grad_lib_path())
+
+
+def _ref_grad():
+    key = ("refgrad", False)
+    if key not in _libs:
+        L = C.CDLL(ref_grad_lib_path())
+        vp, ci = C.c_void_p, C.c_int
+        L.pdaref_grad_last_error.restype = C.c_char_p
+        L.pdaref_rows_strictly_on_bd.restype = C.c_int64
+        L.pdaref_rows_strictly_on_bd.argtypes = [C.c_char_p, vp]
+        L.pdaref_grad_faces.restype = C.c_int64
+        L.pdaref_grad_faces.argtypes = [C.c_char_p, vp, vp, vp]
+        L.pdaref_grad_eval.restype = ci
+        L.pdaref_grad_eval.argtypes = [C.c_char_p, ci, ci, vp, vp, vp, vp]
+        _libs[key] = L
+    return _libs[key]
+
+
+def ref_rows_strictly_on_bd(meshDir):
+    """graphRowsOfCellsStrictlyOnBd() of the unmodified reference's mesh"""
+    L = _ref_grad()
+    n = L.pdaref_rows_strictly_on_bd(str(meshDir).encode(), None)
+    if n < 0:
+        raise RuntimeError("reference: " + L.pdaref_grad_last_error().decode())
+    r = np.zeros(max(n, 1), dtype=np.int32)
+    L.pdaref_rows_strictly_on_bd(str(meshDir).encode(), r.ctypes.data)
+    return r[:n]
+
+
+def ref_gradient(meshDir, field, ndpc=1, scalar_api=False):
+    """The unmodified reference's GradientEvaluator on the mesh in `meshDir`: dict(cellGid, position, parentRow,
+    normalDir, centers [n][3], grad [n][ndpc]); faces in the order of tests_cpp/gradients/main.cc:48-97."""
+    L = _ref_grad()
+    d = str(meshDir).encode()
+    n = L.pdaref_grad_faces(d, None, None, None)
+    if n < 0:
+        raise RuntimeError("reference: " + L.pdaref_grad_last_error().decode())
+    gid, pos, row, nd = (np.zeros(max(n, 1), dtype=np.int32) for _ in range(4))
+    L.pdaref_grad_faces(d, gid.ctypes.data, pos.ctypes.data, row.ctypes.data)
+    grad = np.zeros((max(n, 1), ndpc))
+    cen = np.zeros((max(n, 1), 3))
+    f = np.ascontiguousarray(field, dtype=np.float64)
+    if L.pdaref_grad_eval(d, int(ndpc), int(bool(scalar_api)), f.ctypes.data, grad.ctypes.data, cen.ctypes.data,
+                          nd.ctypes.data):
+        raise RuntimeError("reference: " + L.pdaref_grad_last_error().decode())
+    return dict(cellGid=gid[:n], position=pos[:n], parentRow=row[:n], normalDir=nd[:n], centers=cen[:n], grad=grad[:n])
+
+
+def oracle_gradient(stencil, graph, rowsNearBd, x, y, z, dx, dy, field, ndpc=1):
+    """The C restatement (oracle/pda_oracle.c: or_gradient_faces / or_gradient_eval) on mesh arrays; same dict"""
+    L = _oracle()
+    L.or_gradient_faces.restype = C.c_int64
+    L.or_gradient_faces.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p,
+                                    C.c_double, C.c_double] + [C.c_void_p] * 5
+    L.or_gradient_eval.restype = None
+    L.or_gradient_eval.argtypes = [C.c_int, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_double, C.c_double,
+                                   C.c_void_p, C.c_int, C.c_void_p]
+    graph = np.ascontiguousarray(graph, dtype=np.int32)
+    rows = np.ascontiguousarray(rowsNearBd, dtype=np.int32)
+    x, y, z = (np.ascontiguousarray(a, dtype=np.float64) for a in (x, y, z))
+    head = (int(stencil), graph.ctypes.data, rows.ctypes.data if rows.size else None, int(rows.size), x.ctypes.data,
+            y.ctypes.data, z.ctypes.data, float(dx), float(dy))
+    n = L.or_gradient_faces(*head, None, None, None, None, None)
+    gid, pos, row, nd = (np.zeros(max(n, 1), dtype=np.int32) for _ in range(4))
+    cen = np.zeros((max(n, 1), 3))
+    L.or_gradient_faces(*head, gid.ctypes.data, pos.ctypes.data, row.ctypes.data, nd.ctypes.data, cen.ctypes.data)
+    grad = np.zeros((max(n, 1), ndpc))
+    f = np.ascontiguousarray(field, dtype=np.float64)
+    L.or_gradient_eval(int(stencil), graph.ctypes.data, n, pos.ctypes.data, row.ctypes.data, float(dx), float(dy),
+                       f.ctypes.data, int(ndpc), grad.ctypes.data)
+    return dict(cellGid=gid[:n], position=pos[:n], parentRow=row[:n], normalDir=nd[:n], centers=cen[:n], grad=grad[:n])
