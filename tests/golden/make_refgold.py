@@ -29,3 +29,13 @@ for name, c in CASES.items():
 os.makedirs(os.path.join(HERE, "refgold"), exist_ok=True)
 np.savez_compressed(os.path.join(HERE, "refgold", "refgold.npz"), **out)
 print("wrote %d gold vectors, %d values" % (len(out), sum(v.size for v in out.values())))
+
+# tests_cpp/eigen_2d_euler_riemann_explicit_with_gradients/{firstorder,weno3,weno5}/grad_gold_{init,final}.txt:
+# one row per boundary face (x, y, 4 normal gradients, normal direction), compared by its compare.py at 1e-8
+gout = {}
+for scheme in ("firstorder", "weno3", "weno5"):
+    for which in ("init", "final"):
+        gout["%s/%s" % (scheme, which)] = np.loadtxt(os.path.join(
+            REF, "eigen_2d_euler_riemann_explicit_with_gradients", scheme, "grad_gold_%s.txt" % which))
+np.savez_compressed(os.path.join(HERE, "refgold", "gradients_riemann2d.npz"), **gout)
+print("wrote %d gradient gold tables" % len(gout))

@@ -127,3 +127,18 @@ def test_fixtures_are_current():
         r = ref_gradient(d, g["f3"].ravel(), 3)
         assert np.array_equal(r["grad"], g["grad3"]) and np.array_equal(r["centers"], g["centers"])
         assert np.array_equal(ref_rows_strictly_on_bd(d), g["rowsStrictlyOnBd"])
+
+
+@pytest.mark.parametrize("scheme,stencil", [("firstorder", 3), ("weno3", 5), ("weno5", 7)])
+def test_oracle_reference_regression_initial_gradients(scheme, stencil):
+    """tests_cpp/eigen_2d_euler_riemann_explicit_with_gradients: the t = 0 table (grad_gold_init.txt) from the oracle
+    on the problem's initial condition, the reference's own criterion (compare.py: rtol = atol = 1e-8)"""
+    gold = np.load(os.path.join(GOLDEN, "refgold", "gradients_riemann2d.npz"))["%s/init" % scheme]
+    mesh = pda.create_full_mesh([22, 22], [0.0, 1.0, 0.0, 1.0], stencil)
+    recon = {"firstorder": 0, "weno3": 1, "weno5": 2}[scheme]
+    U = pda.create_problem(mesh, pda.Euler2d.Riemann, pda.InviscidFluxReconstruction(recon), 2).initialCondition()
+    o = oracle_gradient(stencil, mesh.graph(), mesh.graphRowsOfCellsNearBd(), mesh.viewX(), mesh.viewY(), mesh.viewZ(),
+                        mesh.dx(), mesh.dy(), U, 4)
+    t = np.column_stack([o["centers"][:, 0], o["centers"][:, 1], o["grad"], o["normalDir"].astype(float)])
+    t[0, 0], t[0, 1] = float("%.6g" % t[0, 0]), float("%.6g" % t[0, 1])
+    assert t.shape == gold.shape and np.allclose(gold, t, rtol=1e-8, atol=1e-8)
