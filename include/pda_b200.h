@@ -161,6 +161,11 @@ typedef void (*pda_bc_ghost_fn)(void* user, int32_t near_bd_row, const int32_t* 
 typedef void (*pda_bc_factor_fn)(void* user, const int32_t* graph_row, double cell_x, double cell_y, int ndpc,
                                  double* factors);
 pda_status pda_problem_set_bc_callback(pda_problem p, int side, pda_bc_ghost_fn ghost, pda_bc_factor_fn factors, void* user);
+/* setBCPointer(GhostRelativeLocation, ptr) (euler_2d_prob_class.hpp:213-216, swe_2d_prob_class.hpp:224-227,
+ * advection_diffusion_2d_prob_class.hpp:199-202 -> custom_bc_holder.hpp:89-103 -> the functor's setInternalPtr): re-points
+ * the state handed to the host functors of `side` (their `user` argument), e.g. at a neighbouring subdomain's state in
+ * a Schwarz iteration.  PDA_ERR_INVALID when no host functor is installed on that side. */
+pda_status pda_problem_set_bc_pointer(pda_problem p, int side, void* user);
 pda_status pda_problem_free(pda_problem p);
 
 int     pda_problem_num_dof_per_cell(pda_problem p);       /* numDofPerCell()        adapter_cpp.hpp:93-95   */

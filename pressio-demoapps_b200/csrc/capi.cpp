@@ -214,6 +214,10 @@ pda_status pda_problem_set_bc_callback(pda_problem p, int side, pda_bc_ghost_fn 
   return guarded([&] { P(p).setBcCallback(side, ghost, factors, user); });
 }
 
+pda_status pda_problem_set_bc_pointer(pda_problem p, int side, void* user) {
+  return guarded([&] { P(p).setBcPointer(side, user); });
+}
+
 pda_status pda_problem_free(pda_problem p) {
   if (p) { delete p->p; delete p; }
   return PDA_OK;

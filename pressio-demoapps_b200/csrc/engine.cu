@@ -422,6 +422,14 @@ void Problem::setBcCallback(int side, BcGhostFn ghost, BcFactorFn factors, void*
   if (dev_) { dev_->haveGhosts = false; dev_->jacTablesReady = false; }
 }
 
+void Problem::setBcPointer(int side, void* user) {
+  // setBCPointer(rloc, ptr) hands ptr to the functor of that side (custom_bc_holder.hpp:89-103 -> the user's
+  // setInternalPtr); here the functor's state IS the `user` argument of its callbacks
+  if (side < 0 || side > 3) throw Error(kInvalid, "set_bc_pointer: invalid side");
+  if (bc_[side].kind != BC_CALLBACK) throw Error(kInvalid, "set_bc_pointer: no host functor installed on this side");
+  bc_[side].user = user;   // the functors run at every evaluation: nothing cached depends on it
+}
+
 // =============================================================================================== initial condition
 void Problem::initialCondition(double* U) const {
   Mesh& m = *mesh_;

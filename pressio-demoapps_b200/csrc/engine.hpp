@@ -39,6 +39,7 @@ class Problem {
   void initialCondition(double* U) const;
   void setBc(int side, int kind, const double* values);
   void setBcCallback(int side, BcGhostFn ghost, BcFactorFn factors, void* user);
+  void setBcPointer(int side, void* user);   // setBCPointer (euler_2d_prob_class.hpp:213-216)
   void setSource(const double* values);   // nSample doubles (host)
 
   int64_t jacobianNnz();

@@ -182,8 +182,20 @@ struct ApplyLat3d {
   static constexpr size_t smemBytes = (size_t)T * T * T * RS * sizeof(double);
 };
 
-template <int S, int AX, int NC>
-PDA_DEVFN void applyLatLine3(double gamma, const LatticeDesc& L, double hInv, const double* __restrict__ U,
+// One copy of the line code serves the three phases (`ax` is a run-time, warp-uniform argument): the kernel's
+// instruction footprint is a third of the per-axis instantiation (ncu on the first version: `no_instruction`
+// 2.2 of 9.4 stall cycles per issue).  The flux Jacobians are always taken along x of a state whose momentum
+// components 1 and 1+ax are swapped -- the Euler flux along axis ax of q is P F_x(P q) with P that swap -- so
+// D = P (JN' P dN + JP' P dP): four cheap swaps instead of three copies of eulerFluxJacFast.
+PDA_DEVFN void swapMomentum(int ax, double* v) {
+  const double v1 = v[1], v2 = v[2], v3 = v[3];
+  v[1] = (ax == 0) ? v1 : ((ax == 1) ? v2 : v3);
+  v[2] = (ax == 1) ? v1 : v2;
+  v[3] = (ax == 2) ? v1 : v3;
+}
+
+template <int S, int NC>
+PDA_DEVFN void applyLatLine3(double gamma, const LatticeDesc& L, int ax, double hInv, const double* __restrict__ U,
                              const double* __restrict__ B, int ncols, int c0, int64_t ldbRow, int64_t ldbCol,
                              double* __restrict__ R, int64_t ldrRow, int64_t ldrCol, int a, int o1, int o2, bool owns,
                              int cellLocal, double* __restrict__ sR) {
@@ -191,14 +203,13 @@ PDA_DEVFN void applyLatLine3(double gamma, const LatticeDesc& L, double hInv, co
   constexpr int h = (S - 1) / 2;
   using K = ApplyLat3d<NC>;
   const int64_t nx = L.n[0], ny = L.n[1];
-  const int nA = L.n[AX], perA = L.per[AX];
+  const int nA = (ax == 0) ? L.n[0] : ((ax == 1) ? L.n[1] : L.n[2]);
+  const int perA = (ax == 0) ? L.per[0] : ((ax == 1) ? L.per[1] : L.per[2]);
   const int nc = min(NC, ncols - c0);
-  // (a, o1, o2) -> (x, y, z): AX = 0: a = x, (o1, o2) = (y, z); AX = 1: a = y, (o1, o2) = (x, z); AX = 2: a = z, (x, y)
-  auto gidOf = [&](int c) -> int64_t {
-    if (AX == 0) return ((int64_t)o2 * ny + o1) * nx + c;
-    if (AX == 1) return ((int64_t)o2 * ny + c) * nx + o1;
-    return ((int64_t)c * ny + o2) * nx + o1;
-  };
+  // (a, o1, o2) -> (x, y, z): ax = 0: a = x, (o1, o2) = (y, z); ax = 1: a = y, (o1, o2) = (x, z); ax = 2: a = z, (x, y)
+  const int64_t lineBase = (ax == 0) ? ((int64_t)o2 * ny + o1) * nx : ((ax == 1) ? (int64_t)o2 * ny * nx + o1 : (int64_t)o2 * nx + o1);
+  const int64_t lineStride = (ax == 0) ? 1 : ((ax == 1) ? nx : nx * ny);
+  auto gidOf = [&](int c) -> int64_t { return lineBase + (int64_t)c * lineStride; };
   int64_t off[S - 1];
   double q[S - 1][N];
 #pragma unroll
@@ -232,25 +243,34 @@ PDA_DEVFN void applyLatLine3(double gamma, const LatticeDesc& L, double hInv, co
     }
   }
   double JN[N * N], JP[N * N];
-  eulerFluxJacFast<3, AX>(gamma, un, up, JN, JP);
+  swapMomentum(ax, un);
+  swapMomentum(ax, up);
+  eulerFluxJacFast<3, 0>(gamma, un, up, JN, JP);
   double r[NC][N];
 #pragma unroll
-  for (int c = 0; c < NC; ++c)
+  for (int c = 0; c < NC; ++c) {
+    swapMomentum(ax, dN[c]);
+    swapMomentum(ax, dP[c]);
+    double d[N];
 #pragma unroll
     for (int k = 0; k < N; ++k) {
-      double d = 0.0;
+      double dk = 0.0;
 #pragma unroll
-      for (int j = 0; j < N; ++j) d += JN[k * N + j] * dN[c][j] + JP[k * N + j] * dP[c][j];
-      r[c][k] = hInv * (d - __shfl_down_sync(0xffffffffu, d, 1));
+      for (int j = 0; j < N; ++j) dk += JN[k * N + j] * dN[c][j] + JP[k * N + j] * dP[c][j];
+      d[k] = dk;
     }
+    swapMomentum(ax, d);
+#pragma unroll
+    for (int k = 0; k < N; ++k) r[c][k] = hInv * (d[k] - __shfl_down_sync(0xffffffffu, d[k], 1));
+  }
   if (!owns) return;
   double* mine = sR + cellLocal * K::RS;
-  if (AX == 0) {
+  if (ax == 0) {
 #pragma unroll
     for (int c = 0; c < NC; ++c)
 #pragma unroll
       for (int k = 0; k < N; ++k) mine[c * N + k] = r[c][k];
-  } else if (AX == 1) {
+  } else if (ax == 1) {
 #pragma unroll
     for (int c = 0; c < NC; ++c)
 #pragma unroll
@@ -284,27 +304,30 @@ k_applyjac_lattice3d(double gamma, LatticeDesc L, Deltas dl, const double* __res
     hi[ax] = L.per[ax] ? L.n[ax] : L.n[ax] - L.meshHalo;
   }
   const int O[3] = {lo[0] + T * (int)blockIdx.x, lo[1] + T * (int)blockIdx.y, lo[2] + T * (int)blockIdx.z};
-#pragma unroll
+#pragma unroll 1
   for (int ax = 0; ax < 3; ++ax) {
-    const int a1 = (ax == 0) ? 1 : 0, a2 = (ax == 2) ? 1 : 2;   // the two other axes (ascending)
+    // origin / upper bound along the line axis and along the two other axes (ascending)
+    const int Oa = (ax == 0) ? O[0] : ((ax == 1) ? O[1] : O[2]);
+    const int O1 = (ax == 0) ? O[1] : O[0], O2 = (ax == 2) ? O[1] : O[2];
+    const int hia = (ax == 0) ? hi[0] : ((ax == 1) ? hi[1] : hi[2]);
+    const int hi1 = (ax == 0) ? hi[1] : hi[0], hi2 = (ax == 2) ? hi[1] : hi[2];
+    const double hInv = (ax == 0) ? dl.hInv[0] : ((ax == 1) ? dl.hInv[1] : dl.hInv[2]);
 #pragma unroll 1
     for (int round = 0; round < 2; ++round) {
-      const int l = round * K::GROUPS + grp;     // line index in the tile: (u, v) offsets along a1, a2
+      const int l = round * K::GROUPS + grp;     // line index in the tile: (u, v) offsets along the other axes
       const int u = l % T, v = l / T;
-      const int a = O[ax] + f;
-      const int c1 = O[a1] + u, c2 = O[a2] + v;
-      const bool owns = (l < T * T) && (f < T) && (a < hi[ax]) && (c1 < hi[a1]) && (c2 < hi[a2]);
-      const int cc1 = min(c1, hi[a1] - 1), cc2 = min(c2, hi[a2] - 1);
+      const int a = Oa + f;
+      const int c1 = O1 + u, c2 = O2 + v;
+      const bool owns = (l < T * T) && (f < T) && (a < hia) && (c1 < hi1) && (c2 < hi2);
+      const int cc1 = min(c1, hi1 - 1), cc2 = min(c2, hi2 - 1);
       const int uu = min(u, T - 1), vv = min(v, T - 1), ff = min(f, T - 1);
       // tile-local linear index (z*T + y)*T + x
-      int lx, ly, lz;
-      if (ax == 0) { lx = ff; ly = uu; lz = vv; }
-      else if (ax == 1) { lx = uu; ly = ff; lz = vv; }
-      else { lx = uu; ly = vv; lz = ff; }
+      const int lx = (ax == 0) ? ff : uu;
+      const int ly = (ax == 0) ? uu : ((ax == 1) ? ff : vv);
+      const int lz = (ax == 2) ? ff : vv;
       const int cellLocal = (lz * T + ly) * T + lx;
-      if (ax == 0) applyLatLine3<S, 0, NC>(gamma, L, dl.hInv[0], U, B, ncols, c0, ldbRow, ldbCol, R, ldrRow, ldrCol, a, cc1, cc2, owns, cellLocal, sR3);
-      else if (ax == 1) applyLatLine3<S, 1, NC>(gamma, L, dl.hInv[1], U, B, ncols, c0, ldbRow, ldbCol, R, ldrRow, ldrCol, a, cc1, cc2, owns, cellLocal, sR3);
-      else applyLatLine3<S, 2, NC>(gamma, L, dl.hInv[2], U, B, ncols, c0, ldbRow, ldbCol, R, ldrRow, ldrCol, a, cc1, cc2, owns, cellLocal, sR3);
+      applyLatLine3<S, NC>(gamma, L, ax, hInv, U, B, ncols, c0, ldbRow, ldbCol, R, ldrRow, ldrCol, a, cc1, cc2, owns,
+                           cellLocal, sR3);
     }
     __syncthreads();
   }

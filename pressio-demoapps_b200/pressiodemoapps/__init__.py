@@ -125,6 +125,7 @@ _sig("pda_slab_initial_condition", _C.c_int, _vp, _vp)
 _sig("pda_slab_velocity_interior_dev", _C.c_int, _vp, _vp, _dbl, _vp, _vp)
 _sig("pda_slab_velocity_boundary_dev", _C.c_int, _vp, _vp, _dbl, _vp, _vp)
 _sig("pda_problem_set_bc_callback", _C.c_int, _vp, _C.c_int, _GHOST_FN, _FACTOR_FN, _vp)
+_sig("pda_problem_set_bc_pointer", _C.c_int, _vp, _C.c_int, _vp)
 _sig("pda_problem_advance_dev", _C.c_int, _vp, _C.c_int, _vp, _dbl, _dbl, _C.c_int32, _vp)
 _sig("pda_problem_advance_host", _C.c_int, _vp, _C.c_int, _vp, _dbl, _dbl, _C.c_int32)
 _sig("pda_slab_peer_handle", _C.c_int, _vp, _vp)
@@ -463,6 +464,11 @@ class Problem:
         self._bc_keepalive = getattr(self, "_bc_keepalive", {})
         self._bc_keepalive[int(side)] = (cg, cf)
         _check(_lib.pda_problem_set_bc_callback(self._h, int(side), cg, cf, None))
+
+    def setBCPointer(self, side, ptr):
+        """setBCPointer(GhostRelativeLocation, ptr) of the reference's custom-BC problems: `ptr` (an int address or a
+        ctypes pointer) becomes the `user` argument of that side's host functors (pda_problem_set_bc_pointer)."""
+        _check(_lib.pda_problem_set_bc_pointer(self._h, int(side), ptr))
 
     # ---- creators
     def initialCondition(self):

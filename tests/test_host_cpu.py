@@ -243,3 +243,15 @@ def test_cpp_eigen_shim_compiles_and_runs_host_part(tmp_path):
     r = subprocess.run([exe, mdir], capture_output=True, text=True, timeout=300)
     assert r.returncode == 0, r.stdout + r.stderr
     assert "dofs 1600 nnz 55808" in r.stdout and "cpp_shim_demo ok" in r.stdout
+
+
+def test_set_bc_pointer_needs_a_host_functor():
+    """pda_problem_set_bc_pointer (the reference's setBCPointer) only makes sense on a side with a host functor"""
+    mesh = pda.create_full_mesh([10, 10], [-5, 5, -5, 5], 3)
+    p = pda.create_problem(mesh, pda.Swe2d.CustomBCs, R.FirstOrder)
+    with pytest.raises(pda.PdaError, match="no host functor"):
+        p.setBCPointer(0, None)
+    p.setBCFunctor(0, lambda *a: None)
+    p.setBCPointer(0, None)
+    with pytest.raises(pda.PdaError, match="invalid side"):
+        p.setBCPointer(7, None)

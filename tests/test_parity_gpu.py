@@ -604,3 +604,40 @@ def test_matrix_free_apply_jacobian_3d(case):
         Rm = p.createApplyJacobianResult(B)
         p.applyJacobian(U, B, 0.0, Rm)
         assert scaled_err(Rm, J @ B, 1e-11, 1e-9) <= 1.0
+
+
+def test_set_bc_pointer_repoints_host_functor_state():
+    """setBCPointer(loc, ptr) (euler_2d_prob_class.hpp:213-216 -> custom_bc_holder.hpp:89-103): the state handed to a
+    side's host functor can be swapped between evaluations (pda_problem_set_bc_pointer) -- a Dirichlet functor reading
+    its ghost state through that pointer equals the device Dirichlet rule with the respective values, bit for bit."""
+    import ctypes as C
+    mesh = pda.create_full_mesh([20, 18], [-5, 5, -5, 5], 3)
+    valsA = np.array([0.00001, 0.004, 0.001])
+    valsB = np.array([0.5, -0.25, 0.125])
+    p = pda.create_problem(mesh, pda.Swe2d.CustomBCs, R.FirstOrder)
+
+    def ghost(user, row_id, grow, x, y, U, nd, width, out):
+        src = C.cast(user, C.POINTER(C.c_double))
+        for d in range(nd):
+            out[d] = src[d]
+
+    def neumann(user, row_id, grow, x, y, U, nd, width, out):
+        for d in range(nd):
+            out[d] = U[grow[0] * nd + d]
+    cg, cn, cf = pda._GHOST_FN(ghost), pda._GHOST_FN(neumann), pda._FACTOR_FN()
+    pda._check(pda._lib.pda_problem_set_bc_callback(p._h, 0, cg, cf, valsA.ctypes.data))
+    for s in (1, 2, 3):
+        pda._check(pda._lib.pda_problem_set_bc_callback(p._h, s, cn, cf, None))
+    U = perturbed(p)
+    for vals in (valsA, valsB, valsA):
+        p.setBCPointer(0, vals.ctypes.data)
+        V = p.createRightHandSide()
+        p.rightHandSide(U, 0.0, V)
+        q = pda.create_problem(mesh, pda.Swe2d.CustomBCs, R.FirstOrder)
+        q.setBC(0, pda.BC.Dirichlet, vals)
+        for s in (1, 2, 3):
+            q.setBC(s, pda.BC.HomogNeumann)
+        Vq = q.createRightHandSide()
+        q.rightHandSide(U, 0.0, Vq)
+        assert np.array_equal(V, Vq)
+        assert np.array_equal(p.viewGhost(0), q.viewGhost(0))
