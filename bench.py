@@ -511,6 +511,33 @@ def run_b200_arm(args):
                 torch.cuda.empty_cache()
             except Exception as e:
                 line["weno3_reference_pinned"] = {"error": str(e)}
+            # matrix-free applyJacobian (J*v) of the headline problem: no Jacobian of 512^3 WENO5 can be stored
+            # (6.4e10 entries, beyond the reference's int32 indexing); k_applyjac_lattice3d needs U, v and the result
+            try:
+                mesh5 = pda.create_full_mesh([n, n, n], [-1, 1, -1, 1, -1, 1], 7, ("x", "y", "z"))
+                p5 = pda.create_problem(mesh5, pda.Euler3d.PeriodicSmooth, R.Weno5, device=local_rank)
+                U5 = torch.from_numpy(p5.initialCondition()).cuda()
+                b5 = torch.rand_like(U5)
+                r5 = torch.empty_like(U5)
+                for _ in range(2):
+                    p5.applyJacobianDevice(U5.data_ptr(), b5.data_ptr(), 1, 1, 0.0, r5.data_ptr(), st)
+                torch.cuda.synchronize()
+                a5, e5 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                l0 = p5.launchCount()
+                a5.record()
+                for _ in range(3):
+                    p5.applyJacobianDevice(U5.data_ptr(), b5.data_ptr(), 1, 1, 0.0, r5.data_ptr(), st)
+                e5.record()
+                torch.cuda.synchronize()
+                ms5 = a5.elapsed_time(e5) / 3
+                line["apply_jacobian_matrix_free"] = {
+                    "workload": "3D Euler PeriodicSmooth WENO5 %d^3 J*v (no stored Jacobian)" % n, "ms": ms5,
+                    "value": ncells / (ms5 * 1e-3), "unit": UNIT, "kernel": "k_applyjac_lattice3d<7,1>",
+                    "gpu_launches": int(p5.launchCount() - l0), "stored_jacobian_entries": ncells * 475.0}
+                del U5, b5, r5, p5, mesh5
+                torch.cuda.empty_cache()
+            except Exception as e:
+                line["apply_jacobian_matrix_free"] = {"error": str(e)}
         if world == 1 and not args.no_jacobian:
             try:
                 line["jacobian"] = jacobian_leg(torch, pda, local_rank, n2=args.n2)
