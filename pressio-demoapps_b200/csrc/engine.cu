@@ -182,7 +182,7 @@ struct DeviceState {
   DevBuf<double> src;          // per-sample-row source table (diffusion-reaction ProblemA, ADR ProblemA)
   bool srcReady = false;
   // host-pointer pipeline (velocityHost on large lattices)
-  static constexpr int kMaxChunks = 32;
+  static constexpr int kMaxChunks = 128;
   cudaStream_t sH2D = nullptr, sD2H = nullptr;
   cudaEvent_t evIn[kMaxChunks] = {}, evOut[kMaxChunks] = {};
   void ensurePipeline() {
@@ -1417,7 +1417,16 @@ void Problem::velocityHost(const double* U, double t, double* V) {
   //      and c-1; the wrap-around planes of chunk 0 come from the last chunk, which is therefore uploaded first.
   ds.ensurePipeline();
   const int h = (S_ - 1) / 2;
-  const int nChunks = (int)std::min<int64_t>(DeviceState::kMaxChunks, nPlanes / std::max(4, 2 * h));
+  // Small chunks keep the pipeline's head (three uploads before the first kernel) and tail (the last two downloads)
+  // short: the call then costs the box's full-duplex copy time (tools/pcie_peak.py: 114 ms for 5.37 GB each way)
+  // plus a few chunk times; the kernels (16 ms in total) hide behind the copies even at 6 planes per launch.
+  // PDA_HOST_CHUNKS overrides the chunk count (tuning only).
+  static const int chunkLimit = [] {
+    const char* e = std::getenv("PDA_HOST_CHUNKS");
+    const int v = e ? std::atoi(e) : 0;
+    return (v >= 4 && v <= DeviceState::kMaxChunks) ? v : 86;
+  }();
+  const int nChunks = (int)std::max<int64_t>(4, std::min<int64_t>(chunkLimit, nPlanes / std::max(4, 2 * h)));
   const size_t planeDofs = nU / (size_t)nPlanes;
   auto c0 = [&](int c) { return (int32_t)((int64_t)nPlanes * c / nChunks); };
   auto h2d = [&](int c) {

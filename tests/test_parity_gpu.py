@@ -641,3 +641,33 @@ def test_set_bc_pointer_repoints_host_functor_state():
         q.rightHandSide(U, 0.0, Vq)
         assert np.array_equal(V, Vq)
         assert np.array_equal(p.viewGhost(0), q.viewGhost(0))
+
+
+@pytest.mark.parametrize("n,stencil,recon", [([176, 160, 168], 7, "Weno5"), ([200, 168, 150], 5, "Weno3"),
+                                             ([2100, 2050], 7, "Weno5")])
+def test_host_pipeline_equals_device_path(n, stencil, recon):
+    """pda_problem_velocity_host on large periodic lattices (>= 4.2 M cells) runs the chunked H2D -> kernel -> D2H
+    pipeline (chunks of 5-6 planes, evaluatePlanes per chunk): same bits as ONE evaluation of the whole mesh through
+    the device-pointer entry, also on a second call (buffers reused) and from pinned memory"""
+    torch = pytest.importorskip("torch")
+    dim = len(n)
+    bounds = [-1, 1] * dim
+    mesh = pda.create_full_mesh(n, bounds, stencil, ("x", "y", "z")[:dim])
+    fam = pda.Euler3d if dim == 3 else pda.Euler2d
+    p = pda.create_problem(mesh, fam.PeriodicSmooth, getattr(R, recon))
+    U = perturbed(p)
+    dU = torch.from_numpy(U).cuda()
+    dV = torch.empty(p.totalDofSampleMesh(), dtype=torch.float64, device="cuda")
+    p.rightHandSideDevice(dU.data_ptr(), 0.0, dV.data_ptr(), torch.cuda.current_stream().cuda_stream)
+    torch.cuda.synchronize()
+    Vdev = dV.cpu().numpy()
+    V = p.createRightHandSide()
+    p.rightHandSide(U, 0.0, V)
+    assert np.array_equal(V, Vdev)
+    Up = torch.from_numpy(U * 1.25).pin_memory()
+    Vp = torch.empty_like(Up).pin_memory()
+    p.rightHandSide(Up.numpy(), 0.0, Vp.numpy())
+    dU.mul_(1.25)
+    p.rightHandSideDevice(dU.data_ptr(), 0.0, dV.data_ptr(), torch.cuda.current_stream().cuda_stream)
+    torch.cuda.synchronize()
+    assert np.array_equal(Vp.numpy(), dV.cpu().numpy())
