@@ -55,6 +55,25 @@ int main(void) {
     /* 10 SSPRK3 steps with the state resident in HBM */
     CHECK(pda_problem_advance_host(prob, PDA_STEPPER_SSPRK3, U, 0.0, 1e-3, 10));
   }
+  {
+    /* normal gradients of the 4-dof state at the faces on the domain boundary (GradientEvaluator, gradient.hpp) */
+    pda_gradient grad = NULL;
+    int32_t nfaces, k = -1;
+    CHECK(pda_gradient_create(mesh, 4, &grad));
+    nfaces = pda_gradient_num_faces(grad);
+    if (nfaces != 2 * (40 + 30)) return 6;
+    CHECK(pda_gradient_query_face(grad, 0, 0 /* FacePosition::Left of cell 0 */, &k));
+    if (k != 0) return 7;
+    if (pda_device_count() >= 1) {
+      double* g = (double*)malloc(sizeof(double) * 4 * (size_t)nfaces);
+      CHECK(pda_gradient_compute_host(grad, U, 4, g));
+      printf("boundary faces %d, d(rho)/dn at the first face %.6e\n", (int)nfaces, g[0]);
+      free(g);
+    } else if (pda_gradient_compute_host(grad, U, 4, V) != PDA_ERR_NO_DEVICE) {
+      return 8;
+    }
+    CHECK(pda_gradient_free(grad));
+  }
   free(U); free(V); free(J); free(rowptr); free(colidx);
   CHECK(pda_problem_free(prob));
   CHECK(pda_mesh_free(mesh));
