@@ -121,6 +121,18 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------------------------------------ CPU legs
+def use_all_host_threads():
+    """torchrun exports OMP_NUM_THREADS=1 to every rank unless the user set it; the CPU legs (rank 0 only) are meant to
+    use all the host cores this process may run on.  Must run before the OpenMP checker libraries are loaded (libgomp
+    reads the variable once)."""
+    if os.environ.get("TORCHELASTIC_RUN_ID") or int(os.environ.get("WORLD_SIZE", "1")) > 1:
+        try:
+            ncores = len(os.sched_getaffinity(0))
+        except AttributeError:
+            ncores = os.cpu_count() or 1
+        os.environ["OMP_NUM_THREADS"] = str(ncores)
+
+
 def cpu_leg(n_cpu, target_s=12.0):
     """3D Euler WENO5 periodic n_cpu^3 velocity on the host cores: the oracle port with OpenMP (kind 'port')."""
     import pressiodemoapps as pda
@@ -167,6 +179,7 @@ def run_reference_arm(args):
         return
     n_cpu = 128
     steps, warmup = args.steps, args.warmup
+    use_all_host_threads()
     base, sec1, _ = cpu_leg(n_cpu, target_s=3.0)
     # each step = one bounded sample: `per` evaluations of the n_cpu^3 mesh
     per = int(max(1, min(50, 4.0 / sec1)))
