@@ -30,6 +30,14 @@ elif a.workload == "euler2d_jac":
     J = torch.empty(nnz, dtype=torch.float64, device="cuda")
     for _ in range(a.reps):
         p.rightHandSideAndJacobianDevice(U.data_ptr(), 0.0, V.data_ptr(), J.data_ptr(), st)
+elif a.workload == "euler2d_applyvec":   # matrix-free J*v (k_applyjac_lattice2d)
+    mesh = pda.create_full_mesh([a.n, a.n], [0, 1, 0, 1], 7)
+    p = pda.create_problem(mesh, pda.Euler2d.Riemann, R.Weno5)
+    U = torch.from_numpy(p.initialCondition()).cuda()
+    B = torch.rand(p.totalDofStencilMesh(), dtype=torch.float64, device="cuda")
+    Rm = torch.empty(p.totalDofSampleMesh(), dtype=torch.float64, device="cuda")
+    for _ in range(a.reps):
+        p.applyJacobianDevice(U.data_ptr(), B.data_ptr(), 1, 1, 0.0, Rm.data_ptr(), st)
 elif a.workload == "euler2d_apply":
     mesh = pda.create_full_mesh([a.n, a.n], [0, 1, 0, 1], 7)
     p = pda.create_problem(mesh, pda.Euler2d.Riemann, R.Weno5)
