@@ -6,6 +6,34 @@
 
 #include "pda_b200_eigen.hpp"
 
+// the two boundary-condition functors of the reference's tests_cpp/eigen_2d_swe_custom_bcs/main.cc (6-58), argument
+// for argument: ghost fill and Jacobian-factor call operators
+struct Dirichlet {
+  template <class ConnecRowType, class StateT, class T>
+  void operator()(const int, ConnecRowType const&, const double, const double, const StateT&, int numDofPerCell,
+                  const double, T& ghostValues) const {
+    if (numDofPerCell != 3) return;
+    ghostValues(0) = 0.00001; ghostValues(1) = 0.004; ghostValues(2) = 0.001;
+  }
+  template <class ConnecRowType, class FactorsType>
+  void operator()(ConnecRowType const&, const double, const double, int, FactorsType& factorsForBCJac) const {
+    factorsForBCJac = {0., 0., 0.};
+  }
+};
+struct HomogNeumann {
+  template <class ConnecRowType, class StateT, class T>
+  void operator()(const int, ConnecRowType const& connectivityRow, const double, const double, const StateT& currentState,
+                  int numDofPerCell, const double, T& ghostValues) const {
+    const int cellGID = connectivityRow[0];
+    const auto uIndex = cellGID * numDofPerCell;
+    ghostValues[0] = currentState(uIndex); ghostValues[1] = currentState(uIndex + 1); ghostValues[2] = currentState(uIndex + 2);
+  }
+  template <class ConnecRowType, class FactorsType>
+  void operator()(ConnecRowType const&, const double, const double, int, FactorsType& factorsForBCJac) const {
+    factorsForBCJac = {1., 1., 1.};
+  }
+};
+
 int main(int argc, char** argv) {
   namespace pda = pressiodemoapps_b200;
   if (argc < 2) return 2;
@@ -54,6 +82,38 @@ int main(int argc, char** argv) {
     } else {
       try { grads(f); return 7; }
       catch (const std::runtime_error& e) { std::printf("gradients, no device: %s\n", e.what()); }
+    }
+  }
+  // custom boundary conditions through host functors (create_problem_eigen with four functors, swe2d.hpp:187-281)
+  // against the same rules as device tables: identical velocity and Jacobian
+  {
+    const auto fo = pda::InviscidFluxReconstruction::FirstOrder;
+    auto sweF = pda::create_problem_eigen(meshObj, pda::Swe2d::CustomBCs, fo, Dirichlet(), Dirichlet(), HomogNeumann(), HomogNeumann());
+    auto sweD = pda::create_problem_eigen(meshObj, pda::Swe2d::CustomBCs, fo);
+    const double dirich[3] = {0.00001, 0.004, 0.001};
+    for (int side = 0; side < 4; ++side)
+      if (pda_problem_set_bc(sweD.handle(), side, side < 2 ? PDA_BC_DIRICHLET : PDA_BC_HOMOG_NEUMANN, dirich) != PDA_OK) return 8;
+    Eigen::VectorXd u = sweF.initialCondition();
+    for (int i = 0; i < u.size(); ++i) u(i) += 0.5;   // like verifyJacobian, main.cc:66-69
+    auto vF = sweF.createRightHandSide(), vD = sweD.createRightHandSide();
+    auto jF = sweF.createJacobian(), jD = sweD.createJacobian();
+    if (pda_device_count() > 0) {
+      sweF.rightHandSideAndJacobian(u, 0.0, vF, jF);
+      sweD.rightHandSideAndJacobian(u, 0.0, vD, jD);
+      const double dv = (vF - vD).cwiseAbs().maxCoeff();
+      const double dj = (Eigen::VectorXd::Map(jF.valuePtr(), jF.nonZeros()) - Eigen::VectorXd::Map(jD.valuePtr(), jD.nonZeros())).cwiseAbs().maxCoeff();
+      // central finite-difference check of J*a, like the second-order check of the reference test (main.cc:97-104)
+      Eigen::VectorXd a = Eigen::VectorXd::Random(u.size());
+      const double eps = 1e-6;
+      Eigen::VectorXd u2 = u + eps * a, u3 = u - eps * a, v2 = vF, v3 = vF;
+      sweF.rightHandSide(u2, 0.0, v2);
+      sweF.rightHandSide(u3, 0.0, v3);
+      const double fd = ((v2 - v3) / (2.0 * eps) - jF * a).cwiseAbs().maxCoeff();
+      std::printf("custom BC functors vs device rules: |dV|max %.1e |dJ|max %.1e ; |J a - FD|max %.2e\n", dv, dj, fd);
+      if (dv != 0.0 || dj != 0.0 || !(fd < 1e-5)) return 9;
+    } else {
+      try { sweF.rightHandSide(u, 0.0, vF); return 10; }
+      catch (const std::runtime_error& e) { std::printf("custom BC functors, no device: %s\n", e.what()); }
     }
   }
   std::printf("cpp_shim_demo ok\n");

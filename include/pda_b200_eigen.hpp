@@ -8,6 +8,7 @@
 
 #include <algorithm>
 #include <array>
+#include <memory>
 #include <stdexcept>
 #include <string>
 #include <type_traits>
@@ -44,6 +45,43 @@ template <> struct family_of<AdvectionDiffusion2d> { static constexpr int value 
 template <> struct family_of<AdvectionDiffusionReaction2d> { static constexpr int value = PDA_FAMILY_ADVECTION_DIFFUSION_REACTION2D; };
 template <> struct family_of<Advection1d> { static constexpr int value = PDA_FAMILY_ADVECTION1D; };
 template <> struct family_of<DiffusionReaction1d> { static constexpr int value = PDA_FAMILY_DIFFUSION_REACTION1D; };
+// dofs per cell of the 2D families that accept custom boundary-condition functors (compile-time, like the reference's
+// std::array<scalar_type, numDofPerCell> Jacobian factors: swe_2d_prob_class.hpp:1054, euler_2d_prob_class.hpp)
+template <class E> struct custom_bc_ndpc;
+template <> struct custom_bc_ndpc<Swe2d> { static constexpr int value = 3; };
+template <> struct custom_bc_ndpc<Euler2d> { static constexpr int value = 4; };
+template <> struct custom_bc_ndpc<AdvectionDiffusion2d> { static constexpr int value = 2; };
+
+// A user functor with the reference's two call operators (custom_bcs_functions.hpp:60-164; e.g. the Dirichlet /
+// HomogNeumann structs of tests_cpp/eigen_2d_swe_custom_bcs/main.cc:6-58) behind the C callbacks of
+// pda_problem_set_bc_callback: Eigen maps stand in for the reference's graph row, state and ghost-row arguments.
+struct BcFunctorBase {
+  virtual ~BcFunctorBase() = default;
+  int ncols = 0, ghostLen = 0;
+  int32_t nState = 0;
+};
+template <class F, int NDPC>
+struct BcFunctorHolder final : BcFunctorBase {
+  F f;
+  explicit BcFunctorHolder(F ff) : f(std::move(ff)) {}
+  using conn_t = Eigen::Map<const Eigen::Matrix<int32_t, 1, Eigen::Dynamic>>;
+  static void ghost(void* user, int32_t nearBdRow, const int32_t* graphRow, double x, double y, const double* U, int ndpc,
+                    double cellWidth, double* ghostValues) {
+    auto* self = static_cast<BcFunctorHolder*>(user);
+    conn_t conn(graphRow, self->ncols);
+    Eigen::Map<const Eigen::VectorXd> state(U, self->nState);
+    Eigen::Map<Eigen::Matrix<double, 1, Eigen::Dynamic>> gv(ghostValues, self->ghostLen);
+    self->f(static_cast<int>(nearBdRow), conn, x, y, state, ndpc, cellWidth, gv);
+  }
+  static void factors(void* user, const int32_t* graphRow, double x, double y, int ndpc, double* out) {
+    auto* self = static_cast<BcFunctorHolder*>(user);
+    conn_t conn(graphRow, self->ncols);
+    std::array<double, NDPC> fac;
+    for (int d = 0; d < NDPC; ++d) fac[(size_t)d] = out[d];
+    self->f(conn, x, y, ndpc, fac);
+    for (int d = 0; d < NDPC; ++d) out[d] = fac[(size_t)d];
+  }
+};
 }  // namespace impl
 
 // CellCenteredUniformMesh look-alike (impl/mesh_ccu.hpp:115-159)
@@ -189,7 +227,7 @@ class Problem {
   }
   Problem(const Problem&) = delete;
   Problem& operator=(const Problem&) = delete;
-  Problem(Problem&& o) noexcept : h_(o.h_) { o.h_ = nullptr; }
+  Problem(Problem&& o) noexcept : h_(o.h_) { o.h_ = nullptr; for (int i = 0; i < 4; ++i) bc_[i] = std::move(o.bc_[i]); }
   ~Problem() { if (h_) pda_problem_free(h_); }
 
   int numDofPerCell() const { return pda_problem_num_dof_per_cell(h_); }
@@ -251,8 +289,21 @@ class Problem {
   }
   pda_problem handle() const { return h_; }
 
+  // custom boundary conditions: one functor per side (0 Left, 1 Front, 2 Right, 3 Back), kept alive by the problem
+  template <int NDPC, class F>
+  void installBcFunctor(int side, const Mesh& m, int recon, F f) {
+    auto holder = std::make_shared<impl::BcFunctorHolder<F, NDPC>>(std::move(f));
+    holder->ncols = (m.stencilSize() - 1) * m.dimensionality() + 1;
+    holder->nState = totalDofStencilMesh();
+    holder->ghostLen = (recon + 1) * NDPC;   // ghost layers of the scheme x dofs per cell
+    impl::check(pda_problem_set_bc_callback(h_, side, &impl::BcFunctorHolder<F, NDPC>::ghost,
+                                            &impl::BcFunctorHolder<F, NDPC>::factors, holder.get()));
+    bc_[side] = std::move(holder);
+  }
+
  private:
   pda_problem h_ = nullptr;
+  std::shared_ptr<impl::BcFunctorBase> bc_[4];
 };
 
 // create_problem_eigen(mesh, <enum>, recon[, icFlag][, {name: value}])  (euler1d.hpp:82-99, euler2d.hpp:88-186, ...)
@@ -265,6 +316,24 @@ template <class ProbEnum>
 Problem create_problem_eigen(const Mesh& m, ProbEnum e, InviscidFluxReconstruction r,
                              const std::unordered_map<std::string, double>& params, int device = 0) {
   return Problem(m, impl::family_of<ProbEnum>::value, static_cast<int>(e), static_cast<int>(r), 1, params, device);
+}
+
+// create_problem_eigen(mesh, <enum>, recon, BCsLeft, BCsFront, BCsRight, BCsBack[, icFlag])  -- the custom-BC overloads
+// (swe2d.hpp:187-281, euler2d.hpp:188-250, advection_diffusion2d.hpp): arbitrary host functors with the reference's
+// two call operators; evaluated on the host for the boundary cells at every evaluation (the slow, fully general path --
+// device-expressible rules go through pda_problem_set_bc and never leave HBM)
+template <class ProbEnum, class FL, class FF, class FR, class FB,
+          class = std::enable_if_t<!std::is_arithmetic<std::decay_t<FL>>::value &&
+                                   !std::is_same<std::decay_t<FL>, std::unordered_map<std::string, double>>::value>>
+Problem create_problem_eigen(const Mesh& m, ProbEnum e, InviscidFluxReconstruction r, FL&& bcLeft, FF&& bcFront,
+                             FR&& bcRight, FB&& bcBack, int icFlag = 1, int device = 0) {
+  constexpr int nd = impl::custom_bc_ndpc<ProbEnum>::value;
+  Problem p(m, impl::family_of<ProbEnum>::value, static_cast<int>(e), static_cast<int>(r), icFlag, {}, device);
+  p.template installBcFunctor<nd>(0, m, static_cast<int>(r), std::decay_t<FL>(std::forward<FL>(bcLeft)));
+  p.template installBcFunctor<nd>(1, m, static_cast<int>(r), std::decay_t<FF>(std::forward<FF>(bcFront)));
+  p.template installBcFunctor<nd>(2, m, static_cast<int>(r), std::decay_t<FR>(std::forward<FR>(bcRight)));
+  p.template installBcFunctor<nd>(3, m, static_cast<int>(r), std::decay_t<FB>(std::forward<FB>(bcBack)));
+  return p;
 }
 
 }  // namespace pressiodemoapps_b200

@@ -671,3 +671,21 @@ def test_host_pipeline_equals_device_path(n, stencil, recon):
     p.rightHandSideDevice(dU.data_ptr(), 0.0, dV.data_ptr(), torch.cuda.current_stream().cuda_stream)
     torch.cuda.synchronize()
     assert np.array_equal(Vp.numpy(), dV.cpu().numpy())
+
+
+def test_cpp_eigen_shim_on_device(tmp_path):
+    """include/pda_b200_eigen.hpp on a GPU: examples/cpp_shim_demo (prebuilt by __graft_entry__.build() where Eigen is
+    available; travels with the snapshot) creates problems like the reference's tests_cpp mains and checks, on the
+    device, applyJacobian vs J*B, the boundary-face gradients, and custom-BC host FUNCTORS with the reference's two call
+    operators (tests_cpp/eigen_2d_swe_custom_bcs/main.cc) against the device BC tables (bit-equal V and J, FD check)."""
+    import os
+    import subprocess
+    exe = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "examples", "_bin", "cpp_shim_demo")
+    if not os.path.exists(exe):
+        pytest.skip("examples/_bin/cpp_shim_demo not built (needs Eigen at build time)")
+    mdir = os.path.join(str(tmp_path), "mesh")
+    pda.create_full_mesh([20, 20], [0, 1, 0, 1], 7).write(mdir)
+    r = subprocess.run([exe, mdir], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "cpp_shim_demo ok" in r.stdout and "custom BC functors vs device rules: |dV|max 0.0e+00 |dJ|max 0.0e+00" in r.stdout
+    assert "left-wall faces 20" in r.stdout
