@@ -3,6 +3,8 @@
 // pattern; evaluate when a GPU is present.  argv[1] = mesh directory written by create_full_mesh.py / pda_mesh_write.
 #include <cmath>
 #include <cstdio>
+#include <filesystem>
+#include <string>
 
 #include "pda_b200_eigen.hpp"
 
@@ -115,6 +117,47 @@ int main(int argc, char** argv) {
       try { sweF.rightHandSide(u, 0.0, vF); return 10; }
       catch (const std::runtime_error& e) { std::printf("custom BC functors, no device: %s\n", e.what()); }
     }
+  }
+  // the named factories and remaining overloads of the reference's public headers (host side only)
+  {
+    const auto w3 = pda::InviscidFluxReconstruction::Weno3;
+    const auto visc = pda::ViscousFluxReconstruction::FirstOrder;
+    // Gray-Scott wants a periodic 3-point-stencil mesh (diffusion_reaction_2d_prob_class.hpp): written next to argv[1]
+    const std::string dir3 = std::string(argv[1]) + "_s3";
+    {
+      const int32_t n3[3] = {16, 16, 1}, per3[3] = {1, 1, 0};
+      const double b3[6] = {-1.25, 1.25, -1.25, 1.25, 0.0, 0.0};
+      pda_mesh h3 = nullptr;
+      std::filesystem::create_directories(dir3);
+      if (pda_mesh_make_lattice(2, n3, b3, per3, 3, &h3) != PDA_OK || pda_mesh_write(h3, dir3.c_str()) != PDA_OK) return 15;
+      pda_mesh_free(h3);
+    }
+    const auto mesh3 = pda::load_cellcentered_uniform_mesh_eigen(dir3);
+    auto gs = pda::create_gray_scott_2d_problem_eigen(mesh3, visc, 2e-4, 5e-5, 0.042, 0.062);   // the defaults
+    auto gs0 = pda::create_problem_eigen(mesh3, pda::DiffusionReaction2d::GrayScott);
+    auto bur = pda::create_problem_eigen(meshObj, pda::AdvectionDiffusion2d::BurgersOutflow, w3, visc);
+    auto slip = pda::create_slip_wall_swe_2d_problem_eigen(meshObj, w3, 9.8, -3.0, 0.125);
+    auto cs = pda::create_cross_shock_problem_eigen(meshObj, w3, 0.2, 9.0, 1.5);
+    auto cs0 = pda::create_cross_shock_problem_eigen(meshObj, w3);
+    if (gs.numDofPerCell() != 2 || gs0.numDofPerCell() != 2 || bur.numDofPerCell() != 2) return 11;
+    if ((gs.initialCondition() - gs0.initialCondition()).cwiseAbs().maxCoeff() != 0.0) return 12;
+    if (slip.gravity() != 9.8 || slip.coriolis() != -3.0) return 13;
+    if (cs.queryParameter("crossShockDensity") != 0.2 || cs0.queryParameter("crossShockDensity") != 0.1) return 14;
+    // a 1D mesh written next to the 2D one
+    const std::string dir1 = std::string(argv[1]) + "_1d";
+    const int32_t n1[3] = {50, 1, 1}, per1[3] = {1, 0, 0};
+    const double b1[6] = {-1.0, 1.0, 0.0, 0.0, 0.0, 0.0};
+    pda_mesh h1 = nullptr;
+    std::filesystem::create_directories(dir1);
+    if (pda_mesh_make_lattice(1, n1, b1, per1, 3, &h1) != PDA_OK || pda_mesh_write(h1, dir1.c_str()) != PDA_OK) return 15;
+    pda_mesh_free(h1);
+    const auto mesh1 = pda::load_cellcentered_uniform_mesh_eigen(dir1);
+    const auto fo1 = pda::InviscidFluxReconstruction::FirstOrder;   // 3-point-stencil mesh (DiffusionReaction1d needs it)
+    auto adv = pda::create_linear_advection_1d_problem_eigen(mesh1, fo1, 2.5);
+    auto adv2 = pda::create_linear_advection_1d_problem_eigen(mesh1, fo1, pda::InviscidFluxScheme::Rusanov, 2.5);
+    auto dr1 = pda::create_problem_eigen(mesh1, pda::DiffusionReaction1d::ProblemA);
+    if (adv.totalDofStencilMesh() != 50 || adv2.totalDofStencilMesh() != 50 || dr1.numDofPerCell() != 1) return 16;
+    std::printf("named factories ok\n");
   }
   std::printf("cpp_shim_demo ok\n");
   return 0;

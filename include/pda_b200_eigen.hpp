@@ -21,6 +21,9 @@ namespace pressiodemoapps_b200 {
 
 // enumerator order = the reference's (euler1d.hpp:64-69, euler2d.hpp:66-76, euler3d.hpp:65-68, swe2d.hpp:65-68, ...)
 enum class InviscidFluxReconstruction { FirstOrder = 0, Weno3 = 1, Weno5 = 2 };
+enum class InviscidFluxScheme { Rusanov = 0 };            // schemes_info.hpp
+enum class ViscousFluxReconstruction { FirstOrder = 0 };
+enum class ViscousFluxScheme { Central = 0 };
 enum class Euler1d { PeriodicSmooth = 0, Sod, Lax, ShuOsher };
 enum class Euler2d { PeriodicSmooth = 0, KelvinHelmholtz, SedovFull, SedovSymmetry, Riemann, NormalShock,
                      DoubleMachReflection, CrossShock, testingonlyneumann };
@@ -316,6 +319,55 @@ template <class ProbEnum>
 Problem create_problem_eigen(const Mesh& m, ProbEnum e, InviscidFluxReconstruction r,
                              const std::unordered_map<std::string, double>& params, int device = 0) {
   return Problem(m, impl::family_of<ProbEnum>::value, static_cast<int>(e), static_cast<int>(r), 1, params, device);
+}
+
+// ---- the remaining overloads and named factories of the reference's public headers (argument for argument)
+// DiffusionReaction1d / DiffusionReaction2d: (mesh, enum[, ViscousFluxReconstruction])
+// (diffusion_reaction1d.hpp:112-126, diffusion_reaction2d.hpp:126-180)
+inline Problem create_problem_eigen(const Mesh& m, DiffusionReaction1d e, int device = 0) {
+  return Problem(m, PDA_FAMILY_DIFFUSION_REACTION1D, static_cast<int>(e), 0, 1, {}, device);
+}
+inline Problem create_problem_eigen(const Mesh& m, DiffusionReaction2d e,
+                                    ViscousFluxReconstruction = ViscousFluxReconstruction::FirstOrder, int device = 0) {
+  return Problem(m, PDA_FAMILY_DIFFUSION_REACTION2D, static_cast<int>(e), 0, 1, {}, device);
+}
+// create_gray_scott_2d_problem_eigen(mesh, viscRecon, Du, Dv, F, k)  (diffusion_reaction2d.hpp:259-285)
+inline Problem create_gray_scott_2d_problem_eigen(const Mesh& m, ViscousFluxReconstruction, double diffusion_u,
+                                                  double diffusion_v, double feedRate, double killRate, int device = 0) {
+  return Problem(m, PDA_FAMILY_DIFFUSION_REACTION2D, static_cast<int>(DiffusionReaction2d::GrayScott), 0, 1,
+                 {{"Du", diffusion_u}, {"Dv", diffusion_v}, {"F", feedRate}, {"k", killRate}}, device);
+}
+// AdvectionDiffusion2d (Burgers): (mesh, enum, recon, viscRecon[, {name: value}])  (advection_diffusion2d.hpp:79-152)
+inline Problem create_problem_eigen(const Mesh& m, AdvectionDiffusion2d e, InviscidFluxReconstruction r,
+                                    ViscousFluxReconstruction, const std::unordered_map<std::string, double>& params = {},
+                                    int device = 0) {
+  return Problem(m, PDA_FAMILY_ADVECTION_DIFFUSION2D, static_cast<int>(e), static_cast<int>(r), 1, params, device);
+}
+// create_linear_advection_1d_problem_eigen(mesh, recon, [InviscidFluxScheme,] velocity[, ic])  (advection1d.hpp:107-152)
+inline Problem create_linear_advection_1d_problem_eigen(const Mesh& m, InviscidFluxReconstruction r, double velocity,
+                                                        int ic = 1, int device = 0) {
+  return Problem(m, PDA_FAMILY_ADVECTION1D, static_cast<int>(Advection1d::PeriodicLinear), static_cast<int>(r), ic,
+                 {{"velocity", velocity}}, device);
+}
+inline Problem create_linear_advection_1d_problem_eigen(const Mesh& m, InviscidFluxReconstruction r, InviscidFluxScheme,
+                                                        double velocity, int device = 0) {
+  return create_linear_advection_1d_problem_eigen(m, r, velocity, 1, device);
+}
+// create_slip_wall_swe_2d_problem_eigen(mesh, recon, gravity, coriolis, pulseMagnitude)  (swe2d.hpp:283-309, legacy)
+inline Problem create_slip_wall_swe_2d_problem_eigen(const Mesh& m, InviscidFluxReconstruction r, double gravity,
+                                                     double coriolis, double pulseMagnitude, int device = 0) {
+  return Problem(m, PDA_FAMILY_SWE2D, static_cast<int>(Swe2d::SlipWall), static_cast<int>(r), 1,
+                 {{"gravity", gravity}, {"coriolis", coriolis}, {"pulseMagnitude", pulseMagnitude}}, device);
+}
+// create_cross_shock_problem_eigen(mesh, recon[, density, inletXVel, bottomYVel])  (euler2d.hpp:252-298)
+inline Problem create_cross_shock_problem_eigen(const Mesh& m, InviscidFluxReconstruction r, int device = 0) {
+  return Problem(m, PDA_FAMILY_EULER2D, static_cast<int>(Euler2d::CrossShock), static_cast<int>(r), 1, {}, device);
+}
+inline Problem create_cross_shock_problem_eigen(const Mesh& m, InviscidFluxReconstruction r, double density,
+                                                double inletXVel, double bottomYVel, int device = 0) {
+  return Problem(m, PDA_FAMILY_EULER2D, static_cast<int>(Euler2d::CrossShock), static_cast<int>(r), 1,
+                 {{"crossShockDensity", density}, {"crossShockInletXVel", inletXVel}, {"crossShockBottomYVel", bottomYVel}},
+                 device);
 }
 
 // create_problem_eigen(mesh, <enum>, recon, BCsLeft, BCsFront, BCsRight, BCsBack[, icFlag])  -- the custom-BC overloads

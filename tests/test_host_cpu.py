@@ -243,6 +243,7 @@ def test_cpp_eigen_shim_compiles_and_runs_host_part(tmp_path):
     r = subprocess.run([exe, mdir], capture_output=True, text=True, timeout=300)
     assert r.returncode == 0, r.stdout + r.stderr
     assert "dofs 1600 nnz 55808" in r.stdout and "cpp_shim_demo ok" in r.stdout
+    assert "named factories ok" in r.stdout   # create_gray_scott_2d / slip_wall_swe_2d / cross_shock / linear_advection_1d ...
 
 
 def test_set_bc_pointer_needs_a_host_functor():
