@@ -56,7 +56,9 @@ GradientEvaluator::GradientEvaluator(Mesh& mesh, int maxNumDofPerCell) {
   nStencil_ = mesh.nStencil;
   h_[0] = mesh.d[0];
   h_[1] = mesh.d[1];
-  mesh.ensureCoords();
+  // a lattice that has not materialised its coordinates (O(cells) host memory) supplies them per boundary cell
+  const bool analytic = mesh.lattice && !mesh.haveCoords;
+  if (!analytic) mesh.ensureCoords();
   std::vector<int32_t> rows;
   mesh.strictlyOnBdRows(rows);
   const double dxHalf = mesh.d[0] * 0.5, dyHalf = mesh.d[1] * 0.5;
@@ -65,7 +67,9 @@ GradientEvaluator::GradientEvaluator(Mesh& mesh, int maxNumDofPerCell) {
   for (int32_t rowInd : rows) {
     mesh.graphRow(rowInd, cc);
     const int32_t gid = cc[0];
-    const double cx = mesh.x[gid], cy = mesh.y[gid], cz = mesh.z[gid];
+    const double cx = analytic ? mesh.latticeCoord(0, gid % mesh.n[0]) : mesh.x[gid];
+    const double cy = analytic ? mesh.latticeCoord(1, gid / mesh.n[0]) : mesh.y[gid];
+    const double cz = analytic ? mesh.latticeCoord(2, 0) : mesh.z[gid];
     // Left, Front, Right, Back = graph columns 1..4 of the first layer (mesh_ccu.hpp:298-312)
     for (int pos = 0; pos < 4; ++pos) {
       if (cc[1 + pos] != -1) continue;
