@@ -36,6 +36,30 @@ METRIC = "rhs_cell_evals_per_s"
 UNIT = "cells/s"
 FLOPS_PER_CELL = 2673.0    # 3*(5*152+116)+45, each face once
 BYTES_PER_CELL = 80.0      # 2*ndpc*8
+FP64_FMA_PER_SM_CLK = 64   # B200: 64 DFMA lanes per SM and cycle -> nominal 148 x 64 x 2 x 1.965 GHz = 37.2 TFLOP/s
+
+
+def make_config(n, gpus):
+    """the workload, named identically by both arms (--impl b200 and --impl reference) so the driver's same_config
+    check compares like with like; how each arm EXECUTES it (partition, NUMA binding, sample size) sits beside it"""
+    return {"workload": "3D Euler PeriodicSmooth WENO5 %d^3 velocity (cfg 5)" % n, "mesh": [n, n, n],
+            "state_bytes": int(n ** 3 * 40),
+            "l2": "inputs larger than L2 (state %.2f GB per GPU at %d GPU%s)" % (n ** 3 * 40e-9 / gpus, gpus, "" if gpus == 1 else "s")}
+
+
+class StdoutToStderr:
+    """fd 1 -> fd 2 for the whole run; the ONE JSON line goes to the saved original stdout at the end.  NCCL writes its
+    NCCL_DEBUG=INFO lines to the C stdout: this keeps them visible (stderr) without silencing or downgrading NCCL_DEBUG
+    and keeps stdout to exactly one line."""
+
+    def __init__(self):
+        sys.stdout.flush()
+        self.saved = os.dup(1)
+        os.dup2(2, 1)
+
+    def emit(self, text):
+        sys.stdout.flush()
+        os.write(self.saved, (text + "\n").encode())
 
 
 def load_traffic(kernel_key):
@@ -121,33 +145,53 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------------------------------------ CPU legs
-def use_all_host_threads():
-    """torchrun exports OMP_NUM_THREADS=1 to every rank unless the user set it; the CPU legs (rank 0 only) are meant to
-    use all the host cores this process may run on.  Must run before the OpenMP checker libraries are loaded (libgomp
-    reads the variable once)."""
-    if os.environ.get("TORCHELASTIC_RUN_ID") or int(os.environ.get("WORLD_SIZE", "1")) > 1:
-        try:
-            ncores = len(os.sched_getaffinity(0))
-        except AttributeError:
-            ncores = os.cpu_count() or 1
+def bind_openmp():
+    """OMP_NUM_THREADS = the cores this process may run on, OMP_PROC_BIND=true (/root/reference/tests_perf/drive.py:31-35).
+    Must run before libgomp is loaded (it reads the variables once)."""
+    try:
+        ncores = len(os.sched_getaffinity(0))
+    except AttributeError:
+        ncores = os.cpu_count() or 1
+    if os.environ.get("TORCHELASTIC_RUN_ID") or int(os.environ.get("WORLD_SIZE", "1")) > 1 or "OMP_NUM_THREADS" not in os.environ:
         os.environ["OMP_NUM_THREADS"] = str(ncores)
+    os.environ.setdefault("OMP_PROC_BIND", "true")
+    return ncores
 
 
-def cpu_leg(n_cpu, target_s=12.0):
-    """3D Euler WENO5 periodic n_cpu^3 velocity on the host cores: the oracle port with OpenMP (kind 'port')."""
-    import pressiodemoapps as pda
-    from refdrv import OracleProblem
-    mesh = pda.create_full_mesh([n_cpu] * 3, [-1, 1, -1, 1, -1, 1], 7, ("x", "y", "z"))
-    x, y, z = mesh._coords()
-    arrays = dict(dim=3, stencil=7, d=mesh._deltas()[0], graph=mesh.graph(), x=x, y=y, z=z)
-    o = OracleProblem(None, "euler3d", 0, 2, arrays=arrays, omp=True)
-    U = o.initialCondition()
-    t1 = o.time_velocity(U, 0.0, 1, 1)
-    reps = int(max(2, min(200, target_s / max(t1, 1e-6))))
-    sec = o.time_velocity(U, 0.0, 0, reps)
-    return dict(value=n_cpu ** 3 / sec, unit=UNIT, cores=o.num_threads(), kind="port",
-                sample="%d^3 periodic 3D Euler WENO5 (oracle/pda_oracle.c, OpenMP), %d evals, %.3f s/eval"
-                       % (n_cpu, reps, sec)), sec, reps
+class CpuWorkload:
+    """cfg 5 on the host cores: the oracle port in LATTICE mode (oracle/pda_oracle.c or_create_lattice: the n^3 problem
+    itself, connectivity by index arithmetic, no product library involved) with OpenMP.  A sample = the velocity of a
+    contiguous range of z-planes of that problem; consecutive samples walk through the mesh."""
+
+    def __init__(self, n):
+        from refdrv import OracleProblem, lattice_spec
+        self.n = n
+        self.o = OracleProblem(None, "euler3d", 0, 2, lattice=lattice_spec([n] * 3, [-1, 1] * 3, 7, ("x", "y", "z")), omp=True)
+        self.U = self.o.initialCondition()
+        self.V = np.zeros_like(self.U)
+        self.plane = n * n
+        self.next = 0
+
+    def sample(self, planes):
+        """evaluate `planes` z-planes starting where the last sample stopped; returns (cells, seconds)"""
+        planes = max(1, min(int(planes), self.n))
+        if self.next + planes > self.n:
+            self.next = 0
+        p0 = self.next
+        self.next += planes
+        sec = self.o.time_velocity_inner_range(self.U, self.V, p0 * self.plane, (p0 + planes) * self.plane, 0.0, 1)
+        return planes * self.plane, sec
+
+
+def cpu_leg(n, target_s=12.0):
+    """cpu_baseline of the GPU arm: ~target_s of CPU work on the n^3 problem (kind 'port': the reference has no 3D WENO5)"""
+    w = CpuWorkload(n)
+    c1, s1 = w.sample(4)                       # warm-up + rate estimate
+    planes = max(4, min(n, int(target_s * c1 / max(s1, 1e-9) / w.plane)))
+    cells, sec = w.sample(planes)
+    return dict(value=cells / sec, unit=UNIT, cores=w.o.num_threads(), kind="port",
+                sample="%d of the %d z-planes of the %d^3 periodic 3D Euler WENO5 problem (oracle/pda_oracle.c lattice mode, "
+                       "OpenMP, OMP_PROC_BIND=%s), %.2f s" % (planes, n, n, os.environ.get("OMP_PROC_BIND", "unset"), sec))
 
 
 def ref_weno3_leg(n_cpu, target_s=6.0):
@@ -156,12 +200,10 @@ def ref_weno3_leg(n_cpu, target_s=6.0):
     Jacobian is asked for (euler_3d_prob_class.hpp:139-154) -- 17 s at 64^3, 158 s at 128^3 on 8 cores -- and the
     throughput of the evaluation itself does not depend on the mesh size"""
     from refdrv import RefProblem, have_ref
-    import pressiodemoapps as pda
     if not have_ref(omp=True):
         return None
     d = tempfile.mkdtemp(prefix="bench_mesh_")
-    mesh = pda.create_full_mesh([n_cpu] * 3, [-1, 1, -1, 1, -1, 1], 5, ("x", "y", "z"))
-    mesh.write(d)
+    write_full_mesh_text(d, [n_cpu] * 3, [-1, 1, -1, 1, -1, 1], 5, ("x", "y", "z"))
     r = RefProblem(d, "euler3d", 0, 1, omp=True)
     U = r.initialCondition()
     t1 = r.time_velocity(U, 0.0, 1, 1)
@@ -173,56 +215,108 @@ def ref_weno3_leg(n_cpu, target_s=6.0):
                 sample="%d^3 periodic 3D Euler WENO3 (unmodified reference, OpenMP), %d evals" % (n_cpu, reps))
 
 
-def run_reference_arm(args):
+def write_full_mesh_text(outdir, n, bounds, stencil, periodic):
+    """info.dat / coordinates.dat / connectivity.dat of a full periodic 3D (or 2D) mesh in the reference's text format
+    (meshing_scripts/create_full_mesh.py:151-218; natural ordering) written with numpy only -- the
+    reference arm must not load the product library, and /root/reference (with its mesh scripts) is absent on the GPU box"""
+    n = list(n)
+    dim = len(n)
+    d = [(bounds[2 * a + 1] - bounds[2 * a]) / n[a] for a in range(dim)]
+    nn = n + [1] * (3 - dim)
+    idx = np.arange(int(np.prod(nn)), dtype=np.int64)
+    ijk = [idx % nn[0], (idx // nn[0]) % nn[1], idx // (nn[0] * nn[1])]
+    per = [a in periodic for a in ("x", "y", "z")]
+    h = (stencil - 1) // 2
+
+    def nb(axis, off):
+        v = ijk[axis] + off
+        out = v < 0
+        out |= v >= nn[axis]
+        if per[axis]:
+            v = v % nn[axis]
+            out[:] = False
+        c = [ijk[0], ijk[1], ijk[2]]
+        c[axis] = v
+        g = (c[2] * nn[1] + c[1]) * nn[0] + c[0]
+        g[out] = -1
+        return g
+    cols = [idx]
+    for L in range(h):   # 2D: left front right back ; 3D: left front right back bottom top (per layer)
+        sides = [(0, -1), (1, +1), (0, +1), (1, -1)] + ([(2, -1), (2, +1)] if dim == 3 else [])
+        if dim == 1:
+            sides = [(0, -1), (0, +1)]
+        for ax, sg in sides:
+            cols.append(nb(ax, sg * (L + 1)))
+    os.makedirs(outdir, exist_ok=True)
+    with open(os.path.join(outdir, "info.dat"), "w") as f:
+        f.write("dim %1d\n" % dim)
+        for a, nm in enumerate("xyz"[:dim]):
+            f.write("%sMin %.14f\n%sMax %.14f\n" % (nm, min(bounds[2 * a:2 * a + 2]), nm, max(bounds[2 * a:2 * a + 2])))
+        for a, nm in enumerate("xyz"[:dim]):
+            f.write("d%s %.14f\n" % (nm, d[a]))
+        f.write("sampleMeshSize %8d\nstencilMeshSize %8d\nstencilSize %2d\n" % (idx.size, idx.size, stencil))
+        for a, nm in enumerate("xyz"[:dim]):
+            f.write("n%s %8d\n" % (nm, n[a]))
+    coords = [bounds[2 * a] + 0.5 * d[a] + ijk[a] * d[a] for a in range(dim)]
+    np.savetxt(os.path.join(outdir, "coordinates.dat"), np.column_stack([idx] + coords), fmt="%8d " + "%.14f " * dim)
+    np.savetxt(os.path.join(outdir, "connectivity.dat"), np.column_stack(cols), fmt="%8d " * len(cols))
+
+
+def run_reference_arm(args, out):
+    """--impl reference: the CPU implementation of cfg 5 on this box's host cores, with all the threads it can use
+    (OMP_NUM_THREADS = cores, OMP_PROC_BIND=true), on the SAME config as the GPU arm (the n^3 problem itself).  Each
+    step = a bounded sample: a contiguous range of z-planes sized for ~4 s, consecutive steps walking through the mesh.
+    The reference has no 3D WENO5, so this is the oracle port (kind "port"); the UNMODIFIED reference's own
+    3D WENO3 throughput is reported beside it (reference_weno3) with the ratio it implies.  The product library is not
+    loaded by this arm."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    n_cpu = 128
     steps, warmup = args.steps, args.warmup
-    use_all_host_threads()
-    base, sec1, _ = cpu_leg(n_cpu, target_s=3.0)
-    # each step = one bounded sample: `per` evaluations of the n_cpu^3 mesh
-    per = int(max(1, min(50, 4.0 / sec1)))
-    import pressiodemoapps as pda
-    from refdrv import OracleProblem
-    mesh = pda.create_full_mesh([n_cpu] * 3, [-1, 1, -1, 1, -1, 1], 7, ("x", "y", "z"))
-    x, y, z = mesh._coords()
-    o = OracleProblem(None, "euler3d", 0, 2, arrays=dict(dim=3, stencil=7, d=mesh._deltas()[0], graph=mesh.graph(),
-                                                         x=x, y=y, z=z), omp=True)
-    U = o.initialCondition()
+    bind_openmp()
+    w = CpuWorkload(args.n)
+    c1, s1 = w.sample(2)
+    rate = c1 / max(s1, 1e-9)
+    budget = min(4.0, 150.0 / max(steps + warmup, 1))           # the whole run ends within a few minutes
+    planes = max(1, min(args.n, int(budget * rate / w.plane)))
     for _ in range(warmup):
-        o.time_velocity(U, 0.0, 0, 1)
+        w.sample(planes)
+    cells = 0
     t0 = time.perf_counter()
     for _ in range(steps):
-        o.time_velocity(U, 0.0, 0, per)
+        c, _s = w.sample(planes)
+        cells += c
     dt = time.perf_counter() - t0
-    val = n_cpu ** 3 * per * steps / dt
-    cb = dict(value=val, unit=UNIT, cores=o.num_threads(), kind="port",
-              sample="each step = %d evals of a %d^3 periodic 3D Euler WENO5 mesh (oracle port, OpenMP; the reference "
-                     "has no 3D WENO5)" % (per, n_cpu))
+    val = cells / dt
+    cb = dict(value=val, unit=UNIT, cores=w.o.num_threads(), kind="port",
+              sample="each step = %d of the %d z-planes of the %d^3 periodic 3D Euler WENO5 problem (oracle port in lattice "
+                     "mode, OpenMP, OMP_PROC_BIND=%s; the reference has no 3D WENO5)"
+                     % (planes, args.n, args.n, os.environ.get("OMP_PROC_BIND", "unset")))
     line = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
             "warmup": warmup, "ms_per_step": 1e3 * dt / steps, "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": "3D Euler PeriodicSmooth WENO5 %d^3 velocity (cfg 5)" % args.n,
-                       "sampled_on": "%d^3" % n_cpu},
+            "config": make_config(args.n, args.gpus),
+            "execution": {"host_threads": w.o.num_threads(), "cells_per_step": planes * w.plane},
             "cpu_baseline": cb,
-            "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-            "reference_weno3": ref_weno3_leg(64, 4.0)}
-    print(json.dumps(line), flush=True)
+            "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    del w
+    try:
+        line["reference_weno3"] = ref_weno3_leg(64, 4.0)
+    except Exception as e:
+        line["reference_weno3"] = {"unavailable": str(e)}
+    out.emit(json.dumps(line))
 
 
 def ref_jacobian_leg(n2_cpu=512, target_s=6.0):
     """the UNMODIFIED reference (OpenMP build) on cfg 2's problem at a bounded size: 2D Euler Riemann WENO5
     velocity+Jacobian, stored nnz per second on the host cores"""
     from refdrv import RefProblem, have_ref
-    import pressiodemoapps as pda
     if not have_ref(omp=True):
         return {"unavailable": "oracle/_ref/libpda_ref_omp.so did not travel with the snapshot"}
     import shutil
     d = tempfile.mkdtemp(prefix="bench_mesh2d_")
     try:
-        mesh = pda.create_full_mesh([n2_cpu, n2_cpu], [0, 1, 0, 1], 7)
-        mesh.write(d)
+        write_full_mesh_text(d, [n2_cpu, n2_cpu], [0, 1, 0, 1], 7, ())
         r = RefProblem(d, "euler2d", 4, 2, omp=True)
         U = r.initialCondition()
         t1 = r.time_jacobian(U, 0.0, 1, 1)
@@ -319,7 +413,7 @@ def jacobian_leg(torch, pda, dev, n2=2048, steps=3, warmup=1):
                          "algorithmic_bytes": bytes_per_eval}}
 
 
-def run_b200_arm(args):
+def run_b200_arm(args, out):
     import torch
     import pressiodemoapps as pda
     from pressiodemoapps.halo import post_halo_exchange, wait_all, connect_peer_halo
@@ -337,9 +431,8 @@ def run_b200_arm(args):
     dist = None
     if world > 1:
         import torch.distributed as dist
-        # NCCL prints "NCCL version ..." on STDOUT when NCCL_DEBUG=VERSION/INFO: keep stdout to the one JSON line
-        if os.environ.get("NCCL_DEBUG", "").upper() in ("VERSION", "INFO", "TRACE"):
-            os.environ["NCCL_DEBUG"] = "WARN"
+        # NCCL_DEBUG is left as the caller set it: its lines go to the C stdout, which main() has pointed at stderr
+        # (StdoutToStderr); the JSON line is written to the original stdout at the end
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     n = args.n
     K, W = args.steps, args.warmup
@@ -361,7 +454,11 @@ def run_b200_arm(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
-    fp64_peak = pda.measure_fp64_peak(local_rank)
+    # FP64 roofline denominators: (a) nominal = SMs x 64 DFMA lanes x 2 flop x the maximum SM clock nvidia-smi reports
+    # during the timed region (the clock record says whether the run sat at it); (b) the same-process DFMA probe, with
+    # the clock it actually ran at (clock64 / globaltimer inside the kernel) and the DFMA issue rate per SM and cycle
+    fp64_peak, probe_mhz, probe_rate = pda.measure_fp64_peak_ex(local_rank)
+    n_sm = torch.cuda.get_device_properties(local_rank).multi_processor_count
 
     if world == 1:
         p = pda.create_problem(mesh, pda.Euler3d.PeriodicSmooth, R.Weno5, device=local_rank)
@@ -469,29 +566,45 @@ def run_b200_arm(args):
            ("pda_slab_velocity_peer_host" if args.halo == "peer" else "slab: H2D + halo exchange + pda_slab_velocity_*_dev + D2H")}
 
     if rank == 0:
+        sm_max = (clocks or {}).get("sm_max_mhz") or 1965.0
+        nominal_tf = n_sm * FP64_FMA_PER_SM_CLK * 2 * sm_max * 1e6 * 1e-12
+        cfg = make_config(n, world)
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
                 "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
-                "dtype": "f64", "data": "synthetic",
-                "config": {"workload": "3D Euler PeriodicSmooth WENO5 %d^3 velocity (cfg 5)" % n, "mesh": [n, n, n],
-                           "partition": ("z-slabs x%d, halo 3 planes/side: %s" % (world, "copy-engine peer pushes over NVLink + "
-                                         "flags, fused into one kernel launch (no collective)" if args.halo == "peer" else
-                                         "NCCL send/recv, interior/boundary launches")) if world > 1 else "single GPU",
-                           "l2": "inputs larger than L2 (state %.2f GB per GPU)" % (ncells * 40e-9 / world),
-                           "host_numa_binding": numa},
+                "dtype": "f64", "data": "synthetic", "config": cfg,
+                "execution": {"partition": ("z-slabs x%d, halo 3 planes/side: %s" % (world, "copy-engine peer pushes over NVLink + "
+                                            "flags, fused into one kernel launch (no collective)" if args.halo == "peer" else
+                                            "NCCL send/recv, interior/boundary launches")) if world > 1 else "single GPU",
+                              "host_numa_binding": numa},
+                "comm": {"data_plane": ("none (single GPU)" if world == 1 else
+                                        ("copy-engine peer copies + flag words over NVLink peer memory (cudaIpc), fused with the "
+                                         "kernel launch; NO NCCL collective on the data path" if args.halo == "peer" else
+                                         "NCCL send/recv (batch_isend_irecv)")),
+                         "nccl_used_for": None if world == 1 else "process-group init, all-gather of the 64-byte IPC handles (once), "
+                                                                  "barriers and the max-over-ranks reduction of the timings",
+                         "nranks": world, "NCCL_DEBUG": os.environ.get("NCCL_DEBUG"), "nccl_debug_goes_to": "stderr"},
                 "gpu_launches": int(launches), "clocks": clocks, "e2e": e2e,
-                "roofline": {"bound": "hbm", "achieved": ach_gbs, "peak": hbm_peak, "unit": "GB/s",
-                             "frac": ach_gbs / hbm_peak,
+                # the BINDING roofline of the dominant kernel is the FP64 pipe (2673 flop / 80 B = 33 flop/B against a
+                # machine balance of ~5.7): reported at top level against the NOMINAL peak at the recorded clock; the
+                # HBM view (non-binding) and the probe sit beside it
+                "roofline": {"bound": "fp64", "achieved": ach_tf, "peak": nominal_tf, "unit": "TFLOP/s",
+                             "frac": ach_tf / nominal_tf,
+                             "peak_source": "nominal: %d SMs x %d DFMA lanes/clk x 2 flop x %.0f MHz (sm_max during the run)"
+                                            % (n_sm, FP64_FMA_PER_SM_CLK, sm_max),
+                             "flops_per_cell": FLOPS_PER_CELL, "algorithmic_flops": kernel_cells * FLOPS_PER_CELL,
+                             "kernel": "k_euler3d_velocity_tiled<7,7>", "kernel_ms": k_ms,
                              "traffic": (load_traffic("k_euler3d_velocity_tiled<7,7>@512^3") if (world == 1 and n == 512) else None),
-                             "traffic_unit": "bytes per launch (ncu --set full, profiles/ncu_traffic_r01.json)",
-                             "algorithmic_bytes": kernel_cells * BYTES_PER_CELL, "peak_source": peak_src,
-                             "kernel": "k_euler3d_velocity_tiled<7,7>", "kernel_ms": k_ms, "binding": "fp64",
-                             "fp64": {"achieved": ach_tf, "peak": fp64_peak, "unit": "TFLOP/s",
-                                      "frac": ach_tf / fp64_peak if fp64_peak else None,
-                                      "peak_source": "measured DFMA loop (pda_measure_fp64_peak), same process",
-                                      "flops_per_cell": FLOPS_PER_CELL}}}
+                             "traffic_unit": "DRAM bytes per launch (ncu --set full, profiles/ncu_traffic_r01.json)",
+                             "probe": {"achieved_frac": ach_tf / fp64_peak if fp64_peak else None, "peak": fp64_peak,
+                                       "unit": "TFLOP/s", "sm_mhz_under_probe": probe_mhz, "dfma_per_sm_clk": probe_rate,
+                                       "nominal_dfma_per_sm_clk": FP64_FMA_PER_SM_CLK,
+                                       "source": "pure DFMA loop, 8 chains x 64 warps/SM (pda_measure_fp64_peak_ex), same process: "
+                                                 "TFLOP/s from CUDA events; clock and issue rate from clock64/globaltimer in-kernel"},
+                             "hbm": {"bound": "hbm (NOT binding)", "achieved": ach_gbs, "peak": hbm_peak, "unit": "GB/s",
+                                     "frac": ach_gbs / hbm_peak, "algorithmic_bytes": kernel_cells * BYTES_PER_CELL,
+                                     "peak_source": peak_src}}}
         if world == 1 and not args.no_cpu:
-            cb, _, _ = cpu_leg(128, target_s=12.0)
-            line["cpu_baseline"] = cb
+            line["cpu_baseline"] = cpu_leg(n, target_s=12.0)
             try:
                 line["cpu_reference_weno3"] = ref_weno3_leg(64, 5.0)
             except Exception as e:   # the compiled reference is optional on the GPU box
@@ -520,7 +633,8 @@ def run_b200_arm(args):
                 line["weno3_reference_pinned"] = {
                     "workload": "3D Euler PeriodicSmooth WENO3 %d^3 velocity" % n, "ms_per_step": ms3,
                     "value": ncells / (ms3 * 1e-3), "unit": UNIT, "flops_per_cell": fl3,
-                    "fp64_frac": ncells * fl3 / (ms3 * 1e-3) * 1e-12 / fp64_peak if fp64_peak else None,
+                    "fp64_frac": ncells * fl3 / (ms3 * 1e-3) * 1e-12 / nominal_tf,
+                    "fp64_frac_of_probe": ncells * fl3 / (ms3 * 1e-3) * 1e-12 / fp64_peak if fp64_peak else None,
                     "hbm_frac": ncells * BYTES_PER_CELL / (ms3 * 1e-3) * 1e-9 / hbm_peak,
                     "cpu_reference": line.get("cpu_reference_weno3")}
                 del U3, V3, p3, mesh3
@@ -572,7 +686,7 @@ def run_b200_arm(args):
                 line["configs"] = bench_configs.run(hbm_peak, device=local_rank)
             except Exception as e:
                 line["configs"] = {"error": str(e)}
-        print(json.dumps(line), flush=True)
+        out.emit(json.dumps(line))
     if dist is not None:
         dist.barrier()
         dist.destroy_process_group()
@@ -613,10 +727,12 @@ def main():
     ap.add_argument("--no-configs", action="store_true", help="skip the cfg 1-4 legs (tools/bench_configs.py)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
+    out = StdoutToStderr()   # stdout carries exactly one line: the JSON record
     if args.impl == "reference":
-        run_reference_arm(args)
+        run_reference_arm(args, out)
     else:
-        run_b200_arm(args)
+        bind_openmp()        # the cpu_baseline leg (rank 0, N = 1) uses all host cores like the reference arm
+        run_b200_arm(args, out)
 
 
 if __name__ == "__main__":

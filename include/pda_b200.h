@@ -83,6 +83,13 @@ int pda_device_count(void);
 /* measurement helper (not on the evaluation path): peak FP64 FMA throughput of `device` in TFLOP/s from a pure DFMA
  * loop -- the FP64 roofline denominator bench.py reports beside the HBM one (MEASURED_PEAKS.json has no FP64 entry) */
 pda_status pda_measure_fp64_peak(int device, double* tflops, double* sm_mhz_hint);
+/* same probe with its own clock evidence: the SM clock the probe actually ran at (SM cycles from clock64 over elapsed
+ * nanoseconds from globaltimer, inside the kernel) and the DFMA issue rate per SM and cycle that results (the pipe's
+ * nominal rate is 64 per SM and cycle) -- separates "the clock dropped under FP64 load" from "the pipe cannot be fed" */
+pda_status pda_measure_fp64_peak_ex(int device, double* tflops, double* sm_mhz_under_probe, double* dfma_per_sm_clk);
+/* test hook of the reference-order mode: out[i] = the device restatement of glibc's pow(x[i], y) (csrc/glibc_pow.h);
+ * host pointers, synchronous.  tests/ compare it bit for bit with the host libm. */
+pda_status pda_test_glibc_pow(int device, const double* x, double y, double* out, int64_t n);
 
 /* ------------------------------------------------------------------ mesh ---------------------------------------- */
 /* load_cellcentered_uniform_mesh_eigen(dir)  (mesh.hpp:87-91, impl/mesh_ccu.hpp:359-448): reads info.dat,
@@ -146,6 +153,20 @@ pda_status pda_problem_create(pda_mesh mesh, int family, int problem_id, int rec
  * the current time for every SAMPLE cell and hands over the table (sample_mesh_size doubles, host pointer).  Without
  * a call the reference's default functors are tabulated by the library. */
 pda_status pda_problem_set_source(pda_problem p, const double* values);
+
+/* Engine options (no counterpart in the reference: they select between implementations of the SAME interface).
+ *   "jacobian_order" = "fast" (default) | "reference"
+ *     fast:      face-sharing Jacobian kernels with the well-conditioned form of the WENO reconstruction gradients.
+ *                Values agree with the reference to the rounding noise of the reference's OWN gradient formula
+ *                (impl/weno5.hpp:180-434 cancels catastrophically: its values move by up to 180x the 1e-12/1e-10
+ *                tolerance under FMA contraction alone) and sit closer to the exact Jacobian than the reference's.
+ *     reference: every row through one-thread-per-row kernels that keep the reference's formulas, operation order
+ *                and accumulation order, each operation individually rounded and std::pow reproduced bit for bit
+ *                (csrc/kernels_reforder.cu): velocity and Jacobian values within 1e-12 relative / 1e-10 absolute of
+ *                the reference on every golden fixture (in practice identical to the last bit).  Slow by design
+ *                (read-modify-write like Eigen's coeffRef); applyJacobian then multiplies that assembled Jacobian. */
+pda_status pda_problem_set_option(pda_problem p, const char* name, const char* value);
+pda_status pda_problem_get_option(pda_problem p, const char* name, char* value, int capacity);
 
 /* custom BCs (Swe2d::CustomBCs, Euler2d Riemann/NormalShock and AdvectionDiffusion2d custom-BC overloads): one device-expressible rule per side.
  * values: ndpc doubles (Dirichlet ghost state); ignored otherwise.  (custom_bcs_functions.hpp:60-164) */

@@ -52,6 +52,13 @@ typedef struct {
   int32_t *rowsInner, *rowsNearBd;
   int32_t nInner, nNearBd;
   int periodic;
+  /* lattice mode (or_create_lattice): a full mesh in natural ordering whose connectivity is index arithmetic -- no
+   * graph, no per-cell coordinates in memory (a 512^3 stencil-7 graph would be 10 GB).  Same rows, same columns, same
+   * arithmetic as the stored-graph path; tests/test_oracle_cpu.py pins the two against each other bit for bit. */
+  int lattice;
+  int32_t n[3];
+  int per[3];
+  double *cx, *cy, *cz; /* per-axis cell-centre coordinates (as the mesh files carry them), may be NULL */
 } or_mesh;
 
 struct or_problem_s {
@@ -68,7 +75,40 @@ struct or_problem_s {
   long long nnz;
 };
 
-#define G(m, r, c) ((m)->graph[(size_t)(r) * (m)->ncols + (c)])
+/* neighbour `c` of lattice cell r (natural ordering gid = (k*ny + j)*nx + i, natural_order_mesh_{2,3}d.py):
+ * column c-1 = (1D: 2, 2D: 4, 3D: 6) * layer + side; periodic axes wrap, others give -1 outside the domain */
+static inline int32_t lattice_nb(const or_mesh* m, int32_t r, int c) {
+  if (c == 0) return r;
+  const int nside = (m->dim == 1) ? 2 : 2 * m->dim;
+  const int layer = (c - 1) / nside;
+  int side = (c - 1) % nside;
+  if (m->dim == 1) side = side ? 2 : 0;
+  const int32_t nx = m->n[0], ny = m->n[1];
+  /* the (i,j,k) of the row asked last is remembered per thread: a cell's neighbours are asked for in a burst */
+  static __thread int32_t lastRow = -1, lastNx = -1, lastNy = -1, lastIjk[3];
+  if (r != lastRow || nx != lastNx || ny != lastNy) {
+    lastRow = r; lastNx = nx; lastNy = ny;
+    lastIjk[0] = r % nx; lastIjk[1] = (r / nx) % ny; lastIjk[2] = r / (nx * ny);
+  }
+  int32_t ijk[3] = {lastIjk[0], lastIjk[1], lastIjk[2]};
+  /* side: 0 left (-x), 1 front (+y), 2 right (+x), 3 back (-y), 4 bottom (-z), 5 top (+z) */
+  const int axis = (side == 0 || side == 2) ? 0 : ((side == 1 || side == 3) ? 1 : 2);
+  const int dir = (side == 2 || side == 1 || side == 5) ? 1 : -1;
+  int32_t v = ijk[axis] + dir * (layer + 1);
+  if (v < 0 || v >= m->n[axis]) {
+    if (!m->per[axis]) return -1;
+    v = (v % m->n[axis] + m->n[axis]) % m->n[axis];
+  }
+  ijk[axis] = v;
+  return (ijk[2] * ny + ijk[1]) * nx + ijk[0];
+}
+#define G(m, r, c) ((m)->graph ? (m)->graph[(size_t)(r) * (m)->ncols + (c)] : lattice_nb((m), (int32_t)(r), (c)))
+/* cell-centre coordinates: stored per cell, or per axis in lattice mode */
+static inline double mx(const or_mesh* m, int32_t i) { return m->x ? m->x[i] : (m->cx ? m->cx[i % m->n[0]] : 0.); }
+static inline double my(const or_mesh* m, int32_t i) { return m->y ? m->y[i] : (m->cy ? m->cy[(i / m->n[0]) % m->n[1]] : 0.); }
+static inline double mz(const or_mesh* m, int32_t i) { return m->z ? m->z[i] : (m->cz ? m->cz[i / (m->n[0] * m->n[1])] : 0.); }
+/* row lists: identity when every row is an inner row of a lattice (fully periodic) */
+#define ROW_INNER(m, it) ((m)->rowsInner ? (m)->rowsInner[it] : (int32_t)(it))
 
 /* graph column conventions (functor_reconstruct_from_state.hpp:262-267,442-448,624-630):
  * 1D [l0 r0 | l1 r1 | l2 r2]; 2D [l0 f0 r0 b0 | ...]; 3D [l0 f0 r0 ba0 bot0 top0 | ...].
@@ -657,6 +697,7 @@ static int cmp_i32(const void* a, const void* b) {
 /* initializeJacobian: euler_2d_prob_class.hpp:223-237,315-387 (same rule in euler_1d/3d, swe_2d);
  * diffusion_reaction_2d_prob_class.hpp:180-224.  setFromTriplets -> sorted columns, duplicates merged. */
 static void build_pattern(or_problem* p) {
+  if (p->rowptr) return; /* built on demand in lattice mode (the BASELINE-size lattices only evaluate velocities) */
   const or_mesh* m = &p->m;
   const int N = p->ndpc;
   const int nnbInner = (p->S - 1) * m->dim, nnbFirst = 2 * m->dim;
@@ -757,13 +798,13 @@ static or_problem* finish_create(or_problem* p, int family, int probEnum, int re
     p->src = (double*)malloc(sizeof(double) * (size_t)(m->nSample > 0 ? m->nSample : 1));
     for (int32_t r = 0; r < m->nSample; ++r) {
       const int32_t c = G(m, r, 0);
-      const double x = m->x[c], y = m->y[c];
+      const double x = mx(m, c), y = my(m, c);
       if (family == F_DIFFREAC1D) p->src[r] = sin(M_PI * x) * x * x * 4. * cos(4. * M_PI * x);
       else if (family == F_DIFFREAC2D) p->src[r] = sin(M_PI * x * (y - 0.2)) * 4. * sin(4. * M_PI * y * x);
       else p->src[r] = 1.0;
     }
   }
-  build_pattern(p);
+  if (!m->lattice) build_pattern(p);
   return p;
 }
 
@@ -799,9 +840,66 @@ or_problem* or_create_from_arrays(int dim, int stencil, int32_t nSample, int32_t
   return finish_create(p, family, probEnum, recon, icFlag, nParams, names, values);
 }
 
+/* lattice mode: full mesh in natural ordering, n[3] cells (unused axes 1), connectivity by index arithmetic.
+ * dxyz as the mesh files carry them (14-decimal roundings); cx/cy/cz per-axis centre coordinates or NULL (then the
+ * initial condition, the DMR / cross-shock ghost rules and the Euler2d Jacobian factors, which read coordinates, are
+ * not available).  Row classification = mesh_ccu.hpp:385-439 evaluated on indices: a cell is near the boundary when
+ * one of its (mesh stencil-1)/2 layers leaves a non-periodic axis. */
+or_problem* or_create_lattice(int dim, int stencil, const int32_t n[3], const double dxyz[3], const int32_t periodic[3],
+                              const double* cx, const double* cy, const double* cz, int family, int probEnum,
+                              int recon, int icFlag, int nParams, const char* const* names, const double* values) {
+  or_problem* p = (or_problem*)calloc(1, sizeof(or_problem));
+  or_mesh* m = &p->m;
+  m->dim = dim; m->stencil = stencil; m->ncols = (stencil - 1) * dim + 1;
+  m->lattice = 1;
+  long long cells = 1;
+  for (int a = 0; a < 3; ++a) {
+    m->n[a] = (a < dim) ? n[a] : 1;
+    m->per[a] = (a < dim) ? (periodic[a] != 0) : 1;
+    m->d[a] = dxyz[a]; m->dInv[a] = (a < dim) ? 1. / dxyz[a] : 0.;
+    cells *= m->n[a];
+  }
+  if (cells > 2147483647LL / 5) { snprintf(g_err, sizeof g_err, "lattice too large for int32 dof indices"); free(p); return NULL; }
+  m->nSample = m->nStencil = (int32_t)cells;
+  if (cx) { m->cx = (double*)malloc(sizeof(double) * (size_t)m->n[0]); memcpy(m->cx, cx, sizeof(double) * (size_t)m->n[0]); }
+  if (cy) { m->cy = (double*)malloc(sizeof(double) * (size_t)m->n[1]); memcpy(m->cy, cy, sizeof(double) * (size_t)m->n[1]); }
+  if (cz) { m->cz = (double*)malloc(sizeof(double) * (size_t)m->n[2]); memcpy(m->cz, cz, sizeof(double) * (size_t)m->n[2]); }
+  const int h = (stencil - 1) / 2;
+  m->periodic = 1;
+  for (int a = 0; a < dim; ++a) if (!m->per[a]) m->periodic = 0;
+  if (m->periodic) {
+    m->nInner = m->nSample; m->nNearBd = 0; m->rowsInner = NULL;
+    m->rowsNearBd = (int32_t*)malloc(sizeof(int32_t));
+  } else {
+    /* two passes: count, then fill (ascending row order, like classify()) */
+    int32_t nNb = 0;
+    for (int pass = 0; pass < 2; ++pass) {
+      int32_t iIn = 0, iNb = 0;
+      for (int32_t k = 0; k < m->n[2]; ++k)
+        for (int32_t j = 0; j < m->n[1]; ++j)
+          for (int32_t i = 0; i < m->n[0]; ++i) {
+            const int32_t idx[3] = {i, j, k};
+            int bd = 0;
+            for (int a = 0; a < dim; ++a) if (!m->per[a] && (idx[a] < h || idx[a] >= m->n[a] - h)) bd = 1;
+            const int32_t r = (k * m->n[1] + j) * m->n[0] + i;
+            if (pass == 1) { if (bd) m->rowsNearBd[iNb] = r; else m->rowsInner[iIn] = r; }
+            if (bd) ++iNb; else ++iIn;
+          }
+      if (pass == 0) {
+        nNb = iNb;
+        m->nNearBd = nNb; m->nInner = m->nSample - nNb;
+        m->rowsNearBd = (int32_t*)malloc(sizeof(int32_t) * (size_t)(nNb > 0 ? nNb : 1));
+        m->rowsInner = (int32_t*)malloc(sizeof(int32_t) * (size_t)(m->nInner > 0 ? m->nInner : 1));
+      }
+    }
+  }
+  return finish_create(p, family, probEnum, recon, icFlag, nParams, names, values);
+}
+
 void or_destroy(or_problem* p) {
   if (!p) return;
   free(p->m.x); free(p->m.y); free(p->m.z); free(p->m.graph); free(p->m.rowsInner); free(p->m.rowsNearBd);
+  free(p->m.cx); free(p->m.cy); free(p->m.cz);
   for (int s = 0; s < 6; ++s) free(p->ghost[s]);
   free(p->rowptr); free(p->colidx); free(p->src);
   free(p);
@@ -813,7 +911,7 @@ long long or_query(or_problem* p, int what) {
     case 0: return m->dim; case 1: return m->stencil; case 2: return m->nSample; case 3: return m->nStencil;
     case 4: return m->ncols; case 5: return m->nInner; case 6: return m->nNearBd; case 7: return m->periodic;
     case 8: return p->ndpc; case 9: return (long long)m->nStencil * p->ndpc; case 10: return (long long)m->nSample * p->ndpc;
-    case 11: return p->nnz;
+    case 11: build_pattern(p); return p->nnz;
   }
   return -1;
 }
@@ -825,12 +923,14 @@ void or_mesh_arrays(or_problem* p, int32_t* graph, double* x, double* y, double*
   if (x) memcpy(x, m->x, sizeof(double) * (size_t)m->nStencil);
   if (y) memcpy(y, m->y, sizeof(double) * (size_t)m->nStencil);
   if (z) memcpy(z, m->z, sizeof(double) * (size_t)m->nStencil);
-  if (rowsInner) memcpy(rowsInner, m->rowsInner, sizeof(int32_t) * (size_t)m->nInner);
+  if (rowsInner && m->rowsInner) memcpy(rowsInner, m->rowsInner, sizeof(int32_t) * (size_t)m->nInner);
+  else if (rowsInner) for (int32_t i = 0; i < m->nInner; ++i) rowsInner[i] = i;
   if (rowsNearBd) memcpy(rowsNearBd, m->rowsNearBd, sizeof(int32_t) * (size_t)m->nNearBd);
   if (d6) for (int a = 0; a < 3; ++a) { d6[a] = m->d[a]; d6[3 + a] = m->dInv[a]; }
 }
 
 void or_pattern(or_problem* p, int32_t* rowptr, int32_t* colidx) {
+  build_pattern(p);
   memcpy(rowptr, p->rowptr, sizeof(int32_t) * ((size_t)p->m.nSample * p->ndpc + 1));
   memcpy(colidx, p->colidx, sizeof(int32_t) * (size_t)p->nnz);
 }
@@ -843,7 +943,7 @@ void or_ic(or_problem* p, double* U) {
   double prim[5] = {0, 0, 0, 0, 0};
   if (p->family == F_EULER1D) { /* euler_1d_initial_condition.hpp:55-183 */
     for (int32_t i = 0; i < n; ++i) {
-      const double x = m->x[i];
+      const double x = mx(m, i);
       if (p->prob == 0) { prim[0] = 1. + 0.2 * sin(M_PI * x); prim[1] = 1.; prim[2] = 1.; }
       else if (p->prob == 1) {
         if (x <= 0.) { prim[0] = 1.; prim[1] = 0.; prim[2] = 1.; }
@@ -883,7 +983,7 @@ void or_ic(or_problem* p, double* U) {
       memcpy(r2s, t, sizeof t);
     }
     for (int32_t i = 0; i < n; ++i) {
-      const double x = m->x[i], y = m->y[i];
+      const double x = mx(m, i), y = my(m, i);
       double* s = U + 4 * (size_t)i;
       int direct = 0;
       switch (p->prob) {
@@ -933,9 +1033,9 @@ void or_ic(or_problem* p, double* U) {
     const double sRad = 3. * dmin;
     for (int32_t i = 0; i < n; ++i) {
       double* s = U + 5 * (size_t)i;
-      if (p->prob == 0) { prim[0] = 1.0 + 0.2 * sin(M_PI * (m->x[i] + m->y[i] + m->z[i])); prim[1] = prim[2] = prim[3] = 1.0; prim[4] = 1.; }
+      if (p->prob == 0) { prim[0] = 1.0 + 0.2 * sin(M_PI * (mx(m, i) + my(m, i) + mz(m, i))); prim[1] = prim[2] = prim[3] = 1.0; prim[4] = 1.; }
       else {
-        const double myR = sqrt(m->x[i] * m->x[i] + m->y[i] * m->y[i] + m->z[i] * m->z[i]);
+        const double myR = sqrt(mx(m, i) * mx(m, i) + my(m, i) * my(m, i) + mz(m, i) * mz(m, i));
         prim[0] = 1.0; prim[1] = prim[2] = prim[3] = 0.0;
         prim[4] = (myR <= sRad) ? (3. * gm1 * 0.851072) / (4. * M_PI * sRad * sRad * sRad) : 2.5e-5;
       }
@@ -947,13 +1047,13 @@ void or_ic(or_problem* p, double* U) {
     for (int32_t i = 0; i < n; ++i) {
       double* s = U + 3 * (size_t)i;
       if (p->icFlag == 1) {
-        const double dx1 = m->x[i] - p->icp[1], dy1 = m->y[i] - p->icp[2];
+        const double dx1 = mx(m, i) - p->icp[1], dy1 = my(m, i) - p->icp[2];
         const double r = sqrt(dx1 * dx1 + dy1 * dy1);
         s[0] = 1. + p->icp[0] * exp(-(r * r));
       } else {
-        const double dx1 = m->x[i] - p->icp[4], dy1 = m->y[i] - p->icp[5];
+        const double dx1 = mx(m, i) - p->icp[4], dy1 = my(m, i) - p->icp[5];
         const double r1 = sqrt(dx1 * dx1 + dy1 * dy1);
-        const double dx2 = m->x[i] - p->icp[7], dy2 = m->y[i] - p->icp[8];
+        const double dx2 = mx(m, i) - p->icp[7], dy2 = my(m, i) - p->icp[8];
         const double r2 = sqrt(dx2 * dx2 + dy2 * dy2);
         s[0] = 1. + p->icp[3] * exp(-(r1 * r1)) + p->icp[6] * exp(-(r2 * r2));
       }
@@ -969,7 +1069,7 @@ void or_ic(or_problem* p, double* U) {
   }
   if (p->family == F_ADVDIFF2D) { /* advection_diffusion_2d_initial_condition.hpp:54-78 */
     for (int32_t i = 0; i < n; ++i) {
-      const double dx = m->x[i] - p->icp[2], dy = m->y[i] - p->icp[3];
+      const double dx = mx(m, i) - p->icp[2], dy = my(m, i) - p->icp[3];
       const double dxSq = dx * dx, dySq = dy * dy;
       U[2 * (size_t)i] = p->icp[0] * exp(-(dxSq + dySq) / p->icp[1]);
       U[2 * (size_t)i + 1] = p->icp[0] * exp(-(dxSq + dySq) / p->icp[1]);
@@ -978,7 +1078,7 @@ void or_ic(or_problem* p, double* U) {
   }
   if (p->family == F_ADVECTION1D) { /* advection_1d_prob_class.hpp:111-156 */
     for (int32_t i = 0; i < n; ++i) {
-      const double x = m->x[i];
+      const double x = mx(m, i);
       if (p->icFlag == 1) U[i] = sin(M_PI * x);
       else if (p->icFlag == 2) {
         const double dx1Sq = (x - 1.2) * (x - 1.2), dx2Sq = (x - 2.5) * (x - 2.5);
@@ -995,7 +1095,7 @@ void or_ic(or_problem* p, double* U) {
   }
   if (p->family == F_DIFFREAC2D) { /* diffusion_reaction_2d_prob_class.hpp:141-178 */
     for (int32_t i = 0; i < n; ++i) {
-      const int in = fabs(m->x[i]) < 0.1 && fabs(m->y[i]) < 0.1;
+      const int in = fabs(mx(m, i)) < 0.1 && fabs(my(m, i)) < 0.1;
       U[2 * (size_t)i] = in ? 0.5 : 1.; U[2 * (size_t)i + 1] = in ? 0.25 : 0.;
     }
   }
@@ -1086,7 +1186,7 @@ static void fill_ghosts(or_problem* p, const double* U, double t) {
   for (int32_t it = 0; it < m->nNearBd; ++it) {
     const int32_t row = m->rowsNearBd[it];
     const int32_t self = G(m, row, 0);
-    const double myX = m->x[self], myY = m->y[self];
+    const double myX = mx(m, self), myY = my(m, self);
     for (int side = 0; side < (dim == 1 ? 3 : 2 * dim); ++side) {
       if (dim == 1 && side == 1) continue;
       for (int L = 0; L < h; ++L) {
@@ -1190,19 +1290,26 @@ static void flux_jac(const or_problem* p, int axis, double* JL, double* JR, cons
   else or_euler_flux_jac(p->ndpc, JL, JR, qL, qR, n, p->gamma);
 }
 
-/* gather the S stencil values of one dof along an axis: [l_{h-1} .. l0, self, r0 .. r_{h-1}] */
-static void gather(const or_problem* p, const double* U, int32_t row, int32_t gRow, int axis, int S, int dof, double* q,
-                   int32_t* cells) {
+/* stencil cells of a row along an axis: [l_{h-1} .. l0, self, r0 .. r_{h-1}] (-1 = outside the domain) */
+static void gather_cells(const or_problem* p, int32_t row, int axis, int S, int32_t* cells) {
   const or_mesh* m = &p->m;
   const int h = (S - 1) / 2;
   const int sm = side_minus(axis), sp = side_plus(axis);
-  q[h] = U[(size_t)G(m, row, 0) * p->ndpc + dof];
-  if (cells) cells[h] = G(m, row, 0);
+  cells[h] = G(m, row, 0);
   for (int L = 0; L < h; ++L) {
-    const int32_t cl = G(m, row, gcol(m->dim, sm, L)), cr = G(m, row, gcol(m->dim, sp, L));
-    q[h - 1 - L] = sval(p, U, cl, sm, gRow, L, dof);
-    q[h + 1 + L] = sval(p, U, cr, sp, gRow, L, dof);
-    if (cells) { cells[h - 1 - L] = cl; cells[h + 1 + L] = cr; }
+    cells[h - 1 - L] = G(m, row, gcol(m->dim, sm, L));
+    cells[h + 1 + L] = G(m, row, gcol(m->dim, sp, L));
+  }
+}
+/* gather the S stencil values of one dof along an axis from those cells (ghost rows where a cell is missing) */
+static void gather(const or_problem* p, const double* U, const int32_t* cells, int32_t gRow, int axis, int S, int dof,
+                   double* q) {
+  const int h = (S - 1) / 2;
+  const int sm = side_minus(axis), sp = side_plus(axis);
+  q[h] = U[(size_t)cells[h] * p->ndpc + dof];
+  for (int L = 0; L < h; ++L) {
+    q[h - 1 - L] = sval(p, U, cells[h - 1 - L], sm, gRow, L, dof);
+    q[h + 1 + L] = sval(p, U, cells[h + 1 + L], sp, gRow, L, dof);
   }
 }
 
@@ -1248,7 +1355,7 @@ static void jac_factors(const or_problem* p, int32_t row, int axis, double* f) {
   }
   if (p->family == F_EULER3D) { if (p->prob == 1 && has_bd(m, row, sm)) f[axis] = -1.; return; }
   if (p->family != F_EULER2D) return;
-  const double myX = m->x[G(m, row, 0)];
+  const double myX = mx(m, G(m, row, 0));
   switch (p->prob) {
     case E2_SEDOV_SYM: if (has_bd(m, row, sm)) f[axis] = -1.; break;
     case E2_NORMAL_SHOCK: if (axis == 2) f[2] = -1.; break;
@@ -1283,8 +1390,9 @@ static void eval_cell(const or_problem* p, const double* U, int32_t row, int32_t
     int32_t cells[7];
     const int wantGrad = (Jv != NULL) && !nearBd && S > 3;
     double s3[5][3]; /* first-layer stencil (l0, self, r0) per dof: the diffusion term's operands */
+    gather_cells(p, row, axis, S, cells);
     for (int d = 0; d < N; ++d) {
-      gather(p, U, row, gRow, axis, S, d, q, cells);
+      gather(p, U, cells, gRow, axis, S, d, q);
       s3[d][0] = q[(S - 1) / 2 - 1]; s3[d][1] = q[(S - 1) / 2]; s3[d][2] = q[(S - 1) / 2 + 1];
       reconstruct(S, q, &lN[d], &lP[d], &rN[d], &rP[d], wantGrad ? gLN[d] : NULL, wantGrad ? gLP[d] : NULL,
                   wantGrad ? gRN[d] : NULL, wantGrad ? gRP[d] : NULL);
@@ -1499,7 +1607,7 @@ static int evaluate(or_problem* p, const double* U, double t, double* V, double*
   const or_mesh* m = &p->m;
   const int N = p->ndpc;
   if (V) memset(V, 0, sizeof(double) * (size_t)m->nSample * N);
-  if (Jv) memset(Jv, 0, sizeof(double) * (size_t)p->nnz);
+  if (Jv) { build_pattern(p); memset(Jv, 0, sizeof(double) * (size_t)p->nnz); }
   if (p->family == F_DIFFREAC2D && p->prob == 1) { gray_scott(p, U, V, Jv); return 0; }
   if (p->family == F_DIFFREAC2D || p->family == F_DIFFREAC1D) { diffreac_problem_a(p, U, V, Jv); return 0; }
   fill_ghosts(p, U, t);
@@ -1514,7 +1622,7 @@ static int evaluate(or_problem* p, const double* U, double t, double* V, double*
 #ifdef _OPENMP
 #pragma omp for schedule(static)
 #endif
-    for (int32_t it = 0; it < m->nInner; ++it) eval_cell(p, U, m->rowsInner[it], -1, 0, V, Jv);
+    for (int32_t it = 0; it < m->nInner; ++it) eval_cell(p, U, ROW_INNER(m, it), -1, 0, V, Jv);
   }
   return 0;
 }
@@ -1528,6 +1636,31 @@ int or_ghosts(or_problem* p, int side, double* out) {
   const int n = p->m.nNearBd * p->gstride;
   if (out) memcpy(out, p->ghost[side], sizeof(double) * (size_t)n);
   return n;
+}
+
+/* bounded sample of a big workload: velocity of the inner rows [it0, it1) only (positions in graphRowsOfCellsAwayFromBd),
+ * `reps` times, V rows zeroed first like the full evaluation does; returns the seconds spent.  For the CPU-baseline /
+ * reference arm of bench.py: the 512^3 problem itself is evaluated, a slab of planes at a time. */
+double or_time_velocity_inner_range(or_problem* p, const double* U, double t, double* V, int32_t it0, int32_t it1, int reps) {
+  const or_mesh* m = &p->m;
+  const int N = p->ndpc;
+  if (it0 < 0) it0 = 0;
+  if (it1 > m->nInner) it1 = m->nInner;
+  struct timespec a, b;
+  clock_gettime(CLOCK_MONOTONIC, &a);
+  for (int rep = 0; rep < reps; ++rep) {
+    fill_ghosts(p, U, t);
+#ifdef _OPENMP
+#pragma omp parallel for schedule(static)
+#endif
+    for (int32_t it = it0; it < it1; ++it) {
+      const int32_t row = ROW_INNER(m, it);
+      for (int d = 0; d < N; ++d) V[(size_t)row * N + d] = 0.;
+      eval_cell(p, U, row, -1, 0, V, NULL);
+    }
+  }
+  clock_gettime(CLOCK_MONOTONIC, &b);
+  return (double)(b.tv_sec - a.tv_sec) + 1e-9 * (double)(b.tv_nsec - a.tv_nsec);
 }
 
 double or_time_velocity(or_problem* p, const double* U, double t, int warmup, int reps) {

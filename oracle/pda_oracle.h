@@ -22,6 +22,13 @@ or_problem* or_create_from_arrays(int dim, int stencil, int32_t nSample, int32_t
                                   const double* x, const double* y, const double* z, const int32_t* graph,
                                   int family, int probEnum, int recon, int icFlag, int nParams,
                                   const char* const* names, const double* values);
+/* lattice mode: a full mesh in natural ordering evaluated WITHOUT a stored graph (neighbours by index arithmetic, same
+ * rows / columns / arithmetic as the stored-graph path): what makes the BASELINE sizes (512^3, 4096^2) checkable
+ * against the oracle.  cx/cy/cz: per-axis cell-centre coordinates or NULL; no Jacobian pattern at these sizes
+ * unless asked (or_pattern / or_velocity_and_jacobian build it on demand like the other constructors). */
+or_problem* or_create_lattice(int dim, int stencil, const int32_t n[3], const double dxyz[3], const int32_t periodic[3],
+                              const double* cx, const double* cy, const double* cz, int family, int probEnum,
+                              int recon, int icFlag, int nParams, const char* const* names, const double* values);
 void or_destroy(or_problem* p);
 /* replaces the per-sample-row source table of a ProblemA family (nSample doubles) */
 void or_set_source(or_problem* p, const double* values);
@@ -36,6 +43,8 @@ int or_velocity_and_jacobian(or_problem* p, const double* U, double t, double* V
 void or_pattern(or_problem* p, int32_t* rowptr, int32_t* colidx);
 int or_ghosts(or_problem* p, int side, double* out);
 double or_time_velocity(or_problem* p, const double* U, double t, int warmup, int reps);
+/* velocity of the inner rows [it0, it1) only, `reps` times (bounded sample of a big workload); returns seconds */
+double or_time_velocity_inner_range(or_problem* p, const double* U, double t, double* V, int32_t it0, int32_t it1, int reps);
 
 /* leaf functions exposed for the known-answer tests (tests_cpp/weno5/main.cc, weno3/main.cc) */
 void or_weno5(double* uNeg, double* uPos, double qm2, double qm1, double q, double qp1, double qp2, double qp3);

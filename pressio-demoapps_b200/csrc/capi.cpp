@@ -206,6 +206,22 @@ pda_status pda_problem_set_source(pda_problem p, const double* values) {
   return guarded([&] { P(p).setSource(values); });
 }
 
+pda_status pda_problem_set_option(pda_problem p, const char* name, const char* value) {
+  return guarded([&] {
+    if (!name || !value) throw pda::Error(pda::kInvalid, "set_option: null argument");
+    P(p).setOption(name, value);
+  });
+}
+
+pda_status pda_problem_get_option(pda_problem p, const char* name, char* value, int capacity) {
+  return guarded([&] {
+    if (!name || !value || capacity < 1) throw pda::Error(pda::kInvalid, "get_option: null argument");
+    const std::string v = P(p).getOption(name);
+    if ((int)v.size() + 1 > capacity) throw pda::Error(pda::kInvalid, "get_option: buffer too small");
+    std::memcpy(value, v.c_str(), v.size() + 1);
+  });
+}
+
 pda_status pda_problem_set_bc(pda_problem p, int side, int kind, const double* values) {
   return guarded([&] { P(p).setBc(side, kind, values); });
 }

@@ -11,6 +11,7 @@
 #include <map>
 
 #include "common.hpp"
+#include "func_attrs.hpp"
 #include "kernels_generic.cuh"
 #include "kernels_lattice.cuh"
 #include "kernels_tiled.cuh"
@@ -18,6 +19,7 @@
 #include "kernels_jaclattice.cuh"
 #include "kernels_march2d.cuh"
 #include "kernels_applylattice.cuh"
+#include "kernels_reforder.hpp"
 
 namespace pda {
 
@@ -29,6 +31,7 @@ namespace {
     if (e_ != cudaSuccess)                                                                               \
       throw Error(kCuda, std::string(#call) + " failed: " + cudaGetErrorString(e_));                     \
   } while (0)
+
 
 template <class T>
 struct DevBuf {
@@ -163,7 +166,8 @@ struct DeviceState {
   dev::GhostTables tables{};
   int nsides = 0, hS = 0;
   bool haveGhosts = false;
-  bool jacTablesReady = false;
+  bool jacTablesReady = false;        // near-boundary rows
+  bool innerJacTablesReady = false;   // inner rows (graph-driven Jacobian kernels, reference-order mode)
   bool innerRowsReady = false;
   // scratch owned by the problem (host-pointer entry points, applyJacobian)
   DevBuf<double> dU, dV, dJ, dB, dR;
@@ -387,6 +391,41 @@ double Problem::queryParameter(const std::string& name) const {
     if (name == "k") return gs_[3];
   }
   throw Error(kInvalid, "queryParameter: unknown parameter '" + name + "'");
+}
+
+void Problem::setOption(const std::string& name, const std::string& value) {
+  if (name == "jacobian_order") {
+    // "fast" (default): face-sharing kernels, well-conditioned reconstruction gradients (closer to the exact Jacobian
+    // than the reference, not within 1e-12 of it).  "reference": kernels_reforder.cu -- the reference's formulas,
+    // operation order and accumulation order, bit for bit.
+    if (value == "fast") refOrderJac_ = false;
+    else if (value == "reference") refOrderJac_ = true;
+    else throw Error(kInvalid, "set_option: jacobian_order must be \"fast\" or \"reference\"");
+    return;
+  }
+  if (name == "velocity_order") {
+    // "fast" (default): face-sharing kernels, division-free leaf arithmetic (values within 1e-12 / 1e-10 of the
+    // reference at the reference's mesh sizes).  "reference": one thread per row, the reference's operation order,
+    // every operation individually rounded: identical values at ANY mesh size (where hInv * ulp(flux) exceeds 1e-10
+    // -- Mach-10 flows on fine meshes -- no other evaluation order can stay inside the tolerance, the reference's
+    // own compiled with FMA contraction included).
+    if (value == "fast") refOrderVel_ = false;
+    else if (value == "reference") refOrderVel_ = true;
+    else throw Error(kInvalid, "set_option: velocity_order must be \"fast\" or \"reference\"");
+    return;
+  }
+  if (name == "order") {   // both at once
+    setOption("jacobian_order", value);
+    setOption("velocity_order", value);
+    return;
+  }
+  throw Error(kInvalid, "set_option: unknown option '" + name + "'");
+}
+
+std::string Problem::getOption(const std::string& name) const {
+  if (name == "jacobian_order") return refOrderJac_ ? "reference" : "fast";
+  if (name == "velocity_order") return refOrderVel_ ? "reference" : "fast";
+  throw Error(kInvalid, "get_option: unknown option '" + name + "'");
 }
 
 void Problem::setBc(int side, int kind, const double* values) {
@@ -781,7 +820,10 @@ void Problem::jacobianPattern(int32_t* rowptr, int32_t* colidx) {
 
 // =============================================================================================== device set-up
 void Problem::ensureDevice() {
-  if (dev_) return;
+  if (dev_) {   // every caller may allocate right after: the current device must be this problem's
+    PDA_CUDA(cudaSetDevice(device_));
+    return;
+  }
   int ndev = 0;
   if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
     cudaGetLastError();
@@ -1095,9 +1137,15 @@ void Problem::evaluateDev(const double* dU, double t, double* dV, double* dJ, vo
   const int nc = m.ncols();
   dev::Deltas dl{{m.dInv[0], m.dInv[1], m.dInv[2]}};
 
+  // reference-order mode (pda_problem_set_option "jacobian_order" = "reference", kernels_reforder.cu): every row through
+  // the one-thread-per-row kernels that keep the reference's formulas, operation order and accumulation order.  The
+  // diffusion-reaction families have no reconstruction gradients: their kernels already follow the reference's order.
+  const bool refOrder = dJ && refOrderJac_ && family_ != F_DIFFREAC2D && family_ != F_DIFFREAC1D;
+  const bool refVel = !dJ && refOrderVel_ && family_ != F_DIFFREAC2D && family_ != F_DIFFREAC1D;
+  if (refVel) ensureInnerRows();
   // inner rows of a 2D full lattice: face-sharing lattice kernel (kernels_jaclattice.cuh); everything else: staged
   // graph-driven kernel
-  const bool jacLattice = dJ && m.lattice && dim_ == 2 && ds.innerViaLattice && family_ != F_DIFFREAC2D;
+  const bool jacLattice = dJ && !refOrder && m.lattice && dim_ == 2 && ds.innerViaLattice && family_ != F_DIFFREAC2D;
   if (dJ) {
     buildPattern();
     const bool gsLat = family_ == F_DIFFREAC2D && probId_ == 1 && ds.innerViaLattice && m.fullyPeriodic;
@@ -1112,23 +1160,23 @@ void Problem::evaluateDev(const double* dU, double t, double* dV, double* dJ, vo
       }
       ds.latJacReady = true;
     }
-    if (!ds.jacTablesReady) {
-      auto fill = [&](DeviceRowSet& rs) {
-        std::vector<int32_t> base(rs.n), len(rs.n);
-        std::vector<uint8_t> sl((size_t)rs.n * slotCols_);
-        for (int32_t r = 0; r < rs.n; ++r) {
-          const int32_t row = rs.hostRowIds[r];
-          base[r] = cellBase_[row]; len[r] = cellLen_[row];
-          std::memcpy(&sl[(size_t)r * slotCols_], &slots_[(size_t)row * slotCols_], slotCols_);
-        }
-        rs.jBase.upload(base); rs.jLen.upload(len); rs.jSlot.upload(sl);
-      };
-      if (!((jacLattice || gsLat) && !mergedNeighbors_)) { ensureInnerRows(); fill(ds.inner); }
-      fill(ds.nearBd);
-      ds.jacTablesReady = true;
-    }
+    auto fill = [&](DeviceRowSet& rs) {
+      std::vector<int32_t> base(rs.n), len(rs.n);
+      std::vector<uint8_t> sl((size_t)rs.n * slotCols_);
+      for (int32_t r = 0; r < rs.n; ++r) {
+        const int32_t row = rs.hostRowIds[r];
+        base[r] = cellBase_[row]; len[r] = cellLen_[row];
+        std::memcpy(&sl[(size_t)r * slotCols_], &slots_[(size_t)row * slotCols_], slotCols_);
+      }
+      rs.jBase.upload(base); rs.jLen.upload(len); rs.jSlot.upload(sl);
+    };
+    if (!ds.jacTablesReady) { fill(ds.nearBd); ds.jacTablesReady = true; }
+    const bool innerTables = refOrder || !((jacLattice || gsLat) && !mergedNeighbors_);
+    if (innerTables && !ds.innerJacTablesReady) { ensureInnerRows(); fill(ds.inner); ds.innerJacTablesReady = true; }
     // the staged inner-row kernel writes every value once; only rows assembled by read-modify-write need zeros
-    if (gsLat && !mergedNeighbors_) {
+    if (refOrder) {
+      PDA_CUDA(cudaMemsetAsync(dJ, 0, colidx_.size() * sizeof(double), st));   // the reference zeroes J, then accumulates
+    } else if (gsLat && !mergedNeighbors_) {
       // the Gray-Scott lattice kernel writes every value once
     } else if (family_ == F_DIFFREAC2D || family_ == F_DIFFREAC1D || mergedNeighbors_) {
       PDA_CUDA(cudaMemsetAsync(dJ, 0, colidx_.size() * sizeof(double), st));
@@ -1201,6 +1249,44 @@ void Problem::evaluateDev(const double* dU, double t, double* dV, double* dJ, vo
     using Phys = decltype(phys);
     dispatchScheme(S_, [&](auto sTag) {
       constexpr int S = decltype(sTag)::value;
+      if (refOrder || refVel) {
+        dev::RefOrderParams P{};
+        P.family = family_; P.ndpc = ndpc_; P.S = S_; P.dim = dim_; P.gamma = gamma_;
+        for (int a = 0; a < 3; ++a) P.dInv[a] = m.dInv[a];
+        if (family_ == F_SWE2D) { P.gravity = physParams_[0]; P.coriolis = physParams_[1]; }
+        if (family_ == F_ADVDIFF2D) P.diffusion = physParams_[0];
+        if (family_ == F_ADVDIFFREAC2D) {
+          P.adv[0] = physParams_[0]; P.adv[1] = physParams_[1]; P.diffusion = physParams_[2]; P.sigma = physParams_[3];
+          P.src = srcUser_ ? ds.src.p : nullptr;
+        }
+        if (family_ == F_ADVECTION1D) P.adv[0] = physParams_[0];
+        if (refVel) {
+          if (nNb > 0) {
+            dev::launchRefOrderVelocity(P, ds.nearBd.graph.p, ds.nearBd.rowIds.p, nNb, nc, dU, dV, gv.g, gv.stride, true, st);
+            ++launches_;
+          }
+          if (ds.inner.n > 0) {
+            dev::launchRefOrderVelocity(P, ds.inner.graph.p, ds.inner.rowIds.p, ds.inner.n, nc, dU, dV, nullptr, 0, false, st);
+            ++launches_;
+          }
+          return;
+        }
+        if (nNb > 0) {
+          if (dV) {
+            dev::launchRefOrderVelocity(P, ds.nearBd.graph.p, ds.nearBd.rowIds.p, nNb, nc, dU, dV, gv.g, gv.stride, true, st);
+            ++launches_;
+          }
+          dev::launchRefOrderNearBd(P, ds.nearBd.graph.p, ds.nearBd.rowIds.p, nNb, nc, dU, dJ, ds.nearBd.jBase.p,
+                                    ds.nearBd.jLen.p, ds.nearBd.jSlot.p, slotCols_, gv.g, gv.stride, ds.factors.p, st);
+          ++launches_;
+        }
+        if (ds.inner.n > 0) {
+          dev::launchRefOrderInner(P, ds.inner.graph.p, ds.inner.rowIds.p, ds.inner.n, nc, dU, dV, dJ, ds.inner.jBase.p,
+                                   ds.inner.jLen.p, ds.inner.jSlot.p, slotCols_, st);
+          ++launches_;
+        }
+        return;
+      }
       if (nNb > 0) {
         if (dV) {
           dev::k_velocity_rows<Phys, S, true><<<gridFor(nNb, 128), 128, 0, st>>>(phys, ds.nearBd.view(nc), dl, dU, dV, gv);
@@ -1219,11 +1305,7 @@ void Problem::evaluateDev(const double* dU, double t, double* dV, double* dJ, vo
         if constexpr (Phys::dim == 2) {
           using JL = dev::JacLat2d<Phys, S>;
           auto kern = dev::k_jacobian_lattice2d<Phys, S>;
-          static bool configured = false;
-          if (!configured) {
-            PDA_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)JL::smemBytes));
-            configured = true;
-          }
+          ensureFuncAttrs(kern, (int)JL::smemBytes);
           dev::LatticeDesc L;
           for (int a = 0; a < 3; ++a) { L.n[a] = m.n[a]; L.per[a] = m.periodic[a] ? 1 : 0; }
           L.planeBegin = 0; L.planeEnd = m.n[1]; L.haloPlanes = 0; L.slab = 0; L.meshHalo = m.halo();
@@ -1241,11 +1323,7 @@ void Problem::evaluateDev(const double* dU, double t, double* dV, double* dJ, vo
           // staged assembly: every value of the inner rows written once, coalesced (no memset needed for them)
           using JS = dev::JacStage<Phys, S>;
           auto kern = dev::k_jacobian_inner_staged<Phys, S>;
-          static bool configured = false;
-          if (!configured) {
-            PDA_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)JS::smemBytes));
-            configured = true;
-          }
+          ensureFuncAttrs(kern, (int)JS::smemBytes);
           kern<<<gridFor(ds.inner.n, JS::CELLS), JS::THREADS, JS::smemBytes, st>>>(phys, ds.inner.view(nc), dl, dU, dV, dJ,
                                                                                ds.inner.jac(slotCols_));
         } else if (dJ) {
@@ -1372,6 +1450,9 @@ void Problem::evaluatePlanes(const double* dU, double /*t*/, double* dV, void* s
     case F_EULER2D: run(dev::Euler<2>{gamma_}); break;
     case F_EULER3D: run(dev::Euler<3>{gamma_}); break;
     case F_SWE2D: run(dev::Swe2d{physParams_[0], physParams_[1]}); break;
+    case F_ADVDIFF2D:
+      run(dev::Burgers2d{{physParams_[0] * (m.dInv[0] * m.dInv[0]), physParams_[0] * (m.dInv[1] * m.dInv[1])}});
+      break;
     default: throw Error(kUnsupported, "family not supported on device");
   }
   PDA_CUDA(cudaGetLastError());
@@ -1403,7 +1484,9 @@ void Problem::velocityHost(const double* U, double t, double* V) {
   // Host buffers are handed to cudaMemcpyAsync as they are: pinned buffers (cudaHostAlloc / cudaHostRegister /
   // torch pin_memory) stream at PCIe speed and overlap, pageable ones are staged by the driver.
   const int64_t nPlanes = m.n[dim_ - 1];
-  const bool pipelined = ds.innerViaLattice && ds.nearBd.n == 0 && m.fullyPeriodic && dim_ >= 2 &&
+  // only the families evaluatePlanes dispatches: periodic Gray-Scott / ADR lattices take the single-shot path
+  const bool planeFamily = family_ == F_EULER2D || family_ == F_EULER3D || family_ == F_SWE2D || family_ == F_ADVDIFF2D;
+  const bool pipelined = !refOrderVel_ && planeFamily && ds.innerViaLattice && ds.nearBd.n == 0 && m.fullyPeriodic && dim_ >= 2 &&
                          (int64_t)m.nSample >= (int64_t)(1 << 22) && nPlanes >= 16;
   if (!pipelined) {
     PDA_CUDA(cudaMemcpyAsync(ds.dU.p, U, nU * sizeof(double), cudaMemcpyHostToDevice, ds.stream));
@@ -1483,11 +1566,11 @@ void Problem::applyJacobianDev(const double* dU, const double* dB, int ncols, in
   const int32_t nrows = nDofSample();
   const int64_t nJc = nDofStencil();
   Mesh& mm = *mesh_;
-  const bool fused3d = mm.lattice && dim_ == 3 && ds.innerViaLattice && family_ == F_EULER3D &&
+  const bool fused3d = !refOrderJac_ && mm.lattice && dim_ == 3 && ds.innerViaLattice && family_ == F_EULER3D &&
                        mm.n[0] >= 2 * mm.halo() && mm.n[1] >= 2 * mm.halo() && mm.n[2] >= 2 * mm.halo();
-  const bool fused = fused3d ||
+  const bool fused = !refOrderJac_ && (fused3d ||
                      (mm.lattice && dim_ == 2 && ds.innerViaLattice && ncols <= fusedApplyMaxCols() &&
-                      (family_ == F_EULER2D || family_ == F_SWE2D || family_ == F_ADVDIFF2D || family_ == F_ADVDIFFREAC2D));
+                      (family_ == F_EULER2D || family_ == F_SWE2D || family_ == F_ADVDIFF2D || family_ == F_ADVDIFFREAC2D)));
   // the assembled Jacobian (pattern, values scratch) is needed unless every row is matrix-free (periodic lattices)
   if (!(fused && ds.nearBd.n == 0)) {
     buildPattern();
@@ -1536,7 +1619,7 @@ void Problem::applyJacobianDev(const double* dU, const double* dB, int ncols, in
             constexpr int NC = decltype(ncTag)::value;
             using AK = dev::ApplyLat3d<NC>;
             auto kern = dev::k_applyjac_lattice3d<S, NC>;
-            PDA_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)AK::smemBytes));
+            ensureFuncAttrs(kern, (int)AK::smemBytes);
             dim3 grid((unsigned)((w0 + AK::T - 1) / AK::T), (unsigned)((w1 + AK::T - 1) / AK::T), (unsigned)((w2 + AK::T - 1) / AK::T));
             kern<<<grid, AK::THREADS, AK::smemBytes, st>>>(gamma_, L, dl, dU, dB, ncols, c0, ldbRow, ldbCol, dR, ldrRow, ldrCol);
             ++launches_;
@@ -1554,7 +1637,7 @@ void Problem::applyJacobianDev(const double* dU, const double* dB, int ncols, in
           constexpr int NC = 4;
           using AK = dev::ApplyLat2d<Phys, NC>;
           auto kern = dev::k_applyjac_lattice2d<Phys, S, NC>;
-          PDA_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)AK::smemBytes));
+          ensureFuncAttrs(kern, (int)AK::smemBytes);
           dim3 grid((unsigned)((w0 + AK::T - 1) / AK::T), (unsigned)((w1 + AK::T - 1) / AK::T));
           for (int c0 = 0; c0 < ncols; c0 += NC) {
             kern<<<grid, AK::THREADS, AK::smemBytes, st>>>(phys, L, dl, dU, dB, ncols, c0, ldbRow, ldbCol, dR, ldrRow, ldrCol);
@@ -1625,7 +1708,7 @@ void Problem::applyJacobianDev(const double* dU, const double* dB, int ncols, in
     auto launch = [&](auto nTag) {
       constexpr int NN = decltype(nTag)::value;
       auto kern = dev::k_spmm_cells_rowmajor<NN>;
-      PDA_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      ensureFuncAttrs(kern, (int)smem);
       kern<<<grid, 256, smem, st>>>(ncells, order, ds.dCellBase.p, ds.dCellLen.p, ds.dColidx.p, ds.dJ.p, Bp, ncols, Rp, slotDoubles);
     };
     switch (ndpc_) {

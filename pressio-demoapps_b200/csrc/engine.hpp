@@ -41,6 +41,8 @@ class Problem {
   void setBcCallback(int side, BcGhostFn ghost, BcFactorFn factors, void* user);
   void setBcPointer(int side, void* user);   // setBCPointer (euler_2d_prob_class.hpp:213-216)
   void setSource(const double* values);   // nSample doubles (host)
+  void setOption(const std::string& name, const std::string& value);   // pda_problem_set_option
+  std::string getOption(const std::string& name) const;
 
   int64_t jacobianNnz();
   void jacobianPattern(int32_t* rowptr, int32_t* colidx);
@@ -109,6 +111,8 @@ class Problem {
   int32_t slabK0_ = 0, slabK1_ = 0;
   int slabRank_ = 0, slabRanks_ = 1;
 
+  bool refOrderJac_ = false;         // option "jacobian_order" = "reference" (kernels_reforder.cu)
+  bool refOrderVel_ = false;         // option "velocity_order" = "reference"
   bool skipInnerJacobian_ = false;   // applyJacobian, matrix-free inner rows: assemble the near-boundary rows only
   int64_t launches_ = 0;
   std::unique_ptr<DeviceState> dev_;

@@ -11,6 +11,7 @@
 #include <type_traits>
 
 #include "fastmath.cuh"
+#include "kernel_types.cuh"
 #include "physics.cuh"
 
 namespace pda {
@@ -23,18 +24,6 @@ template <int DIM> PDA_DEVFN int gcol(int side, int layer) {
 }
 template <int AX> PDA_DEVFN constexpr int sideMinus() { return AX == 0 ? 0 : (AX == 1 ? 3 : 4); }
 template <int AX> PDA_DEVFN constexpr int sidePlus() { return AX == 0 ? 2 : (AX == 1 ? 1 : 5); }
-
-struct RowSet {
-  const int32_t* graph;   // compact [n][ncols]
-  const int32_t* rowIds;  // sample-mesh row of compact row r
-  int32_t n;
-  int32_t ncols;
-};
-
-struct GhostView {
-  double* g[6];     // per side: [numNearBd][stride]
-  int32_t stride;   // ndpc * (schemeStencil-1)/2
-};
 
 // ------------------------------------------------------------------------------------------------ ghost fill
 // One recipe per (near-bd row, side, layer): ghost[d] = mul[mode][d] * U[src*ndpc+d] + add[mode][d].
@@ -78,7 +67,11 @@ __global__ void k_ghost_fill(const GhostRecipe* __restrict__ rec, const double2*
   double* out = gv.g[side] + (int64_t)r * gv.stride + layer * NDPC;
   const double* in = U + (int64_t)gr.src * NDPC;
 #pragma unroll
-  for (int d = 0; d < NDPC; ++d) out[d] = tab.mul[mode][d] * in[d] + tab.add[mode][d];
+  for (int d = 0; d < NDPC; ++d) {
+    // constant components are ASSIGNED like the reference does (0 * NaN would poison a Dirichlet ghost)
+    const double mul = tab.mul[mode][d];
+    out[d] = (mul == 0.0) ? tab.add[mode][d] : mul * in[d] + tab.add[mode][d];
+  }
 }
 
 // ------------------------------------------------------------------------------------------------ helpers
@@ -206,7 +199,6 @@ PDA_DEVFN void addExtraJacInner(const Phys& phys, const double* u, const uint8_t
   if constexpr (std::is_same<Phys, LinAdv<2>>::value) put(0, slots[0], 0, -phys.sigma);
 }
 
-struct Deltas { double hInv[3]; };
 
 // ------------------------------------------------------------------------------------------------ velocity
 template <class Phys, int S, bool NEARBD>
@@ -240,12 +232,7 @@ k_velocity_rows(Phys phys, RowSet rs, Deltas dl, const double* __restrict__ U, d
 // ------------------------------------------------------------------------------------------------ Jacobian
 // Where the blocks of a cell live in the CSR value array: all ndpc rows of a cell share one column pattern, so
 // entry (k, block slot s, j) sits at  base + k*len + s*ndpc + j.
-struct JacLayout {
-  const int32_t* base;   // [n] rowptr of the cell's first row
-  const int32_t* len;    // [n] entries per row
-  const uint8_t* slot;   // [n][nslotCols] block position of graph column c in the (sorted) row; 0xFF = absent
-  int32_t nslotCols;
-};
+// (struct JacLayout: kernel_types.cuh)
 
 template <int N>
 PDA_DEVFN void addBlockColumn(double* __restrict__ Jv, int64_t base, int32_t len, int slot, int j, const double* col) {

@@ -1,0 +1,866 @@
+// kernels_reforder.cu -- the REFERENCE-ORDER Jacobian mode: velocity + Jacobian of every row evaluated with the
+// reference's own formulas, in its operation order and its accumulation order, every floating-point operation
+// individually rounded (this file is compiled with -fmad=false; IEEE division and square root are nvcc's defaults)
+// and std::pow reproduced bit for bit (glibc_pow.h).  One thread per row, read-modify-write into zeroed values like
+// Eigen's coeffRef: this mode exists for PARITY, not for speed.
+//
+// Why it exists: the reference's WENO gradients (impl/weno5.hpp:180-434, impl/weno3.hpp:116-246) use the form
+// (d(alpha_k) S^-1 + d(S^-1) alpha_k) p_k summed over k, which cancels catastrophically -- its own values move by up
+// to 180x the 1e-12 / 1e-10 parity tolerance when only FMA contraction changes (profiles/jacobian_noise_r01.txt).  The
+// fast kernels (kernels_jaclattice.cuh, kernels_jacobian.cuh) evaluate the well-conditioned form and land CLOSER to
+// the exact Jacobian than the reference, but not within 1e-12 of the reference.  This mode is the arbiter: it
+// matches the reference's values to the last bit of every intermediate, so "same results as the reference" can be
+// checked without a tolerance argument, and the fast kernels are then judged against it.
+//
+// Replaces (per row): euler_2d_prob_class.hpp:633-720 (inner cells) and :723-989 (near-boundary cells) and their
+// 1D / 3D / shallow-water / advection-diffusion siblings; scatter mixin_directional_flux_balance_jacobian.hpp:142-372;
+// leaf math impl/weno{3,5}.hpp, impl/euler_rusanov_flux_{values,jacobian}_function.hpp,
+// impl/swe_rusanov_flux_{values,jacobian}_function.hpp, impl/advection_diffusion_2d_flux_functions.hpp.
+#include "kernels_reforder.hpp"
+
+#include "glibc_pow.h"
+#include "kernel_types.cuh"
+
+namespace pda {
+namespace dev {
+
+namespace ro {
+
+#define RO_FN __device__ __forceinline__
+
+// std::pow as the reference's binary evaluates it (GCC expands exponents -1..2 into multiplications, everything
+// else is a libm call)
+RO_FN double pw2(double x) { return x * x; }
+RO_FN double powLibm(double x, double y) {
+  double r;
+  if (glibcpow::powPositive(x, y, &r)) return r;
+  return pow(x, y);   // zero / negative / non-finite / subnormal arguments: values where no parity is defined
+}
+RO_FN double pw3(double x) { return powLibm(x, 3.0); }
+
+RO_FN int gcolRt(int dim, int side, int layer) {
+  if (dim == 1) return 1 + 2 * layer + (side == 2 ? 1 : 0);
+  return 1 + (dim == 2 ? 4 : 6) * layer + side;
+}
+RO_FN int sideMinusRt(int ax) { return ax == 0 ? 0 : (ax == 1 ? 3 : 4); }
+RO_FN int sidePlusRt(int ax) { return ax == 0 ? 2 : (ax == 1 ? 1 : 5); }
+
+// impl/weno3.hpp:56-114 (values only: the velocity path; note the expanded denominator eps^2 + 2 eps B + B^2 here
+// against pow(eps + B, 2) in the gradient versions -- SURVEY App. C-3)
+RO_FN void weno3Val(double& uNeg, double& uPos, double qim1, double qi, double qip1, double qip2) {
+  const double epsilon = 1.e-6, one = 1., two = 2., three = 3.;
+  const double oneOvtwo = one / two, oneOvthree = one / three, twoOvthree = two / three;
+  {
+    const double p0 = (-qim1 + three * qi) * oneOvtwo;
+    const double p1 = (qi + qip1) * oneOvtwo;
+    const double B0 = (qim1 - qi) * (qim1 - qi);
+    const double B1 = (qi - qip1) * (qi - qip1);
+    const double alpha0 = oneOvthree / (epsilon * epsilon + two * epsilon * B0 + B0 * B0);
+    const double alpha1 = twoOvthree / (epsilon * epsilon + two * epsilon * B1 + B1 * B1);
+    const double alphaSInv = one / (alpha0 + alpha1);
+    const double w0 = alpha0 * alphaSInv, w1 = alpha1 * alphaSInv;
+    uNeg = w0 * p0 + w1 * p1;
+  }
+  {
+    const double p0 = (qi + qip1) * oneOvtwo;
+    const double p1 = (three * qip1 - qip2) * oneOvtwo;
+    const double B0 = (qi - qip1) * (qi - qip1);
+    const double B1 = (qip1 - qip2) * (qip1 - qip2);
+    const double alpha0 = twoOvthree / (epsilon * epsilon + two * epsilon * B0 + B0 * B0);
+    const double alpha1 = oneOvthree / (epsilon * epsilon + two * epsilon * B1 + B1 * B1);
+    const double alphaSInv = one / (alpha0 + alpha1);
+    const double w0 = alpha0 * alphaSInv, w1 = alpha1 * alphaSInv;
+    uPos = w0 * p0 + w1 * p1;
+  }
+}
+
+// impl/weno5.hpp:56-178 (values only)
+RO_FN void weno5Val(double& uNeg, double& uPos, double qim2, double qim1, double qi, double qip1, double qip2,
+                    double qip3) {
+  const double epsilon = 1e-6, one = 1, two = 2, three = 3;
+  const double four = two * two, five = three + two, six = three * two, seven = four + three, ten = five * two;
+  const double eleven = five + six, twelve = six * two, thirteen = six + seven;
+  const double oneOvfour = one / four, oneOvsix = one / six, oneOvten = one / ten, threeOvten = three / ten;
+  const double sixOvten = six / ten, thirteenOvtwelve = thirteen / twelve;
+  {
+    const double p0 = (two * qim2 - seven * qim1 + eleven * qi) * oneOvsix;
+    const double p1 = (-qim1 + five * qi + two * qip1) * oneOvsix;
+    const double p2 = (two * qi + five * qip1 - qip2) * oneOvsix;
+    const double B0 = thirteenOvtwelve * (qim2 - two * qim1 + qi) * (qim2 - two * qim1 + qi) +
+                      oneOvfour * (qim2 - four * qim1 + three * qi) * (qim2 - four * qim1 + three * qi);
+    const double B1 = thirteenOvtwelve * (qim1 - two * qi + qip1) * (qim1 - two * qi + qip1) +
+                      oneOvfour * (qim1 - qip1) * (qim1 - qip1);
+    const double B2 = thirteenOvtwelve * (qi - two * qip1 + qip2) * (qi - two * qip1 + qip2) +
+                      oneOvfour * (three * qi - four * qip1 + qip2) * (three * qi - four * qip1 + qip2);
+    const double alpha0 = oneOvten / (epsilon * epsilon + 2. * epsilon * B0 + B0 * B0);
+    const double alpha1 = sixOvten / (epsilon * epsilon + 2. * epsilon * B1 + B1 * B1);
+    const double alpha2 = threeOvten / (epsilon * epsilon + 2. * epsilon * B2 + B2 * B2);
+    const double alphaSInv = one / (alpha0 + alpha1 + alpha2);
+    const double w0 = alpha0 * alphaSInv, w1 = alpha1 * alphaSInv, w2 = alpha2 * alphaSInv;
+    uNeg = w0 * p0 + w1 * p1 + w2 * p2;
+  }
+  {
+    const double p0 = (-qim1 + five * qi + two * qip1) * oneOvsix;
+    const double p1 = (two * qi + five * qip1 - qip2) * oneOvsix;
+    const double p2 = (eleven * qip1 - seven * qip2 + two * qip3) * oneOvsix;
+    const double B0 = thirteenOvtwelve * (qim1 - two * qi + qip1) * (qim1 - two * qi + qip1) +
+                      oneOvfour * (qim1 - four * qi + three * qip1) * (qim1 - four * qi + three * qip1);
+    const double B1 = thirteenOvtwelve * (qi - two * qip1 + qip2) * (qi - two * qip1 + qip2) +
+                      oneOvfour * (qi - qip2) * (qi - qip2);
+    const double B2 = thirteenOvtwelve * (qip1 - two * qip2 + qip3) * (qip1 - two * qip2 + qip3) +
+                      oneOvfour * (three * qip1 - four * qip2 + qip3) * (three * qip1 - four * qip2 + qip3);
+    const double alpha0 = threeOvten / (epsilon * epsilon + 2. * epsilon * B0 + B0 * B0);
+    const double alpha1 = sixOvten / (epsilon * epsilon + 2. * epsilon * B1 + B1 * B1);
+    const double alpha2 = oneOvten / (epsilon * epsilon + 2. * epsilon * B2 + B2 * B2);
+    const double alphaSInv = one / (alpha0 + alpha1 + alpha2);
+    const double w0 = alpha0 * alphaSInv, w1 = alpha1 * alphaSInv, w2 = alpha2 * alphaSInv;
+    uPos = w0 * p0 + w1 * p1 + w2 * p2;
+  }
+}
+
+// impl/weno3.hpp:116-246
+RO_FN void weno3Grad(double& uNeg, double& uPos, double* duNeg, double* duPos, double qim1, double qi, double qip1,
+                     double qip2) {
+  const double epsilon = 1e-6, one = 1, two = 2, three = 3;
+  const double oneOvtwo = one / two, oneOvthree = one / three, twoOvthree = two / three;
+  {
+    double dp0[3], dp1[3], da0[3], da1[3], dS[3];
+    const double p0 = (-qim1 + three * qi) * oneOvtwo;
+    const double p1 = (qi + qip1) * oneOvtwo;
+    dp0[0] = -1. / 2.; dp0[1] = 3. / 2.; dp0[2] = 0.;
+    dp1[0] = 0.; dp1[1] = 1. / 2.; dp1[2] = 1. / 2.;
+    const double B0 = (qim1 - qi) * (qim1 - qi);
+    const double B1 = (qi - qip1) * (qi - qip1);
+    const double alpha0 = oneOvthree / (epsilon * epsilon + two * epsilon * B0 + B0 * B0);
+    const double alpha1 = twoOvthree / (epsilon * epsilon + two * epsilon * B1 + B1 * B1);
+    const double alphaSInv = one / (alpha0 + alpha1);
+    const double e0 = pw2(qim1 - qi) + epsilon, e1 = pw2(qi - qip1) + epsilon;
+    da0[0] = -4. * (qim1 - qi) / (3. * pw3(e0));
+    da0[1] = 4. * (qim1 - qi) / (3. * pw3(e0));
+    da0[2] = 0.;
+    da1[0] = 0.;
+    da1[1] = -8. * (qi - qip1) / (3. * pw3(e1));
+    da1[2] = 8. * (qi - qip1) / (3. * pw3(e1));
+    const double den = pw2(2. / (3. * pw2(e1)) + 1. / (3. * pw2(e0)));
+    dS[0] = (4. * (qim1 - qi)) / (3. * pw3(e0) * den);
+    dS[1] = -((4. * (qim1 - qi)) / (3. * pw3(e0)) - (8. * (qi - qip1)) / (3. * pw3(e1))) / den;
+    dS[2] = -(8. * (qi - qip1)) / (3. * den * pw3(e1));
+    const double w0 = alpha0 * alphaSInv, w1 = alpha1 * alphaSInv;
+    for (int i = 0; i < 3; i++) {
+      duNeg[i] = (da0[i] * alphaSInv + dS[i] * alpha0) * p0 + dp0[i] * w0;
+      duNeg[i] += (da1[i] * alphaSInv + dS[i] * alpha1) * p1 + dp1[i] * w1;
+    }
+    duNeg[3] = 0.;
+    uNeg = w0 * p0 + w1 * p1;
+  }
+  {
+    double dp0[3], dp1[3], da0[3], da1[3], dS[3];
+    const double p0 = (qi + qip1) * oneOvtwo;
+    const double p1 = (three * qip1 - qip2) * oneOvtwo;
+    const double B0 = (qi - qip1) * (qi - qip1);
+    const double B1 = (qip1 - qip2) * (qip1 - qip2);
+    const double alpha0 = twoOvthree / (epsilon * epsilon + two * epsilon * B0 + B0 * B0);
+    const double alpha1 = oneOvthree / (epsilon * epsilon + two * epsilon * B1 + B1 * B1);
+    const double alphaSInv = one / (alpha0 + alpha1);
+    const double w0 = alpha0 * alphaSInv, w1 = alpha1 * alphaSInv;
+    dp0[0] = 1. / 2.; dp0[1] = 1 / 2.; dp0[2] = 0.;
+    dp1[0] = 0.; dp1[1] = 3. / 2.; dp1[2] = -1. / 2.;
+    const double e0 = pw2(qi - qip1) + epsilon, e1 = pw2(qip1 - qip2) + epsilon;
+    da0[0] = -8. * (qi - qip1) / (3. * pw3(e0));
+    da0[1] = 8. * (qi - qip1) / (3. * pw3(e0));
+    da0[2] = 0.;
+    da1[0] = 0.;
+    da1[1] = -4. * (qip1 - qip2) / (3. * pw3(e1));
+    da1[2] = 4. * (qip1 - qip2) / (3. * pw3(e1));
+    const double den = pw2(1. / (3. * pw2(e1)) + 2. / (3. * pw2(e0)));
+    dS[0] = 8. * (qi - qip1) / (3. * pw3(e0) * den);
+    dS[1] = -(8. * (qi - qip1) / (3 * pw3(e0)) - 4. * (qip1 - qip2) / (3. * pw3(e1))) / den;
+    dS[2] = -4. * (qip1 - qip2) / (3. * den * pw3(e1));
+    for (int i = 0; i < 3; i++) {
+      duPos[i + 1] = (da0[i] * alphaSInv + dS[i] * alpha0) * p0 + dp0[i] * w0;
+      duPos[i + 1] += (da1[i] * alphaSInv + dS[i] * alpha1) * p1 + dp1[i] * w1;
+    }
+    duPos[0] = 0.;
+    uPos = w0 * p0 + w1 * p1;
+  }
+}
+
+// one side of impl/weno5.hpp:180-434: five points v[0..4], linear weights c0,c1,c2 (as quotients like the reference
+// builds them), candidate polynomials and their constant gradients, the three (t, s) pairs of the smoothness indicators
+RO_FN void weno5GradSide(double& u, double* du /*[5]*/, bool neg, double qim2, double qim1, double qi, double qip1,
+                         double qip2, double qip3) {
+  const double epsilon = 1e-6, one = 1, two = 2, three = 3;
+  const double four = two * two, five = three + two, six = three * two, seven = four + three, ten = five * two;
+  const double eleven = five + six, twelve = six * two, thirteen = six + seven;
+  const double oneOvfour = one / four, oneOvsix = one / six, oneOvten = one / ten, threeOvten = three / ten;
+  const double sixOvten = six / ten, thirteenOvtwelve = thirteen / twelve;
+  double p0, p1, p2, B0, B1, B2, alpha0, alpha1, alpha2;
+  double dB0[5], dB1[5], dB2[5], dp0[5], dp1[5], dp2[5];
+  if (neg) {
+    p0 = (two * qim2 - seven * qim1 + eleven * qi) * oneOvsix;
+    p1 = (-qim1 + five * qi + two * qip1) * oneOvsix;
+    p2 = (two * qi + five * qip1 - qip2) * oneOvsix;
+    dp0[0] = 1. / 3.; dp0[1] = -7. / 6.; dp0[2] = 11. / 6.; dp0[3] = 0.; dp0[4] = 0.;
+    dp1[0] = 0.; dp1[1] = -1. / 6.; dp1[2] = 5. / 6.; dp1[3] = 1. / 3.; dp1[4] = 0.;
+    dp2[0] = 0.; dp2[1] = 0.; dp2[2] = 1. / 3.; dp2[3] = 5. / 6.; dp2[4] = -1. / 6.;
+    B0 = thirteenOvtwelve * pw2(qim2 - two * qim1 + qi) + oneOvfour * pw2(qim2 - four * qim1 + three * qi);
+    B1 = thirteenOvtwelve * pw2(qim1 - two * qi + qip1) + oneOvfour * pw2(qim1 - qip1);
+    B2 = thirteenOvtwelve * pw2(qi - two * qip1 + qip2) + oneOvfour * pw2(three * qi - four * qip1 + qip2);
+    dB0[0] = (13. * (qim2 - 2. * qim1 + qi)) / 6. + (qim2 - 4. * qim1 + 3. * qi) / 2.;
+    dB0[1] = -(13. * (qim2 - 2. * qim1 + qi)) / 3. - 2. * (qim2 - 4. * qim1 + 3. * qi);
+    dB0[2] = (13. * (qim2 - 2. * qim1 + qi)) / 6. + (3. * (qim2 - 4. * qim1 + 3. * qi)) / 2.;
+    dB0[3] = 0.; dB0[4] = 0.;
+    dB1[0] = 0.;
+    dB1[1] = (13. * (qip1 + qim1 - 2. * qi)) / 6. + (qim1 - qip1) / 2.;
+    dB1[2] = -(13. * (qip1 + qim1 - 2. * qi)) / 3.;
+    dB1[3] = (13. * (qip1 + qim1 - 2. * qi)) / 6. - (qim1 - qip1) / 2.;
+    dB1[4] = 0.;
+    dB2[0] = 0.; dB2[1] = 0.;
+    dB2[2] = (13. * (qip2 - 2. * qip1 + qi)) / 6. + (3. * (qip2 - 4. * qip1 + 3. * qi)) / 2.;
+    dB2[3] = -(13. * (qip2 - 2. * qip1 + qi)) / 3. - 2. * (qip2 - 4. * qip1 + 3. * qi);
+    dB2[4] = (13. * (qip2 - 2. * qip1 + qi)) / 6. + (qip2 - 4. * qip1 + 3. * qi) / 2.;
+    alpha0 = oneOvten / pw2(epsilon + B0);
+    alpha1 = sixOvten / pw2(epsilon + B1);
+    alpha2 = threeOvten / pw2(epsilon + B2);
+  } else {
+    p0 = (-qim1 + five * qi + two * qip1) * oneOvsix;
+    p1 = (two * qi + five * qip1 - qip2) * oneOvsix;
+    p2 = (eleven * qip1 - seven * qip2 + two * qip3) * oneOvsix;
+    dp0[0] = -1. / 6.; dp0[1] = 5. / 6.; dp0[2] = 1. / 3.; dp0[3] = 0.; dp0[4] = 0.;
+    dp1[0] = 0.; dp1[1] = 1. / 3.; dp1[2] = 5. / 6.; dp1[3] = -1. / 6.; dp1[4] = 0.;
+    dp2[0] = 0.; dp2[1] = 0.; dp2[2] = 11. / 6.; dp2[3] = -7. / 6.; dp2[4] = 1. / 3.;
+    B0 = thirteenOvtwelve * pw2(qim1 - two * qi + qip1) + oneOvfour * pw2(qim1 - four * qi + three * qip1);
+    B1 = thirteenOvtwelve * pw2(qi - two * qip1 + qip2) + oneOvfour * pw2(qi - qip2);
+    B2 = thirteenOvtwelve * pw2(qip1 - two * qip2 + qip3) + oneOvfour * pw2(three * qip1 - four * qip2 + qip3);
+    dB0[0] = (3. * qip1 + qim1 - 4. * qi) / 2. + (13. * (qip1 + qim1 - 2. * qi)) / 6.;
+    dB0[1] = -2. * (3. * qip1 + qim1 - 4. * qi) - (13. * (qip1 + qim1 - 2 * qi)) / 3.;
+    dB0[2] = (3. * (3. * qip1 + qim1 - 4. * qi)) / 2. + (13. * (qip1 + qim1 - 2. * qi)) / 6.;
+    dB0[3] = 0.; dB0[4] = 0.;
+    dB1[0] = 0.;
+    dB1[1] = (13. * (qip2 - 2 * qip1 + qi)) / 6. + (qi - qip2) / 2.;
+    dB1[2] = -(13. * (qip2 - 2. * qip1 + qi)) / 3.;
+    dB1[3] = (13. * (qip2 - 2. * qip1 + qi)) / 6. - (qi - qip2) / 2.;
+    dB1[4] = 0.;
+    dB2[0] = 0.; dB2[1] = 0.;
+    dB2[2] = (13. * (qip3 - 2. * qip2 + qip1)) / 6. + (3. * (qip3 - 4. * qip2 + 3. * qip1)) / 2.;
+    dB2[3] = -(13. * (qip3 - 2. * qip2 + qip1)) / 3. - 2. * (qip3 - 4. * qip2 + 3. * qip1);
+    dB2[4] = (13. * (qip3 - 2. * qip2 + qip1)) / 6. + (qip3 - 4. * qip2 + 3. * qip1) / 2.;
+    alpha0 = threeOvten / pw2(epsilon + B0);
+    alpha1 = sixOvten / pw2(epsilon + B1);
+    alpha2 = oneOvten / pw2(epsilon + B2);
+  }
+  const double alphaSInv = one / (alpha0 + alpha1 + alpha2);
+  // -c / (5 (B+eps)^3): c = 1,6,3 on the minus side, 3,6,1 on the plus side
+  const double n0 = neg ? -1. : -3., n2 = neg ? -3. : -1.;
+  const double f0 = n0 / (5. * pw3(B0 + epsilon));
+  const double f1 = -6. / (5. * pw3(B1 + epsilon));
+  const double f2 = n2 / (5. * pw3(B2 + epsilon));
+  const double fS = -1. / pw2(alpha2 + alpha1 + alpha0);
+  const double w0 = alpha0 * alphaSInv, w1 = alpha1 * alphaSInv, w2 = alpha2 * alphaSInv;
+  for (int i = 0; i < 5; i++) {
+    const double da0 = f0 * dB0[i], da1 = f1 * dB1[i], da2 = f2 * dB2[i];
+    const double dS = fS * (da0 + da1 + da2);
+    double g = (da0 * alphaSInv + dS * alpha0) * p0 + dp0[i] * w0;
+    g += (da1 * alphaSInv + dS * alpha1) * p1 + dp1[i] * w1;
+    g += (da2 * alphaSInv + dS * alpha2) * p2 + dp2[i] * w2;
+    du[i] = g;
+  }
+  u = w0 * p0 + w1 * p1 + w2 * p2;
+}
+
+RO_FN void weno5Grad(double& uNeg, double& uPos, double* duNeg /*[6]*/, double* duPos /*[6]*/, double qim2, double qim1,
+                     double qi, double qip1, double qip2, double qip3) {
+  weno5GradSide(uNeg, duNeg, true, qim2, qim1, qi, qip1, qip2, qip3);
+  duNeg[5] = 0.;
+  weno5GradSide(uPos, duPos + 1, false, qim2, qim1, qi, qip1, qip2, qip3);
+  duPos[0] = 0.;
+}
+
+// impl/euler_rusanov_flux_values_function.hpp:54-208 (N = 3,4,5; n has N-2 entries)
+template <int N>
+RO_FN void eulerFlux(double* F, const double* qL, const double* qR, const double* n, double gamma) {
+  const double half = 0.5, es = 1.e-30;
+  constexpr int nv = N - 2, ie = N - 1;
+  double FL[N], FR[N], vL[3], vR[3];
+  const double rL = qL[0], rR = qR[0];
+  double unL = 0, unR = 0, kL = 0, kR = 0;
+  for (int m = 0; m < nv; ++m) { vL[m] = qL[1 + m] / (rL + es); vR[m] = qR[1 + m] / (rR + es); }
+  if (nv == 1) { unL = vL[0]; unR = vR[0]; kL = vL[0] * vL[0]; kR = vR[0] * vR[0]; }
+  else if (nv == 2) {
+    unL = vL[0] * n[0] + vL[1] * n[1]; unR = vR[0] * n[0] + vR[1] * n[1];
+    kL = vL[0] * vL[0] + vL[1] * vL[1]; kR = vR[0] * vR[0] + vR[1] * vR[1];
+  } else {
+    unL = vL[0] * n[0] + vL[1] * n[1] + vL[2] * n[2]; unR = vR[0] * n[0] + vR[1] * n[1] + vR[2] * n[2];
+    kL = vL[0] * vL[0] + vL[1] * vL[1] + vL[2] * vL[2]; kR = vR[0] * vR[0] + vR[1] * vR[1] + vR[2] * vR[2];
+  }
+  const double pL = (gamma - 1) * (qL[ie] - half * rL * (kL));
+  const double HL = (qL[ie] + pL) / rL;
+  const double pR = (gamma - 1) * (qR[ie] - half * rR * (kR));
+  const double HR = (qR[ie] + pR) / rR;
+  FL[0] = rL * unL; FR[0] = rR * unR;
+  for (int m = 0; m < nv; ++m) {
+    if (nv == 1) { FL[1] = rL * vL[0] * vL[0] + pL; FR[1] = rR * vR[0] * vR[0] + pR; }
+    else { FL[1 + m] = rL * unL * vL[m] + pL * n[m]; FR[1 + m] = rR * unR * vR[m] + pR * n[m]; }
+  }
+  FL[ie] = rL * unL * HL; FR[ie] = rR * unR * HR;
+  const double RT = sqrt(rR / (rL));
+  double v[3], k = 0;
+  for (int m = 0; m < nv; ++m) v[m] = (vL[m] + RT * vR[m]) / (1. + RT);
+  if (nv == 1) k = v[0] * v[0]; else if (nv == 2) k = v[0] * v[0] + v[1] * v[1]; else k = v[0] * v[0] + v[1] * v[1] + v[2] * v[2];
+  const double H = (HL + RT * HR) / (1. + RT);
+  const double a = sqrt((gamma - 1.) * (H - half * (k)));
+  const double smax = (nv == 1) ? fabs(v[0]) + a : sqrt(k) + a;
+  for (int i = 0; i < N; ++i) F[i] = half * (FL[i] + FR[i] + smax * (qL[i] - qR[i]));
+}
+
+// impl/euler_rusanov_flux_jacobian_function.hpp:54-406 ; JL, JR row-major [N][N]
+template <int N>
+RO_FN void eulerFluxJac(double* JL, double* JR, const double* qL, const double* qR, const double* nIn, double gamma) {
+  const double one = 1, two = 2, three = 3, half = 0.5, es = 1.e-30;
+  const double gm1 = gamma - one;
+  constexpr int nv = N - 2, ie = N - 1;
+  double n[3] = {0, 0, 0};
+  if (nv == 1) n[0] = 1.0; else for (int m = 0; m < nv; ++m) n[m] = nIn[m];
+  double vL[3] = {0, 0, 0}, vR[3] = {0, 0, 0}, v[3] = {0, 0, 0};
+  const double rL = qL[0], rR = qR[0];
+  for (int m = 0; m < nv; ++m) { vL[m] = qL[1 + m] / (rL + es); vR[m] = qR[1 + m] / (rR + es); }
+  double unL, unR, kL, kR;
+  if (nv == 1) { unL = vL[0]; unR = vR[0]; kL = vL[0] * vL[0]; kR = vR[0] * vR[0]; }
+  else if (nv == 2) {
+    unL = vL[0] * n[0] + vL[1] * n[1]; unR = vR[0] * n[0] + vR[1] * n[1];
+    kL = vL[0] * vL[0] + vL[1] * vL[1]; kR = vR[0] * vR[0] + vR[1] * vR[1];
+  } else {
+    unL = vL[0] * n[0] + vL[1] * n[1] + vL[2] * n[2]; unR = vR[0] * n[0] + vR[1] * n[1] + vR[2] * n[2];
+    kL = vL[0] * vL[0] + vL[1] * vL[1] + vL[2] * vL[2]; kR = vR[0] * vR[0] + vR[1] * vR[1] + vR[2] * vR[2];
+  }
+  const double pL = gm1 * (qL[ie] - half * rL * (kL));
+  const double HL = (qL[ie] + pL) / rL;
+  const double aL = sqrt(gm1 * (HL - half * (kL)));
+  const double pR = gm1 * (qR[ie] - half * rR * (kR));
+  const double HR = (qR[ie] + pR) / rR;
+  const double aR = sqrt(gm1 * (HR - half * (kR)));
+  const double r = sqrt(rR * rL);
+  const double RT = sqrt(rR / (rL));
+  for (int m = 0; m < nv; ++m) v[m] = (vL[m] + RT * vR[m]) / (one + RT);
+  const double H = (HL + RT * HR) / (one + RT);
+  double k;
+  if (nv == 1) k = v[0] * v[0]; else if (nv == 2) k = v[0] * v[0] + v[1] * v[1]; else k = v[0] * v[0] + v[1] * v[1] + v[2] * v[2];
+  const double a = sqrt(gm1 * (H - half * (k)));
+  const double smax = (nv == 1) ? fabs(v[0]) + a : sqrt(k) + a;
+  double gradL[N], gradR[N];
+  const double VMagSqrRoe = k + es;
+  const double VMagSqrL = kL, VMagSqrR = kR;
+  double VVRoeL, VVRoeR;
+  if (nv == 1) { VVRoeL = vL[0] * v[0]; VVRoeR = vR[0] * v[0]; }
+  else if (nv == 2) { VVRoeL = vL[0] * v[0] + vL[1] * v[1]; VVRoeR = vR[0] * v[0] + vR[1] * v[1]; }
+  else { VVRoeL = vL[0] * v[0] + vL[1] * v[1] + vL[2] * v[2]; VVRoeR = vR[0] * v[0] + vR[1] * v[1] + vR[2] * v[2]; }
+  double rel[3];
+  for (int m = 0; m < nv; ++m) rel[m] = v[m] / sqrt(VMagSqrRoe);
+  double sL = 0, sR = 0;
+  if (nv == 1) { sL = -half * (vL[0] + v[0]) * rel[0]; sR = -half * (vR[0] + v[0]) * rel[0]; }
+  else if (nv == 2) {
+    sL = -half * (vL[0] + v[0]) * rel[0] - half * (vL[1] + v[1]) * rel[1];
+    sR = -half * (vR[0] + v[0]) * rel[0] - half * (vR[1] + v[1]) * rel[1];
+  } else {
+    sL = -half * (vL[0] + v[0]) * rel[0] - half * (vL[1] + v[1]) * rel[1] - half * (vL[2] + v[2]) * rel[2];
+    sR = -half * (vR[0] + v[0]) * rel[0] - half * (vR[1] + v[1]) * rel[1] - half * (vR[2] + v[2]) * rel[2];
+  }
+  gradL[0] = one / (rL + r) * (sL + half * gm1 / a * (half * (VMagSqrRoe + VVRoeL) + half * (HL - H) - aL * aL / gm1 + half * (gamma - two) * VMagSqrL));
+  gradR[0] = one / (rR + r) * (sR + half * gm1 / a * (half * (VMagSqrRoe + VVRoeR) + half * (HR - H) - aR * aR / gm1 + half * (gamma - two) * VMagSqrR));
+  for (int m = 0; m < nv; ++m) {
+    gradL[1 + m] = one / (rL + r) * (rel[m] - half * (gm1 * (v[m] + gm1 * vL[m])) / (a));
+    gradR[1 + m] = one / (rR + r) * (rel[m] - half * (gm1 * (v[m] + gm1 * vR[m])) / (a));
+  }
+  gradL[ie] = half / (rL + r) * gamma * gm1 / (a);
+  gradR[ie] = half / (rR + r) * gamma * gm1 / (a);
+
+  for (int side = 0; side < 2; ++side) {
+    double* J = side == 0 ? JL : JR;
+    const double* vel = side == 0 ? vL : vR;
+    const double un = side == 0 ? unL : unR, k2 = side == 0 ? kL : kR, Hs = side == 0 ? HL : HR;
+    if (nv == 1) {
+      const double u = vel[0];
+      J[0] = 0; J[1] = half; J[2] = 0;
+      J[3] = half * (half * gm1 * u * u - u * u);
+      J[4] = half * ((three - gamma) * u);
+      J[5] = half * gm1;
+      J[6] = half * ((half * gm1 * u * u - Hs) * u);
+      J[7] = half * (Hs - gm1 * u * u);
+      J[8] = half * gamma * u;
+    } else {
+      J[0] = 0;
+      for (int j = 0; j < nv; ++j) J[1 + j] = half * n[j];
+      J[ie] = 0;
+      for (int i = 0; i < nv; ++i) {
+        J[(1 + i) * N] = half * (half * gm1 * k2 * n[i] - vel[i] * un);
+        for (int j = 0; j < nv; ++j) {
+          if (i == j) J[(1 + i) * N + 1 + j] = half * (vel[i] * n[j] - gm1 * vel[j] * n[i] + un);
+          else J[(1 + i) * N + 1 + j] = half * (vel[i] * n[j] - gm1 * vel[j] * n[i]);
+        }
+        J[(1 + i) * N + ie] = half * gm1 * n[i];
+      }
+      J[ie * N] = half * ((half * gm1 * k2 - Hs) * un);
+      for (int j = 0; j < nv; ++j) J[ie * N + 1 + j] = half * (Hs * n[j] - gm1 * vel[j] * un);
+      J[ie * N + ie] = half * gamma * un;
+    }
+  }
+  for (int i = 0; i < N; i++) {
+    JL[i * N + i] += half * smax;
+    for (int j = 0; j < N; j++) JL[i * N + j] += half * gradL[j] * (qL[i] - qR[i]);
+  }
+  for (int i = 0; i < N; i++) {
+    JR[i * N + i] -= half * smax;
+    for (int j = 0; j < N; j++) JR[i * N + j] += half * gradR[j] * (qL[i] - qR[i]);
+  }
+}
+
+// impl/swe_rusanov_flux_values_function.hpp:54-97
+RO_FN void sweFlux(double* F, const double* qL, const double* qR, const double* n, double gravity) {
+  const double half = 0.5, es = 1.e-30;
+  double FL[3], FR[3];
+  const double hL = qL[0];
+  const double uL = qL[1] / (hL + es), vL = qL[2] / (hL + es);
+  const double unL = uL * n[0] + vL * n[1];
+  const double pL = 0.5 * gravity * hL * hL;
+  FL[0] = hL * unL; FL[1] = hL * unL * uL + pL * n[0]; FL[2] = hL * unL * vL + pL * n[1];
+  const double hR = qR[0];
+  const double uR = qR[1] / (hR + es), vR = qR[2] / (hR + es);
+  const double unR = uR * n[0] + vR * n[1];
+  const double pR = 0.5 * gravity * hR * hR;
+  FR[0] = hR * unR; FR[1] = hR * unR * uR + pR * n[0]; FR[2] = hR * unR * vR + pR * n[1];
+  const double hm = 0.5 * (hL + hR);
+  const double um = (unL * powLibm(hL, 0.5) + unR * powLibm(hR, 0.5)) / (powLibm(hL, 0.5) + powLibm(hR, 0.5) + es);
+  const double smax = sqrt(um * um) + sqrt(pw2(sqrt(gravity * hm)));
+  for (int i = 0; i < 3; ++i) F[i] = half * (FL[i] + FR[i] + smax * (qL[i] - qR[i]));
+}
+
+// impl/swe_rusanov_flux_jacobian_function.hpp:54-136
+RO_FN void sweFluxJac(double* JL, double* JR, const double* qL, const double* qR, const double* n, double g) {
+  const double es = 1.e-30;
+  const double hL = qL[0], uL = qL[1] / (hL + es), vL = qL[2] / (hL + es);
+  const double unL = uL * n[0] + vL * n[1];
+  const double hR = qR[0], uR = qR[1] / (hR + es), vR = qR[2] / (hR + es);
+  const double unR = uR * n[0] + vR * n[1];
+  const double hm = 0.5 * (hL + hR);
+  const double um = (unL * powLibm(hL, 0.5) + unR * powLibm(hR, 0.5)) / (powLibm(hL, 0.5) + powLibm(hR, 0.5) + es);
+  const double smax = fabs(um) + fabs(powLibm(g * hm, 0.5));
+  const double termL = (n[0] * qL[1] + n[1] * qL[2]) / pw2(qL[0]);
+  const double termR = (n[0] * qR[1] + n[1] * qR[2]) / pw2(qR[0]);
+  const double hL_sqrt = powLibm(hL, 0.5), hR_sqrt = powLibm(hR, 0.5);
+  const double hsqrt_un = hL_sqrt * unL + hR_sqrt * unR + es;
+  const double pow2_32 = 2.8284271247461903;   // pow(2., 3./2.): folded at compile time (correctly rounded)
+  double dsmaxL[3], dsmaxR[3];
+  dsmaxL[0] = -fabs(hsqrt_un) / (2. * hL_sqrt * pw2(hL_sqrt + hR_sqrt)) +
+              (0.5 * unL / hL_sqrt - hL_sqrt * termL) * hsqrt_un / ((hL_sqrt + hR_sqrt) * fabs(hsqrt_un)) +
+              g / (pow2_32 * powLibm(g * (hL + hR), 0.5));
+  dsmaxL[1] = n[0] * hsqrt_un / (hL_sqrt * (hL_sqrt + hR_sqrt) * fabs(hsqrt_un));
+  dsmaxL[2] = n[1] * hsqrt_un / (hL_sqrt * (hL_sqrt + hR_sqrt) * fabs(hsqrt_un));
+  dsmaxR[0] = -fabs(hsqrt_un) / (2. * hR_sqrt * pw2(hL_sqrt + hR_sqrt)) +
+              (0.5 * unR / hR_sqrt - hR_sqrt * termR) * hsqrt_un / ((hL_sqrt + hR_sqrt) * fabs(hsqrt_un)) +
+              g / (pow2_32 * powLibm(g * (hL + hR), 0.5));
+  dsmaxR[1] = n[0] * hsqrt_un / (hR_sqrt * (hL_sqrt + hR_sqrt) * fabs(hsqrt_un));
+  dsmaxR[2] = n[1] * hsqrt_un / (hR_sqrt * (hL_sqrt + hR_sqrt) * fabs(hsqrt_un));
+  JL[0] = -0.5 * dsmaxL[0] * (qR[0] - qL[0]) + 0.5 * (n[0] * uL + n[1] * vL - qL[0] * termL) + 0.5 * smax;
+  JL[1] = 0.5 * n[0] - 0.5 * dsmaxL[1] * (qR[0] - qL[0]);
+  JL[2] = 0.5 * n[1] - 0.5 * dsmaxL[2] * (qR[0] - qL[0]);
+  JL[3] = 0.5 * (g * n[0] * qL[0] - qL[1] * termL) - 0.5 * dsmaxL[0] * (qR[1] - qL[1]);
+  JL[4] = n[0] * uL + 0.5 * n[1] * vL + 0.5 * smax - 0.5 * dsmaxL[1] * (qR[1] - qL[1]);
+  JL[5] = 0.5 * n[1] * uL - 0.5 * dsmaxL[2] * (qR[1] - qL[1]);
+  JL[6] = 0.5 * (g * n[1] * qL[0] - qL[2] * termL) - 0.5 * dsmaxL[0] * (qR[2] - qL[2]);
+  JL[7] = 0.5 * n[0] * vL - 0.5 * dsmaxL[1] * (qR[2] - qL[2]);
+  JL[8] = n[1] * vL + 0.5 * n[0] * uL + 0.5 * smax - 0.5 * dsmaxL[2] * (qR[2] - qL[2]);
+  JR[0] = -0.5 * dsmaxR[0] * (qR[0] - qL[0]) + 0.5 * (n[0] * uR + n[1] * vR - qR[0] * termR) - 0.5 * smax;
+  JR[1] = 0.5 * n[0] - 0.5 * dsmaxR[1] * (qR[0] - qL[0]);
+  JR[2] = 0.5 * n[1] - 0.5 * dsmaxR[2] * (qR[0] - qL[0]);
+  JR[3] = 0.5 * (g * n[0] * qR[0] - qR[1] * termR) - 0.5 * dsmaxR[0] * (qR[1] - qL[1]);
+  JR[4] = n[0] * uR + 0.5 * n[1] * vR - 0.5 * smax - 0.5 * dsmaxR[1] * (qR[1] - qL[1]);
+  JR[5] = 0.5 * n[1] * uR - 0.5 * dsmaxR[2] * (qR[1] - qL[1]);
+  JR[6] = 0.5 * (g * n[1] * qR[0] - qR[2] * termR) - 0.5 * dsmaxR[0] * (qR[2] - qL[2]);
+  JR[7] = 0.5 * n[0] * vR - 0.5 * dsmaxR[1] * (qR[2] - qL[2]);
+  JR[8] = n[1] * vR + 0.5 * n[0] * uR - 0.5 * smax - 0.5 * dsmaxR[2] * (qR[2] - qL[2]);
+}
+
+// impl/advection_diffusion_2d_flux_functions.hpp:54-114
+RO_FN void burgersFlux(double* F, const double* qL, const double* qR, const double* n) {
+  const double fourInv = 1. / 4.;
+  const double alpha_0 = fmax(fabs(qL[0]), fabs(qR[0]));
+  const double alpha_1 = fmax(fabs(qL[1]), fabs(qR[1]));
+  F[0] = alpha_0 * (qL[0] - qR[0]);
+  F[0] += n[0] * (qL[0] * qL[0] + qR[0] * qR[0]);
+  F[0] += n[1] * (qL[0] * qL[1] + qR[0] * qR[1]);
+  F[0] *= fourInv;
+  F[1] = alpha_1 * (qL[1] - qR[1]);
+  F[1] += n[0] * (qL[0] * qL[1] + qR[0] * qR[1]);
+  F[1] += n[1] * (qL[1] * qL[1] + qR[1] * qR[1]);
+  F[1] *= fourInv;
+}
+RO_FN void burgersFluxJac(double* JL, double* JR, const double* qL, const double* qR, const double* n) {
+  const double two = 2., fourInv = 1. / 4.;
+  if (fabs(qL[0]) > fabs(qR[0])) {
+    JL[0] = (two * qL[0] - qR[0]) * copysign(1., qL[0]) + n[0] * two * qL[0] + n[1] * qL[1];
+    JR[0] = n[0] * two * qR[0] + n[1] * qR[1] - fabs(qL[0]);
+  } else {
+    JL[0] = n[0] * two * qL[0] + n[1] * qL[1] + fabs(qR[0]);
+    JR[0] = (qL[0] - two * qR[0]) * copysign(1., qR[0]) + n[0] * two * qR[0] + n[1] * qR[1];
+  }
+  JL[0] *= fourInv; JR[0] *= fourInv;
+  if (fabs(qL[1]) > fabs(qR[1])) {
+    JL[3] = (two * qL[1] - qR[1]) * copysign(1., qL[1]) + n[0] * qL[0] + n[1] * two * qL[1];
+    JR[3] = n[0] * qR[0] + n[1] * two * qR[1] - fabs(qL[1]);
+  } else {
+    JL[3] = n[0] * qL[0] + n[1] * two * qL[1] + fabs(qR[1]);
+    JR[3] = (qL[1] - two * qR[1]) * copysign(1., qR[1]) + n[0] * qR[0] + n[1] * two * qR[1];
+  }
+  JL[3] *= fourInv; JR[3] *= fourInv;
+  JL[1] = n[1] * qL[0] * fourInv; JL[2] = n[0] * qL[1] * fourInv;
+  JR[1] = n[1] * qR[0] * fourInv; JR[2] = n[0] * qR[1] * fourInv;
+}
+
+enum { F_EULER1D = 1, F_EULER2D = 2, F_EULER3D = 3, F_SWE2D = 4, F_ADVDIFF2D = 6, F_ADVDIFFREAC2D = 7, F_ADVECTION1D = 8 };
+
+template <int N>
+RO_FN void fluxRt(const RefOrderParams& P, int ax, double* F, const double* qL, const double* qR) {
+  double n[3] = {0, 0, 0};
+  n[ax] = 1.0;
+  if constexpr (N == 1) { F[0] = qL[0] * P.adv[ax]; (void)qR; return; }
+  else if constexpr (N == 2) { burgersFlux(F, qL, qR, n); return; }
+  else {
+    if constexpr (N == 3) { if (P.family == F_SWE2D) { sweFlux(F, qL, qR, n, P.gravity); return; } }
+    eulerFlux<N>(F, qL, qR, n, P.gamma);
+  }
+}
+template <int N>
+RO_FN void fluxJacRt(const RefOrderParams& P, int ax, double* JL, double* JR, const double* qL, const double* qR) {
+  double n[3] = {0, 0, 0};
+  n[ax] = 1.0;
+  if constexpr (N == 1) { JL[0] = P.adv[ax]; JR[0] = 0.; (void)qL; (void)qR; return; }
+  else if constexpr (N == 2) { burgersFluxJac(JL, JR, qL, qR, n); return; }
+  else {
+    if constexpr (N == 3) { if (P.family == F_SWE2D) { sweFluxJac(JL, JR, qL, qR, n, P.gravity); return; } }
+    eulerFluxJac<N>(JL, JR, qL, qR, n, P.gamma);
+  }
+}
+
+// inner rows: velocityAndOptionalJacobian of one cell away from the boundary, the reference's loop nest
+// (euler_2d_prob_class.hpp:633-720 -> mixin_directional_flux_balance.hpp:68-84 and
+//  mixin_directional_flux_balance_jacobian.hpp:142-284; first order: :120-140)
+template <int N>
+__global__ void __launch_bounds__(64)
+k_reforder_inner(RefOrderParams P, RowSet rs, const double* __restrict__ U, double* __restrict__ V, double* __restrict__ Jv,
+                 JacLayout jl) {
+  const int32_t r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= rs.n) return;
+  const int32_t* row = rs.graph + (int64_t)r * rs.ncols;
+  const int64_t base = jl.base[r];
+  const int32_t len = jl.len[r];
+  const uint8_t* slots = jl.slot + (int64_t)r * jl.nslotCols;
+  const int S = P.S, h = (S - 1) / 2, dim = P.dim;
+  const int64_t selfCell = row[0];
+  double v[N];
+  for (int d = 0; d < N; ++d) v[d] = 0.0;
+  auto jadd = [&](int k, int col, int j, double val) { Jv[base + (int64_t)k * len + slots[col] * N + j] += val; };
+
+  for (int ax = 0; ax < dim; ++ax) {
+    const double hInv = P.dInv[ax];
+    int cols[7];
+    int64_t cells[7];
+    cols[h] = 0; cells[h] = selfCell;
+    for (int L = 0; L < h; ++L) {
+      cols[h - 1 - L] = gcolRt(dim, sideMinusRt(ax), L);
+      cols[h + 1 + L] = gcolRt(dim, sidePlusRt(ax), L);
+      cells[h - 1 - L] = row[cols[h - 1 - L]];
+      cells[h + 1 + L] = row[cols[h + 1 + L]];
+    }
+    double lN[N], lP[N], rN[N], rP[N];
+    double gLN[N][6], gLP[N][6], gRN[N][6], gRP[N][6];
+    for (int d = 0; d < N; ++d) {
+      double q[7];
+      for (int p = 0; p < S; ++p) q[p] = U[cells[p] * N + d];
+      if (S == 3) { lN[d] = q[0]; lP[d] = q[1]; rN[d] = q[1]; rP[d] = q[2]; }
+      else if (S == 5) {
+        weno3Grad(lN[d], lP[d], gLN[d], gLP[d], q[0], q[1], q[2], q[3]);
+        weno3Grad(rN[d], rP[d], gRN[d], gRP[d], q[1], q[2], q[3], q[4]);
+      } else {
+        weno5Grad(lN[d], lP[d], gLN[d], gLP[d], q[0], q[1], q[2], q[3], q[4], q[5]);
+        weno5Grad(rN[d], rP[d], gRN[d], gRP[d], q[1], q[2], q[3], q[4], q[5], q[6]);
+      }
+    }
+    double FL[N], FR[N];
+    fluxRt<N>(P, ax, FL, lN, lP);
+    fluxRt<N>(P, ax, FR, rN, rP);
+    for (int d = 0; d < N; ++d) v[d] += hInv * (FL[d] - FR[d]);
+
+    double JLN[N * N], JLP[N * N], JRN[N * N], JRP[N * N];
+    fluxJacRt<N>(P, ax, JLN, JLP, lN, lP);
+    fluxJacRt<N>(P, ax, JRN, JRP, rN, rP);
+    if (S == 3) {
+      for (int k = 0; k < N; ++k)
+        for (int j = 0; j < N; ++j) {
+          jadd(k, cols[0], j, JLN[k * N + j] * hInv);
+          jadd(k, 0, j, (JLP[k * N + j] - JRN[k * N + j]) * hInv);
+          jadd(k, cols[2], j, -JRP[k * N + j] * hInv);
+        }
+    } else {
+      for (int k = 0; k < N; ++k)
+        for (int j = 0; j < N; ++j) {
+          for (int mm = 0; mm < S - 1; ++mm) {   // sensitivity of the flux at i-1/2: stencil positions 0..S-2
+            jadd(k, cols[mm], j, JLN[k * N + j] * gLN[j][mm] * hInv);
+            jadd(k, cols[mm], j, JLP[k * N + j] * gLP[j][mm] * hInv);
+          }
+          for (int mm = 0; mm < S - 1; ++mm) {   // flux at i+1/2: stencil positions 1..S-1
+            jadd(k, cols[mm + 1], j, -(JRN[k * N + j] * gRN[j][mm] * hInv));
+            jadd(k, cols[mm + 1], j, -(JRP[k * N + j] * gRP[j][mm] * hInv));
+          }
+        }
+    }
+  }
+  const double* uSelf = U + selfCell * N;
+  const int32_t sampleRow = rs.rowIds[r];
+  if (P.family == F_ADVDIFF2D || P.family == F_ADVDIFFREAC2D) {
+    // advection_diffusion_2d_prob_class.hpp:1157-1201; advection_diffusion_reaction_2d_prob_class.hpp:485-512,1057-1085
+    const bool adr = P.family == F_ADVDIFFREAC2D;
+    const double two = 2.;
+    const double dxInvSq = P.dInv[0] * P.dInv[0], dyInvSq = P.dInv[1] * P.dInv[1];
+    const double diffDxInvSq = P.diffusion * dxInvSq, diffDyInvSq = P.diffusion * dyInvSq;
+    const int64_t iL = row[1], iF = row[2], iR = row[3], iB = row[4];
+    for (int d = 0; d < N; ++d) {
+      v[d] += diffDxInvSq * (U[iR * N + d] - two * uSelf[d] + U[iL * N + d]);
+      v[d] += diffDyInvSq * (U[iF * N + d] - two * uSelf[d] + U[iB * N + d]);
+      jadd(d, 0, d, -two * diffDxInvSq - two * diffDyInvSq);
+      jadd(d, 1, d, diffDxInvSq);
+      jadd(d, 2, d, diffDyInvSq);
+      jadd(d, 3, d, diffDxInvSq);
+      jadd(d, 4, d, diffDyInvSq);
+    }
+    if (adr) {
+      v[0] += P.src ? P.src[sampleRow] : 1.0;
+      v[0] -= P.sigma * uSelf[0];
+      jadd(0, 0, 0, -P.sigma);
+    }
+  }
+  if (P.family == F_SWE2D) {   // swe_2d_prob_class.hpp:984-1012
+    if constexpr (N == 3) {
+      const double f = P.coriolis;
+      v[1] -= f * uSelf[2] / uSelf[0];
+      v[2] += f * uSelf[1] / uSelf[0];
+      jadd(1, 0, 0, f * uSelf[2] / (uSelf[0] * uSelf[0]));
+      jadd(1, 0, 2, -f / uSelf[0]);
+      jadd(2, 0, 1, f / uSelf[0]);
+      jadd(2, 0, 0, -f * uSelf[1] / (uSelf[0] * uSelf[0]));
+    }
+  }
+  if (V) {
+    double* out = V + (int64_t)sampleRow * N;
+    for (int d = 0; d < N; ++d) out[d] = v[d];
+  }
+}
+
+// velocity only (rightHandSide): inner rows and near-boundary rows alike -- stencil values come from U or, where the
+// neighbour is missing, from the ghost rows (functor_fill_stencil.hpp), the value versions of the reconstructions,
+// flux balance per axis (mixin_directional_flux_balance.hpp:68-84), then the problem's extra terms.  NEARBD rows add
+// the diffusion term of the advection-diffusion families right after each axis (advection_diffusion_2d_prob_class.hpp:
+// 959-1000), inner rows after all flux balances (:1167-1201).
+template <int N>
+__global__ void __launch_bounds__(64)
+k_reforder_velocity(RefOrderParams P, RowSet rs, const double* __restrict__ U, double* __restrict__ V, GhostView gv,
+                    int nearBd) {
+  const int32_t r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= rs.n) return;
+  const int32_t* row = rs.graph + (int64_t)r * rs.ncols;
+  const int S = P.S, h = (S - 1) / 2, dim = P.dim;
+  const int64_t selfCell = row[0];
+  const bool advdiff = P.family == F_ADVDIFF2D || P.family == F_ADVDIFFREAC2D;
+  double v[N];
+  for (int d = 0; d < N; ++d) v[d] = 0.0;
+  for (int ax = 0; ax < dim; ++ax) {
+    const double hInv = P.dInv[ax];
+    const int sm = sideMinusRt(ax), sp = sidePlusRt(ax);
+    double lN[N], lP[N], rN[N], rP[N], s3[N][3];
+    for (int d = 0; d < N; ++d) {
+      double q[7];
+      q[h] = U[selfCell * N + d];
+      for (int L = 0; L < h; ++L) {
+        const int32_t cl = row[gcolRt(dim, sm, L)], cr = row[gcolRt(dim, sp, L)];
+        q[h - 1 - L] = (cl < 0) ? gv.g[sm][(int64_t)r * gv.stride + L * N + d] : U[(int64_t)cl * N + d];
+        q[h + 1 + L] = (cr < 0) ? gv.g[sp][(int64_t)r * gv.stride + L * N + d] : U[(int64_t)cr * N + d];
+      }
+      s3[d][0] = q[h - 1]; s3[d][1] = q[h]; s3[d][2] = q[h + 1];
+      if (S == 3) { lN[d] = q[0]; lP[d] = q[1]; rN[d] = q[1]; rP[d] = q[2]; }
+      else if (S == 5) { weno3Val(lN[d], lP[d], q[0], q[1], q[2], q[3]); weno3Val(rN[d], rP[d], q[1], q[2], q[3], q[4]); }
+      else { weno5Val(lN[d], lP[d], q[0], q[1], q[2], q[3], q[4], q[5]); weno5Val(rN[d], rP[d], q[1], q[2], q[3], q[4], q[5], q[6]); }
+    }
+    double FL[N], FR[N];
+    fluxRt<N>(P, ax, FL, lN, lP);
+    fluxRt<N>(P, ax, FR, rN, rP);
+    for (int d = 0; d < N; ++d) v[d] += hInv * (FL[d] - FR[d]);
+    if (nearBd && advdiff) {
+      const double diffInvSq = P.diffusion * (hInv * hInv);
+      for (int d = 0; d < N; ++d) v[d] += diffInvSq * (s3[d][2] - 2. * s3[d][1] + s3[d][0]);
+    }
+  }
+  const double* uSelf = U + selfCell * N;
+  const int32_t sampleRow = rs.rowIds[r];
+  if (advdiff) {
+    const bool adr = P.family == F_ADVDIFFREAC2D;
+    if (!nearBd) {
+      const double two = 2.;
+      const double dxInvSq = P.dInv[0] * P.dInv[0], dyInvSq = P.dInv[1] * P.dInv[1];
+      const double diffDxInvSq = P.diffusion * dxInvSq, diffDyInvSq = P.diffusion * dyInvSq;
+      const int64_t iL = row[1], iF = row[2], iR = row[3], iB = row[4];
+      for (int d = 0; d < N; ++d) {
+        v[d] += diffDxInvSq * (U[iR * N + d] - two * uSelf[d] + U[iL * N + d]);
+        v[d] += diffDyInvSq * (U[iF * N + d] - two * uSelf[d] + U[iB * N + d]);
+      }
+    }
+    if (adr) {
+      v[0] += P.src ? P.src[sampleRow] : 1.0;
+      v[0] -= P.sigma * uSelf[0];
+    }
+  }
+  if (P.family == F_SWE2D) {
+    if constexpr (N == 3) {
+      const double f = P.coriolis;
+      v[1] -= f * uSelf[2] / uSelf[0];
+      v[2] += f * uSelf[1] / uSelf[0];
+    }
+  }
+  double* out = V + (int64_t)sampleRow * N;
+  for (int d = 0; d < N; ++d) out[d] = v[d];
+}
+
+// near-boundary rows: first-order Jacobian whatever the scheme, missing first-layer neighbours folded into the self
+// block with per-dof factors (mixin_directional_flux_balance_jacobian.hpp:287-372, euler_2d_prob_class.hpp:723-989)
+template <int N>
+__global__ void __launch_bounds__(64)
+k_reforder_nearbd(RefOrderParams P, RowSet rs, const double* __restrict__ U, double* __restrict__ Jv, JacLayout jl,
+                  GhostView gv, const double* __restrict__ factors /*[n][dim][N]*/) {
+  const int32_t r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= rs.n) return;
+  const int32_t* row = rs.graph + (int64_t)r * rs.ncols;
+  const int64_t base = jl.base[r];
+  const int32_t len = jl.len[r];
+  const uint8_t* slots = jl.slot + (int64_t)r * jl.nslotCols;
+  const int dim = P.dim;
+  const int64_t selfCell = row[0];
+  auto jadd = [&](int k, int col, int j, double val) { Jv[base + (int64_t)k * len + slots[col] * N + j] += val; };
+  for (int ax = 0; ax < dim; ++ax) {
+    const double hInv = P.dInv[ax];
+    const int sm = sideMinusRt(ax), sp = sidePlusRt(ax);
+    const int cl = gcolRt(dim, sm, 0), cr = gcolRt(dim, sp, 0);
+    const int32_t l0 = row[cl], r0 = row[cr];
+    double qL[N], qC[N], qR[N];
+    for (int d = 0; d < N; ++d) {
+      qL[d] = (l0 < 0) ? gv.g[sm][(int64_t)r * gv.stride + d] : U[(int64_t)l0 * N + d];
+      qC[d] = U[selfCell * N + d];
+      qR[d] = (r0 < 0) ? gv.g[sp][(int64_t)r * gv.stride + d] : U[(int64_t)r0 * N + d];
+    }
+    double JLN[N * N], JLP[N * N], JRN[N * N], JRP[N * N];
+    fluxJacRt<N>(P, ax, JLN, JLP, qL, qC);
+    fluxJacRt<N>(P, ax, JRN, JRP, qC, qR);
+    const double* fac = factors + ((int64_t)r * dim + ax) * N;
+    for (int k = 0; k < N; ++k) for (int j = 0; j < N; ++j) jadd(k, 0, j, (JLP[k * N + j] - JRN[k * N + j]) * hInv);
+    if (l0 != -1) for (int k = 0; k < N; ++k) for (int j = 0; j < N; ++j) jadd(k, cl, j, JLN[k * N + j] * hInv);
+    if (r0 != -1) for (int k = 0; k < N; ++k) for (int j = 0; j < N; ++j) jadd(k, cr, j, -JRP[k * N + j] * hInv);
+    if (l0 == -1) for (int k = 0; k < N; ++k) for (int j = 0; j < N; ++j) jadd(k, 0, j, (fac[j] * JLN[k * N + j]) * hInv);
+    if (r0 == -1) for (int k = 0; k < N; ++k) for (int j = 0; j < N; ++j) jadd(k, 0, j, (fac[j] * -JRP[k * N + j]) * hInv);
+  }
+  const double* uSelf = U + selfCell * N;
+  if (P.family == F_ADVDIFF2D || P.family == F_ADVDIFFREAC2D) {
+    // advection_diffusion_2d_prob_class.hpp:755-792; advection_diffusion_reaction_2d_prob_class.hpp:685-721
+    const bool adr = P.family == F_ADVDIFFREAC2D;
+    const double two = 2.;
+    const double dxInvSq = P.dInv[0] * P.dInv[0], dyInvSq = P.dInv[1] * P.dInv[1];
+    const double diffDxInvSq = P.diffusion * dxInvSq, diffDyInvSq = P.diffusion * dyInvSq;
+    const double dd[4] = {diffDxInvSq, diffDyInvSq, diffDxInvSq, diffDyInvSq};
+    if (adr) {
+      double selfValue = -two * diffDxInvSq - two * diffDyInvSq - P.sigma;
+      for (int c = 1; c <= 4; ++c) { if (row[c] != -1) jadd(0, c, 0, dd[c - 1]); else selfValue += -dd[c - 1]; }
+      jadd(0, 0, 0, selfValue);
+    } else {
+      for (int d = 0; d < N; ++d) jadd(d, 0, d, -two * diffDxInvSq - two * diffDyInvSq);
+      for (int c = 1; c <= 4; ++c)
+        for (int d = 0; d < N; ++d) {
+          if (row[c] != -1) jadd(d, c, d, dd[c - 1]); else jadd(d, 0, d, -dd[c - 1]);
+        }
+    }
+  }
+  if (P.family == F_SWE2D) {
+    if constexpr (N == 3) {
+      const double f = P.coriolis;
+      jadd(1, 0, 0, f * uSelf[2] / (uSelf[0] * uSelf[0]));
+      jadd(1, 0, 2, -f / uSelf[0]);
+      jadd(2, 0, 1, f / uSelf[0]);
+      jadd(2, 0, 0, -f * uSelf[1] / (uSelf[0] * uSelf[0]));
+    }
+  }
+}
+
+__global__ void k_glibc_pow(const double* __restrict__ x, double y, double* __restrict__ out, int64_t n) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = powLibm(x[i], y);
+}
+
+}  // namespace ro
+
+void launchRefOrderInner(const RefOrderParams& P, const int32_t* graph, const int32_t* rowIds, int32_t nRows, int ncols,
+                         const double* U, double* V, double* Jv, const int32_t* jBase, const int32_t* jLen,
+                         const uint8_t* jSlot, int nslotCols, cudaStream_t st) {
+  if (nRows <= 0) return;
+  const RowSet rs{graph, rowIds, nRows, ncols};
+  const JacLayout jl{jBase, jLen, jSlot, nslotCols};
+  const unsigned grid = (unsigned)((nRows + 63) / 64);
+  switch (P.ndpc) {
+    case 1: ro::k_reforder_inner<1><<<grid, 64, 0, st>>>(P, rs, U, V, Jv, jl); break;
+    case 2: ro::k_reforder_inner<2><<<grid, 64, 0, st>>>(P, rs, U, V, Jv, jl); break;
+    case 3: ro::k_reforder_inner<3><<<grid, 64, 0, st>>>(P, rs, U, V, Jv, jl); break;
+    case 4: ro::k_reforder_inner<4><<<grid, 64, 0, st>>>(P, rs, U, V, Jv, jl); break;
+    default: ro::k_reforder_inner<5><<<grid, 64, 0, st>>>(P, rs, U, V, Jv, jl); break;
+  }
+}
+
+void launchRefOrderNearBd(const RefOrderParams& P, const int32_t* graph, const int32_t* rowIds, int32_t nRows, int ncols,
+                          const double* U, double* Jv, const int32_t* jBase, const int32_t* jLen, const uint8_t* jSlot,
+                          int nslotCols, double* const ghost[6], int ghostStride, const double* factors,
+                          cudaStream_t st) {
+  if (nRows <= 0) return;
+  const RowSet rs{graph, rowIds, nRows, ncols};
+  const JacLayout jl{jBase, jLen, jSlot, nslotCols};
+  GhostView gv;
+  for (int s = 0; s < 6; ++s) gv.g[s] = ghost[s];
+  gv.stride = ghostStride;
+  const unsigned grid = (unsigned)((nRows + 63) / 64);
+  switch (P.ndpc) {
+    case 1: ro::k_reforder_nearbd<1><<<grid, 64, 0, st>>>(P, rs, U, Jv, jl, gv, factors); break;
+    case 2: ro::k_reforder_nearbd<2><<<grid, 64, 0, st>>>(P, rs, U, Jv, jl, gv, factors); break;
+    case 3: ro::k_reforder_nearbd<3><<<grid, 64, 0, st>>>(P, rs, U, Jv, jl, gv, factors); break;
+    case 4: ro::k_reforder_nearbd<4><<<grid, 64, 0, st>>>(P, rs, U, Jv, jl, gv, factors); break;
+    default: ro::k_reforder_nearbd<5><<<grid, 64, 0, st>>>(P, rs, U, Jv, jl, gv, factors); break;
+  }
+}
+
+void launchRefOrderVelocity(const RefOrderParams& P, const int32_t* graph, const int32_t* rowIds, int32_t nRows, int ncols,
+                            const double* U, double* V, double* const ghost[6], int ghostStride, bool nearBd,
+                            cudaStream_t st) {
+  if (nRows <= 0) return;
+  const RowSet rs{graph, rowIds, nRows, ncols};
+  GhostView gv;
+  for (int s = 0; s < 6; ++s) gv.g[s] = ghost ? ghost[s] : nullptr;
+  gv.stride = ghostStride;
+  const unsigned grid = (unsigned)((nRows + 63) / 64);
+  const int nb = nearBd ? 1 : 0;
+  switch (P.ndpc) {
+    case 1: ro::k_reforder_velocity<1><<<grid, 64, 0, st>>>(P, rs, U, V, gv, nb); break;
+    case 2: ro::k_reforder_velocity<2><<<grid, 64, 0, st>>>(P, rs, U, V, gv, nb); break;
+    case 3: ro::k_reforder_velocity<3><<<grid, 64, 0, st>>>(P, rs, U, V, gv, nb); break;
+    case 4: ro::k_reforder_velocity<4><<<grid, 64, 0, st>>>(P, rs, U, V, gv, nb); break;
+    default: ro::k_reforder_velocity<5><<<grid, 64, 0, st>>>(P, rs, U, V, gv, nb); break;
+  }
+}
+
+void launchGlibcPow(const double* x, double y, double* out, int64_t n, cudaStream_t st) {
+  if (n <= 0) return;
+  ro::k_glibc_pow<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(x, y, out, n);
+}
+
+}  // namespace dev
+}  // namespace pda

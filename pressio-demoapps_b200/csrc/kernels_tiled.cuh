@@ -24,8 +24,10 @@
 // belong to the near-boundary kernel and are not stored), and for slab-local storage (multi-GPU).
 #pragma once
 #include <cstdint>
+#include <cstdlib>
 
 #include "fastmath.cuh"
+#include "func_attrs.hpp"
 #include "kernels_lattice.cuh"
 
 namespace pda {
@@ -358,19 +360,14 @@ void launchLattice3dTiled(const Phys& phys, const dev::LatticeDesc& L, const dev
   using T = dev::Tile3dSmem<S, TY>;
   constexpr size_t smem = T::template bytes<5>();
   auto kern = (L.slab == 2) ? dev::k_euler3d_velocity_tiled<S, TY, true> : dev::k_euler3d_velocity_tiled<S, TY, false>;
-  static bool configured = false;
-  if (!configured) {
-    for (auto k : {dev::k_euler3d_velocity_tiled<S, TY, true>, dev::k_euler3d_velocity_tiled<S, TY, false>}) {
-      cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-      cudaFuncSetAttribute(k, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
-    }
-    configured = true;
-  }
+  ensureFuncAttrs(kern, (int)smem, true);   // per device (func_attrs.hpp)
   const int planes = L.planeEnd - L.planeBegin;
   if (planes <= 0) return;
   const int gx = (L.n[0] + 31) / 32, gy = (L.n[1] + TY - 1) / TY;
   // z chunks: long enough to amortise the ghost step (1/LZ extra z faces), short enough to fill 148 SMs x 2 CTAs
-  int LZ = 64;
+  // (PDA_TILED_LZ overrides the start value: tuning only)
+  static const int lzStart = [] { const char* e = std::getenv("PDA_TILED_LZ"); const int v = e ? std::atoi(e) : 0; return v >= 8 ? v : 64; }();
+  int LZ = lzStart;
   while (LZ > 8 && (int64_t)gx * gy * ((planes + LZ - 1) / LZ) < 148 * 2 * 4) LZ /= 2;
   // peer mode: at least two chunks, so that no CTA needs both halos and the pushes overlap interior work
   if (L.slab == 2) while (LZ > 8 && (planes + LZ - 1) / LZ < 2) LZ /= 2;

@@ -72,6 +72,8 @@ _sig("pda_last_error", _cp)
 _sig("pda_version", _cp)
 _sig("pda_device_count", _C.c_int)
 _sig("pda_measure_fp64_peak", _C.c_int, _C.c_int, _C.POINTER(_dbl), _vp)
+_sig("pda_measure_fp64_peak_ex", _C.c_int, _C.c_int, _C.POINTER(_dbl), _C.POINTER(_dbl), _C.POINTER(_dbl))
+_sig("pda_test_glibc_pow", _C.c_int, _C.c_int, _vp, _dbl, _vp, _i64)
 _sig("pda_mesh_load", _C.c_int, _cp, _C.POINTER(_vp))
 _sig("pda_mesh_make_lattice", _C.c_int, _C.c_int, _vp, _vp, _vp, _C.c_int, _C.POINTER(_vp))
 _sig("pda_mesh_make_sample", _C.c_int, _vp, _vp, _i64, _C.POINTER(_vp))
@@ -102,6 +104,8 @@ _sig("pda_problem_create", _C.c_int, _vp, _C.c_int, _C.c_int, _C.c_int, _C.c_int
      _C.POINTER(_vp))
 _sig("pda_problem_set_bc", _C.c_int, _vp, _C.c_int, _C.c_int, _vp)
 _sig("pda_problem_set_source", _C.c_int, _vp, _vp)
+_sig("pda_problem_set_option", _C.c_int, _vp, _cp, _cp)
+_sig("pda_problem_get_option", _C.c_int, _vp, _cp, _vp, _C.c_int)
 _sig("pda_problem_free", _C.c_int, _vp)
 _sig("pda_problem_num_dof_per_cell", _C.c_int, _vp)
 _sig("pda_problem_total_dof_sample_mesh", _i32, _vp)
@@ -151,10 +155,28 @@ def measure_fp64_peak(device=0):
     return v.value
 
 
+def measure_fp64_peak_ex(device=0):
+    """(TFLOP/s, SM MHz the probe ran at, DFMA lanes issued per SM and cycle): the probe with its own clock evidence"""
+    v, mhz, rate = _dbl(), _dbl(), _dbl()
+    _check(_lib.pda_measure_fp64_peak_ex(int(device), _C.byref(v), _C.byref(mhz), _C.byref(rate)))
+    return v.value, mhz.value, rate.value
+
+
+def _device_glibc_pow(x, y, device=0):
+    """test hook: the device restatement of glibc's pow (csrc/glibc_pow.h) applied to a host array"""
+    x = _np.ascontiguousarray(x, dtype=_np.float64)
+    out = _np.zeros_like(x)
+    _check(_lib.pda_test_glibc_pow(int(device), x.ctypes.data, float(y), out.ctypes.data, x.size))
+    return out
+
+
 def _f64(a, n=None, name="array"):
-    """float64, 1-D (or C/F 2-D) contiguous numpy view -- like Eigen::Ref the reference binds (adapter_py.hpp)."""
+    """float64, contiguous (C order, or F order for a 2-D operand) numpy array -- what the reference's pybind/Eigen::Ref
+    binding accepts (adapter_py.hpp); a strided view is refused instead of reading or writing the wrong memory."""
     if not isinstance(a, _np.ndarray) or a.dtype != _np.float64:
         raise TypeError("%s must be a float64 numpy array" % name)
+    if not (a.flags["C_CONTIGUOUS"] or (a.ndim == 2 and a.flags["F_CONTIGUOUS"])):
+        raise TypeError("%s must be contiguous (got a strided view)" % name)
     if n is not None and a.size != n:
         raise ValueError("%s has %d entries, expected %d" % (name, a.size, n))
     return a
@@ -419,6 +441,15 @@ class Problem:
         self.setSourceTable(_np.array(tab))
         self._source_t = time
 
+    # ---- engine options (pda_problem_set_option): "jacobian_order" = "fast" | "reference"
+    def setOption(self, name, value):
+        _check(_lib.pda_problem_set_option(self._h, str(name).encode(), str(value).encode()))
+
+    def getOption(self, name):
+        buf = _C.create_string_buffer(64)
+        _check(_lib.pda_problem_get_option(self._h, str(name).encode(), buf, 64))
+        return buf.value.decode()
+
     # ---- sizes / parameters
     def numDofPerCell(self): return _lib.pda_problem_num_dof_per_cell(self._h)
     def totalDofSampleMesh(self): return _lib.pda_problem_total_dof_sample_mesh(self._h)
@@ -547,6 +578,9 @@ class Problem:
         ncols = 1 if operand.ndim == 1 else operand.shape[1]
         if operand.shape[0] != self.totalDofStencilMesh():
             raise ValueError("operand has %d rows, expected %d" % (operand.shape[0], self.totalDofStencilMesh()))
+        want = (self.totalDofSampleMesh(),) if operand.ndim == 1 else (self.totalDofSampleMesh(), ncols)
+        if tuple(result.shape) != want:
+            raise ValueError("result has shape %s, expected %s" % (tuple(result.shape), want))
         if operand.ndim == 1 or (operand.flags["F_CONTIGUOUS"] and not operand.flags["C_CONTIGUOUS"]):
             layout = 0
             if operand.ndim == 2 and not result.flags["F_CONTIGUOUS"]:
@@ -561,12 +595,15 @@ class Problem:
 
     # ---- evaluation (device pointers: ints from tensor.data_ptr(); stream = cudaStream_t as int)
     def rightHandSideDevice(self, dU, time, dV, stream=0):
+        self._refresh_source(time)
         _check(_lib.pda_problem_velocity_dev(self._h, dU, float(time), dV, stream))
 
     def rightHandSideAndJacobianDevice(self, dU, time, dV, dJvalues, stream=0):
+        self._refresh_source(time)
         _check(_lib.pda_problem_velocity_and_jacobian_dev(self._h, dU, float(time), dV, dJvalues, stream))
 
     def applyJacobianDevice(self, dU, dB, ncols, layout, time, dR, stream=0):
+        self._refresh_source(time)
         _check(_lib.pda_problem_apply_jacobian_dev(self._h, dU, dB, int(ncols), int(layout), float(time), dR, stream))
 
     # ---- test hooks / instrumentation
@@ -588,9 +625,25 @@ class Problem:
         """`nsteps` steps of `stepper` ("euler", "rk2", "rk4", "ssprk3") on the GPU; `state` (numpy, updated in place)
         crosses PCIe once each way"""
         _f64(state, self.totalDofStencilMesh(), "state")
+        self._check_source_for_advance(startTime)
         _check(_lib.pda_problem_advance_host(self._h, _STEPPERS[stepper], state.ctypes.data, float(startTime), float(dt), int(nsteps)))
 
+    def _check_source_for_advance(self, startTime):
+        # the device-resident steppers evaluate every stage on the GPU from ONE source table: a host functor f(x[,y],t)
+        # is tabulated at the start time; a time-DEPENDENT one cannot be honoured across stages and steps
+        if self._source is None:
+            return
+        xs, ys = self._src_xy
+        probe = [(float(xs[0]), float(ys[0])), (float(xs[-1]), float(ys[-1]))]
+        one_d = self._mesh.dimensionality() == 1
+        f = (lambda x, y, t: self._source(x, t)) if one_d else self._source
+        if any(f(x, y, float(startTime)) != f(x, y, float(startTime) + 1.0) for x, y in probe):
+            raise PdaError(5, "advance: the source functor depends on time; the device-resident steppers use one source "
+                              "table for all stages -- step on the host with advanceRK2/RK4/SSP3 instead")
+        self._refresh_source(startTime)
+
     def advanceDevice(self, stepper, dU, dt, nsteps, startTime=0.0, stream=0):
+        self._check_source_for_advance(startTime)
         _check(_lib.pda_problem_advance_dev(self._h, _STEPPERS[stepper], dU, float(startTime), float(dt), int(nsteps), stream))
 
     # ---- slab decomposition (one process per GPU)
@@ -790,9 +843,13 @@ class GradientEvaluator:
         nd = int(numDofPerCell)
         if nd > self._max or nd < 1:   # let the library produce the reference's message
             _check(_lib.pda_gradient_compute_host(self._h, None, nd, None))
-        field = _f64(field, self._nStencil * nd, "field")
+        if not isinstance(field, _np.ndarray) or field.dtype != _np.float64:
+            raise TypeError("field must be a float64 numpy array")
+        if field.size != self._nStencil * nd:
+            raise ValueError("field has %d entries, expected %d" % (field.size, self._nStencil * nd))
+        fld = _np.ascontiguousarray(field)   # kept alive in a local for the duration of the C call
         out = _np.zeros((self.numFaces(), nd))
-        _check(_lib.pda_gradient_compute_host(self._h, _np.ascontiguousarray(field).ctypes.data, nd, out.ctypes.data))
+        _check(_lib.pda_gradient_compute_host(self._h, fld.ctypes.data, nd, out.ctypes.data))
         self.normalGradients[:, :nd] = out
         return out
 

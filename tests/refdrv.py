@@ -159,6 +159,8 @@ def _oracle(omp=False):
         L.or_create.argtypes = [C.c_char_p, ci, ci, ci, ci, ci, vp, vp]
         L.or_create_from_arrays.restype = vp
         L.or_create_from_arrays.argtypes = [ci, ci, C.c_int32, C.c_int32, vp, vp, vp, vp, vp, ci, ci, ci, ci, ci, vp, vp]
+        L.or_create_lattice.restype = vp
+        L.or_create_lattice.argtypes = [ci, ci, vp, vp, vp, vp, vp, vp, ci, ci, ci, ci, ci, vp, vp]
         L.or_destroy.argtypes = [vp]
         L.or_set_source.argtypes = [vp, vp]
         L.or_query.restype = C.c_longlong
@@ -174,6 +176,8 @@ def _oracle(omp=False):
         L.or_ghosts.argtypes = [vp, ci, vp]
         L.or_time_velocity.restype = cd
         L.or_time_velocity.argtypes = [vp, vp, cd, ci, ci]
+        L.or_time_velocity_inner_range.restype = cd
+        L.or_time_velocity_inner_range.argtypes = [vp, vp, cd, vp, C.c_int32, C.c_int32, ci]
         L.or_weno5.argtypes = [vp, vp] + [cd] * 6
         L.or_weno3.argtypes = [vp, vp] + [cd] * 4
         L.or_weno5_grad.argtypes = [vp] * 4 + [cd] * 6
@@ -189,13 +193,26 @@ def _oracle(omp=False):
 class OracleProblem:
     """Plain-C restatement (oracle/pda_oracle.c); same interface as RefProblem."""
 
-    def __init__(self, meshDir, family, probEnum, recon, icFlag=1, params=None, omp=False, arrays=None):
+    def __init__(self, meshDir, family, probEnum, recon, icFlag=1, params=None, omp=False, arrays=None, lattice=None):
+        """mesh: a directory in the reference's text format, `arrays` (graph + coordinates), or `lattice` = dict(dim,
+        stencil, n, d, periodic[, cx, cy, cz]): a full mesh in natural ordering WITHOUT a stored graph -- the way the
+        BASELINE sizes (512^3, 4096^2) are evaluated (see lattice_spec())."""
         self.L = _oracle(omp)
         params = params or {}
         names = (C.c_char_p * max(1, len(params)))(*[k.encode() for k in params])
         vals = (C.c_double * max(1, len(params)))(*[float(v) for v in params.values()])
         fam = FAM[family] if isinstance(family, str) else int(family)
-        if arrays is not None:
+        self._lazy_nnz = lattice is not None
+        if lattice is not None:
+            a = lattice
+            n3 = (C.c_int32 * 3)(*(list(a["n"]) + [1, 1, 1])[:3])
+            d3 = (C.c_double * 3)(*(list(a["d"]) + [0.0, 0.0, 0.0])[:3])
+            per = (C.c_int32 * 3)(*(list(a["periodic"]) + [1, 1, 1])[:3])
+            ax = [None if a.get(k) is None else np.ascontiguousarray(a[k], dtype=np.float64) for k in ("cx", "cy", "cz")]
+            self.h = self.L.or_create_lattice(int(a["dim"]), int(a["stencil"]), n3, d3, per,
+                                              *[None if v is None else v.ctypes.data for v in ax], fam,
+                                              int(probEnum), int(recon), int(icFlag), len(params), names, vals)
+        elif arrays is not None:
             a = arrays
             d = np.ascontiguousarray(a["d"], dtype=np.float64)
             g = np.ascontiguousarray(a["graph"], dtype=np.int32)
@@ -210,7 +227,14 @@ class OracleProblem:
             raise RuntimeError("oracle: " + self.L.or_last_error().decode())
         q = lambda i: int(self.L.or_query(self.h, i))
         (self.dim, self.stencil, self.nSample, self.nStencil, self.ncols, self.nInner, self.nNearBd,
-         self.periodic, self.ndpc, self.nDofStencil, self.nDofSample, self.nnz) = [q(i) for i in range(12)]
+         self.periodic, self.ndpc, self.nDofStencil, self.nDofSample) = [q(i) for i in range(11)]
+        self._nnz = None if self._lazy_nnz else q(11)   # lattice mode builds the pattern on demand only
+
+    @property
+    def nnz(self):
+        if self._nnz is None:
+            self._nnz = int(self.L.or_query(self.h, 11))
+        return self._nnz
 
     def __del__(self):
         if getattr(self, "h", None):
@@ -241,8 +265,8 @@ class OracleProblem:
         self.L.or_ic(self.h, U.ctypes.data)
         return U
 
-    def velocity(self, U, t=0.0):
-        V = np.zeros(self.nDofSample)
+    def velocity(self, U, t=0.0, out=None):
+        V = np.zeros(self.nDofSample) if out is None else out
         self.L.or_velocity(self.h, U.ctypes.data, float(t), V.ctypes.data)
         return V
 
@@ -266,6 +290,10 @@ class OracleProblem:
 
     def time_velocity(self, U, t=0.0, warmup=1, reps=5):
         return float(self.L.or_time_velocity(self.h, U.ctypes.data, float(t), warmup, reps))
+
+    def time_velocity_inner_range(self, U, V, it0, it1, t=0.0, reps=1):
+        """seconds for `reps` evaluations of the inner rows [it0, it1) (a bounded sample of a big workload)"""
+        return float(self.L.or_time_velocity_inner_range(self.h, U.ctypes.data, float(t), V.ctypes.data, int(it0), int(it1), int(reps)))
 
 
 def oracle_leaf():
@@ -384,3 +412,24 @@ def oracle_gradient(stencil, graph, rowsNearBd, x, y, z, dx, dy, field, ndpc=1):
     L.or_gradient_eval(int(stencil), graph.ctypes.data, n, pos.ctypes.data, row.ctypes.data, float(dx), float(dy),
                        f.ctypes.data, int(ndpc), grad.ctypes.data)
     return dict(cellGid=gid[:n], position=pos[:n], parentRow=row[:n], normalDir=nd[:n], centers=cen[:n], grad=grad[:n])
+
+
+def lattice_spec(n, bounds, stencil, periodic=()):
+    """dict for OracleProblem(lattice=...): cells per axis, dx and per-axis centre coordinates exactly as the reference's
+    mesh files carry them -- create_full_mesh.py writes dx and every coordinate with "%.14f" and the C++ loader reads
+    those roundings back (meshing_scripts/create_full_mesh.py:151-218, impl/mesh_read_info.hpp:84-99)."""
+    n = list(n)
+    dim = len(n)
+    if dim == 2 and n[1] == 1:
+        dim, n = 1, n[:1]
+    d, axes = [], []
+    for a in range(dim):
+        lo, hi = float(bounds[2 * a]), float(bounds[2 * a + 1])
+        dx = (hi - lo) / n[a]
+        ox = lo + 0.5 * dx   # natural_order_mesh_{2,3}d.py: ox = lo + 0.5*dx, x = ox + gi*dx (unrounded dx)
+        axes.append(np.array([float("%.14f" % (ox + i * dx)) for i in range(n[a])]))
+        d.append(float("%.14f" % dx))
+    while len(axes) < 3:
+        axes.append(None)
+    return dict(dim=dim, stencil=int(stencil), n=n, d=d, periodic=[1 if a in periodic else 0 for a in ("x", "y", "z")[:dim]],
+                cx=axes[0], cy=axes[1], cz=axes[2])

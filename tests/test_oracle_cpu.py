@@ -156,3 +156,43 @@ def test_golden_regenerates_from_live_reference(load_golden, tmp_path):
     mesh.write(str(tmp_path))
     r = RefProblem(str(tmp_path), m["family"], m["prob"], m["recon"], m["ic"], m["params"])
     assert np.array_equal(r.velocity(g["U"], m["t"]), g["V"])
+
+
+@pytest.mark.parametrize("fam,prob,recon,n,bounds,per,sten", [
+    ("euler3d", 0, 2, [9, 8, 7], [-1, 1, -1, 1, -1, 1], ("x", "y", "z"), 7),
+    ("euler3d", 1, 1, [10, 9, 8], [0, 1, 0, 1, 0, 1], (), 5),
+    ("euler2d", 6, 1, [40, 12], [0, 4, 0, 1], (), 5),
+    ("euler2d", 4, 2, [20, 18], [0, 1, 0, 1], (), 7),
+    ("swe2d", 0, 1, [17, 19], [-5, 5, -5, 5], (), 5),
+    ("euler1d", 1, 2, [50, 1], [-0.5, 0.5], (), 7),
+    ("diffreac2d", 1, 0, [16, 12], [-1.25, 1.25, -1.25, 1.25], ("x", "y"), 3),
+    ("advdiff2d", 1, 1, [14, 15], [-1, 1, -1, 1], (), 5),
+])
+def test_lattice_mode_equals_stored_graph_mode(fam, prob, recon, n, bounds, per, sten):
+    """or_create_lattice (connectivity by index arithmetic, what makes 512^3 / 4096^2 checkable) gives the SAME bits as
+    the stored-graph oracle that the golden fixtures pin: classification, initial condition, velocity at two times,
+    Jacobian values and pattern."""
+    import pressiodemoapps as pda
+    from refdrv import lattice_spec
+    mesh = pda.create_full_mesh(n, bounds, sten, per)
+    x, y, z = mesh._coords()
+    oa = OracleProblem(None, fam, prob, recon, arrays=dict(dim=mesh.dimensionality(), stencil=sten, d=mesh._deltas()[0],
+                                                           graph=mesh.graph(), x=x, y=y, z=z))
+    spec = lattice_spec(n, bounds, sten, per)
+    assert np.array_equal(np.array(spec["d"]), mesh._deltas()[0][:spec["dim"]])
+    for a, c in zip(("cx", "cy", "cz"), (x, y, z)):
+        if spec[a] is not None:
+            assert set(spec[a]) == set(np.unique(c))
+    ol = OracleProblem(None, fam, prob, recon, lattice=spec)
+    assert (oa.nSample, oa.nInner, oa.nNearBd, oa.periodic) == (ol.nSample, ol.nInner, ol.nNearBd, ol.periodic)
+    U = oa.initialCondition()
+    assert np.array_equal(U, ol.initialCondition())
+    rng = np.random.default_rng(1)
+    U = U * (1 + 1e-3 * rng.uniform(-1, 1, U.size)) if np.any(U) else 0.1 * rng.uniform(-1, 1, U.size)
+    for t in (0.0, 0.07):
+        assert np.array_equal(oa.velocity(U, t), ol.velocity(U, t), equal_nan=True)
+    Va, Ja = oa.velocityAndJacobian(U, 0.0)
+    Vl, Jl = ol.velocityAndJacobian(U, 0.0)
+    assert np.array_equal(Va, Vl, equal_nan=True) and np.array_equal(Ja, Jl, equal_nan=True)
+    for a, b in zip(oa.pattern(), ol.pattern()):
+        assert np.array_equal(a, b)

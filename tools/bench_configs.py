@@ -54,9 +54,15 @@ def measure(p, hbm_gbs, jac=True, apply_cols=0, reps=5, t=0.0):
             del Jv
             B = torch.rand(p.totalDofStencilMesh(), apply_cols, dtype=torch.float64, device="cuda")
             Rm = torch.empty(p.totalDofSampleMesh(), apply_cols, dtype=torch.float64, device="cuda")
-            ms = _time(lambda: p.applyJacobianDevice(U.data_ptr(), B.data_ptr(), apply_cols, 1, t, Rm.data_ptr(), st), max(2, reps // 2))
-            out["apply_jacobian"] = {"ms": ms, "cols": apply_cols, "layout": "row-major",
-                                     "nnz_cols_per_s": nnz * apply_cols / (ms * 1e-3)}
+            # the reference's harness hands over a COLUMN-major operand (tests_perf/main.py:37: order='F'): that layout is
+            # the headline number; the same memory read as row-major [rows][cols] is reported beside it
+            ms_f = _time(lambda: p.applyJacobianDevice(U.data_ptr(), B.data_ptr(), apply_cols, 0, t, Rm.data_ptr(), st), max(2, reps // 2))
+            ms_c = _time(lambda: p.applyJacobianDevice(U.data_ptr(), B.data_ptr(), apply_cols, 1, t, Rm.data_ptr(), st), max(2, reps // 2))
+            compulsory = (nnz * 8.0 + 8.0 * apply_cols * (p.totalDofStencilMesh() + p.totalDofSampleMesh()) + 2 * ndpc * 8.0 * ncell)
+            out["apply_jacobian"] = {"ms": ms_f, "cols": apply_cols, "layout": "col-major (order='F', as tests_perf/main.py:37)",
+                                     "nnz_cols_per_s": nnz * apply_cols / (ms_f * 1e-3),
+                                     "hbm_frac_of_compulsory": compulsory / (ms_f * 1e-3) * 1e-9 / hbm_gbs,
+                                     "compulsory_bytes": compulsory, "row_major_ms": ms_c}
             b1 = torch.rand(p.totalDofStencilMesh(), dtype=torch.float64, device="cuda")
             r1 = torch.empty(p.totalDofSampleMesh(), dtype=torch.float64, device="cuda")
             ms = _time(lambda: p.applyJacobianDevice(U.data_ptr(), b1.data_ptr(), 1, 1, t, r1.data_ptr(), st), max(2, reps // 2))
@@ -119,11 +125,44 @@ def run(hbm_gbs, small=False, device=0):
         return dict(workload="3D Euler PeriodicSmooth %s %d^3 (Jacobian: nnz must fit int32 like the reference's "
                              "SparseMatrix<double,RowMajor,int32_t>)" % (rec.name, n), **measure(p, hbm_gbs, reps=3))
 
+    def cfg3_custom(mode):
+        # Swe2d::CustomBCs with the Dirichlet / HomogNeumann functors of
+        # /root/reference/tests_cpp/eigen_2d_swe_custom_bcs/main.cc:6-58 -- left: Dirichlet state, other sides: homogeneous
+        # Neumann.  "device": the rules as device tables (pda_problem_set_bc, state never leaves HBM);
+        # "host": the SAME rules as host functors (pda_problem_set_bc_callback): every evaluation copies the state to
+        # the host, runs the functors for the boundary cells and uploads the ghost rows -- the cost is reported, not hidden
+        n = 512 if small else 4096
+        mesh = pda.create_full_mesh([n, n], [-5, 5, -5, 5], 5)
+        p = pda.create_problem(mesh, pda.Swe2d.CustomBCs, R.Weno3, device=device)
+        dirich = [1.0, 0.0, 0.0]
+        if mode == "device":
+            p.setBC(0, pda.BC.Dirichlet, dirich)
+            for sd in (1, 2, 3):
+                p.setBC(sd, pda.BC.HomogNeumann)
+        else:
+            import ctypes as C
+            lib = C.CDLL(os.path.join(ROOT, "examples", "_bin", "libbc_functors.so"))
+            ghost_t = pda._GHOST_FN
+            fac_t = pda._FACTOR_FN
+            keep = []
+            for sd in range(4):
+                g = C.cast(getattr(lib, "bc_ghost_dirichlet" if sd == 0 else "bc_ghost_neumann"), ghost_t)
+                f = C.cast(getattr(lib, "bc_factor_dirichlet" if sd == 0 else "bc_factor_neumann"), fac_t)
+                keep.append((g, f))
+                pda._check(pda._lib.pda_problem_set_bc_callback(p._h, sd, g, f, None))
+            p._keep_bc = (lib, keep)
+        r = measure(p, hbm_gbs, jac=False, reps=5 if mode == "device" else 2)
+        return dict(workload="2D SWE CustomBCs Weno3 %dx%d (left Dirichlet, others homogeneous Neumann), BC rules on the %s"
+                             % (n, n, "device (tables)" if mode == "device" else "HOST (compiled C functors through the "
+                                "callback entry: state D2H + ghost rows H2D per evaluation)"), **r)
+
     guarded("cfg1_euler1d_sod_weno5", cfg1)
     guarded("cfg2_euler2d_riemann_weno5", cfg2)
     guarded("cfg3_swe_firstorder", lambda: cfg3("swe_fo"))
     guarded("cfg3_swe_weno3", lambda: cfg3("swe_w3"))
     guarded("cfg3_gray_scott", lambda: cfg3("gs"))
+    guarded("cfg3_swe_custom_bcs_device_rules", lambda: cfg3_custom("device"))
+    guarded("cfg3_swe_custom_bcs_host_functors", lambda: cfg3_custom("host"))
     guarded("cfg4_dmr_sample_weno3", lambda: cfg4(R.Weno3, 5))
     guarded("cfg4_dmr_sample_weno5", lambda: cfg4(R.Weno5, 7))
     guarded("cfg5_euler3d_weno3_jacobian", lambda: cfg5_jac(R.Weno3, 5, 160))   # 160^3 * 325 = 1.33 G nnz
