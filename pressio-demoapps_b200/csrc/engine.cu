@@ -15,6 +15,7 @@
 #include "kernels_generic.cuh"
 #include "kernels_lattice.cuh"
 #include "kernels_tiled.cuh"
+#include "kernels_tiled2.cuh"
 #include "kernels_jacobian.cuh"
 #include "kernels_jaclattice.cuh"
 #include "kernels_march2d.cuh"
@@ -1187,6 +1188,35 @@ void Problem::evaluateDev(const double* dU, double t, double* dV, double* dJ, vo
     }
   }
 
+  // ---- diffusion-reaction families in reference-order mode: the -fmad=false twins of the kernels below
+  if ((family_ == F_DIFFREAC2D || family_ == F_DIFFREAC1D) && ((dJ && refOrderJac_) || (!dJ && refOrderVel_))) {
+    ensureInnerRows();   // all rows of these families
+    if (dJ && !ds.innerJacTablesReady) {
+      std::vector<int32_t> base(ds.inner.n), len(ds.inner.n);
+      std::vector<uint8_t> sl((size_t)ds.inner.n * slotCols_);
+      for (int32_t r = 0; r < ds.inner.n; ++r) {
+        const int32_t row = ds.inner.hostRowIds[r];
+        base[r] = cellBase_[row]; len[r] = cellLen_[row];
+        std::memcpy(&sl[(size_t)r * slotCols_], &slots_[(size_t)row * slotCols_], slotCols_);
+      }
+      ds.inner.jBase.upload(base); ds.inner.jLen.upload(len); ds.inner.jSlot.upload(sl);
+      ds.innerJacTablesReady = true;
+    }
+    if (dJ) PDA_CUDA(cudaMemsetAsync(dJ, 0, colidx_.size() * sizeof(double), st));
+    if (family_ == F_DIFFREAC2D && probId_ == 1) {
+      if (!m.fullyPeriodic) throw Error(kInvalid, "GrayScott requires a periodic mesh");
+      dev::launchRefOrderGrayScott(gs_, m.dInv[0], m.dInv[1], ds.inner.graph.p, ds.inner.rowIds.p, ds.inner.n, nc, dU, dV, dJ,
+                                   ds.inner.jBase.p, ds.inner.jLen.p, ds.inner.jSlot.p, slotCols_, st);
+    } else {
+      ensureSource();
+      dev::launchRefOrderDiffReac(dim_, physParams_[0], physParams_[1], m.dInv[0], m.dInv[1], ds.inner.graph.p,
+                                  ds.inner.rowIds.p, ds.inner.n, nc, dU, ds.src.p, dV, dJ, ds.inner.jBase.p, ds.inner.jLen.p,
+                                  ds.inner.jSlot.p, slotCols_, st);
+    }
+    ++launches_;
+    PDA_CUDA(cudaGetLastError());
+    return;
+  }
   // ---- Gray-Scott: one fused kernel over all rows
   if (family_ == F_DIFFREAC2D && probId_ == 1) {
     dev::GrayScottParams gp{gs_[0], gs_[1], gs_[2], gs_[3], m.dInv[0] * m.dInv[0], m.dInv[1] * m.dInv[1]};

@@ -795,6 +795,97 @@ k_reforder_nearbd(RefOrderParams P, RowSet rs, const double* __restrict__ U, dou
   }
 }
 
+// Gray-Scott (diffusion_reaction_2d_prob_class.hpp:459-529) and DiffusionReaction{1d,2d}::ProblemA
+// (diffusion_reaction_1d_prob_class.hpp:211-302, diffusion_reaction_2d_prob_class.hpp:306-456) in the reference's
+// operation order: no reconstruction here, the only difference to the fast kernels is that nothing is contracted
+// into an FMA.  One thread per sample row over ALL rows; Jv zeroed on entry.
+__global__ void __launch_bounds__(128)
+k_reforder_gray_scott(double Du, double Dv, double F, double kk, double dxInv, double dyInv, RowSet rs,
+                      const double* __restrict__ U, double* __restrict__ V, double* __restrict__ Jv, JacLayout jl) {
+  const int32_t r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= rs.n) return;
+  const int32_t* row = rs.graph + (int64_t)r * rs.ncols;
+  const double one = 1, two = 2;
+  const double dxInvSq = dxInv * dxInv, dyInvSq = dyInv * dyInv;
+  const double uDx = Du * dxInvSq, uDy = Du * dyInvSq, vDx = Dv * dxInvSq, vDy = Dv * dyInvSq;
+  const int64_t si = (int64_t)row[0] * 2, sl = (int64_t)row[1] * 2, sf = (int64_t)row[2] * 2, sr = (int64_t)row[3] * 2,
+                sb = (int64_t)row[4] * 2;
+  const double u = U[si], v = U[si + 1];
+  const double uvSquared = u * v * v;
+  if (V) {
+    const int64_t vi = (int64_t)rs.rowIds[r] * 2;
+    V[vi] = F * (one - u) - uvSquared + uDx * (U[sr] - two * U[si] + U[sl]) + uDy * (U[sb] - two * U[si] + U[sf]);
+    V[vi + 1] = -(F + kk) * v + uvSquared + vDx * (U[sr + 1] - two * U[si + 1] + U[sl + 1]) +
+                vDy * (U[sb + 1] - two * U[si + 1] + U[sf + 1]);
+  }
+  if (Jv) {
+    const int64_t base = jl.base[r];
+    const int32_t len = jl.len[r];
+    const uint8_t* slots = jl.slot + (int64_t)r * jl.nslotCols;
+    double* r0 = Jv + base;
+    double* r1 = Jv + base + len;
+    const int s0 = slots[0], s1 = slots[1], s2 = slots[2], s3 = slots[3], s4 = slots[4];
+    r0[2 * s0] += -two * uDx - two * uDy - v * v - F;
+    r0[2 * s0 + 1] += -(two * u * v);
+    r0[2 * s1] += uDx; r0[2 * s2] += uDy; r0[2 * s3] += uDx; r0[2 * s4] += uDy;
+    r1[2 * s0] += v * v;
+    r1[2 * s0 + 1] += -two * vDx - two * vDy + two * u * v - (F + kk);
+    r1[2 * s1 + 1] += vDx; r1[2 * s2 + 1] += vDy; r1[2 * s3 + 1] += vDx; r1[2 * s4 + 1] += vDy;
+  }
+}
+
+__global__ void __launch_bounds__(128)
+k_reforder_diffreac(int dim, double D, double kR, double dxInv, double dyInv, RowSet rs, const double* __restrict__ U,
+                    const double* __restrict__ src, double* __restrict__ V, double* __restrict__ Jv, JacLayout jl) {
+  const int32_t r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= rs.n) return;
+  const int32_t* row = rs.graph + (int64_t)r * rs.ncols;
+  const double two = 2., three = 3.;
+  const double dxInvSq = dxInv * dxInv, dyInvSq = dyInv * dyInv;
+  const double twoReacCoeff = kR * two;
+  const double diffDxInvSq = D * dxInvSq, diffDyInvSq = D * dyInvSq;
+  const int32_t smPt = rs.rowIds[r];
+  const double u = U[row[0]];
+  const int64_t base = Jv ? jl.base[r] : 0;
+  const uint8_t* slots = jl.slot + (int64_t)r * jl.nslotCols;
+  if (dim == 1) {
+    const int32_t iL = row[1], iR = row[2];
+    const double sL = (iL != -1) ? U[iL] : -u, sR = (iR != -1) ? U[iR] : -u;
+    if (V) {
+      double v = src[smPt];
+      v += kR * u * u;
+      const double fd = sR - two * u + sL;
+      v += dxInvSq * D * fd;
+      V[smPt] = v;
+    }
+    if (Jv) {
+      const bool nb = (iL == -1) || (iR == -1);
+      Jv[base + slots[0]] += (nb ? -three * diffDxInvSq : -two * diffDxInvSq) + twoReacCoeff * u;
+      if (iL != -1) Jv[base + slots[1]] += diffDxInvSq;
+      if (iR != -1) Jv[base + slots[2]] += diffDxInvSq;
+    }
+  } else {
+    const int32_t iL = row[1], iF = row[2], iR = row[3], iB = row[4];
+    const double sL = (iL != -1) ? U[iL] : -u, sR = (iR != -1) ? U[iR] : -u;
+    const double sB = (iB != -1) ? U[iB] : -u, sF = (iF != -1) ? U[iF] : -u;
+    if (V) {
+      double v = src[smPt];
+      v += kR * u * u;
+      v += dxInvSq * D * (sR - two * u + sL);
+      v += dyInvSq * D * (sF - two * u + sB);
+      V[smPt] = v;
+    }
+    if (Jv) {
+      double selfValue = -two * diffDxInvSq - two * diffDyInvSq + twoReacCoeff * u;
+      if (iL != -1) Jv[base + slots[1]] += diffDxInvSq; else selfValue += -diffDxInvSq;
+      if (iF != -1) Jv[base + slots[2]] += diffDyInvSq; else selfValue += -diffDyInvSq;
+      if (iR != -1) Jv[base + slots[3]] += diffDxInvSq; else selfValue += -diffDxInvSq;
+      if (iB != -1) Jv[base + slots[4]] += diffDyInvSq; else selfValue += -diffDyInvSq;
+      Jv[base + slots[0]] += selfValue;
+    }
+  }
+}
+
 __global__ void k_glibc_pow(const double* __restrict__ x, double y, double* __restrict__ out, int64_t n) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) out[i] = powLibm(x[i], y);
@@ -855,6 +946,25 @@ void launchRefOrderVelocity(const RefOrderParams& P, const int32_t* graph, const
     case 4: ro::k_reforder_velocity<4><<<grid, 64, 0, st>>>(P, rs, U, V, gv, nb); break;
     default: ro::k_reforder_velocity<5><<<grid, 64, 0, st>>>(P, rs, U, V, gv, nb); break;
   }
+}
+
+void launchRefOrderGrayScott(const double gs[4], double dxInv, double dyInv, const int32_t* graph, const int32_t* rowIds,
+                             int32_t nRows, int ncols, const double* U, double* V, double* Jv, const int32_t* jBase,
+                             const int32_t* jLen, const uint8_t* jSlot, int nslotCols, cudaStream_t st) {
+  if (nRows <= 0) return;
+  const RowSet rs{graph, rowIds, nRows, ncols};
+  const JacLayout jl{jBase, jLen, jSlot, nslotCols};
+  ro::k_reforder_gray_scott<<<(unsigned)((nRows + 127) / 128), 128, 0, st>>>(gs[0], gs[1], gs[2], gs[3], dxInv, dyInv, rs, U, V, Jv, jl);
+}
+
+void launchRefOrderDiffReac(int dim, double D, double kR, double dxInv, double dyInv, const int32_t* graph,
+                            const int32_t* rowIds, int32_t nRows, int ncols, const double* U, const double* src, double* V,
+                            double* Jv, const int32_t* jBase, const int32_t* jLen, const uint8_t* jSlot, int nslotCols,
+                            cudaStream_t st) {
+  if (nRows <= 0) return;
+  const RowSet rs{graph, rowIds, nRows, ncols};
+  const JacLayout jl{jBase, jLen, jSlot, nslotCols};
+  ro::k_reforder_diffreac<<<(unsigned)((nRows + 127) / 128), 128, 0, st>>>(dim, D, kR, dxInv, dyInv, rs, U, src, V, Jv, jl);
 }
 
 void launchGlibcPow(const double* x, double y, double* out, int64_t n, cudaStream_t st) {

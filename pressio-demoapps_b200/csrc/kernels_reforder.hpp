@@ -38,6 +38,14 @@ void launchRefOrderNearBd(const RefOrderParams& P, const int32_t* graph, const i
 void launchRefOrderVelocity(const RefOrderParams& P, const int32_t* graph, const int32_t* rowIds, int32_t nRows, int ncols,
                             const double* U, double* V, double* const ghost[6], int ghostStride, bool nearBd,
                             cudaStream_t st);
+// the diffusion-reaction families (no reconstruction; the reference's operation order, nothing contracted)
+void launchRefOrderGrayScott(const double gs[4], double dxInv, double dyInv, const int32_t* graph, const int32_t* rowIds,
+                             int32_t nRows, int ncols, const double* U, double* V, double* Jv, const int32_t* jBase,
+                             const int32_t* jLen, const uint8_t* jSlot, int nslotCols, cudaStream_t st);
+void launchRefOrderDiffReac(int dim, double D, double kR, double dxInv, double dyInv, const int32_t* graph,
+                            const int32_t* rowIds, int32_t nRows, int ncols, const double* U, const double* src, double* V,
+                            double* Jv, const int32_t* jBase, const int32_t* jLen, const uint8_t* jSlot, int nslotCols,
+                            cudaStream_t st);
 // test hook: out[i] = the device restatement of glibc's pow(x[i], y)
 void launchGlibcPow(const double* x, double y, double* out, int64_t n, cudaStream_t st);
 

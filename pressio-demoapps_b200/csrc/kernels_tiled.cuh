@@ -352,10 +352,17 @@ k_euler3d_velocity_tiled(double gamma, LatticeDesc L, Deltas dl, const double* _
 
 }  // namespace dev
 
+// second generation (kernels_tiled2.cuh): cell-based WENO edges along z and x; PDA_TILED_V2=0 keeps this file's kernel
+bool tiledV2Enabled();
+template <class Phys, int S>
+void launchLattice3dTiled2(const Phys& phys, const dev::LatticeDesc& L, const dev::Deltas& dl, const double* dU,
+                           double* dV, cudaStream_t st);
+
 template <class Phys, int S>
 void launchLattice3dTiled(const Phys& phys, const dev::LatticeDesc& L, const dev::Deltas& dl, const double* dU,
                           double* dV, cudaStream_t st) {
   static_assert(Phys::dim == 3 && Phys::ndpc == 5, "Euler3d kernel");
+  if (tiledV2Enabled()) { launchLattice3dTiled2<Phys, S>(phys, L, dl, dU, dV, st); return; }
   constexpr int TY = 7;   // 7 cell warps + 1 edge warp = 256 threads, 2 CTAs per SM at 128 registers
   using T = dev::Tile3dSmem<S, TY>;
   constexpr size_t smem = T::template bytes<5>();

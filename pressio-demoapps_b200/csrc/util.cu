@@ -36,6 +36,23 @@ __global__ void __launch_bounds__(256) k_dfma_peak_clocked(double* out, int iter
   }
 }
 
+__global__ void __launch_bounds__(256) k_dfma_peak16(double* out, int iters, double a, double b) {
+  double x[16], m[16], c[16];
+#pragma unroll
+  for (int i = 0; i < 16; ++i) { x[i] = threadIdx.x * 1e-9 + i; m[i] = a - 1e-9 * i; c[i] = b * (i + 1); }
+  for (int it = 0; it < iters; ++it) {
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+#pragma unroll
+      for (int i = 0; i < 16; ++i) x[i] = fma(x[i], m[i], c[i]);
+    }
+  }
+  double s = 0.0;
+#pragma unroll
+  for (int i = 0; i < 16; ++i) s += x[i];
+  if (s == 123.456) out[0] = s;
+}
+
 __global__ void __launch_bounds__(256) k_dfma_peak(double* out, int iters, double a, double b) {
   // 8 independent dependency chains per thread: enough ILP to cover the DFMA latency at 8 warps/scheduler
   double x0 = threadIdx.x * 1e-9, x1 = x0 + 1, x2 = x0 + 2, x3 = x0 + 3, x4 = x0 + 4, x5 = x0 + 5, x6 = x0 + 6, x7 = x0 + 7;
@@ -105,11 +122,33 @@ extern "C" pda_status pda_measure_fp64_peak_ex(int device, double* tflops, doubl
     for (int b = 0; b < blocks; ++b) { cyc += (double)h[2 * b]; ns += (double)h[2 * b + 1]; }
     delete[] h;
     cyc /= blocks; ns /= blocks;
-    mhz = cyc / ns * 1e3;
-    // DFMA warp-lanes issued per SM and cycle: perSm CTAs x threads x 64 FMA per iteration x iters over the CTA's cycles
-    rate = (double)perSm * threads * 64.0 * iters / cyc;
+    mhz = cyc / ns * 1e3;   // SM cycles per microsecond while the DFMA loop runs
   }
   cudaFree(d); cudaFree(rec);
+  // second probe shape: 16 independent chains with DISTINCT multiplier / addend registers per chain (no operand shared
+  // between neighbouring DFMAs); the better of the two is the measured peak
+  {
+    double* d2 = nullptr;
+    if (cudaMalloc(&d2, 8) == cudaSuccess) {
+      const int blocks2 = prop.multiProcessorCount * 4, it2 = 4096;
+      cudaEvent_t e0, e1;
+      cudaEventCreate(&e0); cudaEventCreate(&e1);
+      for (int rep = 0; rep < 5; ++rep) {
+        cudaEventRecord(e0);
+        k_dfma_peak16<<<blocks2, 256>>>(d2, it2, 0.999999, 1e-9);
+        cudaEventRecord(e1);
+        if (cudaEventSynchronize(e1) != cudaSuccess) break;
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, e0, e1);
+        const double tf = 2.0 * 16.0 * 8.0 * it2 * (double)blocks2 * 256 / (ms * 1e-3) * 1e-12;
+        if (rep > 0 && tf > *tflops) *tflops = tf;
+      }
+      cudaEventDestroy(e0); cudaEventDestroy(e1);
+      cudaFree(d2);
+    }
+  }
+  // DFMA lanes issued per SM and cycle = measured throughput / 2 flop / SMs / the clock the probe ran at
+  rate = (*tflops) * 1e12 / 2.0 / prop.multiProcessorCount / (mhz * 1e6);
   if (sm_mhz_under_probe) *sm_mhz_under_probe = mhz;
   if (dfma_per_sm_clk) *dfma_per_sm_clk = rate;
   return PDA_OK;

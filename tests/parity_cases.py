@@ -156,7 +156,7 @@ def full_rows_vs_sample_oracle(fam, prob, recon, n, bounds, sten, frac, t=0.0, o
     Jsub = Jf.data[idx]
     return dict(V=err_stats(Vf.reshape(-1, ndpc)[gids].ravel(), Vo), J=err_stats(Jsub, Jo), rows=int(gids.size),
                 near_bd_rows=int(full.numCellsNearBd()), nnz_checked=int(Jo.size), nnz_full=int(Jf.data.size), gpu_s=tg,
-                order=order)
+                order=order, Jsub=Jsub, Jo=Jo, smesh=smesh, Us=Us)
 
 
 def _ranges(starts, ends):

@@ -32,14 +32,30 @@ def test_cfg2_2048sq_velocity_vs_oracle():
     assert s["nan_mismatch"] == 0 and s["strict"] <= 1.0, s
 
 
-def test_cfg2_2048sq_jacobian_rows_vs_oracle():
-    """cfg 2: 869 M-entry Jacobian; 1 % random rows + all 24,540 near-boundary rows entry by entry.  The fast kernels'
-    WENO Jacobian entries are judged by the documented rule (rounding noise of the reference's own gradient formula);
-    here: strict first, else within 4x the tolerance on a smooth-region Riemann state (measured reference noise 1.3-2.4x,
-    profiles/jacobian_noise_r01.txt)."""
+def test_cfg2_2048sq_jacobian_rows_vs_oracle(tmp_path):
+    """cfg 2: 869 M-entry Jacobian; 1 % random rows + all 24,540 near-boundary rows, entry by entry against the oracle
+    on the sample mesh made of those cells.  Velocity: strict.  Jacobian of the default (fast) kernels: strict first;
+    the Riemann state carries shocks where the reference's own WENO-gradient formula is noise-limited, so where strict
+    fails the documented rule applies (tests/conftest.py::assert_jacobian_parity): the CUDA values must be at least as
+    close to the exact (80-bit) Jacobian as the reference's double-precision values are."""
+    from conftest import assert_jacobian_parity
+    from refdrv import exact_velocity_and_jacobian
     s = full_rows_vs_sample_oracle("euler2d", pda.Euler2d.Riemann, R.Weno5, [2048, 2048], [0, 1, 0, 1], 7, 0.01)
     assert s["V"]["strict"] <= 1.0, s["V"]
-    assert s["J"]["nan_mismatch"] == 0 and s["J"]["strict"] <= 4.0, s["J"]
+    assert s["J"]["nan_mismatch"] == 0
+
+    def exact():
+        s["smesh"].write(str(tmp_path))
+        return exact_velocity_and_jacobian(str(tmp_path), "euler2d", int(pda.Euler2d.Riemann), int(R.Weno5), 1, None, s["Us"], 0.0)[1]
+    assert_jacobian_parity(s["Jsub"], s["Jo"], exact)
+
+
+def test_cfg2_reference_order_jacobian_rows_1024sq():
+    """the reference-order mode on the same problem at 1024^2 (it needs the stored graph and read-modify-write, so a
+    quarter-size mesh): strict AND bit for bit on 1 % random rows + every near-boundary row"""
+    s = full_rows_vs_sample_oracle("euler2d", pda.Euler2d.Riemann, R.Weno5, [1024, 1024], [0, 1, 0, 1], 7, 0.01, order="reference")
+    assert s["V"]["strict"] <= 1.0 and s["V"]["bits"] == 0, s["V"]
+    assert s["J"]["strict"] <= 1.0 and s["J"]["bits"] == 0, {k: v for k, v in s["J"].items()}
 
 
 @pytest.mark.parametrize("fam,prob,recon,sten,bounds,per", [
@@ -64,8 +80,8 @@ def test_cfg4_dmr_sample_mesh_vs_oracle(recon, sten, t):
     full = pda.create_full_mesh(n, bounds, sten)
     Uf = perturb_inplace(make_problem(full, "euler2d", pda.Euler2d.DoubleMachReflection, recon).initialCondition())
     ref = sample_mesh_case("euler2d", pda.Euler2d.DoubleMachReflection, recon, n, bounds, sten, gids, t, "reference", Uf)
-    for k in ("V", "V2", "J"):
-        assert ref[k]["nan_mismatch"] == 0 and ref[k]["strict"] <= 1.0, (k, ref[k])
+    for k in ("V", "V2", "J"):   # strict, and in fact bit for bit (every entry, NaN positions included)
+        assert ref[k]["nan_mismatch"] == 0 and ref[k]["strict"] <= 1.0 and ref[k]["bits"] == 0, (k, ref[k])
     fast = sample_mesh_case("euler2d", pda.Euler2d.DoubleMachReflection, recon, n, bounds, sten, gids, t, "fast", Uf)
     for k in ("V", "V2"):
         assert fast[k]["nan_mismatch"] == 0 and (fast[k]["strict"] <= 1.0 or fast[k]["field"] <= 1.0), (k, fast[k])
