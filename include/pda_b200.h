@@ -103,6 +103,18 @@ pda_status pda_mesh_make_lattice(int dim, const int32_t n[3], const double bound
 /* native replacement of meshing_scripts/create_sample_mesh.py: sample cells = gids (any order, sorted internally)
  * of `full`; stencil mesh = sample cells + their stencil neighbours, renumbered by ascending full-mesh gid. */
 pda_status pda_mesh_make_sample(pda_mesh full, const int32_t* gids, int64_t ngids, pda_mesh* out);
+/* Shard `rank` of `nranks` of a full lattice cut into slabs along its slowest axis ("each GPU owns its slab of
+ * U, V and the corresponding row block of J; physical-boundary GPUs fill ghosts locally").  The result is an ordinary
+ * mesh in the sense of create_sample_mesh.py -- sample cells = the owned cells, stencil cells = owned planes plus
+ * (stencil-1)/2 HALO planes per side wherever a neighbouring rank (or the periodic image) owns them, none at a physical
+ * boundary -- numbered plane after plane: [lower halo | owned | upper halo].  Every problem family, boundary condition,
+ * the Jacobian (rows = owned dofs, LOCAL column ids) and applyJacobian work on it through the usual entry points; the
+ * caller keeps the halo planes of the state (and of an applyJacobian operand) current by exchanging them with the ring
+ * neighbours (pressiodemoapps.sharded: NCCL send/recv between processes, peer copies inside one process).
+ * Any lattice, periodic or not, any nranks with at least (stencil-1)/2 planes per rank.
+ * info = {plane_cells, k0, k1, halo_planes_below, halo_planes_above, rank, nranks, dim}. */
+pda_status pda_mesh_make_slab_window(pda_mesh full, int rank, int nranks, pda_mesh* out);
+pda_status pda_mesh_slab_window_info(pda_mesh m, int64_t info[8]);
 /* mesh from caller arrays (graph row-major [nSample][(stencil-1)*dim+1]) */
 pda_status pda_mesh_from_arrays(int dim, int stencil, int32_t nSample, int32_t nStencil, const double dxyz[3],
                                 const double* x, const double* y, const double* z, const int32_t* graph,

@@ -88,6 +88,24 @@ pda_status pda_mesh_make_sample(pda_mesh full, const int32_t* gids, int64_t ngid
   });
 }
 
+pda_status pda_mesh_make_slab_window(pda_mesh full, int rank, int nranks, pda_mesh* out) {
+  return guarded([&] {
+    if (!out) throw pda::Error(pda::kInvalid, "mesh_make_slab_window: null output");
+    *out = new pda_mesh_s{pda::Mesh::makeWindow(M(full), rank, nranks)};
+  });
+}
+
+pda_status pda_mesh_slab_window_info(pda_mesh m, int64_t info[8]) {
+  return guarded([&] {
+    if (!info) throw pda::Error(pda::kInvalid, "mesh_slab_window_info: null output");
+    const pda::Mesh& w = M(m);
+    if (!w.window) throw pda::Error(pda::kInvalid, "mesh_slab_window_info: not a slab window mesh");
+    info[0] = w.winPlaneCells; info[1] = w.winK0; info[2] = w.winK1; info[3] = w.winHLo; info[4] = w.winHHi;
+    info[5] = w.winRank; info[6] = w.winRanks;
+    info[7] = w.dim;
+  });
+}
+
 pda_status pda_mesh_from_arrays(int dim, int stencil, int32_t nSample, int32_t nStencil, const double dxyz[3],
                                 const double* x, const double* y, const double* z, const int32_t* graph,
                                 pda_mesh* out) {

@@ -12,7 +12,9 @@
 //          same cell-based code for the two cells on either side (identical bits to an interior face);
 //       y: face-based as before (the y neighbours live in other warps: sharing would need a second barrier);
 //   * the 8-instruction square root (cellmath.cuh) in the Rusanov flux: 3 x 5 instructions fewer per face;
-//   * ONE copy each of the cell reconstruction, the face reconstruction and the flux, driven by a phase loop.
+//   * ONE copy each of the cell reconstruction and the face reconstruction (two of the flux); inside a phase the five
+//     dofs form one straight-line block so that their dependency chains interleave (a first version that branched per
+//     dof ran at 58 % FP64-pipe utilisation against 73 %: profiles/ncu_velocity_r02.txt).
 // FP64 instructions per cell: z 5*57+104, x 5*57+104, y 5*76+104 = 1262 (+ edge warp 9 %) against 1485 (+ 9.5 %).
 #pragma once
 #include <cstdint>
@@ -54,7 +56,6 @@ k_euler3d_velocity_tiled2(double gamma, LatticeDesc L, Deltas dl, const double* 
   constexpr int oE = oFy0 + 2 * kFx;               // [TY][TX][N] carried right-edge value eR(k) of the z march
   constexpr int oBar = oE + N * TY * TX;           // mbarrier
   constexpr int slotStride = N * TY * TX;
-  enum { PH_Z = 0, PH_Y = 1, PH_X = 2, PH_YE = 3, PH_XEA = 4, PH_XEB = 5 };
 
   extern __shared__ __align__(16) double smem[];
   uint64_t* bar = reinterpret_cast<uint64_t*>(&smem[oBar + (oBar & 1)]);
@@ -179,67 +180,59 @@ k_euler3d_velocity_tiled2(double gamma, LatticeDesc L, Deltas dl, const double* 
       cpAsyncWaitAll();   // this thread's column cell of plane k+h (fetched one step ago) has landed
       if (k + 1 < k1) { int sl = slot0 + 2 * h - 1; if (sl >= R) sl -= R; fetchColumn(k + 1 + h, sl); }
     }
-    // phases: cell warps Z (every step), Y, X (real steps); edge warp YE, XEA, XEB (real steps)
-    const int pBegin = edgeWarp ? PH_YE : PH_Z;
-    const int pEnd = edgeWarp ? (ghost ? PH_YE : PH_XEB + 1) : (ghost ? PH_Y : PH_X + 1);
+    // Two CELL-based phases, then one FACE-based phase; inside a phase the five dofs are one straight-line block (the
+    // compiler interleaves their dependency chains), control flow only between phases:
+    //   cell warps: Z (every step), X, then Y;   edge warp: the two cells of its tile-boundary x face (XEA, XEB), then YE
     double v[N], dFx[N], uN[N], uP[N];
+    const int nCellPhases = edgeWarp ? (ghost ? 0 : 2) : (ghost ? 1 : 2);
 #pragma unroll 1
-    for (int ph = pBegin; ph < pEnd; ++ph) {
-      if (ph == PH_Y || ph == PH_YE) {   // plane k (issued one z-face computation ago) must have landed
+    for (int it = 0; it < nCellPhases; ++it) {
+      const bool phZ = !edgeWarp && it == 0;
+      if (!phZ && (edgeWarp ? it == 0 : it == 1)) {   // first phase of the step that reads the plane tile
         if (useTma) { mbarWait(bar, parity); parity ^= 1u; }
         else { cpAsyncWaitAll(); __syncthreads(); }
       }
-      const bool cellKind = (ph == PH_Z || ph == PH_X || ph == PH_XEA || ph == PH_XEB);
       int offs[NQ];
-      if (ph == PH_Z) {
+      if (phZ) {
         int sl = slot0;
 #pragma unroll
         for (int o = 0; o < 2 * h - 1; ++o) { offs[o] = zMine + sl * slotStride; sl = (sl + 1 == R) ? 0 : sl + 1; }
-      } else if (ph == PH_Y || ph == PH_YE) {
-        const int row0 = (ph == PH_Y) ? ty : TY;
-#pragma unroll
-        for (int o = 0; o < 2 * h; ++o) offs[o] = oP + ((row0 + o) * PX + (tx + HX)) * N;
       } else {
         // cell whose edge values are wanted, in tile columns: own cell (X); left / right cell of the boundary face (XEA / XEB)
-        const int row = (ph == PH_X) ? (ty + h) : (eRow + h);
-        const int cc = (ph == PH_X) ? tx : ((eSide ? TX - 1 : -1) + (ph == PH_XEB ? 1 : 0));
+        const int row = edgeWarp ? (eRow + h) : (ty + h);
+        const int cc = edgeWarp ? ((eSide ? TX - 1 : -1) + it) : tx;
 #pragma unroll
         for (int o = 0; o < 2 * h - 1; ++o) offs[o] = oP + (row * PX + (cc + HX - hc + o)) * N;
       }
+      double eL[N], eR[N];
 #pragma unroll
       for (int d = 0; d < N; ++d) {
-        double q[NQ], x0v, x1v;
-        if (cellKind) {
+        double q[NQ];
 #pragma unroll
-          for (int o = 0; o < 2 * h - 1; ++o) q[o] = smem[offs[o] + d];
-          cellEdgesFast<S>(q, x0v, x1v);      // (eL, eR)
-        } else {
-#pragma unroll
-          for (int o = 0; o < 2 * h; ++o) q[o] = smem[offs[o] + d];
-          reconFaceFast<S>(q, x0v, x1v);      // (uNeg, uPos)
-        }
-        if (ph == PH_Z) {                     // face k+1/2 = (eR(k) carried, eL(k+1)); carry eR(k+1)
-          uP[d] = x0v; uN[d] = smem[eMine + d]; smem[eMine + d] = x1v;
-        } else if (ph == PH_X) {              // left face of my cell = (eR of lane-1, my eL)
-          uP[d] = x0v; uN[d] = __shfl_up_sync(0xffffffffu, x1v, 1);
-        } else if (ph == PH_XEA) {
-          uN[d] = x1v;
-        } else if (ph == PH_XEB) {
-          uP[d] = x0v;
-        } else {
-          uN[d] = x0v; uP[d] = x1v;
-        }
+        for (int o = 0; o < 2 * h - 1; ++o) q[o] = smem[offs[o] + d];
+        cellEdgesFast<S>(q, eL[d], eR[d]);
       }
-      if (ph == PH_XEA || (ph == PH_Z && ghostA)) continue;   // no face yet
+      if (phZ) {                    // face k+1/2 = (eR(k) carried, eL(k+1)); carry eR(k+1)
+#pragma unroll
+        for (int d = 0; d < N; ++d) { uP[d] = eL[d]; uN[d] = smem[eMine + d]; smem[eMine + d] = eR[d]; }
+        if (ghostA) continue;       // no face yet
+      } else if (!edgeWarp) {       // X: left face of my cell = (eR of lane-1, my eL)
+#pragma unroll
+        for (int d = 0; d < N; ++d) { uP[d] = eL[d]; uN[d] = __shfl_up_sync(0xffffffffu, eR[d], 1); }
+      } else if (it == 0) {         // XEA: left cell of the boundary face
+#pragma unroll
+        for (int d = 0; d < N; ++d) uN[d] = eR[d];
+        continue;
+      } else {                      // XEB: right cell
+#pragma unroll
+        for (int d = 0; d < N; ++d) uP[d] = eL[d];
+      }
       double F[N];
-      eulerFlux3dFast8(gamma, (ph == PH_Z) ? 2 : ((ph == PH_Y || ph == PH_YE) ? 1 : 0), uN, uP, F);
-      if (ph == PH_Z) {
+      eulerFlux3dFast8(gamma, phZ ? 2 : 0, uN, uP, F);
+      if (phZ) {
 #pragma unroll
         for (int d = 0; d < N; ++d) { v[d] = dl.hInv[2] * (Fz[d] - F[d]); Fz[d] = F[d]; }   // z term, added last
-      } else if (ph == PH_Y) {
-#pragma unroll
-        for (int d = 0; d < N; ++d) smem[oFy + (ty * TX + tx) * N + d] = F[d];
-      } else if (ph == PH_X) {
+      } else if (!edgeWarp) {
         // FxL - FxR: lane 0's own left flux is meaningless (no lane -1) and lane 31 has no lane +1: both tile-boundary
         // fluxes come from the edge warp after the barrier (x + 0 is exact until then)
 #pragma unroll
@@ -247,13 +240,27 @@ k_euler3d_velocity_tiled2(double gamma, LatticeDesc L, Deltas dl, const double* 
           const double r = __shfl_down_sync(0xffffffffu, F[d], 1);
           dFx[d] = ((tx == 0) ? 0.0 : F[d]) - ((tx == TX - 1) ? 0.0 : r);
         }
-      } else if (ph == PH_YE) {
-#pragma unroll
-        for (int d = 0; d < N; ++d) smem[oFy + (TY * TX + tx) * N + d] = F[d];
       } else if (tx < 2 * TY) {
 #pragma unroll
         for (int d = 0; d < N; ++d) smem[oXe + (eRow * 2 + eSide) * N + d] = F[d];
       }
+    }
+    if (!ghost) {   // FACE-based phase: y back face of my cell (cell warps) / y faces of row TY (edge warp)
+      const int row0 = edgeWarp ? TY : ty;
+      int offs[NQ];
+#pragma unroll
+      for (int o = 0; o < 2 * h; ++o) offs[o] = oP + ((row0 + o) * PX + (tx + HX)) * N;
+#pragma unroll
+      for (int d = 0; d < N; ++d) {
+        double q[NQ];
+#pragma unroll
+        for (int o = 0; o < 2 * h; ++o) q[o] = smem[offs[o] + d];
+        reconFaceFast<S>(q, uN[d], uP[d]);
+      }
+      double F[N];
+      eulerFlux3dFast8(gamma, 1, uN, uP, F);
+#pragma unroll
+      for (int d = 0; d < N; ++d) smem[oFy + (row0 * TX + tx) * N + d] = F[d];
     }
     slot0 = (slot0 + 1 == R) ? 0 : slot0 + 1;
     if (ghost) continue;   // ghost steps: only the carried edge value / the bottom flux of the first plane

@@ -427,6 +427,87 @@ Mesh Mesh::makeSample(Mesh& full, const int32_t* gidsIn, int64_t ngids) {
   return m;
 }
 
+Mesh Mesh::makeWindow(Mesh& full, int rank, int nranks) {
+  if (!full.lattice || full.nSample != full.nStencil) throw Error(kInvalid, "slab window: source must be a full lattice");
+  if (nranks < 1 || rank < 0 || rank >= nranks) throw Error(kInvalid, "slab window: invalid rank / nranks");
+  const int dim = full.dim, ax = dim - 1;
+  const int32_t nk = full.n[ax];
+  const int h = full.halo();
+  const int32_t k0 = (int32_t)((int64_t)nk * rank / nranks), k1 = (int32_t)((int64_t)nk * (rank + 1) / nranks);
+  if (k1 - k0 < h) throw Error(kInvalid, "slab window: fewer planes per rank than the stencil halo");
+  const bool per = full.periodic[ax];
+  int64_t planeCells = 1;
+  for (int a = 0; a < ax; ++a) planeCells *= full.n[a];
+  // halo planes exist where a neighbour owns them: every side of a periodic axis cut into > 1 slabs, interior sides otherwise
+  const int hLo = (nranks == 1) ? 0 : ((per || rank > 0) ? h : 0);
+  const int hHi = (nranks == 1) ? 0 : ((per || rank < nranks - 1) ? h : 0);
+  const int32_t nOwned = k1 - k0, nLocalPlanes = hLo + nOwned + hHi;
+  if ((int64_t)nLocalPlanes * planeCells > INT32_MAX) throw Error(kTooLarge, "slab window: too many local cells for int32 ids");
+  // local plane of global plane p (p may be the periodic image of a plane outside [0,nk))
+  auto localPlane = [&](int32_t p) -> int32_t {
+    for (int s : {0, -1, 1}) {
+      const int64_t q = (int64_t)p + (int64_t)s * nk;
+      if (!per && s != 0) continue;
+      if (q >= (int64_t)k0 - hLo && q < (int64_t)k1 + hHi) return (int32_t)(q - (k0 - hLo));
+    }
+    return -1;
+  };
+  Mesh m;
+  m.dim = dim; m.stencil = full.stencil;
+  m.nSample = (int32_t)(nOwned * planeCells);
+  m.nStencil = (int32_t)(nLocalPlanes * planeCells);
+  for (int a = 0; a < 3; ++a) { m.d[a] = full.d[a]; m.dInv[a] = full.dInv[a]; }
+  std::memcpy(m.bounds, full.bounds, sizeof m.bounds);
+  m.hasBounds = full.hasBounds;
+  m.isSample = true;
+  m.window = true;
+  m.winK0 = k0; m.winK1 = k1; m.winHLo = hLo; m.winHHi = hHi; m.winRank = rank; m.winRanks = nranks;
+  m.winPlaneCells = planeCells;
+  const int nc = full.ncols();
+  m.graph.resize((size_t)m.nSample * nc);
+#pragma omp parallel for schedule(static)
+  for (int32_t r = 0; r < m.nSample; ++r) {
+    const int32_t gid = (int32_t)((int64_t)k0 * planeCells + r);
+    int32_t row[32];
+    full.latticeRow(gid, row);
+    int32_t* out = &m.graph[(size_t)r * nc];
+    for (int c = 0; c < nc; ++c) {
+      if (row[c] < 0) { out[c] = -1; continue; }
+      const int32_t pg = (int32_t)(row[c] / planeCells);
+      int32_t lp;
+      if (c == 0) lp = hLo + (int32_t)(r / planeCells);
+      else {
+        // the neighbour's plane as the stencil reaches it: own plane + offset, before any periodic wrap
+        const int32_t own = k0 + (int32_t)(r / planeCells);
+        int32_t off = pg - own;
+        if (per) { if (off > nk / 2) off -= nk; else if (off < -(nk / 2)) off += nk; }
+        lp = localPlane(own + off);
+        if (lp < 0 && nranks == 1 && per) lp = ((own + off) % nk + nk) % nk;   // single slab: the wrap stays inside
+      }
+      if (lp < 0) throw Error(kInvalid, "slab window: a stencil neighbour falls outside the window");
+      out[c] = (int32_t)((int64_t)lp * planeCells + row[c] % planeCells);
+    }
+  }
+  m.haveGraph = true;
+  m.x.resize(m.nStencil); m.y.resize(m.nStencil); m.z.resize(m.nStencil);
+  m.stencilGids.resize(m.nStencil);
+  const int32_t nx = full.n[0], ny = full.n[1];
+#pragma omp parallel for schedule(static)
+  for (int32_t s = 0; s < m.nStencil; ++s) {
+    const int32_t lp = (int32_t)(s / planeCells);
+    int32_t gp = k0 - hLo + lp;                        // global plane (wrapped into the domain)
+    if (per) gp = ((gp % nk) + nk) % nk;
+    const int32_t g = (int32_t)((int64_t)gp * planeCells + s % planeCells);
+    m.stencilGids[s] = g;
+    m.x[s] = full.latticeCoord(0, g % nx);
+    m.y[s] = (dim >= 2) ? full.latticeCoord(1, (g / nx) % ny) : 0.0;
+    m.z[s] = (dim >= 3) ? full.latticeCoord(2, g / (nx * ny)) : 0.0;
+  }
+  m.haveCoords = true;
+  m.classifyFromGraph();
+  return m;
+}
+
 // --------------------------------------------------------------------------------------------------- writer
 void Mesh::write(const std::string& dir) {
   ensureGraph();

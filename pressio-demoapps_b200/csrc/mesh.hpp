@@ -30,6 +30,13 @@ struct Mesh {
   bool isSample = false;
   bool fullyPeriodic = false;
 
+  // slab window of a full lattice (multi-GPU shard, makeWindow): the rank owns planes [winK0, winK1) of the slowest axis;
+  // local cells = [winHLo halo planes | owned planes | winHHi halo planes], plane after plane, local id = local plane *
+  // planeCells + position in the plane.  Rows (sample cells) = the owned cells in that order.
+  bool window = false;
+  int32_t winK0 = 0, winK1 = 0, winHLo = 0, winHHi = 0, winRank = 0, winRanks = 1;
+  int64_t winPlaneCells = 0;
+
   // materialised arrays (always present for loaded / sample meshes, lazily built for lattices)
   std::vector<double> x, y, z;                 // [nStencil]
   std::vector<int32_t> graph;                  // [nSample][ncols()]
@@ -64,6 +71,10 @@ struct Mesh {
   static Mesh makeLattice(int dim, const int32_t n[3], const double bounds[6], const int32_t periodic[3], int stencil);
   static Mesh load(const std::string& dir);
   static Mesh makeSample(Mesh& full, const int32_t* gids, int64_t ngids);
+  // shard `rank` of `nranks` of a full lattice cut into slabs along its slowest axis: a sample-mesh-like mesh whose
+  // stencil cells are the owned planes plus (stencil-1)/2 halo planes per side where a neighbour rank (or the periodic
+  // image) exists -- none at a physical boundary, where the usual near-boundary rows / ghost cells take over
+  static Mesh makeWindow(Mesh& full, int rank, int nranks);
   static Mesh fromArrays(int dim, int stencil, int32_t nSample, int32_t nStencil, const double dxyz[3],
                          const double* x, const double* y, const double* z, const int32_t* graph);
   void write(const std::string& dir);

@@ -19,6 +19,7 @@ from enum import IntEnum as _IntEnum
 
 __all__ = [
     "CellCenteredUniformMesh", "load_cellcentered_uniform_mesh", "create_full_mesh", "create_sample_mesh", "mesh_from_arrays",
+    "create_slab_window_mesh",
     "InviscidFluxReconstruction", "InviscidFluxScheme", "ViscousFluxReconstruction", "ViscousFluxScheme",
     "Euler1d", "Euler2d", "Euler3d", "Swe2d", "DiffusionReaction1d", "DiffusionReaction2d", "AdvectionDiffusion2d",
     "AdvectionDiffusionReaction2d", "Advection1d",
@@ -77,6 +78,8 @@ _sig("pda_test_glibc_pow", _C.c_int, _C.c_int, _vp, _dbl, _vp, _i64)
 _sig("pda_mesh_load", _C.c_int, _cp, _C.POINTER(_vp))
 _sig("pda_mesh_make_lattice", _C.c_int, _C.c_int, _vp, _vp, _vp, _C.c_int, _C.POINTER(_vp))
 _sig("pda_mesh_make_sample", _C.c_int, _vp, _vp, _i64, _C.POINTER(_vp))
+_sig("pda_mesh_make_slab_window", _C.c_int, _vp, _C.c_int, _C.c_int, _C.POINTER(_vp))
+_sig("pda_mesh_slab_window_info", _C.c_int, _vp, _vp)
 _sig("pda_mesh_from_arrays", _C.c_int, _C.c_int, _C.c_int, _i32, _i32, _vp, _vp, _vp, _vp, _vp, _C.POINTER(_vp))
 _sig("pda_mesh_write", _C.c_int, _vp, _cp)
 _sig("pda_mesh_free", _C.c_int, _vp)
@@ -375,6 +378,20 @@ def mesh_from_arrays(dim, stencilSize, dxyz, x, y, z, graph, detect_lattice=Fals
     _check(_lib.pda_mesh_from_arrays(int(dim), int(stencilSize), g.shape[0], x.size, d.ctypes.data, x.ctypes.data,
                                      y.ctypes.data, z.ctypes.data, g.ctypes.data, _C.byref(h)))
     return CellCenteredUniformMesh(_handle=h)
+
+
+def create_slab_window_mesh(fullMesh, rank, nranks):
+    """Shard `rank` of `nranks` of a full lattice cut into slabs along its slowest axis (pda_mesh_make_slab_window):
+    sample cells = owned cells, stencil cells = [lower halo planes | owned planes | upper halo planes].  See
+    pressiodemoapps.sharded for the halo exchange and the sharded evaluation helpers."""
+    h = _vp()
+    _check(_lib.pda_mesh_make_slab_window(fullMesh._h, int(rank), int(nranks), _C.byref(h)))
+    m = CellCenteredUniformMesh(_handle=h)
+    info = (_C.c_int64 * 8)()
+    _check(_lib.pda_mesh_slab_window_info(m._h, info))
+    m.window = dict(plane_cells=int(info[0]), k0=int(info[1]), k1=int(info[2]), halo_lo=int(info[3]), halo_hi=int(info[4]),
+                    rank=int(info[5]), nranks=int(info[6]), dim=int(info[7]))
+    return m
 
 
 def create_sample_mesh(fullMesh, sampleMeshGids):
