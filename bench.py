@@ -65,11 +65,14 @@ class StdoutToStderr:
 def load_traffic(kernel_key):
     """DRAM bytes per launch (dram__bytes_read.sum + dram__bytes_write.sum) of the dominant kernels from the committed
     `ncu --set full` captures (profiles/ncu_traffic_r01.json, written by tools/ncu_summary.py --traffic)"""
-    p = os.path.join(ROOT, "profiles", "ncu_traffic_r01.json")
-    if not os.path.exists(p):
-        return None
-    with open(p) as f:
-        return json.load(f).get(kernel_key)
+    for name in ("ncu_traffic_r02.json", "ncu_traffic_r01.json"):
+        p = os.path.join(ROOT, "profiles", name)
+        if os.path.exists(p):
+            with open(p) as f:
+                v = json.load(f).get(kernel_key)
+            if v is not None:
+                return v
+    return None
 
 
 def load_peaks():
@@ -569,6 +572,7 @@ def run_b200_arm(args, out):
         sm_max = (clocks or {}).get("sm_max_mhz") or 1965.0
         nominal_tf = n_sm * FP64_FMA_PER_SM_CLK * 2 * sm_max * 1e6 * 1e-12
         cfg = make_config(n, world)
+        kname = "k_euler3d_velocity_tiled<7,7>" if os.environ.get("PDA_TILED_V2", "1")[:1] == "0" else "k_euler3d_velocity_tiled2<7,7>"
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
                 "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
                 "dtype": "f64", "data": "synthetic", "config": cfg,
@@ -592,9 +596,9 @@ def run_b200_arm(args, out):
                              "peak_source": "nominal: %d SMs x %d DFMA lanes/clk x 2 flop x %.0f MHz (sm_max during the run)"
                                             % (n_sm, FP64_FMA_PER_SM_CLK, sm_max),
                              "flops_per_cell": FLOPS_PER_CELL, "algorithmic_flops": kernel_cells * FLOPS_PER_CELL,
-                             "kernel": "k_euler3d_velocity_tiled<7,7>", "kernel_ms": k_ms,
-                             "traffic": (load_traffic("k_euler3d_velocity_tiled<7,7>@512^3") if (world == 1 and n == 512) else None),
-                             "traffic_unit": "DRAM bytes per launch (ncu --set full, profiles/ncu_traffic_r01.json)",
+                             "kernel": kname, "kernel_ms": k_ms,
+                             "traffic": (load_traffic(kname + "@512^3") if (world == 1 and n == 512) else None),
+                             "traffic_unit": "DRAM bytes per launch (ncu --set full, profiles/ncu_traffic_r02.json)",
                              "probe": {"achieved_frac": ach_tf / fp64_peak if fp64_peak else None, "peak": fp64_peak,
                                        "unit": "TFLOP/s", "sm_mhz_under_probe": probe_mhz, "dfma_per_sm_clk": probe_rate,
                                        "nominal_dfma_per_sm_clk": FP64_FMA_PER_SM_CLK,

@@ -159,6 +159,7 @@ struct DeviceState {
   cudaStream_t stream = nullptr;
   DeviceRowSet inner, nearBd;
   bool innerViaLattice = false;
+  bool windowLattice = false;   // slab window (Mesh::makeWindow): inner rows through the structured kernels on the local lattice
   // ghosts
   DevBuf<double> ghost[6];
   DevBuf<dev::GhostRecipe> recipes;
@@ -857,6 +858,11 @@ void Problem::ensureDevice() {
   ds->hS = (S_ - 1) / 2;
   ds->nsides = (dim_ == 1) ? 3 : 2 * dim_;
   dev_ = std::move(ds);
+  // slab window: velocity (2D / 3D) and the 2D Jacobian of the inner rows run the structured kernels on the window's
+  // local lattice; everything else (near-boundary rows, other families, reference-order mode) stays graph-driven
+  dev_->windowLattice = m.window && dim_ >= 2 && m.n[0] >= 2 * m.halo() && m.n[1] >= 2 * m.halo() &&
+                        (dim_ == 2 || m.n[2] >= 2 * m.halo()) &&
+                        (family_ == F_EULER2D || family_ == F_EULER3D || family_ == F_SWE2D || family_ == F_ADVDIFF2D);
   if (!dev_->innerViaLattice) ensureInnerRows();
 }
 
@@ -1328,9 +1334,45 @@ void Problem::evaluateDev(const double* dU, double t, double* dV, double* dJ, vo
           ++launches_;
         }
       }
+      const int64_t winShift = m.window ? (int64_t)m.winHLo * m.winPlaneCells * ndpc_ : 0;   // V rows = owned cells only
       if (ds.innerViaLattice && !dJ) {
         launchLatticeVelocity<Phys, S>(phys, m, dl, dU, dV, st, 0, m.n[dim_ - 1], 0);
         ++launches_;
+      } else if (ds.windowLattice && !dJ) {
+        if constexpr (Phys::dim >= 2 && !std::is_same<Phys, dev::LinAdv<2>>::value) {
+          launchLatticeVelocity<Phys, S>(phys, m, dl, dU, dV - winShift, st, 0, m.n[dim_ - 1], 0);
+          ++launches_;
+        }
+      } else if (ds.windowLattice && dJ && dim_ == 2 && !mergedNeighbors_ && !skipInnerJacobian_) {
+        if constexpr (Phys::dim == 2 && !std::is_same<Phys, dev::LinAdv<2>>::value) {
+          using JL = dev::JacLat2d<Phys, S>;
+          auto kern = dev::k_jacobian_lattice2d<Phys, S>;
+          ensureFuncAttrs(kern, (int)JL::smemBytes);
+          if (!ds.latJacReady) {   // tables indexed by LOCAL cell id
+            std::vector<int32_t> base((size_t)m.nStencil, 0);
+            std::vector<uint4> padded((size_t)m.nStencil, make_uint4(0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu));
+            if (slotCols_ > 16) throw Error(kUnsupported, "lattice Jacobian: slot table wider than 16 columns");
+            const size_t off = (size_t)m.winHLo * (size_t)m.winPlaneCells;
+            for (size_t r = 0; r < cellBase_.size(); ++r) {
+              base[off + r] = cellBase_[r];
+              std::memcpy(&padded[off + r], &slots_[r * slotCols_], (size_t)slotCols_);
+            }
+            ds.latBase.upload(base);
+            ds.latSlots.upload(padded);
+            ds.latJacReady = true;
+          }
+          dev::LatticeDesc L;
+          for (int a = 0; a < 3; ++a) { L.n[a] = m.n[a]; L.per[a] = m.periodic[a] ? 1 : 0; }
+          L.planeBegin = 0; L.planeEnd = m.n[1]; L.haloPlanes = 0; L.slab = 0; L.meshHalo = m.halo();
+          L.haloLo = L.haloHi = nullptr; L.flagLo = L.flagHi = nullptr; L.epoch = 0;
+          const int w0 = L.per[0] ? m.n[0] : m.n[0] - 2 * m.halo(), w1 = m.n[1] - 2 * m.halo();
+          if (w0 > 0 && w1 > 0) {
+            dev::JacLatTables jt{ds.latBase.p, ds.latSlots.p, ndpc_ * (1 + dim_ * (S - 1))};
+            dim3 grid((unsigned)((w0 + JL::T - 1) / JL::T), (unsigned)((w1 + JL::T - 1) / JL::T));
+            kern<<<grid, JL::THREADS, JL::smemBytes, st>>>(phys, L, dl, jt, dU, dV ? dV - winShift : nullptr, dJ);
+            ++launches_;
+          }
+        }
       } else if (jacLattice && !mergedNeighbors_) {
         if constexpr (Phys::dim == 2) {
           using JL = dev::JacLat2d<Phys, S>;

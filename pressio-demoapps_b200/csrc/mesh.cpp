@@ -463,6 +463,10 @@ Mesh Mesh::makeWindow(Mesh& full, int rank, int nranks) {
   m.window = true;
   m.winK0 = k0; m.winK1 = k1; m.winHLo = hLo; m.winHHi = hHi; m.winRank = rank; m.winRanks = nranks;
   m.winPlaneCells = planeCells;
+  // the local cells form a lattice themselves: nLocalPlanes planes, NOT periodic along the slab axis, whose "near the
+  // boundary" planes at an artificial edge are exactly the halo planes (not owned, never evaluated).  The structured
+  // kernels run on this descriptor (engine.cu, window fast path); m.lattice stays false: rows != cells here.
+  for (int a = 0; a < 3; ++a) { m.n[a] = (a < ax) ? full.n[a] : (a == ax ? nLocalPlanes : 1); m.periodic[a] = (a < ax) ? full.periodic[a] : false; }
   const int nc = full.ncols();
   m.graph.resize((size_t)m.nSample * nc);
 #pragma omp parallel for schedule(static)
