@@ -307,7 +307,7 @@ void launchLattice3dTiled2(const Phys& phys, const dev::LatticeDesc& L, const de
   if (planes <= 0) return;
   const int gx = (L.n[0] + 31) / 32, gy = (L.n[1] + TY - 1) / TY;
   // z chunks: long enough to amortise the two ghost steps, short enough to fill 148 SMs x 2 CTAs with >= 4 waves
-  static const int lzStart = [] { const char* e = std::getenv("PDA_TILED_LZ"); const int v = e ? std::atoi(e) : 0; return v >= 8 ? v : 128; }();
+  static const int lzStart = [] { const char* e = std::getenv("PDA_TILED_LZ"); const int v = e ? std::atoi(e) : 0; return v >= 8 ? v : 64; }();
   int LZ = lzStart;
   while (LZ > 8 && (int64_t)gx * gy * ((planes + LZ - 1) / LZ) < 148 * 2 * 4) LZ /= 2;
   if (L.slab == 2) while (LZ > 8 && (planes + LZ - 1) / LZ < 2) LZ /= 2;   // peer mode: no CTA needs both halos

@@ -30,6 +30,8 @@ __all__ = [
     "FacePosition", "GradientEvaluator",
 ]
 
+__version__ = "0.16.0"   # the reference release this module mirrors (/root/reference/version.txt)
+
 _HERE = _os.path.dirname(_os.path.abspath(__file__))
 _LIBPATH = _os.path.join(_os.path.dirname(_HERE), "lib", "libpda_b200.so")
 

@@ -689,3 +689,29 @@ def test_cpp_eigen_shim_on_device(tmp_path):
     assert r.returncode == 0, r.stdout + r.stderr
     assert "cpp_shim_demo ok" in r.stdout and "custom BC functors vs device rules: |dV|max 0.0e+00 |dJ|max 0.0e+00" in r.stdout
     assert "left-wall faces 20" in r.stdout
+
+
+def test_two_devices_in_one_process():
+    """kernel attributes (dynamic shared memory > 48 KB) are per DEVICE: a second problem on another GPU of the same
+    process must get its own set-up (func_attrs.hpp).  Needs two GPUs; identical results on both."""
+    if pda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    mesh3 = pda.create_full_mesh([40, 21, 16], [-1, 1, -1, 1, -1, 1], 7, ("x", "y", "z"))
+    mesh2 = pda.create_full_mesh([64, 48], [0, 1, 0, 1], 7)
+    out = []
+    for dev in (0, 1):
+        p3 = pda.create_problem(mesh3, pda.Euler3d.PeriodicSmooth, R.Weno5, device=dev)
+        U3 = perturbed(p3)
+        V3 = p3.createRightHandSide()
+        p3.rightHandSide(U3, 0.0, V3)                      # tiled 3D kernel: ~105 KB dynamic shared memory
+        p2 = pda.create_problem(mesh2, pda.Euler2d.Riemann, R.Weno5, device=dev)
+        U2 = perturbed(p2)
+        J = p2.createJacobian()
+        V2 = p2.createRightHandSide()
+        p2.rightHandSideAndJacobian(U2, 0.0, V2, J)        # lattice Jacobian kernel: > 48 KB too
+        B = np.random.default_rng(2).uniform(-1, 1, (U2.size, 3))
+        Rm = p2.createApplyJacobianResult(B)
+        p2.applyJacobian(U2, B, 0.0, Rm)
+        out.append((V3, V2, J.data.copy(), Rm))
+    for a, b in zip(out[0], out[1]):
+        assert np.array_equal(a, b)

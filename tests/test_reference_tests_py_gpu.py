@@ -1,0 +1,34 @@
+"""The reference's own Python regression tests, UNMODIFIED: every /root/reference/tests_py/**/test_*.py (staged under
+oracle/_ref/tests_py by __graft_entry__.build(), see there) is executed by pytest in a subprocess whose PYTHONPATH puts
+this repo's `pressiodemoapps` module first -- the same `import pressiodemoapps as pda` the scripts were written for now
+resolves to the B200 engine (ctypes -> C-ABI -> CUDA kernels).  They load the reference's committed text meshes, run
+its RK4 / SSPRK3 loops around rightHandSide (one applyJacobian too) and compare with its gold files at its tolerances."""
+import glob
+import os
+import subprocess
+import sys
+
+import pytest
+
+from conftest import ROOT
+
+pytestmark = pytest.mark.gpu
+STAGED = os.path.join(ROOT, "oracle", "_ref", "tests_py")
+SCRIPTS = sorted(os.path.relpath(p, STAGED) for p in glob.glob(os.path.join(STAGED, "**", "test_*.py"), recursive=True))
+
+
+@pytest.mark.skipif(not SCRIPTS, reason="oracle/_ref/tests_py not staged (build() copies it where /root/reference exists)")
+@pytest.mark.parametrize("script", SCRIPTS or ["none"])
+def test_reference_python_test_runs_unmodified(script):
+    path = os.path.join(STAGED, script)
+    env = dict(os.environ)
+    env["PYTHONPATH"] = os.path.join(ROOT, "pressio-demoapps_b200") + os.pathsep + env.get("PYTHONPATH", "")
+    r = subprocess.run([sys.executable, "-m", "pytest", "-q", "-x", "-p", "no:cacheprovider", "--rootdir", os.path.dirname(path), path],
+                       cwd=os.path.dirname(path), env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=900)
+    assert r.returncode == 0, r.stdout[-4000:]
+
+
+def test_all_reference_scripts_are_covered():
+    if not SCRIPTS:
+        pytest.skip("oracle/_ref/tests_py not staged")
+    assert len(SCRIPTS) == 23
