@@ -555,16 +555,19 @@ def run_b200_arm(args, out):
     ach_tf = kernel_cells * FLOPS_PER_CELL / (k_ms * 1e-3) * 1e-12
 
     # ---- end to end through the host-pointer C-ABI call (pinned host buffers, copies inside the timed region)
-    for _ in range(min(W, 2)):
-        e2e_step()
-    barrier()
-    t0 = time.perf_counter()
-    for _ in range(K):
-        e2e_step()
-    barrier()
-    e2e_s = max_over_ranks(time.perf_counter() - t0) / K
-    e2e = {"value": ncells / e2e_s, "unit": UNIT, "h2d_bytes_per_step": int(hU.numel() * 8 * world),
-           "d2h_bytes_per_step": int(hV.numel() * 8 * world), "ms_per_step": e2e_s * 1e3,
+    if args.no_e2e:
+        e2e_s = float("nan")
+    else:
+        for _ in range(min(W, 2)):
+            e2e_step()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(K):
+            e2e_step()
+        barrier()
+        e2e_s = max_over_ranks(time.perf_counter() - t0) / K
+    e2e = {"value": None if args.no_e2e else ncells / e2e_s, "unit": UNIT, "h2d_bytes_per_step": int(hU.numel() * 8 * world),
+           "d2h_bytes_per_step": int(hV.numel() * 8 * world), "ms_per_step": None if args.no_e2e else e2e_s * 1e3,
            "api": "pda_problem_velocity_host" if world == 1 else
            ("pda_slab_velocity_peer_host" if args.halo == "peer" else "slab: H2D + halo exchange + pda_slab_velocity_*_dev + D2H")}
 
@@ -727,6 +730,7 @@ def main():
                     help="N>1 halo exchange: peer-memory pushes fused with the kernel (default) or NCCL send/recv")
     ap.add_argument("--no-numa-bind", action="store_true", help="do not pin the process to its GPU's NUMA node")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true", help="skip the host-pointer end-to-end leg (tuning sessions only)")
     ap.add_argument("--no-jacobian", action="store_true")
     ap.add_argument("--no-configs", action="store_true", help="skip the cfg 1-4 legs (tools/bench_configs.py)")
     args = ap.parse_args()
