@@ -39,3 +39,16 @@ for scheme in ("firstorder", "weno3", "weno5"):
             REF, "eigen_2d_euler_riemann_explicit_with_gradients", scheme, "grad_gold_%s.txt" % which))
 np.savez_compressed(os.path.join(HERE, "refgold", "gradients_riemann2d.npz"), **gout)
 print("wrote %d gradient gold tables" % len(gout))
+
+# the IMPLICIT-run tests (tests_cpp/*_implicit), tests/refgold_implicit.py
+from refgold_implicit import CASES as ICASES, gold_key as igold_key   # noqa: E402
+iout = {}
+for name, c in ICASES.items():
+    for scheme in c["schemes"]:
+        for check, fname in c["checks"].items():
+            if check == "rho_linf":
+                continue
+            path = os.path.join(REF, c["ref_dir"], fname) if c["subdirs"] is False else os.path.join(REF, c["ref_dir"], scheme, fname)
+            iout[igold_key(name, scheme, check)] = np.loadtxt(path)
+np.savez_compressed(os.path.join(HERE, "refgold", "refgold_implicit.npz"), **iout)
+print("wrote %d implicit gold vectors, %d values" % (len(iout), sum(v.size for v in iout.values())))
