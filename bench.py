@@ -332,6 +332,41 @@ def ref_jacobian_leg(n2_cpu=512, target_s=6.0):
         shutil.rmtree(d, ignore_errors=True)
 
 
+def run_cpu_legs(args, out):
+    """--impl cpu-legs (internal): the CPU baselines of the GPU arm, in their OWN process.  OMP_PROC_BIND=true makes
+    libgomp pin the initial thread to the first place when the library loads; set in the GPU process (round 2, first
+    sessions) it left the main thread of EVERY rank on core 0 -- eight launching threads on one core: the N = 8 step went
+    from 2.13 to 3.24 ms with an unchanged 2.15 ms kernel.  The GPU process therefore never sets it."""
+    bind_openmp()
+    res = {}
+    try:
+        res["cpu_baseline"] = cpu_leg(args.n, target_s=12.0)
+    except Exception as e:
+        res["cpu_baseline"] = {"unavailable": str(e)}
+    try:
+        res["cpu_reference_weno3"] = ref_weno3_leg(64, 5.0)
+    except Exception as e:   # the compiled reference is optional on the GPU box
+        res["cpu_reference_weno3"] = {"unavailable": str(e)}
+    if not args.no_jacobian:
+        try:
+            res["jacobian_cpu_baseline"] = ref_jacobian_leg()
+        except Exception as e:
+            res["jacobian_cpu_baseline"] = {"unavailable": str(e)}
+    out.emit(json.dumps(res))
+
+
+def cpu_legs_subprocess(n, jacobian=True):
+    env = {k: v for k, v in os.environ.items()
+           if k not in ("RANK", "LOCAL_RANK", "WORLD_SIZE", "OMP_NUM_THREADS", "OMP_PROC_BIND", "TORCHELASTIC_RUN_ID")}
+    env["CUDA_VISIBLE_DEVICES"] = ""
+    cmd = [sys.executable, os.path.abspath(__file__), "--impl", "cpu-legs", "--n", str(n)] + ([] if jacobian else ["--no-jacobian"])
+    try:
+        r = subprocess.run(cmd, env=env, stdout=subprocess.PIPE, stderr=subprocess.PIPE, timeout=600)
+        return json.loads(r.stdout.decode().strip().splitlines()[-1])
+    except Exception as e:
+        return {"error": "cpu legs failed: %s" % e}
+
+
 class numa_local:
     """Context manager: while active, the calling THREAD runs on the CPUs of the NUMA node its GPU hangs off (sysfs
     local_cpulist of the GPU's PCI function), so that pinned host buffers allocated and first-touched inside are
@@ -610,12 +645,10 @@ def run_b200_arm(args, out):
                              "hbm": {"bound": "hbm (NOT binding)", "achieved": ach_gbs, "peak": hbm_peak, "unit": "GB/s",
                                      "frac": ach_gbs / hbm_peak, "algorithmic_bytes": kernel_cells * BYTES_PER_CELL,
                                      "peak_source": peak_src}}}
+        cpu = cpu_legs_subprocess(n, jacobian=not args.no_jacobian) if (world == 1 and not args.no_cpu) else {}
         if world == 1 and not args.no_cpu:
-            line["cpu_baseline"] = cpu_leg(n, target_s=12.0)
-            try:
-                line["cpu_reference_weno3"] = ref_weno3_leg(64, 5.0)
-            except Exception as e:   # the compiled reference is optional on the GPU box
-                line["cpu_reference_weno3"] = {"unavailable": str(e)}
+            line["cpu_baseline"] = cpu.get("cpu_baseline", {"unavailable": cpu.get("error", "cpu legs did not run")})
+            line["cpu_reference_weno3"] = cpu.get("cpu_reference_weno3")
         if world == 1:
             del dU, dV
             torch.cuda.empty_cache()
@@ -679,10 +712,7 @@ def run_b200_arm(args, out):
             try:
                 line["jacobian"] = jacobian_leg(torch, pda, local_rank, n2=args.n2)
                 if not args.no_cpu:
-                    try:
-                        line["jacobian"]["cpu_baseline"] = ref_jacobian_leg()
-                    except Exception as e:
-                        line["jacobian"]["cpu_baseline"] = {"unavailable": str(e)}
+                    line["jacobian"]["cpu_baseline"] = cpu.get("jacobian_cpu_baseline", {"unavailable": cpu.get("error", "not run")})
             except Exception as e:
                 line["jacobian"] = {"error": str(e)}
         if world == 1 and not args.no_configs:
@@ -723,7 +753,7 @@ def main():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference", "cpu-legs"])
     ap.add_argument("--n", type=int, default=512, help="cells per axis of the 3D mesh (BASELINE: 512)")
     ap.add_argument("--n2", type=int, default=2048, help="cells per axis of the 2D Jacobian mesh (BASELINE: 2048)")
     ap.add_argument("--halo", default="peer", choices=["peer", "nccl"],
@@ -738,8 +768,11 @@ def main():
     out = StdoutToStderr()   # stdout carries exactly one line: the JSON record
     if args.impl == "reference":
         run_reference_arm(args, out)
+    elif args.impl == "cpu-legs":
+        run_cpu_legs(args, out)
     else:
-        bind_openmp()        # the cpu_baseline leg (rank 0, N = 1) uses all host cores like the reference arm
+        # no OpenMP binding in the GPU process (see run_cpu_legs); torchrun's OMP_NUM_THREADS=1 is irrelevant here
+        os.environ.pop("OMP_PROC_BIND", None)
         run_b200_arm(args, out)
 
 
