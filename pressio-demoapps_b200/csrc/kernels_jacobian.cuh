@@ -39,52 +39,100 @@ struct JacStage {
   static constexpr size_t smemBytes = (size_t)CELLS * STRIDE * 8;
 };
 
-// one (axis AX, face) role of one cell; `face` 0 = left/back/bottom face, 1 = right/front/top
-template <class Phys, int S, int AX>
-PDA_DEVFN void jacobianFaceRole(const Phys& phys, const int32_t* __restrict__ row, const double* __restrict__ U,
+// Rusanov flux and flux Jacobians along a RUN-TIME axis.  Euler and shallow water: the flux along axis a is
+// P F_x(P q) with P the swap of momentum components 1 and 1+a, so ONE copy of the x-direction code serves every axis
+// (JN = P JN' P: rows and columns swapped); the scalar families keep their two small per-axis instances.
+template <class Phys>
+PDA_DEVFN void faceFluxAndJacAxis(const Phys& phys, int axis, double* un, double* up, double* F, double* JN, double* JP) {
+  constexpr int N = Phys::ndpc, DIM = Phys::dim;
+  constexpr bool kSwap = std::is_same<Phys, Euler<2>>::value || std::is_same<Phys, Euler<3>>::value || std::is_same<Phys, Swe2d>::value;
+  if constexpr (DIM == 1) {
+    faceFlux2d<Phys, 0>(phys, un, up, F);
+    faceFluxJac2d<Phys, 0>(phys, un, up, JN, JP);
+  } else if constexpr (kSwap) {
+    auto swp = [&](double& a, double& b, bool on) { const double t = a; a = on ? b : a; b = on ? t : b; };
+    auto swapVec = [&](double* v) {
+      swp(v[1], v[2], axis == 1);
+      if constexpr (DIM == 3) swp(v[1], v[3], axis == 2);
+    };
+    swapVec(un); swapVec(up);
+    faceFlux2d<Phys, 0>(phys, un, up, F);
+    faceFluxJac2d<Phys, 0>(phys, un, up, JN, JP);
+    swapVec(F);
+#pragma unroll
+    for (int k = 0; k < N; ++k) { swapVec(JN + k * N); swapVec(JP + k * N); }        // columns
+#pragma unroll
+    for (int j = 0; j < N; ++j) {                                                    // rows
+      swp(JN[1 * N + j], JN[2 * N + j], axis == 1); swp(JP[1 * N + j], JP[2 * N + j], axis == 1);
+      if constexpr (DIM == 3) { swp(JN[1 * N + j], JN[3 * N + j], axis == 2); swp(JP[1 * N + j], JP[3 * N + j], axis == 2); }
+    }
+  } else {
+    if (axis == 0) { faceFlux2d<Phys, 0>(phys, un, up, F); faceFluxJac2d<Phys, 0>(phys, un, up, JN, JP); }
+    else { faceFlux2d<Phys, 1>(phys, un, up, F); faceFluxJac2d<Phys, 1>(phys, un, up, JN, JP); }
+  }
+}
+
+// one (axis, face) role of one cell; `face` 0 = left/back/bottom face, 1 = right/front/top.
+// ONE copy of the code for every axis (run-time `axis`, warp-uniform) and every dof: the loops over the dofs are ROLLED
+// (the WENO5 3D instance of the per-axis, fully unrolled version was 325 KB of SASS and stalled on instruction fetch);
+// the arrays a rolled loop would index at run time (flux Jacobian column j, self-block column j) are ROTATED by one
+// column per iteration instead, so that they stay in registers.
+template <class Phys, int S>
+PDA_DEVFN void jacobianFaceRole(const Phys& phys, int axis, const int32_t* __restrict__ row, const double* __restrict__ U,
                                 double hInv, int face, double* __restrict__ my, const uint8_t* __restrict__ slots,
                                 double* selfAcc /*[N*N], L lane only*/, double* dF /*[N] F_L - F_R, L lane only*/) {
   constexpr int N = Phys::ndpc;
   constexpr int h = (S - 1) / 2;
   constexpr int DIM = Phys::dim;
   constexpr int ROWLEN = JacStage<Phys, S>::ROWLEN;
-  int32_t cells[S];
-  stencilCells<DIM, S, AX>(row, cells);
+  const int sm = (axis == 0) ? 0 : (axis == 1 ? 3 : 4), sp = (axis == 0) ? 2 : (axis == 1 ? 1 : 5);
+  // graph column of stencil position pos: 0..h-1 = minus layers (far..near), h = self, h+1.. = plus layers
+  auto colOf = [&](int pos) -> int {
+    return (pos == h) ? 0 : (pos < h ? gcol<DIM>(sm, h - 1 - pos) : gcol<DIM>(sp, pos - h - 1));
+  };
   int sl[S];   // block slot of each stencil position
-  sl[h] = slots[0];
 #pragma unroll
-  for (int L = 0; L < h; ++L) {
-    sl[h - 1 - L] = slots[gcol<DIM>(sideMinus<AX>(), L)];
-    sl[h + 1 + L] = slots[gcol<DIM>(sidePlus<AX>(), L)];
-  }
+  for (int p = 0; p < S; ++p) sl[p] = slots[colOf(p)];
+  int64_t fc[S - 1];   // the face's stencil: cells at positions face .. face+S-2 (element offsets into U)
+#pragma unroll
+  for (int p = 0; p < S - 1; ++p) fc[p] = (int64_t)row[colOf(p + face)] * N;
   const double sgn = (face == 0) ? hInv : -hInv;
   double un[N], up[N];
 #pragma unroll
+  for (int d = 0; d < N; ++d) { un[d] = 0.0; up[d] = 0.0; }
+#pragma unroll 1
   for (int d = 0; d < N; ++d) {
     double q[S - 1];
 #pragma unroll
-    for (int p = 0; p < S - 1; ++p) q[p] = U[(int64_t)cells[p + face] * N + d];
-    reconFaceFast<S>(q, un[d], up[d]);
+    for (int p = 0; p < S - 1; ++p) q[p] = U[fc[p] + d];
+    double a, b;
+    reconFaceFast<S>(q, a, b);
+#pragma unroll
+    for (int i = 0; i < N - 1; ++i) { un[i] = un[i + 1]; up[i] = up[i + 1]; }
+    un[N - 1] = a; up[N - 1] = b;
   }
   double F[N], JN[N * N], JP[N * N];
-  faceFlux2d<Phys, AX>(phys, un, up, F);
-  faceFluxJac2d<Phys, AX>(phys, un, up, JN, JP);
+  faceFluxAndJacAxis<Phys>(phys, axis, un, up, F, JN, JP);
 #pragma unroll
   for (int d = 0; d < N; ++d) {
     const double other = __shfl_xor_sync(0xffffffffu, F[d], 1);
     dF[d] = F[d] - other;   // meaningful in the L lane: F_L - F_R
   }
+#pragma unroll
+  for (int i = 0; i < N * N; ++i) { JN[i] *= sgn; JP[i] *= sgn; selfAcc[i] = 0.0; }
   // chain rule: d(flux)/d(u_p) = JN * diag(d uNeg/d u_p) + JP * diag(d uPos/d u_p).  The L lane owns stencil
   // positions 0..h, the R lane h+1..S-1; position p receives the L face's column m = p and the R face's m = p-1.
-#pragma unroll
+#pragma unroll 1
   for (int j = 0; j < N; ++j) {
     double q[S - 1], gN[S - 1], gP[S - 1];
 #pragma unroll
-    for (int p = 0; p < S - 1; ++p) q[p] = U[(int64_t)cells[p + face] * N + j];
+    for (int p = 0; p < S - 1; ++p) q[p] = U[fc[p] + j];
     reconFaceGradFast<S>(q, gN, gP);
+    double selfCol[N];
+#pragma unroll
+    for (int k = 0; k < N; ++k) selfCol[k] = 0.0;
 #pragma unroll
     for (int s = 0; s <= h; ++s) {
-      constexpr int dummy = 0; (void)dummy;
       const int pOwnL = s, pOwnR = h + 1 + s;          // positions owned by the L / R lane in this round
       const bool rHas = (pOwnR <= S - 1);
       // gradient columns (compile-time indices, selected by the lane's face):
@@ -99,18 +147,28 @@ PDA_DEVFN void jacobianFaceRole(const Phys& phys, const int32_t* __restrict__ ro
       const double gPt = (face == 0) ? (LtValid ? gP[cLt] : 0.0) : (RtValid ? gP[cRt] : 0.0);
 #pragma unroll
       for (int k = 0; k < N; ++k) {
-        const double jn = sgn * JN[k * N + j], jp = sgn * JP[k * N + j];
+        const double jn = JN[k * N], jp = JP[k * N];   // column j (rotated to the front)
         const double mine = jn * gNm + jp * gPm;
         const double theirs = jn * gNt + jp * gPt;
         const double got = __shfl_xor_sync(0xffffffffu, theirs, 1);
         const double val = mine + got;
         if (face == 0) {
-          if (pOwnL == h) selfAcc[k * N + j] = val;                       // self block: stored in axis order later
+          if (pOwnL == h) selfCol[k] = val;                                // self block: stored in axis order later
           else my[k * ROWLEN + sl[pOwnL] * N + j] = val;
         } else if (rHas) {
           my[k * ROWLEN + sl[pOwnR] * N + j] = val;
         }
       }
+    }
+    // rotate: column j+1 of the flux Jacobians to the front, this iteration's self-block column in at the back
+#pragma unroll
+    for (int k = 0; k < N; ++k) {
+#pragma unroll
+      for (int i = 0; i < N - 1; ++i) {
+        JN[k * N + i] = JN[k * N + i + 1]; JP[k * N + i] = JP[k * N + i + 1];
+        selfAcc[k * N + i] = selfAcc[k * N + i + 1];
+      }
+      selfAcc[k * N + N - 1] = selfCol[k];
     }
   }
 }
@@ -148,9 +206,8 @@ k_jacobian_inner_staged(Phys phys, RowSet rs, Deltas dl, const double* __restric
   double* my = sJ + (size_t)c * STRIDE;
   if (axis == 0 && face == 0) sBase[c] = valid ? (int64_t)jl.base[r] : -1;
   double selfAcc[N * N], dF[N];
-  if (axis == 0) jacobianFaceRole<Phys, S, 0>(phys, row, U, dl.hInv[0], face, my, slots, selfAcc, dF);
-  if constexpr (DIM >= 2) { if (axis == 1) jacobianFaceRole<Phys, S, 1>(phys, row, U, dl.hInv[1], face, my, slots, selfAcc, dF); }
-  if constexpr (DIM >= 3) { if (axis == 2) jacobianFaceRole<Phys, S, 2>(phys, row, U, dl.hInv[2], face, my, slots, selfAcc, dF); }
+  const double hInvAx = (axis == 0) ? dl.hInv[0] : (axis == 1 ? dl.hInv[1] : dl.hInv[2]);
+  jacobianFaceRole<Phys, S>(phys, axis, row, U, hInvAx, face, my, slots, selfAcc, dF);
   // self block and velocity: x, then y, then z (the reference's accumulation order), one barrier apart
   const int sSelf = slots[0];
 #pragma unroll

@@ -1,0 +1,5 @@
+from . import _Nothing
+
+
+def __getattr__(name):
+    return _Nothing()

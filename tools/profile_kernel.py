@@ -61,5 +61,36 @@ elif a.workload == "euler2d_vel":
     V = torch.empty(p.totalDofSampleMesh(), dtype=torch.float64, device="cuda")
     for _ in range(a.reps):
         p.rightHandSideDevice(U.data_ptr(), 0.0, V.data_ptr(), st)
+elif a.workload.startswith("swe_"):      # swe_{fo,weno3,weno5}_{vel,jac}: SWE slip wall on an n x n lattice (cfg 3)
+    _, sch, what = a.workload.split("_")
+    rec = {"weno5": R.Weno5, "weno3": R.Weno3, "fo": R.FirstOrder}[sch]
+    mesh = pda.create_full_mesh([a.n, a.n], [-5, 5, -5, 5], 3 + 2 * int(rec))
+    p = pda.create_problem(mesh, pda.Swe2d.SlipWall, rec)
+    U = torch.from_numpy(p.initialCondition()).cuda()
+    V = torch.empty(p.totalDofSampleMesh(), dtype=torch.float64, device="cuda")
+    if what == "jac":
+        J = torch.empty(p.jacobianPattern()[1].size, dtype=torch.float64, device="cuda")
+    for _ in range(a.reps):
+        if what == "jac":
+            p.rightHandSideAndJacobianDevice(U.data_ptr(), 0.0, V.data_ptr(), J.data_ptr(), st)
+        else:
+            p.rightHandSideDevice(U.data_ptr(), 0.0, V.data_ptr(), st)
+elif a.workload.startswith("jac3d_"):    # jac3d_{weno3,weno5}: 3D Euler velocity + Jacobian (graph-driven staged kernel)
+    rec = {"weno5": R.Weno5, "weno3": R.Weno3, "fo": R.FirstOrder}[a.workload.split("_")[1]]
+    mesh = pda.create_full_mesh([a.n] * 3, [-1, 1, -1, 1, -1, 1], 3 + 2 * int(rec), ("x", "y", "z"))
+    p = pda.create_problem(mesh, pda.Euler3d.PeriodicSmooth, rec)
+    U = torch.from_numpy(p.initialCondition()).cuda()
+    V = torch.empty(p.totalDofSampleMesh(), dtype=torch.float64, device="cuda")
+    J = torch.empty(p.jacobianPattern()[1].size, dtype=torch.float64, device="cuda")
+    for _ in range(a.reps):
+        p.rightHandSideAndJacobianDevice(U.data_ptr(), 0.0, V.data_ptr(), J.data_ptr(), st)
+elif a.workload == "euler2d_apply_f":    # 25-column COLUMN-major operand (tests_perf/main.py:37 order='F')
+    mesh = pda.create_full_mesh([a.n, a.n], [0, 1, 0, 1], 7)
+    p = pda.create_problem(mesh, pda.Euler2d.Riemann, R.Weno5)
+    U = torch.from_numpy(p.initialCondition()).cuda()
+    B = torch.rand(25, p.totalDofStencilMesh(), dtype=torch.float64, device="cuda")
+    Rm = torch.empty(25, p.totalDofSampleMesh(), dtype=torch.float64, device="cuda")
+    for _ in range(a.reps):
+        p.applyJacobianDevice(U.data_ptr(), B.data_ptr(), 25, 0, 0.0, Rm.data_ptr(), st)
 torch.cuda.synchronize()
 print("done", p.launchCount())
