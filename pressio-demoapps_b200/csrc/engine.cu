@@ -1128,6 +1128,12 @@ void dispatchScheme(int S, F&& f) {
 
 inline int gridFor(int64_t n, int block) { return (int)((n + block - 1) / block); }
 // operands up to this many columns take the matrix-free inner-row kernel (PDA_FUSED_APPLY_MAX_COLS overrides: tuning)
+// PDA_JAC_FO_MARCH=0 keeps the tile kernel for first-order schemes (A/B measurements)
+inline bool jacFoMarchEnabled() {
+  static const bool on = [] { const char* e = std::getenv("PDA_JAC_FO_MARCH"); return !(e && e[0] == '0'); }();
+  return on;
+}
+
 inline int fusedApplyMaxCols() {
   static const int v = [] { const char* e = std::getenv("PDA_FUSED_APPLY_MAX_COLS"); return e ? std::atoi(e) : 12; }();
   return v;
@@ -1385,8 +1391,20 @@ void Problem::evaluateDev(const double* dU, double t, double* dV, double* dJ, vo
           const int w0 = L.per[0] ? m.n[0] : m.n[0] - 2 * m.halo(), w1 = L.per[1] ? m.n[1] : m.n[1] - 2 * m.halo();
           if (w0 > 0 && w1 > 0 && !skipInnerJacobian_) {
             dev::JacLatTables jt{ds.latBase.p, ds.latSlots.p, ndpc_ * (1 + dim_ * (S - 1))};
-            dim3 grid((unsigned)((w0 + JL::T - 1) / JL::T), (unsigned)((w1 + JL::T - 1) / JL::T));
-            kern<<<grid, JL::THREADS, JL::smemBytes, st>>>(phys, L, dl, jt, dU, dV, dJ);
+            if (S == 3 && jacFoMarchEnabled()) {
+              // first-order scheme: y-marching warps, every face once, chunks streamed out per strip row
+              using JM = dev::JacMarchFo<Phys>;
+              auto kfo = dev::k_jacobian_march2d_fo<Phys, JM::MIN_CTAS>;
+              ensureFuncAttrs(kfo, (int)JM::smemBytes);
+              const int64_t nStrips = (w0 + JM::W - 1) / JM::W;
+              int LY = 64;
+              while (LY > 8 && nStrips * ((w1 + LY - 1) / LY) < (int64_t)148 * 16 * 4) LY /= 2;
+              const int64_t tasks = nStrips * ((w1 + LY - 1) / LY);
+              kfo<<<(unsigned)((tasks + JM::WARPS - 1) / JM::WARPS), 32 * JM::WARPS, JM::smemBytes, st>>>(phys, L, dl, jt, dU, dV, dJ, LY);
+            } else {
+              dim3 grid((unsigned)((w0 + JL::T - 1) / JL::T), (unsigned)((w1 + JL::T - 1) / JL::T));
+              kern<<<grid, JL::THREADS, JL::smemBytes, st>>>(phys, L, dl, jt, dU, dV, dJ);
+            }
             ++launches_;
           }
         }

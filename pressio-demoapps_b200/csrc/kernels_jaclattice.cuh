@@ -287,5 +287,189 @@ k_jacobian_lattice2d(Phys phys, LatticeDesc L, Deltas dl, JacLatTables jt, const
   }
 }
 
+// ------------------------------------------------------------------------------------------------------------------
+// First-order scheme on 2D full lattices: velocity + Jacobian by Y-MARCHING warps (the layout of k_velocity_march2d).
+//
+// With a first-order reconstruction the face states are the two adjacent cells, so a block of the Jacobian IS a scaled
+// flux Jacobian: for cell (i,j) with left/right faces l, r and back/front faces b, f
+//     left nb  hx JN(l)      right nb  -hx JP(r)      back nb  hy JN(b)      front nb  -hy JP(f)
+//     self     hx (JP(l) - JN(r))  +  hy (JP(b) - JN(f))                       (x part, then y part: the reference's order)
+// (swe_2d_prob_class.hpp:556-640, euler_2d_prob_class.hpp:633-720 with the first-order functor; scatter
+// mixin_directional_flux_balance_jacobian.hpp:142-284).  The kernel is bound by the stores (45 doubles out per 3 in for
+// shallow water), and the tile kernel above reaches 25 % of the HBM peak on it (one CTA of 8 warps per SM: its tile of
+// staged chunks fills the shared memory).  Here:
+//   * a warp owns a strip of 30 columns (+ one feeder lane per side) and marches along y; every face is evaluated ONCE:
+//     a lane computes the left face of its cell and receives the right face from lane+1 by shuffle; the front face of
+//     row j is carried in registers as the back face of row j+1;
+//   * the lanes assemble their cells' chunks in a per-warp shared-memory slab (32 x CHUNK, odd stride) and the warp
+//     streams the 30 chunks -- consecutive inner cells = ONE contiguous range of the CSR value array -- with coalesced
+//     stores, every value written once (no memset, no read-modify-write);
+//   * no CTA barrier; 4 warps per CTA, several CTAs per SM.
+template <class Phys>
+struct JacMarchFo {
+  static constexpr int N = Phys::ndpc;
+  static constexpr int ROWLEN = N * 5;
+  static constexpr int CHUNK = N * ROWLEN;
+  static constexpr int STRIDE = CHUNK | 1;
+  static constexpr int WARPS = 4;
+  static constexpr int W = 30;
+  static constexpr size_t smemBytes = (size_t)WARPS * 32 * STRIDE * sizeof(double);
+  // CTAs per SM the register allocation is capped for: shallow water at 4 (128 registers) spills 108 bytes and runs
+  // 2.03 ms at 4096^2, at 3 (167 registers, no spills, 12 warps/SM) 1.71 ms
+  static constexpr int MIN_CTAS = (N <= 2) ? 4 : (N == 3 ? 3 : 2);
+};
+
+template <class Phys, int MINB>
+__global__ void __launch_bounds__(128, MINB)
+k_jacobian_march2d_fo(Phys phys, LatticeDesc L, Deltas dl, JacLatTables jt, const double* __restrict__ U,
+                      double* __restrict__ V, double* __restrict__ Jv, int LY) {
+  using K = JacMarchFo<Phys>;
+  constexpr int N = K::N, ROWLEN = K::ROWLEN, CHUNK = K::CHUNK, STRIDE = K::STRIDE, W = K::W;
+  extern __shared__ __align__(16) double sAll[];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  double* const slab = sAll + (size_t)warp * 32 * STRIDE;
+  double* const mine = slab + lane * STRIDE;
+  const int nx = L.n[0], ny = L.n[1];
+  const int lo0 = L.per[0] ? 0 : L.meshHalo, hi0 = L.per[0] ? nx : nx - L.meshHalo;
+  const int yb = L.per[1] ? 0 : L.meshHalo, ye = L.per[1] ? ny : ny - L.meshHalo;
+  const int nStrips = (hi0 - lo0 + W - 1) / W;
+  const int wid = blockIdx.x * K::WARPS + warp;
+  const int strip = wid % nStrips, chunk = wid / nStrips;
+  const int j0 = yb + chunk * LY;
+  if (j0 >= ye) return;
+  const int j1 = min(j0 + LY, ye);
+  const int xFirst = lo0 + strip * W;          // first output column of the strip (lane 1)
+  const int x = xFirst - 1 + lane;
+  int xc = x;
+  if (L.per[0]) { xc %= nx; if (xc < 0) xc += nx; }
+  else xc = (xc < 0) ? 0 : (xc >= nx ? nx - 1 : xc);
+  const bool outLane = (lane >= 1) && (lane <= W) && (x < hi0);
+  const int nOut = min(W, hi0 - xFirst);       // output cells of this strip
+  const double hx = dl.hInv[0], hy = dl.hInv[1];
+
+  auto rowIdx = [&](int r) -> int {
+    if (L.per[1]) { r %= ny; if (r < 0) r += ny; return r; }
+    return (r < 0) ? 0 : (r >= ny ? ny - 1 : r);
+  };
+  auto rowPtr = [&](int r) -> const double* { return U + ((int64_t)rowIdx(r) * nx + xc) * N; };
+
+  double qc[N], qn[N];                         // rows j and j+1 of this lane's column
+  loadCell<N>(rowPtr(j0 - 1), qc);
+  loadCell<N>(rowPtr(j0), qn);
+  double FyB[N];                               // flux through the back face of the current row
+#pragma unroll
+  for (int d = 0; d < N; ++d) FyB[d] = 0.0;
+  auto slotsOf = [&](int j) -> uint4 { return outLane ? __ldg(jt.cellSlots + (int64_t)j * nx + x) : make_uint4(0, 0, 0, 0); };
+  auto slotIn = [](const uint4& sv, int c) -> int {
+    const unsigned w = (c < 4) ? sv.x : (c < 8 ? sv.y : (c < 12 ? sv.z : sv.w));
+    return (int)((w >> (8 * (c & 3))) & 0xffu);
+  };
+  uint4 sv = make_uint4(0, 0, 0, 0);           // block slots of the current row's cell (set by the previous step)
+
+  for (int j = j0 - 1; j < j1; ++j) {
+    const bool ghost = (j < j0);
+    double nxt[N];
+    const bool more = (j + 1 < j1);
+    if (more) loadCell<N>(rowPtr(j + 2), nxt);           // lands while this row is computed
+    // ---- front y face (j+1/2): uNeg = row j, uPos = row j+1
+    double FyF[N], JNf[N * N], JPf[N * N];
+    {
+      double a[N], b[N];
+#pragma unroll
+      for (int d = 0; d < N; ++d) { a[d] = qc[d]; b[d] = qn[d]; }
+      faceFlux2d<Phys, 1>(phys, a, b, FyF);
+      faceFluxJac2d<Phys, 1>(phys, a, b, JNf, JPf);
+#pragma unroll
+      for (int e = 0; e < N * N; ++e) { JNf[e] *= hy; JPf[e] *= hy; }
+    }
+    if (!ghost) {
+      const int64_t gidSelf = (int64_t)j * nx + x;
+      const int s0 = slotIn(sv, 0) * N, sL = slotIn(sv, 1) * N, sF = slotIn(sv, 2) * N, sR = slotIn(sv, 3) * N;
+      // ---- x left face of this lane's cell: uNeg = lane-1's cell, uPos = mine.  The back-face terms of this row (back
+      //      block, hy JP(b) in the self block) are already in the slab: the previous step stored them.
+      double Fx[N], v[N];
+      {
+        double a[N], b[N], JNx[N * N], JPx[N * N];
+#pragma unroll
+        for (int d = 0; d < N; ++d) { b[d] = qc[d]; a[d] = __shfl_up_sync(0xffffffffu, qc[d], 1); }
+        faceFlux2d<Phys, 0>(phys, a, b, Fx);
+        faceFluxJac2d<Phys, 0>(phys, a, b, JNx, JPx);
+#pragma unroll
+        for (int k = 0; k < N; ++k)
+#pragma unroll
+          for (int jj = 0; jj < N; ++jj) {
+            const double jn = hx * JNx[k * N + jj], jp = hx * JPx[k * N + jj];
+            const double jnR = __shfl_down_sync(0xffffffffu, jn, 1), jpR = __shfl_down_sync(0xffffffffu, jp, 1);
+            mine[k * ROWLEN + sL + jj] = jn;
+            mine[k * ROWLEN + sR + jj] = -jpR;
+            mine[k * ROWLEN + sF + jj] = -JPf[k * N + jj];
+            double* self = mine + k * ROWLEN + s0 + jj;
+            *self = (jp - jnR) + (*self - JNf[k * N + jj]);     // x part, then y part (the reference's order)
+          }
+      }
+#pragma unroll
+      for (int d = 0; d < N; ++d) {
+        const double FxR = __shfl_down_sync(0xffffffffu, Fx[d], 1);
+        v[d] = hx * (Fx[d] - FxR);
+        v[d] += hy * (FyB[d] - FyF[d]);
+      }
+      if (outLane) {
+        if constexpr (PhysTraits<Phys>::hasDiffusion) {
+          auto wrapI = [&](int c, int n) { return c < 0 ? c + n : (c >= n ? c - n : c); };
+          int32_t row5[5];
+          row5[0] = (int32_t)gidSelf;
+          row5[1] = j * nx + wrapI(x - 1, nx);
+          row5[2] = wrapI(j + 1, ny) * nx + x;
+          row5[3] = j * nx + wrapI(x + 1, nx);
+          row5[4] = wrapI(j - 1, ny) * nx + x;
+          addDiffusionInner<Phys>(phys, row5, U, v);
+        }
+        addForcing<Phys>(phys, qc, v, (int32_t)gidSelf);
+        if (V) {
+          double* out = V + gidSelf * N;
+#pragma unroll
+          for (int d = 0; d < N; ++d) out[d] = v[d];
+        }
+        uint8_t slots[16];
+#pragma unroll
+        for (int c = 0; c < 16; ++c) slots[c] = (uint8_t)slotIn(sv, c);
+        addExtraJacInner<Phys>(phys, qc, slots, [&](int k, int slot, int jj, double val) {
+          mine[k * ROWLEN + slot * N + jj] += val;
+        });
+      }
+      __syncwarp();
+      // ---- stream the strip's chunks out (lanes 1..nOut): one contiguous range of the CSR value array
+      if (nOut > 0) {
+        double* dst = Jv + __ldg(jt.cellBase + (int64_t)j * nx + xFirst);
+        const int total = nOut * CHUNK;
+        for (int e = lane; e < total; e += 32) {
+          const int c = e / CHUNK, w = e - c * CHUNK;
+          dst[e] = slab[(c + 1) * STRIDE + w];
+        }
+      }
+      __syncwarp();
+    }
+    // ---- this front face is the back face of row j+1: its terms go into the (now free) slab row right away, so no
+    //      flux Jacobian is carried in registers across steps
+    if (more) {
+      sv = slotsOf(j + 1);
+      const int s0 = slotIn(sv, 0) * N, sB = slotIn(sv, 4) * N;
+#pragma unroll
+      for (int k = 0; k < N; ++k)
+#pragma unroll
+        for (int jj = 0; jj < N; ++jj) {
+          mine[k * ROWLEN + sB + jj] = JNf[k * N + jj];
+          mine[k * ROWLEN + s0 + jj] = JPf[k * N + jj];
+        }
+    }
+#pragma unroll
+    for (int d = 0; d < N; ++d) { FyB[d] = FyF[d]; qc[d] = qn[d]; }
+    if (more) {
+#pragma unroll
+      for (int d = 0; d < N; ++d) qn[d] = nxt[d];
+    }
+  }
+}
+
 }  // namespace dev
 }  // namespace pda

@@ -24,8 +24,12 @@
 namespace pda {
 namespace dev {
 
+// First-order instances of the small systems are latency-bound at 16 warps/SM (ncu, SWE 4096^2: FP64 pipe 52 %, stall
+// "wait" 2.5 of 6 cycles per issue, DRAM 2 TB/s): they fit 80 registers -> 24 warps/SM
+template <class Phys, int S> struct March2dOcc { static constexpr int minCtas = (S == 7) ? 4 : ((Phys::ndpc <= 3) ? (S == 3 ? 6 : 5) : 1); };
+
 template <class Phys, int S>
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(128, March2dOcc<Phys, S>::minCtas)
 k_velocity_march2d(Phys phys, LatticeDesc L, Deltas dl, const double* __restrict__ U, double* __restrict__ V, int LY) {
   constexpr int N = Phys::ndpc;
   constexpr int h = (S - 1) / 2;

@@ -187,6 +187,26 @@ def _f64(a, n=None, name="array"):
     return a
 
 
+def _f64_in(a, n=None, name="array"):
+    """INPUT arguments (state, applyJacobian operand): the reference binds them as `const Eigen::Ref<const ...>&`
+    (adapter_py.hpp:153-185), for which pybind11 converts -- an integer array (tests_py/1d_linear_adv passes
+    np.arange(n)) or a strided view is copied into a contiguous float64 temporary.  Outputs stay strict (_f64): a copy
+    there would silently drop the result."""
+    if isinstance(a, _np.ndarray) and a.dtype == _np.float64 and \
+            (a.flags["C_CONTIGUOUS"] or (a.ndim == 2 and a.flags["F_CONTIGUOUS"])):
+        b = a
+    else:
+        try:
+            b = _np.array(a, dtype=_np.float64, order="A")
+        except (TypeError, ValueError):
+            raise TypeError("%s must be convertible to a float64 numpy array" % name)
+        if not (b.flags["C_CONTIGUOUS"] or (b.ndim == 2 and b.flags["F_CONTIGUOUS"])):
+            b = _np.ascontiguousarray(b)
+    if n is not None and b.size != n:
+        raise ValueError("%s has %d entries, expected %d" % (name, b.size, n))
+    return b
+
+
 # ------------------------------------------------------------------------------------------------ enums
 class InviscidFluxReconstruction(_IntEnum):
     FirstOrder = 0
@@ -564,7 +584,7 @@ class Problem:
 
     # ---- evaluation (host buffers)
     def rightHandSide(self, state, time, V):
-        _f64(state, self.totalDofStencilMesh(), "state")
+        state = _f64_in(state, self.totalDofStencilMesh(), "state")
         _f64(V, self.totalDofSampleMesh(), "rhs")
         self._refresh_source(time)
         _check(_lib.pda_problem_velocity_host(self._h, state.ctypes.data, float(time), V.ctypes.data))
@@ -579,7 +599,7 @@ class Problem:
             self.rightHandSide(state, time, V)
 
     def rightHandSideAndJacobian(self, state, time, V, J):
-        _f64(state, self.totalDofStencilMesh(), "state")
+        state = _f64_in(state, self.totalDofStencilMesh(), "state")
         vals = J.data if hasattr(J, "data") and not isinstance(J, _np.ndarray) else J
         _f64(vals, self.jacobianPattern()[1].size, "jacobian values")
         vp = None if V is None else _f64(V, self.totalDofSampleMesh(), "rhs").ctypes.data
@@ -591,8 +611,8 @@ class Problem:
         self.rightHandSideAndJacobian(state, time, None, J)
 
     def applyJacobian(self, state, operand, time, result):
-        _f64(state, self.totalDofStencilMesh(), "state")
-        _f64(operand, None, "operand")
+        state = _f64_in(state, self.totalDofStencilMesh(), "state")
+        operand = _f64_in(operand, None, "operand")
         _f64(result, None, "result")
         ncols = 1 if operand.ndim == 1 else operand.shape[1]
         if operand.shape[0] != self.totalDofStencilMesh():

@@ -256,3 +256,27 @@ def test_set_bc_pointer_needs_a_host_functor():
     p.setBCPointer(0, None)
     with pytest.raises(pda.PdaError, match="invalid side"):
         p.setBCPointer(7, None)
+
+
+def test_input_arrays_convert_like_pybind_const_ref_outputs_stay_strict():
+    """adapter_py.hpp:153-185 binds state / operand as `const Eigen::Ref<const ...>&`: pybind11 converts an integer array
+    (tests_py/1d_linear_adv/test_1d_linear_adv.py hands over np.arange(n)) or a strided view into a contiguous float64
+    temporary; results are non-const Refs: wrong dtype or a strided view is refused."""
+    f_in, f_out = pda._f64_in, pda._f64
+    a = f_in(np.arange(6), 6, "operand")
+    assert a.dtype == np.float64 and a.flags["C_CONTIGUOUS"] and np.array_equal(a, np.arange(6.0))
+    base = np.arange(12.0)
+    v = f_in(base[::2], 6, "state")
+    assert v.flags["C_CONTIGUOUS"] and np.array_equal(v, base[::2]) and v.base is not base
+    same = np.zeros(4)
+    assert f_in(same, 4) is same                       # no copy when the array is already acceptable
+    fm = np.asfortranarray(np.arange(12.0).reshape(4, 3))
+    assert f_in(fm) is fm                              # col-major operands keep their layout
+    im = np.asfortranarray(np.arange(12).reshape(4, 3))
+    assert f_in(im).flags["F_CONTIGUOUS"]
+    with pytest.raises(ValueError):
+        f_in(np.arange(5), 6, "operand")
+    with pytest.raises(TypeError):
+        f_out(np.arange(6), 6, "result")
+    with pytest.raises(TypeError):
+        f_out(base[::2], 6, "result")
