@@ -1134,6 +1134,12 @@ inline bool jacFoMarchEnabled() {
   return on;
 }
 
+// PDA_JAC_WENO_MARCH=0 keeps the tile kernel for WENO3/5 on the 1-3 dof systems (A/B measurements)
+inline bool jacWenoMarchEnabled() {
+  static const bool on = [] { const char* e = std::getenv("PDA_JAC_WENO_MARCH"); return !(e && e[0] == '0'); }();
+  return on;
+}
+
 inline int fusedApplyMaxCols() {
   static const int v = [] { const char* e = std::getenv("PDA_FUSED_APPLY_MAX_COLS"); return e ? std::atoi(e) : 12; }();
   return v;
@@ -1401,6 +1407,18 @@ void Problem::evaluateDev(const double* dU, double t, double* dV, double* dJ, vo
               while (LY > 8 && nStrips * ((w1 + LY - 1) / LY) < (int64_t)148 * 16 * 4) LY /= 2;
               const int64_t tasks = nStrips * ((w1 + LY - 1) / LY);
               kfo<<<(unsigned)((tasks + JM::WARPS - 1) / JM::WARPS), 32 * JM::WARPS, JM::smemBytes, st>>>(phys, L, dl, jt, dU, dV, dJ, LY);
+            } else if (S > 3 && Phys::ndpc <= 3 && jacWenoMarchEnabled()) {
+              // WENO on the small systems: same marching layout with the chain rule in it
+              if constexpr (S > 3 && Phys::ndpc <= 3) {
+                using JM = dev::JacMarchWeno<Phys, S>;
+                auto kw = dev::k_jacobian_march2d_weno<Phys, S>;
+                ensureFuncAttrs(kw, (int)JM::smemBytes);
+                const int64_t nStrips = (w0 + JM::W - 1) / JM::W;
+                int LY = 64;
+                while (LY > 8 && nStrips * ((w1 + LY - 1) / LY) < (int64_t)148 * 16 * 4) LY /= 2;
+                const int64_t tasks = nStrips * ((w1 + LY - 1) / LY);
+                kw<<<(unsigned)((tasks + JM::WARPS - 1) / JM::WARPS), 32 * JM::WARPS, JM::smemBytes, st>>>(phys, L, dl, jt, dU, dV, dJ, LY);
+              }
             } else {
               dim3 grid((unsigned)((w0 + JL::T - 1) / JL::T), (unsigned)((w1 + JL::T - 1) / JL::T));
               kern<<<grid, JL::THREADS, JL::smemBytes, st>>>(phys, L, dl, jt, dU, dV, dJ);

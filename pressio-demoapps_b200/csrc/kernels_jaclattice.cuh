@@ -471,5 +471,235 @@ k_jacobian_march2d_fo(Phys phys, LatticeDesc L, Deltas dl, JacLatTables jt, cons
   }
 }
 
+// ------------------------------------------------------------------------------------------------------------------
+// WENO3 / WENO5 on the SMALL systems (1-3 dofs per cell): the y-marching layout of k_jacobian_march2d_fo with the chain rule
+// in it.  With  t_f[k][m][j] = h ( JN[k][j] d(uNeg_j)/d(q_m) + JP[k][j] d(uPos_j)/d(q_m) )  for face f and the m-th cell of its
+// stencil, the block of a cell at stencil position P of an axis is  t_lower[k][P][j] - t_upper[k][P-1][j]  (lower = left /
+// back face, upper = right / front face of the cell) -- same algebra as jacLatLine above.  Per step and lane: ONE x face
+// (the right face's products arrive from lane+1 by shuffle) and ONE y face (the front face; its products are the back-face
+// terms of row j+1 and are written into the lane's slab row for the next step as soon as the current row has been streamed
+// out).  Chunks are assembled in a per-warp slab and streamed out coalesced; no tile, no CTA barrier, CTAs of 2 warps so that
+// several fit next to each other (the tile kernel keeps ONE 8-warp CTA per SM: its 15 x 15 tile of chunks fills the shared memory).
+template <class Phys, int S>
+struct JacMarchWeno {
+  static constexpr int N = Phys::ndpc;
+  static constexpr int h = (S - 1) / 2;
+  static constexpr int NBLK = 1 + 2 * (S - 1);
+  static constexpr int ROWLEN = N * NBLK;
+  static constexpr int CHUNK = N * ROWLEN;
+  static constexpr int STRIDE = CHUNK | 1;
+  static constexpr int WARPS = 2;
+  static constexpr int W = 32 - 2 * h;
+  static constexpr size_t smemBytes = (size_t)WARPS * 32 * STRIDE * sizeof(double);
+  static constexpr int FIT = (int)(220 * 1024 / smemBytes);
+  static constexpr int MIN_CTAS = FIT > 5 ? 5 : (FIT < 1 ? 1 : FIT);   // 5 CTAs of 64 threads: 204 registers
+};
+
+template <class Phys, int S>
+__global__ void __launch_bounds__(32 * JacMarchWeno<Phys, S>::WARPS, JacMarchWeno<Phys, S>::MIN_CTAS)
+k_jacobian_march2d_weno(Phys phys, LatticeDesc L, Deltas dl, JacLatTables jt, const double* __restrict__ U,
+                        double* __restrict__ V, double* __restrict__ Jv, int LY) {
+  using K = JacMarchWeno<Phys, S>;
+  constexpr int N = K::N, h = K::h, ROWLEN = K::ROWLEN, CHUNK = K::CHUNK, STRIDE = K::STRIDE, W = K::W;
+  constexpr int M = 2 * h;            // cells per face stencil
+  constexpr int R = 2 * h + 1;        // ring rows j-h .. j+h
+  extern __shared__ __align__(16) double sAll[];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  double* const slab = sAll + (size_t)warp * 32 * STRIDE;
+  double* const mine = slab + lane * STRIDE;
+  const int nx = L.n[0], ny = L.n[1];
+  const int lo0 = L.per[0] ? 0 : L.meshHalo, hi0 = L.per[0] ? nx : nx - L.meshHalo;
+  const int yb = L.per[1] ? 0 : L.meshHalo, ye = L.per[1] ? ny : ny - L.meshHalo;
+  const int nStrips = (hi0 - lo0 + W - 1) / W;
+  const int wid = blockIdx.x * K::WARPS + warp;
+  const int strip = wid % nStrips, chunk = wid / nStrips;
+  const int j0 = yb + chunk * LY;
+  if (j0 >= ye) return;
+  const int j1 = min(j0 + LY, ye);
+  const int xFirst = lo0 + strip * W;          // first output column of the strip (lane h)
+  const int x = xFirst - h + lane;
+  int xc = x;
+  if (L.per[0]) { xc %= nx; if (xc < 0) xc += nx; }
+  else xc = (xc < 0) ? 0 : (xc >= nx ? nx - 1 : xc);
+  const bool outLane = (lane >= h) && (lane <= 31 - h) && (x < hi0);
+  const int nOut = min(W, hi0 - xFirst);
+  const double hx = dl.hInv[0], hy = dl.hInv[1];
+
+  auto rowPtr = [&](int r) -> const double* {
+    if (L.per[1]) { r %= ny; if (r < 0) r += ny; }
+    else r = (r < 0) ? 0 : (r >= ny ? ny - 1 : r);
+    return U + ((int64_t)r * nx + xc) * N;
+  };
+  auto slotsOf = [&](int j) -> uint4 { return outLane ? __ldg(jt.cellSlots + (int64_t)j * nx + x) : make_uint4(0, 0, 0, 0); };
+  auto slotIn = [](const uint4& sv, int c) -> int {
+    const unsigned w = (c < 4) ? sv.x : (c < 8 ? sv.y : (c < 12 ? sv.z : sv.w));
+    return (int)((w >> (8 * (c & 3))) & 0xffu);
+  };
+  // slab offset of the block at stencil position P of axis AX (self at P = h)
+  auto posSlot = [&](const uint4& sv, int ax, int P) -> int {
+    const int sm = (ax == 0) ? 0 : 3, sp = (ax == 0) ? 2 : 1;
+    const int c = (P == h) ? 0 : (P < h ? gcol<2>(sm, h - 1 - P) : gcol<2>(sp, P - h - 1));
+    return slotIn(sv, c) * N;
+  };
+
+  double q[R][N];
+#pragma unroll
+  for (int i = 0; i < R; ++i) loadCell<N>(rowPtr(j0 - 1 - h + i), q[i]);
+  double FyB[N];
+#pragma unroll
+  for (int d = 0; d < N; ++d) FyB[d] = 0.0;
+  uint4 sv = make_uint4(0, 0, 0, 0);
+
+  for (int j = j0 - 1; j < j1; ++j) {
+    const bool ghost = (j < j0);
+    double nxt[N];
+    const bool more = (j + 1 < j1);
+    if (more) loadCell<N>(rowPtr(j + 1 + h), nxt);
+    // ---- x left face of this lane's cell FIRST (stencil from the neighbouring lanes' row-j values): its temporaries are
+    //      dead before the y face is evaluated, whose products must stay live until the row has been streamed out
+    double Fx[N];
+    if (!ghost) {
+      double uN[N], uP[N], gN[N][M], gP[N][M];
+#pragma unroll
+      for (int d = 0; d < N; ++d) {
+        double sq[M];
+#pragma unroll
+        for (int o = 0; o < M; ++o)
+          sq[o] = (o == h) ? q[h][d] : __shfl_sync(0xffffffffu, q[h][d], (lane + o - h) & 31);
+        reconFaceFast<S>(sq, uN[d], uP[d]);
+        reconFaceGradFast<S>(sq, gN[d], gP[d]);
+      }
+      double JN[N * N], JP[N * N];
+      faceFlux2d<Phys, 0>(phys, uN, uP, Fx);
+      faceFluxJac2d<Phys, 0>(phys, uN, uP, JN, JP);
+      int sx[R];
+#pragma unroll
+      for (int P = 0; P < R; ++P) sx[P] = posSlot(sv, 0, P);
+#pragma unroll
+      for (int k = 0; k < N; ++k)
+#pragma unroll
+        for (int jj = 0; jj < N; ++jj) {
+          const double jn = hx * JN[k * N + jj], jp = hx * JP[k * N + jj];
+          double own[M], rgt[M];
+#pragma unroll
+          for (int m = 0; m < M; ++m) {
+            own[m] = jn * gN[jj][m] + jp * gP[jj][m];
+            rgt[m] = __shfl_down_sync(0xffffffffu, own[m], 1);
+          }
+#pragma unroll
+          for (int P = 0; P < R; ++P) {
+            const double val = ((P < M) ? own[P] : 0.0) - ((P >= 1) ? rgt[P - 1] : 0.0);
+            double* dst = mine + k * ROWLEN + sx[P] + jj;
+            if (P == h) *dst += val;      // self block: the back-face term of the y axis is already in the slab
+            else *dst = val;
+          }
+        }
+    }
+    // ---- front y face (j+1/2): rows j-h+1 .. j+h = ring rows 1 .. 2h
+    double FyF[N], tF[N * N][M];
+    {
+      double uN[N], uP[N], gN[N][M], gP[N][M];
+#pragma unroll
+      for (int d = 0; d < N; ++d) {
+        double sq[M];
+#pragma unroll
+        for (int o = 0; o < M; ++o) sq[o] = q[1 + o][d];
+        reconFaceFast<S>(sq, uN[d], uP[d]);
+        reconFaceGradFast<S>(sq, gN[d], gP[d]);
+      }
+      double JN[N * N], JP[N * N];
+      faceFlux2d<Phys, 1>(phys, uN, uP, FyF);
+      faceFluxJac2d<Phys, 1>(phys, uN, uP, JN, JP);
+#pragma unroll
+      for (int k = 0; k < N; ++k)
+#pragma unroll
+        for (int jj = 0; jj < N; ++jj) {
+          const double jn = hy * JN[k * N + jj], jp = hy * JP[k * N + jj];
+#pragma unroll
+          for (int m = 0; m < M; ++m) tF[k * N + jj][m] = jn * gN[jj][m] + jp * gP[jj][m];
+        }
+    }
+    if (!ghost) {
+      const int64_t gidSelf = (int64_t)j * nx + x;
+      // ---- y blocks: the back-face terms t_b[P] (P = 0..2h-1) are already in the slab; position P gets - t_f[P-1]
+#pragma unroll
+      for (int P = 1; P <= M; ++P) {
+        const int sl = posSlot(sv, 1, P);
+#pragma unroll
+        for (int k = 0; k < N; ++k)
+#pragma unroll
+          for (int jj = 0; jj < N; ++jj) {
+            double* dst = mine + k * ROWLEN + sl + jj;
+            if (P == M) *dst = -tF[k * N + jj][M - 1];
+            else *dst -= tF[k * N + jj][P - 1];
+          }
+      }
+      double v[N];
+#pragma unroll
+      for (int d = 0; d < N; ++d) {
+        const double FxR = __shfl_down_sync(0xffffffffu, Fx[d], 1);
+        v[d] = hx * (Fx[d] - FxR);
+        v[d] += hy * (FyB[d] - FyF[d]);
+      }
+      if (outLane) {
+        if constexpr (PhysTraits<Phys>::hasDiffusion) {
+          auto wrapI = [&](int c, int n) { return c < 0 ? c + n : (c >= n ? c - n : c); };
+          int32_t row5[5];
+          row5[0] = (int32_t)gidSelf;
+          row5[1] = j * nx + wrapI(x - 1, nx);
+          row5[2] = wrapI(j + 1, ny) * nx + x;
+          row5[3] = j * nx + wrapI(x + 1, nx);
+          row5[4] = wrapI(j - 1, ny) * nx + x;
+          addDiffusionInner<Phys>(phys, row5, U, v);
+        }
+        addForcing<Phys>(phys, q[h], v, (int32_t)gidSelf);
+        if (V) {
+          double* out = V + gidSelf * N;
+#pragma unroll
+          for (int d = 0; d < N; ++d) out[d] = v[d];
+        }
+        uint8_t slots[16];
+#pragma unroll
+        for (int c = 0; c < 16; ++c) slots[c] = (uint8_t)slotIn(sv, c);
+        addExtraJacInner<Phys>(phys, q[h], slots, [&](int k, int slot, int jj, double val) {
+          mine[k * ROWLEN + slot * N + jj] += val;
+        });
+      }
+      __syncwarp();
+      if (nOut > 0) {
+        double* dst = Jv + __ldg(jt.cellBase + (int64_t)j * nx + xFirst);
+        const int total = nOut * CHUNK;
+        for (int e = lane; e < total; e += 32) {
+          const int c = e / CHUNK, w = e - c * CHUNK;
+          dst[e] = slab[(c + h) * STRIDE + w];
+        }
+      }
+      __syncwarp();
+    }
+    // ---- this front face is the back face of row j+1: its products go into the (now free) slab row, positions 0..2h-1
+    if (more) {
+      sv = slotsOf(j + 1);
+#pragma unroll
+      for (int m = 0; m < M; ++m) {
+        const int sl = posSlot(sv, 1, m);
+#pragma unroll
+        for (int k = 0; k < N; ++k)
+#pragma unroll
+          for (int jj = 0; jj < N; ++jj) mine[k * ROWLEN + sl + jj] = tF[k * N + jj][m];
+      }
+    }
+#pragma unroll
+    for (int d = 0; d < N; ++d) FyB[d] = FyF[d];
+#pragma unroll
+    for (int i = 0; i < R - 1; ++i)
+#pragma unroll
+      for (int d = 0; d < N; ++d) q[i][d] = q[i + 1][d];
+    if (more) {
+#pragma unroll
+      for (int d = 0; d < N; ++d) q[R - 1][d] = nxt[d];
+    }
+  }
+}
+
 }  // namespace dev
 }  // namespace pda

@@ -354,7 +354,8 @@ def test_slab_peer_mode_equals_full(nranks, n, recon):
             assert np.array_equal(Vs[r].cpu().numpy(), Vfull[k0 * pd:k1 * pd]), (it, r)
 
 
-@pytest.mark.parametrize("case", ["euler_weno5", "euler_weno3_per", "swe_weno5", "euler_fo", "burgers_weno5_per"])
+@pytest.mark.parametrize("case", ["euler_weno5", "euler_weno3_per", "swe_weno5", "euler_fo", "burgers_weno5_per",
+                                  "swe_fo", "swe_weno3", "burgers_fo_per", "burgers_weno3_out", "swe_weno3_on_s7_mesh"])
 def test_lattice_and_graph_jacobian_kernels_agree(case):
     """medium-size property: the face-sharing lattice Jacobian kernel (kernels_jaclattice.cuh: full 2D lattices) and
     the graph-driven staged kernel (same mesh handed over as arrays => not recognised as a lattice) give the same
@@ -371,6 +372,25 @@ def test_lattice_and_graph_jacobian_kernels_agree(case):
     elif case == "euler_fo":
         n, bounds, st, per = [40, 37], [0, 1, 0, 1], 3, ()
         mk = lambda m: pda.create_problem(m, pda.Euler2d.Riemann, R.FirstOrder)
+    # the y-marching Jacobian kernels (k_jacobian_march2d_fo / _weno): several strips (30 / 28 / 26 output columns per
+    # warp), several y chunks, ragged last strip, periodic wrap, a scheme stencil narrower than the mesh stencil
+    elif case == "swe_fo":
+        n, bounds, st, per = [95, 41], [-5, 5, -5, 5], 3, ()
+        mk = lambda m: pda.create_problem(m, pda.Swe2d.SlipWall, R.FirstOrder)
+    elif case == "swe_weno3":
+        n, bounds, st, per = [90, 44], [-5, 5, -5, 5], 5, ()
+        mk = lambda m: pda.create_problem(m, pda.Swe2d.SlipWall, R.Weno3)
+    elif case == "swe_weno3_on_s7_mesh":
+        n, bounds, st, per = [66, 37], [-5, 5, -5, 5], 7, ()
+        mk = lambda m: pda.create_problem(m, pda.Swe2d.SlipWall, R.Weno3)
+    elif case == "burgers_fo_per":
+        n, bounds, st, per = [64, 33], [-1, 1, -1, 1], 3, ("x", "y")
+        mk = lambda m: pda.create_problem(m, pda.AdvectionDiffusion2d.BurgersPeriodic, R.FirstOrder,
+                                          pda.ViscousFluxReconstruction.FirstOrder)
+    elif case == "burgers_weno3_out":
+        n, bounds, st, per = [61, 35], [-1, 1, -1, 1], 5, ()
+        mk = lambda m: pda.create_problem(m, pda.AdvectionDiffusion2d.BurgersOutflow, R.Weno3,
+                                          pda.ViscousFluxReconstruction.FirstOrder)
     else:
         n, bounds, st, per = [48, 40], [-1, 1, -1, 1], 7, ("x", "y")
         mk = lambda m: pda.create_problem(m, pda.AdvectionDiffusion2d.BurgersPeriodic, R.Weno5,
