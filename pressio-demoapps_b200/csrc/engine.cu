@@ -1430,7 +1430,9 @@ void Problem::evaluateDev(const double* dU, double t, double* dV, double* dJ, vo
         if (dJ && !mergedNeighbors_) {
           // staged assembly: every value of the inner rows written once, coalesced (no memset needed for them)
           using JS = dev::JacStage<Phys, S>;
-          auto kern = dev::k_jacobian_inner_staged<Phys, S>;
+          // register cap: MIN_CTAS CTAs per SM (more warps, some spills) or 1 (PDA_JAC_STAGED_OCC=0: A/B measurements)
+          static const bool occ = [] { const char* e = std::getenv("PDA_JAC_STAGED_OCC"); return !(e && e[0] == '0'); }();
+          auto kern = occ ? dev::k_jacobian_inner_staged<Phys, S, JS::MIN_CTAS> : dev::k_jacobian_inner_staged<Phys, S, 1>;
           ensureFuncAttrs(kern, (int)JS::smemBytes);
           kern<<<gridFor(ds.inner.n, JS::CELLS), JS::THREADS, JS::smemBytes, st>>>(phys, ds.inner.view(nc), dl, dU, dV, dJ,
                                                                                ds.inner.jac(slotCols_));

@@ -55,8 +55,7 @@ PDA_DEVFN void applyLatLine(const Phys& phys, const LatticeDesc& L, double hInv,
     double qd[S - 1], gN[S - 1], gP[S - 1];
 #pragma unroll
     for (int m = 0; m < S - 1; ++m) qd[m] = q[m][j];
-    reconFaceFast<S>(qd, un[j], up[j]);
-    reconFaceGradFast<S>(qd, gN, gP);
+    reconFaceValGradFast<S>(qd, un[j], up[j], gN, gP);
     if (NC == 4 && vec4) {
       // row-major operand, 4 aligned columns: the 4 values of a (cell, dof) are one 32-byte sector -> LDG.256
       double sN[4] = {0.0, 0.0, 0.0, 0.0}, sP[4] = {0.0, 0.0, 0.0, 0.0};
@@ -226,8 +225,7 @@ PDA_DEVFN void applyLatLine3(double gamma, const LatticeDesc& L, int ax, double 
     double qd[S - 1], gN[S - 1], gP[S - 1];
 #pragma unroll
     for (int m = 0; m < S - 1; ++m) qd[m] = q[m][j];
-    reconFaceFast<S>(qd, un[j], up[j]);
-    reconFaceGradFast<S>(qd, gN, gP);
+    reconFaceValGradFast<S>(qd, un[j], up[j], gN, gP);
 #pragma unroll
     for (int c = 0; c < NC; ++c) {
       double sN = 0.0, sP = 0.0;
@@ -242,26 +240,19 @@ PDA_DEVFN void applyLatLine3(double gamma, const LatticeDesc& L, int ax, double 
       dN[c][j] = sN; dP[c][j] = sP;
     }
   }
-  double JN[N * N], JP[N * N];
+  // D = P (JN' P dN + JP' P dP) as ONE Jacobian-vector product of the x-direction flux (no N x N matrices)
   swapMomentum(ax, un);
   swapMomentum(ax, up);
-  eulerFluxJacFast<3, 0>(gamma, un, up, JN, JP);
+#pragma unroll
+  for (int c = 0; c < NC; ++c) { swapMomentum(ax, dN[c]); swapMomentum(ax, dP[c]); }
+  double d[NC][N];
+  eulerFluxJvpFast<3, 0, NC>(gamma, un, up, dN, dP, d);
   double r[NC][N];
 #pragma unroll
   for (int c = 0; c < NC; ++c) {
-    swapMomentum(ax, dN[c]);
-    swapMomentum(ax, dP[c]);
-    double d[N];
+    swapMomentum(ax, d[c]);
 #pragma unroll
-    for (int k = 0; k < N; ++k) {
-      double dk = 0.0;
-#pragma unroll
-      for (int j = 0; j < N; ++j) dk += JN[k * N + j] * dN[c][j] + JP[k * N + j] * dP[c][j];
-      d[k] = dk;
-    }
-    swapMomentum(ax, d);
-#pragma unroll
-    for (int k = 0; k < N; ++k) r[c][k] = hInv * (d[k] - __shfl_down_sync(0xffffffffu, d[k], 1));
+    for (int k = 0; k < N; ++k) r[c][k] = hInv * (d[c][k] - __shfl_down_sync(0xffffffffu, d[c][k], 1));
   }
   if (!owns) return;
   double* mine = sR + cellLocal * K::RS;

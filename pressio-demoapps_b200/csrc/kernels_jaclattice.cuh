@@ -566,8 +566,7 @@ k_jacobian_march2d_weno(Phys phys, LatticeDesc L, Deltas dl, JacLatTables jt, co
 #pragma unroll
         for (int o = 0; o < M; ++o)
           sq[o] = (o == h) ? q[h][d] : __shfl_sync(0xffffffffu, q[h][d], (lane + o - h) & 31);
-        reconFaceFast<S>(sq, uN[d], uP[d]);
-        reconFaceGradFast<S>(sq, gN[d], gP[d]);
+        reconFaceValGradFast<S>(sq, uN[d], uP[d], gN[d], gP[d]);
       }
       double JN[N * N], JP[N * N];
       faceFlux2d<Phys, 0>(phys, uN, uP, Fx);
@@ -604,8 +603,7 @@ k_jacobian_march2d_weno(Phys phys, LatticeDesc L, Deltas dl, JacLatTables jt, co
         double sq[M];
 #pragma unroll
         for (int o = 0; o < M; ++o) sq[o] = q[1 + o][d];
-        reconFaceFast<S>(sq, uN[d], uP[d]);
-        reconFaceGradFast<S>(sq, gN[d], gP[d]);
+        reconFaceValGradFast<S>(sq, uN[d], uP[d], gN[d], gP[d]);
       }
       double JN[N * N], JP[N * N];
       faceFlux2d<Phys, 1>(phys, uN, uP, FyF);

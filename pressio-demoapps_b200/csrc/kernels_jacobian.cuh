@@ -37,6 +37,12 @@ struct JacStage {
   static constexpr int CELLS = FIT >= 64 ? 64 : (FIT >= 48 ? 48 : (FIT >= 32 ? 32 : 16));
   static constexpr int THREADS = CELLS * 2 * DIM;
   static constexpr size_t smemBytes = (size_t)CELLS * STRIDE * 8;
+  // CTAs per SM the register allocation is capped for: as many as the staged chunks leave room for (<= 4)
+  static constexpr int FIT_CTAS = (int)(220 * 1024 / smemBytes);
+  static constexpr int WANT_CTAS = FIT_CTAS > 4 ? 4 : (FIT_CTAS < 1 ? 1 : FIT_CTAS);
+  // measured (B200, session 11): the cap pays where the spills stay small -- 3D WENO3 160^3 8.10 -> 5.84 ms, cfg 4 WENO3
+  // 0.254 -> 0.227 ms -- and loses for the WENO5 instances (3D 4.54 -> 5.24 ms with 284 bytes of spills): those stay uncapped
+  static constexpr int MIN_CTAS = (S == 7) ? 1 : ((THREADS * WANT_CTAS <= 512) ? WANT_CTAS : (512 / THREADS < 1 ? 1 : 512 / THREADS));
 };
 
 // Rusanov flux and flux Jacobians along a RUN-TIME axis.  Euler and shallow water: the flux along axis a is
@@ -183,8 +189,8 @@ __global__ void k_zero_cell_chunks(const int32_t* __restrict__ base, const int32
   for (int e = lane; e < cnt; e += 32) dst[e] = 0.0;
 }
 
-template <class Phys, int S>
-__global__ void __launch_bounds__(JacStage<Phys, S>::THREADS)
+template <class Phys, int S, int MINB>
+__global__ void __launch_bounds__(JacStage<Phys, S>::THREADS, MINB)
 k_jacobian_inner_staged(Phys phys, RowSet rs, Deltas dl, const double* __restrict__ U, double* __restrict__ V,
                         double* __restrict__ Jv, JacLayout jl) {
   using J = JacStage<Phys, S>;

@@ -294,11 +294,9 @@ inline bool tiledV2Enabled() {
   return on;
 }
 
-template <class Phys, int S>
-void launchLattice3dTiled2(const Phys& phys, const dev::LatticeDesc& L, const dev::Deltas& dl, const double* dU,
-                           double* dV, cudaStream_t st) {
-  static_assert(Phys::dim == 3 && Phys::ndpc == 5, "Euler3d kernel");
-  constexpr int TY = 7;   // 7 cell warps + 1 edge warp = 256 threads, 2 CTAs per SM at 128 registers
+template <class Phys, int S, int TY>
+void launchLattice3dTiled2T(const Phys& phys, const dev::LatticeDesc& L, const dev::Deltas& dl, const double* dU,
+                            double* dV, cudaStream_t st) {
   using T = dev::Tile3dSmem2<S, TY>;
   constexpr size_t smem = T::template bytes<5>();
   auto kern = (L.slab == 2) ? dev::k_euler3d_velocity_tiled2<S, TY, true> : dev::k_euler3d_velocity_tiled2<S, TY, false>;
@@ -306,15 +304,32 @@ void launchLattice3dTiled2(const Phys& phys, const dev::LatticeDesc& L, const de
   const int planes = L.planeEnd - L.planeBegin;
   if (planes <= 0) return;
   const int gx = (L.n[0] + 31) / 32, gy = (L.n[1] + TY - 1) / TY;
-  // z chunks: long enough to amortise the two ghost steps, short enough to fill 148 SMs x 2 CTAs with >= 4 waves
+  // z chunks: long enough to amortise the two ghost steps, short enough to fill the SMs with >= 4 waves
+  constexpr int ctasPerSm = (TY <= 7) ? 2 : 1;
   static const int lzStart = [] { const char* e = std::getenv("PDA_TILED_LZ"); const int v = e ? std::atoi(e) : 0; return v >= 8 ? v : 64; }();
   int LZ = lzStart;
-  while (LZ > 8 && (int64_t)gx * gy * ((planes + LZ - 1) / LZ) < 148 * 2 * 4) LZ /= 2;
+  // long slabs: 128-plane chunks halve the ghost-step share as long as >= 16 waves remain (512^3: 14.84 -> 14.76 ms)
+  if (lzStart == 64 && L.slab != 2 && (int64_t)gx * gy * (planes / 128) >= 148 * ctasPerSm * 16) LZ = 128;
+  while (LZ > 8 && (int64_t)gx * gy * ((planes + LZ - 1) / LZ) < 148 * ctasPerSm * 4) LZ /= 2;
   if (L.slab == 2) while (LZ > 8 && (planes + LZ - 1) / LZ < 2) LZ /= 2;   // peer mode: no CTA needs both halos
   const int gz = (planes + LZ - 1) / LZ;
   dim3 grid(gx, gy, gz), block(32, TY + 1);
   const int useTma = (L.n[0] % 2 == 0) && (L.n[0] >= T::PX) && ((reinterpret_cast<uintptr_t>(dU) & 15) == 0);
   kern<<<grid, block, smem, st>>>(phys.gamma, L, dl, dU, dV, LZ, useTma);
+}
+
+template <class Phys, int S>
+void launchLattice3dTiled2(const Phys& phys, const dev::LatticeDesc& L, const dev::Deltas& dl, const double* dU,
+                           double* dV, cudaStream_t st) {
+  static_assert(Phys::dim == 3 && Phys::ndpc == 5, "Euler3d kernel");
+  // TY = 7: 7 cell warps + 1 edge warp = 256 threads, 2 CTAs per SM at 128 registers (default).
+  // TY = 15 (PDA_TILED_TY=15): 15 + 1 warps = 512 threads, ONE CTA per SM: half the edge-warp and y-halo overhead, a
+  // 16-warp barrier -- an experiment, WENO5 only
+  static const int ty = [] { const char* e = std::getenv("PDA_TILED_TY"); return e ? std::atoi(e) : 7; }();
+  if constexpr (S == 7) {
+    if (ty == 15 && L.slab != 2) { launchLattice3dTiled2T<Phys, S, 15>(phys, L, dl, dU, dV, st); return; }
+  }
+  launchLattice3dTiled2T<Phys, S, 7>(phys, L, dl, dU, dV, st);
 }
 
 }  // namespace pda

@@ -78,7 +78,11 @@ def run(hbm_gbs, small=False, device=0):
     R = pda.InviscidFluxReconstruction
     res = {}
 
+    only = os.environ.get("PDA_BENCH_ONLY")   # comma-separated substrings of config names (tuning sessions)
+
     def guarded(name, fn):
+        if only and not any(o in name for o in only.split(",")):
+            return
         try:
             res[name] = fn()
         except Exception as e:   # a config that fails is reported, not hidden
