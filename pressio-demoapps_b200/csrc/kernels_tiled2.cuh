@@ -311,7 +311,10 @@ void launchLattice3dTiled2T(const Phys& phys, const dev::LatticeDesc& L, const d
   // long slabs: 128-plane chunks halve the ghost-step share as long as >= 16 waves remain (512^3: 14.84 -> 14.76 ms)
   if (lzStart == 64 && L.slab != 2 && (int64_t)gx * gy * (planes / 128) >= 148 * ctasPerSm * 16) LZ = 128;
   while (LZ > 8 && (int64_t)gx * gy * ((planes + LZ - 1) / LZ) < 148 * ctasPerSm * 4) LZ /= 2;
-  if (L.slab == 2) while (LZ > 8 && (planes + LZ - 1) / LZ < 2) LZ /= 2;   // peer mode: no CTA needs both halos
+  // peer mode: at least 2 z chunks, so that no CTA needs both halos (the chunk that needs the lower halo at its start is
+  // scheduled last); PDA_PEER_MINCHUNKS=1 lifts that for experiments
+  static const int minChunks = [] { const char* e = std::getenv("PDA_PEER_MINCHUNKS"); const int v = e ? std::atoi(e) : 2; return v >= 1 ? v : 2; }();
+  if (L.slab == 2) while (LZ > 8 && (planes + LZ - 1) / LZ < minChunks) LZ /= 2;
   const int gz = (planes + LZ - 1) / LZ;
   dim3 grid(gx, gy, gz), block(32, TY + 1);
   const int useTma = (L.n[0] % 2 == 0) && (L.n[0] >= T::PX) && ((reinterpret_cast<uintptr_t>(dU) & 15) == 0);
