@@ -1731,9 +1731,7 @@ void Problem::applyJacobianDev(const double* dU, const double* dB, int ncols, in
             auto kern = dev::k_applyjac_lattice3d<S, NC>;
             ensureFuncAttrs(kern, (int)AK::smemBytes);
             dim3 grid((unsigned)((w0 + AK::T - 1) / AK::T), (unsigned)((w1 + AK::T - 1) / AK::T), (unsigned)((w2 + AK::T - 1) / AK::T));
-            static const int prefetchOn = [] { const char* e = std::getenv("PDA_APPLY3D_PREFETCH"); return (e && e[0] == '0') ? 0 : 1; }();
-            kern<<<grid, AK::THREADS, AK::smemBytes, st>>>(gamma_, L, dl, dU, dB, ncols, c0, ldbRow, ldbCol, dR, ldrRow, ldrCol,
-                                                           prefetchOn);
+            kern<<<grid, AK::THREADS, AK::smemBytes, st>>>(gamma_, L, dl, dU, dB, ncols, c0, ldbRow, ldbCol, dR, ldrRow, ldrCol);
             ++launches_;
           };
           int c0 = 0;

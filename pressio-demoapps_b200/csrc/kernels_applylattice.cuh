@@ -172,6 +172,9 @@ k_applyjac_lattice2d(Phys phys, LatticeDesc L, Deltas dl, const double* __restri
 // indexing), while J*v needs the state, the operand and the result only.
 // Tile = 7 x 7 x 7 cells; a line (7 cells + the closing face) occupies 8 lanes, a warp carries 4 lines; phases x, y, z
 // with the partial result parked in shared memory in between.
+// Tried and dropped (session 14): `prefetch.global.L1` of the stencil the next (phase, round) will read, against the
+// long_scoreboard stalls ncu reports (2.5 of 8 cycles per issue): 81 -> 94 ms at 512^3 -- the 24 prefetch instructions per
+// line compete for the same LSU slots as the loads they were meant to hide.
 // ---------------------------------------------------------------------------------------------------------------
 template <int NC>
 struct ApplyLat3d {
@@ -282,7 +285,7 @@ template <int S, int NC>
 __global__ void __launch_bounds__(ApplyLat3d<NC>::THREADS, (NC == 1 ? 2 : 1))
 k_applyjac_lattice3d(double gamma, LatticeDesc L, Deltas dl, const double* __restrict__ U, const double* __restrict__ B,
                      int ncols, int c0, int64_t ldbRow, int64_t ldbCol, double* __restrict__ R, int64_t ldrRow,
-                     int64_t ldrCol, int prefetchOn) {
+                     int64_t ldrCol) {
   using K = ApplyLat3d<NC>;
   constexpr int T = K::T;
   extern __shared__ __align__(16) double sR3[];
@@ -295,66 +298,28 @@ k_applyjac_lattice3d(double gamma, LatticeDesc L, Deltas dl, const double* __res
     hi[ax] = L.per[ax] ? L.n[ax] : L.n[ax] - L.meshHalo;
   }
   const int O[3] = {lo[0] + T * (int)blockIdx.x, lo[1] + T * (int)blockIdx.y, lo[2] + T * (int)blockIdx.z};
-  // line of this thread in phase `ax`, round `round`: position a along the axis, clamped coordinates on the two others
-  auto lineOf = [&](int ax, int round, int& a, int& cc1, int& cc2, bool& owns, int& cellLocal) {
+#pragma unroll 1
+  for (int ax = 0; ax < 3; ++ax) {
+    // origin / upper bound along the line axis and along the two other axes (ascending)
     const int Oa = (ax == 0) ? O[0] : ((ax == 1) ? O[1] : O[2]);
     const int O1 = (ax == 0) ? O[1] : O[0], O2 = (ax == 2) ? O[1] : O[2];
     const int hia = (ax == 0) ? hi[0] : ((ax == 1) ? hi[1] : hi[2]);
     const int hi1 = (ax == 0) ? hi[1] : hi[0], hi2 = (ax == 2) ? hi[1] : hi[2];
-    const int l = round * K::GROUPS + grp;     // line index in the tile: (u, v) offsets along the other axes
-    const int u = l % T, v = l / T;
-    a = Oa + f;
-    const int c1 = O1 + u, c2 = O2 + v;
-    owns = (l < T * T) && (f < T) && (a < hia) && (c1 < hi1) && (c2 < hi2);
-    cc1 = min(c1, hi1 - 1); cc2 = min(c2, hi2 - 1);
-    const int uu = min(u, T - 1), vv = min(v, T - 1), ff = min(f, T - 1);
-    // tile-local linear index (z*T + y)*T + x
-    const int lx = (ax == 0) ? ff : uu;
-    const int ly = (ax == 0) ? uu : ((ax == 1) ? ff : vv);
-    const int lz = (ax == 2) ? ff : vv;
-    cellLocal = (lz * T + ly) * T + lx;
-  };
-  // L1 prefetch of the stencil the NEXT (phase, round) of this thread will read (state and first operand column): the
-  // 60 dependent-free loads at the top of a line were the first stall of this kernel (ncu: long_scoreboard 2.5 of 8
-  // cycles per issue at 14 warps/SM); prefetches hold no registers
-  auto prefetchLine = [&](int ax, int round) {
-    constexpr int h = (S - 1) / 2;
-    int a, o1, o2, cl; bool owns;
-    lineOf(ax, round, a, o1, o2, owns, cl);
-    const int64_t nx = L.n[0], ny = L.n[1];
-    const int nA = (ax == 0) ? L.n[0] : ((ax == 1) ? L.n[1] : L.n[2]);
-    const int perA = (ax == 0) ? L.per[0] : ((ax == 1) ? L.per[1] : L.per[2]);
-    const int64_t lineBase = (ax == 0) ? ((int64_t)o2 * ny + o1) * nx : ((ax == 1) ? (int64_t)o2 * ny * nx + o1 : (int64_t)o2 * nx + o1);
-    const int64_t lineStride = (ax == 0) ? 1 : ((ax == 1) ? nx : nx * ny);
-    // along x the 8 lanes of a line cover consecutive cells: only the line's ends add new sectors -> lanes 0 and 7
-    // prefetch the outer stencil cells; along y / z every lane has its own rows
-#pragma unroll
-    for (int m = 0; m < S - 1; ++m) {
-      int c = a - h + m;
-      if (perA) { c %= nA; if (c < 0) c += nA; }
-      else c = (c < 0) ? 0 : (c >= nA ? nA - 1 : c);
-      const int64_t off = (lineBase + (int64_t)c * lineStride) * 5;
-      if (ax != 0 || m == 0 || m == S - 2) {
-        const double* pu = U + off;
-        const double* pb = B + off * ldbRow + (int64_t)c0 * ldbCol;
-        asm volatile("prefetch.global.L1 [%0];" ::"l"(pu));
-        asm volatile("prefetch.global.L1 [%0];" ::"l"(pu + 4));
-        asm volatile("prefetch.global.L1 [%0];" ::"l"(pb));
-        asm volatile("prefetch.global.L1 [%0];" ::"l"(pb + 4 * ldbRow));
-      }
-    }
-  };
-#pragma unroll 1
-  for (int ax = 0; ax < 3; ++ax) {
     const double hInv = (ax == 0) ? dl.hInv[0] : ((ax == 1) ? dl.hInv[1] : dl.hInv[2]);
 #pragma unroll 1
     for (int round = 0; round < 2; ++round) {
-      int a, cc1, cc2, cellLocal; bool owns;
-      lineOf(ax, round, a, cc1, cc2, owns, cellLocal);
-      if (prefetchOn) {
-        if (round == 0) prefetchLine(ax, 1);
-        else if (ax < 2) prefetchLine(ax + 1, 0);
-      }
+      const int l = round * K::GROUPS + grp;     // line index in the tile: (u, v) offsets along the other axes
+      const int u = l % T, v = l / T;
+      const int a = Oa + f;
+      const int c1 = O1 + u, c2 = O2 + v;
+      const bool owns = (l < T * T) && (f < T) && (a < hia) && (c1 < hi1) && (c2 < hi2);
+      const int cc1 = min(c1, hi1 - 1), cc2 = min(c2, hi2 - 1);
+      const int uu = min(u, T - 1), vv = min(v, T - 1), ff = min(f, T - 1);
+      // tile-local linear index (z*T + y)*T + x
+      const int lx = (ax == 0) ? ff : uu;
+      const int ly = (ax == 0) ? uu : ((ax == 1) ? ff : vv);
+      const int lz = (ax == 2) ? ff : vv;
+      const int cellLocal = (lz * T + ly) * T + lx;
       applyLatLine3<S, NC>(gamma, L, ax, hInv, U, B, ncols, c0, ldbRow, ldbCol, R, ldrRow, ldrCol, a, cc1, cc2, owns,
                            cellLocal, sR3);
     }
