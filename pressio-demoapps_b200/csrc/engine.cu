@@ -20,6 +20,7 @@
 #include "kernels_jaclattice.cuh"
 #include "kernels_march2d.cuh"
 #include "kernels_applylattice.cuh"
+#include "kernels_applytiled3d.cuh"
 #include "kernels_reforder.hpp"
 
 namespace pda {
@@ -1725,6 +1726,14 @@ void Problem::applyJacobianDev(const double* dU, const double* dB, int ncols, in
       if (w0 > 0 && w1 > 0 && w2 > 0) {
         dispatchScheme(S_, [&](auto sTag) {
           constexpr int S = decltype(sTag)::value;
+          if (ldbRow == 1 && ldrRow == 1 && applyTiled3dEnabled() && mm.n[0] >= 2 * mm.halo() + 2) {
+            // contiguous operand columns (vector, column-major): the tiled (value, tangent) kernel, one launch per column
+            for (int c = 0; c < ncols; ++c) {
+              launchApplyTiled3d<S>(gamma_, L, dl, dU, dB + (int64_t)c * ldbCol, dR + (int64_t)c * ldrCol, st);
+              ++launches_;
+            }
+            return;
+          }
           auto pass = [&](auto ncTag, int c0) {
             constexpr int NC = decltype(ncTag)::value;
             using AK = dev::ApplyLat3d<NC>;

@@ -599,11 +599,21 @@ def test_matrix_free_apply_jacobian_equals_assembled(case):
             assert scaled_err(Rm, J @ B, 1e-11, 1e-9) <= 1.0
 
 
-@pytest.mark.parametrize("case", ["per_weno5", "per_weno3", "sedov_weno3", "per_fo_ragged"])
+@pytest.mark.parametrize("case", ["per_weno5", "per_weno3", "sedov_weno3", "per_fo_ragged", "per_weno5_tma", "sedov_weno3_tma",
+                                  "sedov_weno5_tma"])
 def test_matrix_free_apply_jacobian_3d(case):
-    """3D lattices: applyJacobian never assembles the inner rows (k_applyjac_lattice3d, 7^3 tiles, x/y/z phases); equals
-    J @ B of the assembled Jacobian, incl. near-boundary rows (Sedov symmetry walls) and ragged tiles"""
-    if case == "per_weno5":
+    """3D lattices: applyJacobian never assembles the inner rows: vectors and column-major operands go column by column
+    through the tiled (value, tangent) kernel k_applyjac_tiled3d (TMA-staged tiles once nx >= 40 and even: the *_tma
+    cases; 8-byte cp.async copies otherwise), row-major multi-column operands through the line kernel
+    k_applyjac_lattice3d (7^3 tiles, x/y/z phases); both equal J @ B of the assembled Jacobian, incl. near-boundary rows
+    (Sedov symmetry walls) and ragged tiles"""
+    if case == "per_weno5_tma":
+        p = pda.create_problem(pda.create_full_mesh([48, 9, 8], [-1, 1, -1, 1, -1, 1], 7, ("x", "y", "z")), pda.Euler3d.PeriodicSmooth, R.Weno5)
+    elif case == "sedov_weno3_tma":
+        p = pda.create_problem(pda.create_full_mesh([44, 16, 7], [0, 1, 0, 1, 0, 1], 5), pda.Euler3d.SedovSymmetry, R.Weno3)
+    elif case == "sedov_weno5_tma":
+        p = pda.create_problem(pda.create_full_mesh([70, 8, 9], [0, 1, 0, 1, 0, 1], 7), pda.Euler3d.SedovSymmetry, R.Weno5)
+    elif case == "per_weno5":
         p = pda.create_problem(pda.create_full_mesh([10, 9, 8], [-1, 1, -1, 1, -1, 1], 7, ("x", "y", "z")), pda.Euler3d.PeriodicSmooth, R.Weno5)
     elif case == "per_weno3":
         p = pda.create_problem(pda.create_full_mesh([16, 15, 9], [-1, 1, -1, 1, -1, 1], 5, ("x", "y", "z")), pda.Euler3d.PeriodicSmooth, R.Weno3)
