@@ -84,18 +84,28 @@ PDA_DEVFN void applyLatLine(const Phys& phys, const LatticeDesc& L, double hInv,
       }
     }
   }
-  double JN[N * N], JP[N * N];
-  faceFluxJac2d<Phys, AX>(phys, un, up, JN, JP);
   double r[NC][N];
+  if constexpr (std::is_same<Phys, Euler<2>>::value) {
+    // Euler: the Jacobian-vector product of the Rusanov flux in closed form (no N x N matrices, fastmath.cuh)
+    double D[NC][N];
+    eulerFluxJvpFast<2, AX, NC>(phys.gamma, un, up, dN, dP, D);
 #pragma unroll
-  for (int c = 0; c < NC; ++c)
+    for (int c = 0; c < NC; ++c)
 #pragma unroll
-    for (int k = 0; k < N; ++k) {
-      double d = 0.0;
+      for (int k = 0; k < N; ++k) r[c][k] = hInv * (D[c][k] - __shfl_down_sync(0xffffffffu, D[c][k], 1));
+  } else {
+    double JN[N * N], JP[N * N];
+    faceFluxJac2d<Phys, AX>(phys, un, up, JN, JP);
 #pragma unroll
-      for (int j = 0; j < N; ++j) d += JN[k * N + j] * dN[c][j] + JP[k * N + j] * dP[c][j];
-      r[c][k] = hInv * (d - __shfl_down_sync(0xffffffffu, d, 1));
-    }
+    for (int c = 0; c < NC; ++c)
+#pragma unroll
+      for (int k = 0; k < N; ++k) {
+        double d = 0.0;
+#pragma unroll
+        for (int j = 0; j < N; ++j) d += JN[k * N + j] * dN[c][j] + JP[k * N + j] * dP[c][j];
+        r[c][k] = hInv * (d - __shfl_down_sync(0xffffffffu, d, 1));
+      }
+  }
   if (!owns) return;
   double* mine = sR + cellLocal * K::RS;
   if (AX == 0) {
