@@ -21,6 +21,7 @@
 #include "kernels_march2d.cuh"
 #include "kernels_applylattice.cuh"
 #include "kernels_applytiled3d.cuh"
+#include "kernels_applymarch2d.cuh"
 #include "kernels_reforder.hpp"
 
 namespace pda {
@@ -1753,6 +1754,19 @@ void Problem::applyJacobianDev(const double* dU, const double* dB, int ncols, in
         using Phys = decltype(phys);
         dispatchScheme(S_, [&](auto sTag) {
           constexpr int S = decltype(sTag)::value;
+          if constexpr (std::is_same<Phys, dev::Euler<2>>::value) {
+            // contiguous operand columns of 2D Euler: the y-marching (value, tangent) kernel, one launch per column;
+            // requires 16-byte aligned columns for the 256-bit cell loads
+            // (operands with several columns keep the tile kernel: it shares the reconstruction gradients between 4 columns)
+            if (ncols == 1 && applyMarch2dEnabled() &&
+                ((reinterpret_cast<uintptr_t>(dB) | reinterpret_cast<uintptr_t>(dR)) & 31) == 0) {
+              for (int c = 0; c < ncols; ++c) {
+                launchApplyMarch2dEuler<S>(gamma_, L, dl, dU, dB + (int64_t)c * ldbCol, dR + (int64_t)c * ldrCol, st);
+                ++launches_;
+              }
+              return;
+            }
+          }
           constexpr int NC = 4;
           using AK = dev::ApplyLat2d<Phys, NC>;
           auto kern = dev::k_applyjac_lattice2d<Phys, S, NC>;
