@@ -1442,6 +1442,9 @@ void Problem::evaluateDev(const double* dU, double t, double* dV, double* dJ, vo
           dev::k_jacobian_inner_rows<Phys, S><<<gridFor(ds.inner.n, 128), 128, 0, st>>>(phys, ds.inner.view(nc), dl, dU, dV, dJ,
                                                                                         ds.inner.jac(slotCols_));
         } else {
+          // (a variant with one lane per (cell, axis, face) -- 2*dim lanes per cell, fluxes merged by shuffle -- was measured on
+          // cfg 4 and is SLOWER: 41 -> 47 us (WENO3), 54 -> 64 us (WENO5): every face gathers its own stencil, 4(S-1) instead
+          // of 2S cells per cell, and the gathers, not the arithmetic, are what this kernel waits for)
           dev::k_velocity_rows<Phys, S, false><<<gridFor(ds.inner.n, 128), 128, 0, st>>>(phys, ds.inner.view(nc), dl, dU, dV, gv);
         }
         ++launches_;
@@ -1754,18 +1757,14 @@ void Problem::applyJacobianDev(const double* dU, const double* dB, int ncols, in
         using Phys = decltype(phys);
         dispatchScheme(S_, [&](auto sTag) {
           constexpr int S = decltype(sTag)::value;
-          if constexpr (std::is_same<Phys, dev::Euler<2>>::value) {
-            // contiguous operand columns of 2D Euler: the y-marching (value, tangent) kernel, one launch per column;
-            // requires 16-byte aligned columns for the 256-bit cell loads
-            // (operands with several columns keep the tile kernel: it shares the reconstruction gradients between 4 columns)
-            if (ncols == 1 && applyMarch2dEnabled() &&
-                ((reinterpret_cast<uintptr_t>(dB) | reinterpret_cast<uintptr_t>(dR)) & 31) == 0) {
-              for (int c = 0; c < ncols; ++c) {
-                launchApplyMarch2dEuler<S>(gamma_, L, dl, dU, dB + (int64_t)c * ldbCol, dR + (int64_t)c * ldrCol, st);
-                ++launches_;
-              }
-              return;
-            }
+          // ONE operand column: the y-marching (value, tangent) kernel; the vector loads of 2- and 4-dof cells need a
+          // 32-byte aligned operand / result (operands with several columns keep the tile kernel: it shares the
+          // reconstruction gradients between 4 columns)
+          if (ncols == 1 && applyMarch2dEnabled() &&
+              ((reinterpret_cast<uintptr_t>(dB) | reinterpret_cast<uintptr_t>(dR)) & 31) == 0) {
+            launchApplyMarch2d<Phys, S>(phys, L, dl, dU, dB, dR, st);
+            ++launches_;
+            return;
           }
           constexpr int NC = 4;
           using AK = dev::ApplyLat2d<Phys, NC>;

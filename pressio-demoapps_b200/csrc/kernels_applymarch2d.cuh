@@ -1,11 +1,12 @@
-// kernels_applymarch2d.cuh -- matrix-free J*b of 2D Euler on full lattices for ONE contiguous operand column (vector
+// kernels_applymarch2d.cuh -- matrix-free J*b of the 2D families on full lattices for ONE contiguous operand column (vector
 // operands, columns of a column-major operand), on the skeleton of the 2D velocity kernel (kernels_march2d.cuh): a warp
 // owns a strip of 32-2h columns and marches along y with a REGISTER ring of 2h+1 rows of the state AND of the operand;
 // the x stencil comes from the neighbouring lanes by shuffle; every face once: the front y-face tangent flux of row j is
 // the back one of row j+1, a lane computes the left face of its cell and receives the right one from lane+1.
 // Per face: reconstruction values + gradients in one pass, two dot products with the operand stencil, and the tangent
-// of the Rusanov flux as one closed-form Jacobian-vector product (eulerFluxJvpFast) -- the velocity kernel with
-// (value, tangent) pairs.  Replaces Eigen's J * b (adapter_cpp.hpp:231-259) for the Newton-Krylov J*v; the tile kernel
+// of the Rusanov flux (Euler: one closed-form Jacobian-vector product, eulerFluxJvpFast; shallow water, Burgers,
+// advection-diffusion-reaction: their small flux Jacobians times the directional derivatives, plus the point / diffusion
+// terms applied to the operand) -- the velocity kernel with (value, tangent) pairs.  Replaces Eigen's J * b (adapter_cpp.hpp:231-259) for the Newton-Krylov J*v; the tile kernel
 // k_applyjac_lattice2d (kernels_applylattice.cuh) keeps the other families and row-major multi-column operands.
 #pragma once
 #include "kernels_march2d.cuh"
@@ -13,11 +14,57 @@
 namespace pda {
 namespace dev {
 
-template <int S>
+// tangent of the face flux along AX: closed-form Jacobian-vector product for Euler, flux Jacobians times the two
+// directional derivatives for the small systems (9 / 4 / 1 entries per side)
+template <class Phys, int AX>
+PDA_DEVFN void faceFluxTangent(const Phys& phys, const double* uN, const double* uP, const double* dN, const double* dP,
+                               double* D) {
+  constexpr int N = Phys::ndpc;
+  if constexpr (std::is_same<Phys, Euler<2>>::value) {
+    double a[1][4], b[1][4], out[1][4];
+#pragma unroll
+    for (int d = 0; d < 4; ++d) { a[0][d] = dN[d]; b[0][d] = dP[d]; }
+    eulerFluxJvpFast<2, AX, 1>(phys.gamma, uN, uP, a, b, out);
+#pragma unroll
+    for (int d = 0; d < 4; ++d) D[d] = out[0][d];
+  } else {
+    double JN[N * N], JP[N * N];
+    faceFluxJac2d<Phys, AX>(phys, uN, uP, JN, JP);
+#pragma unroll
+    for (int k = 0; k < N; ++k) {
+      double s = 0.0;
+#pragma unroll
+      for (int j = 0; j < N; ++j) s += JN[k * N + j] * dN[j] + JP[k * N + j] * dP[j];
+      D[k] = s;
+    }
+  }
+}
+
+// tangent flux of one face from the 2h stencil values of the state (q) and of the operand (b) per dof
+template <class Phys, int S, int AX>
+PDA_DEVFN void faceTangentOf(const Phys& phys, const double (*q)[Phys::ndpc], const double (*b)[Phys::ndpc], double* D) {
+  constexpr int N = Phys::ndpc;
+  constexpr int M = S - 1;
+  double uN[N], uP[N], dN[N], dP[N];
+#pragma unroll
+  for (int d = 0; d < N; ++d) {
+    double s[M], gN[M], gP[M];
+#pragma unroll
+    for (int o = 0; o < M; ++o) s[o] = q[o][d];
+    reconFaceValGradFast<S>(s, uN[d], uP[d], gN, gP);
+    double sN = 0.0, sP = 0.0;
+#pragma unroll
+    for (int o = 0; o < M; ++o) { sN = fma(gN[o], b[o][d], sN); sP = fma(gP[o], b[o][d], sP); }
+    dN[d] = sN; dP[d] = sP;
+  }
+  faceFluxTangent<Phys, AX>(phys, uN, uP, dN, dP, D);
+}
+
+template <class Phys, int S>
 __global__ void __launch_bounds__(128, 2)
-k_applyjac_march2d_euler(double gamma, LatticeDesc L, Deltas dl, const double* __restrict__ U, const double* __restrict__ B,
-                         double* __restrict__ Rout, int LY) {
-  constexpr int N = 4;
+k_applyjac_march2d(Phys phys, LatticeDesc L, Deltas dl, const double* __restrict__ U, const double* __restrict__ B,
+                   double* __restrict__ Rout, int LY) {
+  constexpr int N = Phys::ndpc;
   constexpr int h = (S - 1) / 2;
   constexpr int W = 32 - 2 * h;
   constexpr int R = 2 * h + 1;
@@ -43,27 +90,6 @@ k_applyjac_march2d_euler(double gamma, LatticeDesc L, Deltas dl, const double* _
     else r = (r < 0) ? 0 : (r >= ny ? ny - 1 : r);
     return ((int64_t)r * nx + xc) * N;
   };
-  // tangent flux of one face from the 2h stencil values of the state (q) and of the operand (b) per dof
-  auto faceTangent = [&](auto axTag, const double (*q)[N], const double (*b)[N], double* D) {
-    constexpr int AX = decltype(axTag)::value;
-    double uN[N], uP[N], dN[1][N], dP[1][N];
-#pragma unroll
-    for (int d = 0; d < N; ++d) {
-      double s[M], gN[M], gP[M];
-#pragma unroll
-      for (int o = 0; o < M; ++o) s[o] = q[o][d];
-      reconFaceValGradFast<S>(s, uN[d], uP[d], gN, gP);
-      double sN = 0.0, sP = 0.0;
-#pragma unroll
-      for (int o = 0; o < M; ++o) { sN = fma(gN[o], b[o][d], sN); sP = fma(gP[o], b[o][d], sP); }
-      dN[0][d] = sN; dP[0][d] = sP;
-    }
-    double out[1][N];
-    eulerFluxJvpFast<2, AX, 1>(gamma, uN, uP, dN, dP, out);
-#pragma unroll
-    for (int d = 0; d < N; ++d) D[d] = out[0][d];
-  };
-
   double q[R][N], b[R][N];
 #pragma unroll
   for (int i = 0; i < R; ++i) {
@@ -86,7 +112,7 @@ k_applyjac_march2d_euler(double gamma, LatticeDesc L, Deltas dl, const double* _
     }
     // ---- front y face (j+1/2): rows j-h+1 .. j+h
     double DyF[N];
-    faceTangent(std::integral_constant<int, 1>{}, q + 1, b + 1, DyF);
+    faceTangentOf<Phys, S, 1>(phys, q + 1, b + 1, DyF);
     if (!ghost) {
       // ---- x left face of this lane's cell from the neighbouring lanes' row-j values
       double sq[M][N], sb[M][N], Dx[N];
@@ -97,13 +123,31 @@ k_applyjac_march2d_euler(double gamma, LatticeDesc L, Deltas dl, const double* _
           sq[o][d] = (o == h) ? q[h][d] : __shfl_sync(0xffffffffu, q[h][d], (lane + o - h) & 31);
           sb[o][d] = (o == h) ? b[h][d] : __shfl_sync(0xffffffffu, b[h][d], (lane + o - h) & 31);
         }
-      faceTangent(std::integral_constant<int, 0>{}, sq, sb, Dx);
+      faceTangentOf<Phys, S, 0>(phys, sq, sb, Dx);
       double v[N];
 #pragma unroll
       for (int d = 0; d < N; ++d) {
         const double DxR = __shfl_down_sync(0xffffffffu, Dx[d], 1);
         v[d] = dl.hInv[0] * (Dx[d] - DxR);
         v[d] += dl.hInv[1] * (DyB[d] - DyF[d]);
+      }
+      if constexpr (std::is_same<Phys, Swe2d>::value || PhysTraits<Phys>::hasDiffusion || std::is_same<Phys, LinAdv<2>>::value) {
+        // point terms and diffusion: the entries addExtraJacInner adds to J, applied to the operand.  The "slot" handed to
+        // it is the graph column itself (0 self, 1 left, 2 front, 3 right, 4 back); the operand values of those cells
+        // sit in the ring (front / back) and in the neighbouring lanes (left / right)
+        double nbv[5][N];
+#pragma unroll
+        for (int d = 0; d < N; ++d) {
+          nbv[0][d] = b[h][d];
+          nbv[1][d] = __shfl_sync(0xffffffffu, b[h][d], (lane - 1) & 31);
+          nbv[2][d] = b[h + 1][d];
+          nbv[3][d] = __shfl_sync(0xffffffffu, b[h][d], (lane + 1) & 31);
+          nbv[4][d] = b[h - 1][d];
+        }
+        uint8_t ident[16];
+#pragma unroll
+        for (int c = 0; c < 16; ++c) ident[c] = (uint8_t)c;
+        addExtraJacInner<Phys>(phys, q[h], ident, [&](int k, int col, int jj, double xv) { v[k] += xv * nbv[col][jj]; });
       }
       if (outLane) storeBlockRow<N>(Rout + ((int64_t)j * nx + x) * N, v);
     }
@@ -128,8 +172,8 @@ inline bool applyMarch2dEnabled() {
   return on;
 }
 
-template <int S>
-void launchApplyMarch2dEuler(double gamma, const dev::LatticeDesc& L, const dev::Deltas& dl, const double* dU, const double* dB,
+template <class Phys, int S>
+void launchApplyMarch2d(const Phys& phys, const dev::LatticeDesc& L, const dev::Deltas& dl, const double* dU, const double* dB,
                              double* dR, cudaStream_t st) {
   constexpr int h = (S - 1) / 2, W = 32 - 2 * h;
   const int lo0 = L.per[0] ? 0 : L.meshHalo, hi0 = L.per[0] ? L.n[0] : L.n[0] - L.meshHalo;
@@ -139,7 +183,7 @@ void launchApplyMarch2dEuler(double gamma, const dev::LatticeDesc& L, const dev:
   int LY = 64;
   while (LY > 8 && nStrips * ((ye - yb + LY - 1) / LY) < (int64_t)148 * 8 * 4) LY /= 2;
   const int64_t tasks = nStrips * ((ye - yb + LY - 1) / LY);
-  dev::k_applyjac_march2d_euler<S><<<(unsigned)((tasks + 3) / 4), 128, 0, st>>>(gamma, L, dl, dU, dB, dR, LY);
+  dev::k_applyjac_march2d<Phys, S><<<(unsigned)((tasks + 3) / 4), 128, 0, st>>>(phys, L, dl, dU, dB, dR, LY);
 }
 
 }  // namespace pda

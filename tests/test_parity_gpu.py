@@ -564,13 +564,20 @@ def test_slab_decomposition_2d_equals_full(nranks, n, recon, sten):
 
 
 @pytest.mark.parametrize("case", ["euler_riemann_weno5", "euler_per_weno3", "swe_weno5", "burgers_per_weno5", "adr_weno3",
-                                  "euler_tiny_per"])
+                                  "euler_tiny_per", "swe_fo", "burgers_out_weno3", "euler_fo_wide"])
 def test_matrix_free_apply_jacobian_equals_assembled(case):
-    """operands with <= 12 columns on 2D lattices take the matrix-free inner-row kernel (kernels_applylattice.cuh: the
-    directional derivative of every face flux, no CSR values stored); result must equal J @ B of the assembled Jacobian
-    for vectors and both matrix layouts, incl. point / diffusion terms, periodic wrap and tiny meshes"""
+    """operands with <= 12 columns on 2D lattices take the matrix-free inner-row kernels -- vectors the y-marching
+    (value, tangent) kernel (kernels_applymarch2d.cuh), several columns the tile kernel (kernels_applylattice.cuh): the
+    directional derivative of every face flux, no CSR values stored; result must equal J @ B of the assembled Jacobian
+    for vectors and both matrix layouts, incl. point / diffusion terms, periodic wrap, several strips and tiny meshes"""
     V = pda.ViscousFluxReconstruction.FirstOrder
-    if case == "euler_riemann_weno5":
+    if case == "swe_fo":
+        p = pda.create_problem(pda.create_full_mesh([70, 21], [-5, 5, -5, 5], 3), pda.Swe2d.SlipWall, R.FirstOrder)
+    elif case == "burgers_out_weno3":
+        p = pda.create_problem(pda.create_full_mesh([63, 19], [-1, 1, -1, 1], 5), pda.AdvectionDiffusion2d.BurgersOutflow, R.Weno3, V)
+    elif case == "euler_fo_wide":
+        p = pda.create_problem(pda.create_full_mesh([100, 17], [0, 1, 0, 1], 3), pda.Euler2d.Riemann, R.FirstOrder)
+    elif case == "euler_riemann_weno5":
         p = pda.create_problem(pda.create_full_mesh([47, 33], [0, 1, 0, 1], 7), pda.Euler2d.Riemann, R.Weno5)
     elif case == "euler_per_weno3":
         p = pda.create_problem(pda.create_full_mesh([40, 31], [-1, 1, -1, 1], 7, ("x", "y")), pda.Euler2d.PeriodicSmooth, R.Weno3)
