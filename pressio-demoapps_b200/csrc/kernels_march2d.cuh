@@ -73,9 +73,17 @@ k_velocity_march2d(Phys phys, LatticeDesc L, Deltas dl, const double* __restrict
 
   // the march starts one row early ("ghost" step: only the y face below the first row), so that EVERY y face comes
   // from the same code -> a row's result does not depend on where chunks / slabs are cut (bit-exact decompositions)
+  // shallow water, first order: the face states are cell values, so 1/h and sqrt(h) are computed once per cell (when its
+  // row enters the ring) instead of once per adjacent face: the kernel is FP64-bound (ncu: pipe 61 %, DRAM 2.3 TB/s)
+  constexpr bool kSwePre = std::is_same<Phys, Swe2d>::value && S == 3;
   double q[R][N];
+  double pre[R][2];
 #pragma unroll
-  for (int i = 0; i < R; ++i) loadCell<N>(rowPtr(j0 - 1 - h + i), q[i]);
+  for (int i = 0; i < R; ++i) {
+    loadCell<N>(rowPtr(j0 - 1 - h + i), q[i]);
+    if constexpr (kSwePre) { pre[i][0] = rcpFast(q[i][0]); pre[i][1] = sqrtFast(q[i][0]); }
+  }
+  (void)pre;
   double FyB[N];
 #pragma unroll
   for (int d = 0; d < N; ++d) FyB[d] = 0.0;
@@ -87,23 +95,34 @@ k_velocity_march2d(Phys phys, LatticeDesc L, Deltas dl, const double* __restrict
     if (more) loadCell<N>(rowPtr(j + 1 + h), nxt);   // lands while this row is computed
     // ---- front y face (j+1/2): rows j-h+1 .. j+h
     double FyF[N];
-    yFace(q + 1, FyF);
+    if constexpr (kSwePre) sweFluxFastPre<1>(phys.g, q[1], q[2], pre[1][0], pre[1][1], pre[2][0], pre[2][1], FyF);
+    else yFace(q + 1, FyF);
     if (ghost) {
 #pragma unroll
       for (int d = 0; d < N; ++d) FyB[d] = FyF[d];
 #pragma unroll
-      for (int i = 0; i < R - 1; ++i)
+      for (int i = 0; i < R - 1; ++i) {
 #pragma unroll
         for (int d = 0; d < N; ++d) q[i][d] = q[i + 1][d];
+        if constexpr (kSwePre) { pre[i][0] = pre[i + 1][0]; pre[i][1] = pre[i + 1][1]; }
+      }
       if (more) {
 #pragma unroll
         for (int d = 0; d < N; ++d) q[R - 1][d] = nxt[d];
+        if constexpr (kSwePre) { pre[R - 1][0] = rcpFast(nxt[0]); pre[R - 1][1] = sqrtFast(nxt[0]); }
       }
       continue;
     }
     // ---- x left face of this lane's cell from the neighbouring lanes' row-j values
     double Fx[N];
-    {
+    if constexpr (kSwePre) {
+      double qL[N];
+#pragma unroll
+      for (int d = 0; d < N; ++d) qL[d] = __shfl_sync(0xffffffffu, q[h][d], (lane - 1) & 31);
+      const double iLft = __shfl_sync(0xffffffffu, pre[h][0], (lane - 1) & 31);
+      const double sLft = __shfl_sync(0xffffffffu, pre[h][1], (lane - 1) & 31);
+      sweFluxFastPre<0>(phys.g, qL, q[h], iLft, sLft, pre[h][0], pre[h][1], Fx);
+    } else {
       double uN[N], uP[N];
 #pragma unroll
       for (int d = 0; d < N; ++d) {
@@ -141,12 +160,15 @@ k_velocity_march2d(Phys phys, LatticeDesc L, Deltas dl, const double* __restrict
     }
     // ---- rotate the ring
 #pragma unroll
-    for (int i = 0; i < R - 1; ++i)
+    for (int i = 0; i < R - 1; ++i) {
 #pragma unroll
       for (int d = 0; d < N; ++d) q[i][d] = q[i + 1][d];
+      if constexpr (kSwePre) { pre[i][0] = pre[i + 1][0]; pre[i][1] = pre[i + 1][1]; }
+    }
     if (more) {
 #pragma unroll
       for (int d = 0; d < N; ++d) q[R - 1][d] = nxt[d];
+      if constexpr (kSwePre) { pre[R - 1][0] = rcpFast(nxt[0]); pre[R - 1][1] = sqrtFast(nxt[0]); }
     }
   }
 }
