@@ -1697,28 +1697,35 @@ void Problem::applyJacobianDev(const double* dU, const double* dB, int ncols, in
     // ---- matrix-free inner rows (kernels_applylattice.cuh); near-boundary rows through the assembled path
     const int64_t ldbRow = (layout == 1) ? ncols : 1, ldbCol = (layout == 1) ? 1 : nJc;
     const int64_t ldrRow = (layout == 1) ? ncols : 1, ldrCol = (layout == 1) ? 1 : nrows;
-    if (ds.nearBd.n > 0) {
-      skipInnerJacobian_ = true;
-      try { evaluateDev(dU, t, ds.dV.p, ds.dJ.p, st); } catch (...) { skipInnerJacobian_ = false; throw; }
-      skipInnerJacobian_ = false;
-      if (!ds.spmmFewReady) { ds.dCellBase.upload(cellBase_); ds.dCellLen.upload(cellLen_); ds.spmmFewReady = true; }
-      const unsigned gridNb = (unsigned)gridFor((int64_t)ds.nearBd.n * 32, 256);
-      auto nbLaunch = [&](auto nTag) {
-        constexpr int NN = decltype(nTag)::value;
-        for (int c0 = 0; c0 < ncols; ++c0) {
-          dev::k_spmm_cells_fewcols<NN, 1><<<gridNb, 256, 0, st>>>(ds.nearBd.n, ds.nearBd.rowIds.p, ds.dCellBase.p, ds.dCellLen.p,
-                                                                   ds.dColidx.p, ds.dJ.p, dB, c0, ldbRow, ldbCol, dR, ldrRow, ldrCol);
-          ++launches_;
+    // near-boundary rows: assembled (first-order Jacobian with ghost factors) and multiplied per column
+    auto nearBdRows = [&]() {
+      if (ds.nearBd.n > 0) {
+        skipInnerJacobian_ = true;
+        try { evaluateDev(dU, t, ds.dV.p, ds.dJ.p, st); } catch (...) { skipInnerJacobian_ = false; throw; }
+        skipInnerJacobian_ = false;
+        if (!ds.spmmFewReady) { ds.dCellBase.upload(cellBase_); ds.dCellLen.upload(cellLen_); ds.spmmFewReady = true; }
+        const unsigned gridNb = (unsigned)gridFor((int64_t)ds.nearBd.n * 32, 256);
+        auto nbLaunch = [&](auto nTag) {
+          constexpr int NN = decltype(nTag)::value;
+          for (int c0 = 0; c0 < ncols; ++c0) {
+            dev::k_spmm_cells_fewcols<NN, 1><<<gridNb, 256, 0, st>>>(ds.nearBd.n, ds.nearBd.rowIds.p, ds.dCellBase.p, ds.dCellLen.p,
+                                                                     ds.dColidx.p, ds.dJ.p, dB, c0, ldbRow, ldbCol, dR, ldrRow, ldrCol);
+            ++launches_;
+          }
+        };
+        switch (ndpc_) {
+          case 1: nbLaunch(std::integral_constant<int, 1>{}); break;
+          case 2: nbLaunch(std::integral_constant<int, 2>{}); break;
+          case 3: nbLaunch(std::integral_constant<int, 3>{}); break;
+          case 4: nbLaunch(std::integral_constant<int, 4>{}); break;
+          default: nbLaunch(std::integral_constant<int, 5>{}); break;
         }
-      };
-      switch (ndpc_) {
-        case 1: nbLaunch(std::integral_constant<int, 1>{}); break;
-        case 2: nbLaunch(std::integral_constant<int, 2>{}); break;
-        case 3: nbLaunch(std::integral_constant<int, 3>{}); break;
-        case 4: nbLaunch(std::integral_constant<int, 4>{}); break;
-        default: nbLaunch(std::integral_constant<int, 5>{}); break;
       }
-    }
+    };
+    // row-major operands with several columns on 3D lattices: transposed around the tiled single-column kernel (the inner
+    // kernel then fills whole columns of a scratch result, so the near-boundary rows are written afterwards)
+    const bool rowMajor3dTiled = fused3d && layout == 1 && ncols > 1 && applyTiled3dEnabled();
+    if (!rowMajor3dTiled) nearBdRows();
     dev::Deltas dl{{mm.dInv[0], mm.dInv[1], mm.dInv[2]}};
     dev::LatticeDesc L;
     for (int a = 0; a < 3; ++a) { L.n[a] = mm.n[a]; L.per[a] = mm.periodic[a] ? 1 : 0; }
@@ -1730,12 +1737,31 @@ void Problem::applyJacobianDev(const double* dU, const double* dB, int ncols, in
       if (w0 > 0 && w1 > 0 && w2 > 0) {
         dispatchScheme(S_, [&](auto sTag) {
           constexpr int S = decltype(sTag)::value;
-          if (ldbRow == 1 && ldrRow == 1 && applyTiled3dEnabled() && mm.n[0] >= 2 * mm.halo() + 2) {
+          if (ldbRow == 1 && ldrRow == 1 && applyTiled3dEnabled()) {
             // contiguous operand columns (vector, column-major): the tiled (value, tangent) kernel, one launch per column
             for (int c = 0; c < ncols; ++c) {
               launchApplyTiled3d<S>(gamma_, L, dl, dU, dB + (int64_t)c * ldbCol, dR + (int64_t)c * ldrCol, st);
               ++launches_;
             }
+            return;
+          }
+          if (rowMajor3dTiled) {
+            auto transpose = [&](const double* in, int64_t rows, int64_t cols, double* out) {
+              const int64_t tiles = ((rows + 31) / 32) * ((cols + 31) / 32);
+              dev::k_transpose<<<(unsigned)tiles, 256, 0, st>>>(in, rows, cols, out);
+              ++launches_;
+            };
+            ds.dBt.alloc((size_t)nJc * ncols);
+            ds.dRt.alloc((size_t)nrows * ncols);
+            const bool skinny = ncols <= 16;
+            if (skinny) { dev::k_split_columns<<<gridFor(nJc, 256), 256, 0, st>>>(dB, nJc, ncols, ds.dBt.p); ++launches_; }
+            else transpose(dB, nJc, ncols, ds.dBt.p);            // [nJc][ncols] -> [ncols][nJc]
+            for (int c = 0; c < ncols; ++c) {
+              launchApplyTiled3d<S>(gamma_, L, dl, dU, ds.dBt.p + (int64_t)c * nJc, ds.dRt.p + (int64_t)c * nrows, st);
+              ++launches_;
+            }
+            if (skinny) { dev::k_merge_columns<<<gridFor(nrows, 256), 256, 0, st>>>(ds.dRt.p, nrows, ncols, dR); ++launches_; }
+            else transpose(ds.dRt.p, ncols, nrows, dR);          // [ncols][nrows] -> [nrows][ncols]
             return;
           }
           auto pass = [&](auto ncTag, int c0) {
@@ -1790,6 +1816,7 @@ void Problem::applyJacobianDev(const double* dU, const double* dB, int ncols, in
         }
       }
     }
+    if (rowMajor3dTiled) nearBdRows();
     PDA_CUDA(cudaGetLastError());
     return;
   }

@@ -791,5 +791,21 @@ k_transpose(const double* __restrict__ in, int64_t rows, int64_t cols, double* _
   }
 }
 
+// the same for SKINNY matrices (a few columns / a few rows: row-major multi-column operands around the single-column
+// J*v kernel): one thread per long-axis index, the short axis in a loop -- both sides stay coalesced, no 32x32 tiles that
+// would be 1/16 full
+__global__ void __launch_bounds__(256)
+k_split_columns(const double* __restrict__ in, int64_t rows, int nc, double* __restrict__ out) {   // [rows][nc] -> [nc][rows]
+  const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= rows) return;
+  for (int c = 0; c < nc; ++c) out[(int64_t)c * rows + r] = in[r * nc + c];
+}
+__global__ void __launch_bounds__(256)
+k_merge_columns(const double* __restrict__ in, int64_t rows, int nc, double* __restrict__ out) {   // [nc][rows] -> [rows][nc]
+  const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= rows) return;
+  for (int c = 0; c < nc; ++c) out[r * nc + c] = in[(int64_t)c * rows + r];
+}
+
 }  // namespace dev
 }  // namespace pda
