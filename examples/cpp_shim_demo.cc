@@ -56,6 +56,17 @@ int main(int argc, char** argv) {
     const double err = (J * B - R).cwiseAbs().maxCoeff();
     std::printf("|V|max %.6e  |J*B - applyJacobian|max %.3e\n", V.cwiseAbs().maxCoeff(), err);
     if (!(err < 1e-9)) return 4;
+    // reference-order mode (the reference's formulas and operation order): a second evaluation through the same
+    // surface; the values may differ from the fast kernels only at the conditioning level of the WENO gradients
+    appObj.setOption("order", "reference");
+    if (appObj.getOption("jacobian_order") != "reference") return 7;
+    auto V2 = appObj.createRightHandSide();
+    auto J2 = appObj.createJacobian();
+    appObj.rightHandSideAndJacobian(state, 0.0, V2, J2);
+    const double dv = (V2 - V).cwiseAbs().maxCoeff();
+    std::printf("reference-order vs fast: |dV|max %.3e\n", dv);
+    if (!(dv < 1e-9 * (1.0 + V.cwiseAbs().maxCoeff()))) return 8;
+    appObj.setOption("order", "fast");
   } else {
     try { appObj.rightHandSide(state, 0.0, V); return 5; }   // must refuse: no CPU fallback
     catch (const std::runtime_error& e) { std::printf("no device: %s\n", e.what()); }

@@ -94,6 +94,19 @@ class Mesh {
   using index_t = int32_t;
   using graph_t = Eigen::Matrix<int32_t, Eigen::Dynamic, Eigen::Dynamic, Eigen::RowMajor>;
   explicit Mesh(const std::string& dir) { impl::check(pda_mesh_load(dir.c_str(), &h_)); }
+  // slab window of a full lattice for rank `rank` of `nranks` (multi-GPU sharding, pda_mesh_make_slab_window): owned
+  // planes plus halo planes where a neighbour rank exists; an ordinary mesh for every problem factory
+  static Mesh slabWindow(const Mesh& full, int rank, int nranks) {
+    Mesh w;
+    impl::check(pda_mesh_make_slab_window(full.handle(), rank, nranks, &w.h_));
+    return w;
+  }
+  // {plane_cells, k0, k1, halo_planes_below, halo_planes_above, rank, nranks, dim}
+  std::array<int64_t, 8> slabWindowInfo() const {
+    std::array<int64_t, 8> info{};
+    impl::check(pda_mesh_slab_window_info(h_, info.data()));
+    return info;
+  }
   Mesh(const Mesh&) = delete;
   Mesh& operator=(const Mesh&) = delete;
   Mesh(Mesh&& o) noexcept : h_(o.h_) { o.h_ = nullptr; }
@@ -142,6 +155,7 @@ class Mesh {
   pda_mesh handle() const { return h_; }
 
  private:
+  Mesh() = default;   // slabWindow()
   index_t firstLayer_(index_t rowInd, int col) const {
     if (graphCache_.size() == 0) graphCache_ = graph();
     return graphCache_(rowInd, col);
@@ -240,6 +254,15 @@ class Problem {
     double v;
     impl::check(pda_problem_query_parameter(h_, name.c_str(), &v));
     return v;
+  }
+  // evaluation mode (an extension of the reference's surface, include/pda_b200.h pda_problem_set_option):
+  // setOption("order", "reference") -> the reference's formulas, operation and accumulation order (values bit-identical
+  // to the CPU reference); "fast" (default) -> the structured kernels
+  void setOption(const std::string& name, const std::string& value) { impl::check(pda_problem_set_option(h_, name.c_str(), value.c_str())); }
+  std::string getOption(const std::string& name) const {
+    char buf[64] = {0};
+    impl::check(pda_problem_get_option(h_, name.c_str(), buf, (int)sizeof(buf)));
+    return std::string(buf);
   }
   double gamma() const { return queryParameter("gamma"); }
   double gravity() const { return queryParameter("gravity"); }
